@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 hot path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): batched Chamfer distance forward + backward,
+B=32 pairs per GPU, N=M=2048, synthetic unit-sphere clouds, fp32.  One step = ChamferLoss(pred, target) and
+its backward over one batch.  Multi-GPU: every rank runs its own batch of 32 pairs (weak scaling, no data-path
+collective) and all-reduces the loss scalar asynchronously, as the reference's logging does per step.
+
+Prints ONE JSON line on rank 0 (see the task contract): metric/value (device-resident inputs, CUDA events,
+max over ranks), roofline of the dominant kernel (FP32 FMA pipe for the Chamfer tile kernel), cpu_baseline
+(the oracle port of the reference's CPU path on this host's cores), e2e (host buffers through the public
+API: H2D of every step's inputs from pinned memory + D2H of the loss), clocks, gpu_launches; plus the encoder
+clouds/s figure and secondary rooflines as extra keys.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+B, N, M = 32, 2048, 2048                 # cfg2
+ENC_B, ENC_N, ENC_DIMS = 256, 2048, [64, 128, 1024]   # cfg3
+RING_BYTES = 288 << 20                   # inputs cycled through a ring larger than the 126 MB L2
+FLOP_PER_PAIR = 8.0 * N * M              # every pairwise squared distance counted once
+BWD_BYTES_PER_PAIR = 56.0 * (N + M)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-encoder", action="store_true", help="skip the encoder clouds/s side measurement")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# synthetic inputs: CPU generator -> identical bits everywhere
+# ----------------------------------------------------------------------------------------------------
+def sphere(gen, b, n):
+    x = torch.randn(b, n, 3, generator=gen)
+    return (x / x.norm(dim=2, keepdim=True).clamp_min(1e-12)).contiguous()
+
+
+def make_ring(rank: int, slots: int):
+    gen = torch.Generator(device="cpu").manual_seed(1234 + 2 + 1000 * rank)
+    return [(sphere(gen, B, N), sphere(gen, B, M)) for _ in range(slots)]
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU op sequence (oracle port) on this host's cores
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_step(pc1, pc2):
+    from oracle import oracle as O
+    a = pc1.clone().requires_grad_(True)
+    b = pc2.clone().requires_grad_(True)
+    loss = O.ref_port_chamfer_loss(a, b)       # utils/losses.py:62-75 as written (torch.cdist -> min -> mean)
+    loss.backward()
+    return float(loss.item())
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    gen = torch.Generator(device="cpu").manual_seed(1234 + 2)
+    pc1, pc2 = sphere(gen, B, N), sphere(gen, B, M)
+    steps, warm = max(1, min(args.steps, 12)), max(1, min(args.warmup, 2))
+    for _ in range(warm):
+        cpu_reference_step(pc1, pc2)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(pc1, pc2)
+    dt = time.perf_counter() - t0
+    value = steps * B / dt
+    sample = f"{steps} steps of ChamferLoss fwd+bwd on B={B}, N=M={N} (torch CPU ops of the reference, all host threads)"
+    print(json.dumps({
+        "impl": "reference", "metric": "chamfer_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "chamfer_fwd_bwd B=32 N=M=2048 sphere (BASELINE configs[1])", "B": B, "N": N, "M": M},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import gan_rl_3d_b200 as rlg
+    import importlib
+    D = importlib.import_module("gan-rl_3d_b200.distributed")
+    _lib = importlib.import_module("gan-rl_3d_b200._lib")
+    import torch.distributed as dist
+
+    rank, local_rank, world = D.init_from_env("nccl")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU path)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    peaks, peaks_src = load_peaks()
+    K, W = args.steps, max(3, args.warmup)
+
+    slot_bytes = (B * N + B * M) * 3 * 4
+    slots = max(8, RING_BYTES // slot_bytes)
+    ring_host = make_ring(rank, slots)
+    ring = [(a.to(dev), b.to(dev)) for a, b in ring_host]
+    crit = rlg.ChamferLoss()
+    loss_buf = torch.zeros(64, device=dev)
+    launches = {"n": 0}
+
+    def step(k, reduce_loss=True):
+        a, b = ring[k % slots]
+        a.requires_grad_(True); b.requires_grad_(True)
+        a.grad = None; b.grad = None
+        loss = crit(a, b)
+        loss.backward()
+        launches["n"] += 4                        # tile + finalize + bwd own + bwd scatter (our kernels)
+        if world > 1 and reduce_loss:
+            slot = loss_buf[k % 64: k % 64 + 1]
+            slot.copy_(loss.detach().reshape(1))
+            dist.all_reduce(slot, op=dist.ReduceOp.SUM, async_op=True)   # logged scalar, off the critical path
+        return loss
+
+    for k in range(W):
+        step(k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches["n"] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(K):
+        step(W + k)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    n_launches = launches["n"]
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = K * B * world / (ms * 1e-3)
+
+    # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region ----------------
+    pinned = [(a.pin_memory(), b.pin_memory()) for a, b in ring_host[:min(slots, 32)]]
+    nb = len(pinned)
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+    def e2e_step(k):
+        a, b = pinned[k % nb]
+        da = a.to(dev, non_blocking=True).requires_grad_(True)
+        db = b.to(dev, non_blocking=True)
+        loss = crit(da, db)
+        loss.backward()
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=False)    # what loss.item() does (train:242)
+        return loss_host
+
+    Ke = max(10, min(K, 500))
+    for k in range(3):
+        e2e_step(k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for k in range(Ke):
+        e2e_step(k)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = Ke * B * world / float(t.item())
+    if rank == 0:
+        clocks = sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel: the Chamfer tile kernel, timed alone with CUDA events -----
+    a, b = ring[0]
+    a = a.detach(); b = b.detach()
+    d1, d2, i1, i2, m1, m2 = rlg.chamfer_nearest(a, b)
+    ws = torch.empty(lib.rlg_chamfer_ws_bytes(B, N, M), dtype=torch.uint8, device=dev)
+    ws.fill_(0xFF)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def tile_only(x, y):
+        rc = lib.rlg_chamfer_fwd(x.data_ptr(), y.data_ptr(), B, N, M, d1.data_ptr(), d2.data_ptr(), i1.data_ptr(),
+                                 i2.data_ptr(), None, None, ws.data_ptr(), ws.numel(),
+                                 _lib.CHAMFER_WS_CLEAN | _lib.CHAMFER_TILE_ONLY, stream)
+        _lib.check("rlg_chamfer_fwd", rc)
+
+    for k in range(20):
+        tile_only(*[t_.detach() for t_ in ring[k % slots]])
+    torch.cuda.synchronize()
+    reps = 400
+    e0.record()
+    for k in range(reps):
+        x, y = ring[k % slots]
+        tile_only(x.detach(), y.detach())
+    e1.record()
+    torch.cuda.synchronize()
+    tile_ms = e0.elapsed_time(e1) / reps
+    achieved_tflops = FLOP_PER_PAIR * B / (tile_ms * 1e-3) / 1e12
+
+    peak = (ctypes_float6(lib, dev))
+    fp32_theory = peak[2]
+    roofline = {"bound": "fp32", "kernel": "chamfer_tile_kernel<8>", "achieved": achieved_tflops, "peak": fp32_theory,
+                "unit": "TFLOP/s", "frac": achieved_tflops / fp32_theory, "traffic": None,
+                "peak_source": f"theoretical FP32 FMA: {int(peak[3])} SMs x 128 lanes x 2 flop x {peak[1]:.0f} MHz "
+                               "(MEASURED_PEAKS.json has no FP32 entry; north_star names the FFMA peak)",
+                "peak_measured_ffma": peak[0], "peak_measured_ffma2": peak[4], "mix_ceiling_tflops": peak[5],
+                "frac_of_measured_ffma": achieved_tflops / peak[0] if peak[0] else None,
+                "launch_us": tile_ms * 1e3, "algorithmic_flop_per_launch": FLOP_PER_PAIR * B}
+
+    # backward: HBM-bound by bytes, launch-bound at this size
+    g = torch.full((B,), 0.5 / B, device=dev)
+    for _ in range(10):
+        rlg.chamfer_backward(a, b, d1, d2, i1, i2, g, g)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        rlg.chamfer_backward(a, b, d1, d2, i1, i2, g, g)
+    e1.record()
+    torch.cuda.synchronize()
+    bwd_ms = e0.elapsed_time(e1) / reps
+    bwd_gbs = BWD_BYTES_PER_PAIR * B / (bwd_ms * 1e-3) / 1e9
+    roofline_bwd = {"bound": "hbm", "kernel": "chamfer_bwd_own_kernel+chamfer_bwd_scatter_kernel", "achieved": bwd_gbs,
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": bwd_gbs / peaks["hbm_gbs"], "traffic": None,
+                    "peak_source": f"{peaks_src} MEASURED_PEAKS.json hbm_gbs", "launch_us": bwd_ms * 1e3,
+                    "note": "7.3 MB per call: launch-latency bound at this shape"}
+
+    extra = {}
+    if not args.no_encoder:
+        extra.update(encoder_side_measurement(rlg, dev, peaks, peaks_src))
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        pc1, pc2 = ring_host[0]
+        cpu_reference_step(pc1, pc2)
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < 12.0 and n < 40:
+            cpu_reference_step(pc1, pc2)
+            n += 1
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": n * B / dt, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"{n} steps of ChamferLoss fwd+bwd, B={B}, N=M={N}, torch CPU ops as the reference "
+                                  f"runs them (oracle port), {dt:.1f} s"}
+
+    out = {
+        "metric": "chamfer_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "chamfer_fwd_bwd B=32 N=M=2048 sphere (BASELINE configs[1])", "B_per_gpu": B, "N": N,
+                   "M": M, "global_batch": B * world, "parallelism": f"batch-sharded dp{world}",
+                   "l2_policy": f"inputs cycle through a ring of {slots} batches = {slots * slot_bytes >> 20} MiB > 126 MB L2",
+                   "step": "ChamferLoss forward + backward (autograd), loss all-reduce async when n_gpus > 1"},
+        "roofline": roofline, "roofline_bwd": roofline_bwd, "cpu_baseline": cpu_baseline,
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": slot_bytes, "d2h_bytes_per_step": 4,
+                "steps": Ke, "how": "pinned host clouds -> .to(device) -> ChamferLoss -> backward -> loss to host, every step"},
+        "gpu_launches": n_launches, "clocks": clocks,
+    }
+    out.update(extra)
+    print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def ctypes_float6(lib, dev):
+    import ctypes
+    out = (ctypes.c_float * 6)()
+    scratch = torch.zeros(64, device=dev)
+    rc = lib.rlg_fp32_peak(out, 6, scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    if rc != 0:
+        raise RuntimeError(f"rlg_fp32_peak rc={rc}: {lib.rlg_last_error()}")
+    return [float(v) for v in out]
+
+
+def encoder_side_measurement(rlg, dev, peaks, peaks_src):
+    """Encoder clouds/s at cfg3 (B=256, N=2048, dims 3->64->128->1024 + max-pool), the second half of the
+    BASELINE metric.  Reported as extra keys of the same JSON line."""
+    from oracle import oracle as O
+    torch.manual_seed(0)
+    enc = rlg.PointNetEncoder(3, 128, ENC_DIMS)
+    O.randomize_bn(enc, 0)
+    enc = enc.eval().to(dev)
+    gen = torch.Generator(device="cpu").manual_seed(1234 + 3)
+    xs = [sphere(gen, ENC_B, ENC_N).to(dev) for _ in range(4)]
+    with torch.no_grad():
+        for k in range(2):
+            enc(xs[k % 4])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for k in range(reps):
+            enc(xs[k % 4])
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flop = 2.0 * ENC_N * (3 * 64 + 64 * 128 + 128 * 1024) * ENC_B
+    tf = flop / (ms * 1e-3) / 1e12
+    return {"encoder": {"metric": "encoder_clouds_per_s", "value": ENC_B / (ms * 1e-3), "unit": "clouds/s",
+                        "config": {"workload": "PointNet encoder 3->64->128->1024 + max-pool, B=256, N=2048 (BASELINE configs[2])"},
+                        "path": "fp32 CUDA-core fused trunk (rlg_encoder_fwd)", "ms_per_step": ms,
+                        "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"],
+                                     "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops_sustained"], "traffic": None,
+                                     "peak_source": f"{peaks_src} MEASURED_PEAKS.json bf16_tflops_sustained"}}}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

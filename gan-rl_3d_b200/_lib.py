@@ -1,0 +1,76 @@
+"""ctypes binding of librlg_b200.so (include/rlg_b200.h).
+
+The product path has no CPU implementation: if the library is missing or a call fails this module raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "lib", "librlg_b200.so")
+
+_lib: Optional[ctypes.CDLL] = None
+
+c_float_p = ctypes.POINTER(ctypes.c_float)
+c_int32_p = ctypes.POINTER(ctypes.c_int32)
+
+
+class RlgLayer(ctypes.Structure):
+    """struct rlg_layer (include/rlg_b200.h)."""
+    _fields_ = [("w", ctypes.c_void_p), ("b", ctypes.c_void_p),
+                ("c_in", ctypes.c_int32), ("c_out", ctypes.c_int32)]
+
+
+class RlgError(RuntimeError):
+    def __init__(self, fn: str, code: int, msg: str):
+        super().__init__(f"{fn} failed with code {code}: {msg}")
+        self.code = code
+
+
+# every symbol include/rlg_b200.h declares; tests/test_abi.py checks the .so exports each of them
+EXPORTS = {
+    "rlg_version": (ctypes.c_int, []),
+    "rlg_last_error": (ctypes.c_char_p, []),
+    "rlg_device_sm_count": (ctypes.c_int, []),
+    "rlg_chamfer_ws_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "rlg_chamfer_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint, ctypes.c_void_p]),
+    "rlg_chamfer_bwd": (ctypes.c_int, [ctypes.c_void_p] * 8 + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3),
+    "rlg_encoder_ws_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(RlgLayer), ctypes.c_int]),
+    "rlg_encoder_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(RlgLayer),
+                                       ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "rlg_fp32_peak": (ctypes.c_int, [c_float_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+}
+
+CHAMFER_WS_CLEAN = 1
+CHAMFER_ALGO_SIMPLE = 2
+CHAMFER_TILE_ONLY = 4
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the in-tree library.  Raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python gan-rl_3d_b200/build.py` (or __graft_entry__.build()). "
+            "There is no CPU fallback for the B200 hot path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in EXPORTS.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(fn: str, rc: int) -> None:
+    if rc != 0:
+        msg = load().rlg_last_error()
+        raise RlgError(fn, rc, msg.decode("utf-8", "replace") if msg else "")

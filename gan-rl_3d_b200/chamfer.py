@@ -1,0 +1,164 @@
+"""Batched Chamfer distance on B200: torch.autograd.Function over the C ABI, plus mirrors of the reference's
+loss API (utils/losses.py:13-75 of phanich004/GAN-RL_3D) with the same names, arguments and return shapes.
+
+    chamfer_distance_l2(pc1, pc2) -> (dist1 (B,), dist2 (B,))       utils/losses.py:13-39
+    chamfer_distance(pc1, pc2, bidirectional=True) -> (B,)           utils/losses.py:42-59
+    ChamferLoss(bidirectional=True)(pred, target) -> 0-dim           utils/losses.py:62-75
+
+Inputs must be CUDA fp32 (B,N,3)/(B,M,3) with N,M >= 1; there is no CPU implementation here.
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def is_hot_path_input(pc1, pc2) -> bool:
+    """The input contract of the CUDA path.  Anything else is not the hot path."""
+    return (isinstance(pc1, torch.Tensor) and isinstance(pc2, torch.Tensor)
+            and pc1.is_cuda and pc2.is_cuda and pc1.device == pc2.device
+            and pc1.dtype == torch.float32 and pc2.dtype == torch.float32
+            and pc1.dim() == 3 and pc2.dim() == 3 and pc1.shape[2] == 3 and pc2.shape[2] == 3
+            and pc1.shape[0] == pc2.shape[0] and pc1.shape[1] >= 1 and pc2.shape[1] >= 1)
+
+
+def _require_hot_path(pc1, pc2) -> None:
+    if not is_hot_path_input(pc1, pc2):
+        def d(t):
+            return f"{tuple(t.shape)} {t.dtype} {t.device}" if isinstance(t, torch.Tensor) else repr(type(t))
+        raise ValueError("gan-rl_3d_b200 Chamfer needs CUDA float32 tensors (B,N,3) and (B,M,3) on one device with "
+                         f"N,M >= 1; got {d(pc1)} and {d(pc2)}. There is no CPU path.")
+
+
+class _Workspace:
+    """Caller-owned workspace of rlg_chamfer_fwd, cached per (device, stream, shape).  The forward leaves it
+    in the all-ones state it needs on entry, so repeat calls skip the memset (RLG_CHAMFER_WS_CLEAN)."""
+    _cache: Dict[tuple, "_Workspace"] = {}
+
+    def __init__(self, nbytes: int, device: torch.device):
+        self.buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        self.clean = False
+
+    @classmethod
+    def get(cls, device: torch.device, stream: int, B: int, N: int, M: int) -> "_Workspace":
+        key = (device.index, stream, B, N, M)
+        ws = cls._cache.get(key)
+        if ws is None:
+            if len(cls._cache) > 64:
+                cls._cache.clear()
+            nbytes = _lib.load().rlg_chamfer_ws_bytes(B, N, M)
+            ws = cls(nbytes, device)
+            cls._cache[key] = ws
+        return ws
+
+
+def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = True, simple: bool = False):
+    """Nearest neighbours in both directions (no autograd).
+
+    Returns (d1 (B,N) fp32, d2 (B,M) fp32, i1 (B,N) int32, i2 (B,M) int32, mean1 (B,), mean2 (B,)):
+    exactly torch.min(torch.cdist(pc1,pc2), 2) / (…, 1) of utils/losses.py:29-33 with cdist in direct mode,
+    and torch.mean(…, dim=1) of :36-37."""
+    _require_hot_path(pc1, pc2)
+    lib = _lib.load()
+    pc1 = pc1.contiguous()
+    pc2 = pc2.contiguous()
+    B, N, _ = pc1.shape
+    M = pc2.shape[1]
+    dev = pc1.device
+    d1 = torch.empty((B, N), dtype=torch.float32, device=dev)
+    d2 = torch.empty((B, M), dtype=torch.float32, device=dev)
+    i1 = torch.empty((B, N), dtype=torch.int32, device=dev)
+    i2 = torch.empty((B, M), dtype=torch.int32, device=dev)
+    m1 = torch.empty((B,), dtype=torch.float32, device=dev) if want_means else None
+    m2 = torch.empty((B,), dtype=torch.float32, device=dev) if want_means else None
+    if B == 0:
+        return d1, d2, i1, i2, m1, m2
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws = _Workspace.get(dev, stream, B, N, M)
+        flags = 0
+        if simple:
+            flags |= _lib.CHAMFER_ALGO_SIMPLE
+        elif ws.clean:
+            flags |= _lib.CHAMFER_WS_CLEAN
+        ws.clean = False
+        rc = lib.rlg_chamfer_fwd(pc1.data_ptr(), pc2.data_ptr(), B, N, M,
+                                 d1.data_ptr(), d2.data_ptr(), i1.data_ptr(), i2.data_ptr(),
+                                 m1.data_ptr() if want_means else None, m2.data_ptr() if want_means else None,
+                                 ws.buf.data_ptr(), ws.buf.numel(), flags, stream)
+        _lib.check("rlg_chamfer_fwd", rc)
+        ws.clean = not simple
+    return d1, d2, i1, i2, m1, m2
+
+
+def chamfer_backward(pc1, pc2, d1, d2, i1, i2, g1, g2) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Gradient of (mean1, mean2) w.r.t. (pc1, pc2) for upstream (g1 (B,), g2 (B,)); None = zero."""
+    lib = _lib.load()
+    B, N, _ = pc1.shape
+    M = pc2.shape[1]
+    gpc1 = torch.empty_like(pc1)
+    gpc2 = torch.empty_like(pc2)
+    if B == 0:
+        return gpc1, gpc2
+    g1 = g1.contiguous().float() if g1 is not None else None
+    g2 = g2.contiguous().float() if g2 is not None else None
+    with torch.cuda.device(pc1.device):
+        stream = torch.cuda.current_stream(pc1.device).cuda_stream
+        rc = lib.rlg_chamfer_bwd(pc1.data_ptr(), pc2.data_ptr(), d1.data_ptr(), d2.data_ptr(),
+                                 i1.data_ptr(), i2.data_ptr(),
+                                 g1.data_ptr() if g1 is not None else None,
+                                 g2.data_ptr() if g2 is not None else None,
+                                 B, N, M, gpc1.data_ptr(), gpc2.data_ptr(), stream)
+        _lib.check("rlg_chamfer_bwd", rc)
+    return gpc1, gpc2
+
+
+class ChamferFn(torch.autograd.Function):
+    """(pc1 (B,N,3), pc2 (B,M,3)) -> (mean1 (B,), mean2 (B,)), the two outputs of the reference's
+    chamfer_distance_l2 (utils/losses.py:13-39).  Saves the per-point distances and int32 argmin indices
+    instead of the reference's (B,N,M) matrix."""
+
+    @staticmethod
+    def forward(ctx, pc1, pc2):
+        pc1c, pc2c = pc1.contiguous(), pc2.contiguous()
+        d1, d2, i1, i2, m1, m2 = chamfer_nearest(pc1c, pc2c, want_means=True)
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(pc1c, pc2c, d1, d2, i1, i2)
+        return m1, m2
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        pc1, pc2, d1, d2, i1, i2 = ctx.saved_tensors
+        gpc1, gpc2 = chamfer_backward(pc1, pc2, d1, d2, i1, i2, g1, g2)
+        return (gpc1 if ctx.needs_input_grad[0] else None, gpc2 if ctx.needs_input_grad[1] else None)
+
+
+# ---- mirrors of the reference API -------------------------------------------------------------------
+def chamfer_distance_l2(pc1: torch.Tensor, pc2: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Drop-in for utils/losses.py:13-39.  Returns (dist1 (B,), dist2 (B,)): the mean over points of the
+    (non-squared) L2 distance to the nearest point of the other cloud, in each direction."""
+    _require_hot_path(pc1, pc2)
+    return ChamferFn.apply(pc1, pc2)
+
+
+def chamfer_distance(pc1: torch.Tensor, pc2: torch.Tensor, bidirectional: bool = True) -> torch.Tensor:
+    """Drop-in for utils/losses.py:42-59."""
+    dist1, dist2 = chamfer_distance_l2(pc1, pc2)
+    if bidirectional:
+        return (dist1 + dist2) / 2.0
+    return dist1
+
+
+class ChamferLoss(nn.Module):
+    """Drop-in for utils/losses.py:62-75."""
+
+    def __init__(self, bidirectional: bool = True):
+        super().__init__()
+        self.bidirectional = bidirectional
+
+    def forward(self, pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        return torch.mean(chamfer_distance(pred, target, self.bidirectional))

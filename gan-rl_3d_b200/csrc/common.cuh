@@ -1,0 +1,59 @@
+// common.cuh -- shared host/device helpers for librlg_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/rlg_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "librlg_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace rlg {
+
+// thread-local last-error text (api.cu)
+void set_error(const char *fmt, ...);
+int  fail(int code, const char *fmt, ...);
+int  check_launch(const char *what);
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int sm_count();
+
+typedef unsigned long long u64;
+
+// ---- packed fp32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2) ------------------------------
+// One instruction issues two IEEE fp32 operations, halving the issue-slot cost of the distance math.
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+    u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+    u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
+// 3-input min (FMNMX3).  NaN operands are dropped, like fminf.
+__device__ __forceinline__ float min3(float a, float b, float c) {
+    float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r;
+}
+
+// Squared distance in the reference's direct-mode operation order (see include/rlg_b200.h).
+__device__ __forceinline__ float sqdist(float px, float py, float pz, float qx, float qy, float qz) {
+    float d0 = __fsub_rn(px, qx), d1 = __fsub_rn(py, qy), d2 = __fsub_rn(pz, qz);
+    float t = __fmul_rn(d0, d0);
+    t = __fmaf_rn(d1, d1, t);
+    t = __fmaf_rn(d2, d2, t);
+    return t;
+}
+
+}  // namespace rlg

@@ -1,0 +1,135 @@
+/*
+ * rlg_b200.h -- C ABI of librlg_b200.so: the B200 (sm_100a) hot path of RL-GAN-Net point-cloud
+ * completion (phanich004/GAN-RL_3D): batched Chamfer distance and the PointNet encoder + max-pool.
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; these entry points are what a
+ * binding for its two choke points would call (citations into /root/reference):
+ *
+ *   rlg_chamfer_fwd   replaces  utils/losses.py:29-37   (torch.cdist -> min x2 -> mean) inside
+ *                               chamfer_distance_l2 (utils/losses.py:13-39)
+ *   rlg_chamfer_bwd   replaces  the autograd graph of the above (MeanBackward, MinBackward0 x2,
+ *                               EuclideanDistBackward0) reached from loss.backward()
+ *                               (train_rl_gan_net.py:239)
+ *   rlg_encoder_*     replaces  models/autoencoder.py:65-71 (transpose, point_mlp, max over points)
+ *                               inside PointNetEncoder.forward (models/autoencoder.py:56-76), eval mode
+ *
+ * Conventions
+ *   - extern "C", C types only.  Every pointer marked "device" is a CUDA device pointer on the
+ *     CURRENT device; the caller owns every buffer including the workspace.  The library never
+ *     allocates or frees device memory, never synchronises, never copies host<->device, and
+ *     enqueues all work on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream), so every call is CUDA-graph capturable.
+ *   - Return value: 0 = ok; negative = argument error detected on the host before any launch
+ *     (RLG_ERR_*); positive = the cudaError_t of a failed launch.  rlg_last_error() returns a
+ *     thread-local message for the last non-zero return.
+ *   - All tensors are contiguous, row-major, fp32 unless noted; indices are int32.
+ *   - There is no CPU implementation behind this ABI: without a CUDA device every compute call
+ *     fails with a positive cudaError_t.
+ */
+#ifndef RLG_B200_H
+#define RLG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLG_ABI_VERSION 1
+
+#define RLG_ERR_NULL_POINTER   (-1)
+#define RLG_ERR_BAD_SHAPE      (-2)   /* B < 0, N < 1, M < 1 (the reference raises IndexError for empty clouds) */
+#define RLG_ERR_WORKSPACE      (-3)   /* workspace missing, misaligned (256 B) or too small */
+#define RLG_ERR_UNSUPPORTED    (-4)   /* layer shape / option the kernel does not cover */
+#define RLG_ERR_TOO_LARGE      (-5)   /* index would not fit the packed 32-bit fields */
+
+/* flags for rlg_chamfer_fwd */
+#define RLG_CHAMFER_WS_CLEAN   1u     /* workspace is known to hold the all-ones pattern the previous
+                                         rlg_chamfer_fwd left behind on the same shape: skip the memset */
+#define RLG_CHAMFER_ALGO_SIMPLE 2u    /* run the simple one-thread-per-query kernel (cross-check path) */
+#define RLG_CHAMFER_TILE_ONLY  4u     /* measurement aid: enqueue only the distance/min tile kernel (no finalize,
+                                         outputs untouched, workspace left dirty) so it can be timed alone */
+
+int rlg_version(void);
+const char *rlg_last_error(void);
+
+/* Number of SMs of the current device (used by callers to size batches); <0 on error. */
+int rlg_device_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Chamfer distance, forward  (utils/losses.py:29-37)
+ *
+ *   pc1 (B,N,3), pc2 (B,M,3)                      device, fp32
+ *   d1 (B,N)  min_j |pc1[b,i]-pc2[b,j]|_2         device, fp32   (NOT squared; = torch.min(cdist,2)[0])
+ *   i1 (B,N)  argmin_j, lowest index on ties      device, int32  (= torch.min(cdist,2)[1])
+ *   d2 (B,M), i2 (B,M)                            the same from pc2 to pc1 (torch.min(cdist,1))
+ *   mean1 (B), mean2 (B)                          device, fp32, nullable as a pair: torch.mean(d, dim=1)
+ *   ws                                            device, >= rlg_chamfer_ws_bytes(B,N,M), 256-B aligned
+ *
+ * Distances are computed in the direct-difference form  t=d0*d0; t=fma(d1,d1,t); t=fma(d2,d2,t);
+ * sqrtf(min t)  and are bit-identical to ATen's direct-mode cdist; argmin is taken over t.
+ * Non-finite coordinates are outside the contract (NaN distances are ignored, not propagated).
+ * --------------------------------------------------------------------------------------------- */
+size_t rlg_chamfer_ws_bytes(int B, int N, int M);
+
+int rlg_chamfer_fwd(const float *pc1, const float *pc2, int B, int N, int M,
+                    float *d1, float *d2, int32_t *i1, int32_t *i2,
+                    float *mean1, float *mean2,
+                    void *ws, size_t ws_bytes, unsigned flags, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Chamfer distance, backward
+ *
+ *   g1 (B), g2 (B)      device, fp32: upstream gradients of mean1, mean2 (nullable individually = 0)
+ *   gpc1 (B,N,3), gpc2 (B,M,3)   device, fp32, fully overwritten:
+ *       gpc1[b,i] = g1[b]/N * (pc1[b,i]-pc2[b,i1])/d1[b,i]  -  sum_{j: i2[b,j]==i} g2[b]/M * (pc2[b,j]-pc1[b,i])/d2[b,j]
+ *       (and symmetrically for gpc2); a term is 0 where its distance is 0 (EuclideanDistBackward0).
+ * --------------------------------------------------------------------------------------------- */
+int rlg_chamfer_bwd(const float *pc1, const float *pc2,
+                    const float *d1, const float *d2, const int32_t *i1, const int32_t *i2,
+                    const float *g1, const float *g2, int B, int N, int M,
+                    float *gpc1, float *gpc2, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * PointNet encoder: shared per-point MLP + global max-pool  (models/autoencoder.py:65-71), eval mode.
+ *
+ * The caller folds each Conv1d(k=1)+BatchNorm1d pair into one affine layer
+ *       W' = W * gamma/sqrt(var+eps),  b' = (b-mean)*gamma/sqrt(var+eps) + beta
+ * and passes the folded layers; every layer is followed by ReLU (autoencoder.py:33-45).
+ *
+ *   x (B,N,3)                      device fp32
+ *   layers[l].w (c_out,c_in)       device fp32 row-major;  layers[l].b (c_out) device fp32
+ *   pooled (B, c_out of last)      device fp32 = torch.max(point_mlp(x^T), dim=2)[0]
+ *   argmax (B, c_out of last)      device int32, nullable: a point index attaining the max
+ *
+ * rlg_encoder_fwd      fp32 CUDA-core path, any layer widths (c_in of layer 0 must be 3).
+ * rlg_encoder_fwd_bf16 tcgen05/TMEM path: layers >= 1 run as bf16 x bf16 -> fp32 GEMMs on the 5th-gen
+ *                      tensor cores; needs every width to be a multiple of 64 and the packed weights
+ *                      produced by rlg_encoder_pack_bf16.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct rlg_layer {
+    const float *w;     /* device, (c_out, c_in) row-major, BatchNorm already folded */
+    const float *b;     /* device, (c_out) */
+    int32_t c_in;
+    int32_t c_out;
+} rlg_layer;
+
+size_t rlg_encoder_ws_bytes(int B, int N, const rlg_layer *layers, int L);
+
+int rlg_encoder_fwd(const float *x, int B, int N, const rlg_layer *layers, int L,
+                    float *pooled, int32_t *argmax,
+                    void *ws, size_t ws_bytes, void *stream);
+
+/* FP32 CUDA-core peak microbenchmark (measurement helper, not on the hot path; it synchronises).
+ * Fills host array out[0..5]:
+ *   [0] measured scalar FFMA TFLOP/s     [1] max SM clock (MHz)      [2] theoretical SMs*128*2*clock TFLOP/s
+ *   [3] SM count                         [4] measured packed FFMA2 TFLOP/s
+ *   [5] the Chamfer inner-loop instruction mix without memory traffic, as 8 flop per pair (TFLOP/s)
+ * scratch_dev: any device buffer of >= 4 bytes. */
+int rlg_fp32_peak(float *out_host, int n_out, void *scratch_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLG_B200_H */

@@ -1,0 +1,313 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+CPU checkers for the hot path of phanich004/GAN-RL_3D (batched Chamfer distance + PointNet encoder).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module; nothing under gan-rl_3d_b200/ does.
+
+Oracles (citations into /root/reference):
+  O_ref_port   `ref_port_*`     the reference's own op sequence restated in our words
+                                (utils/losses.py:29-37,54-59,75; models/autoencoder.py:20-76).
+                                tests/test_oracle.py asserts it is bit-identical to the real reference
+                                functions whenever /root/reference is mounted (build container), and
+                                against tests/golden/ everywhere.
+  O_direct     `chamfer_direct` plain-C direct-difference restatement (oracle/chamfer_oracle.c), the
+                                branch torch.cdist itself takes for N,M <= 25; bit-exact target of the
+                                CUDA kernel for distances and indices.
+  O_f64        `chamfer_f64`    the same in float64 = truth for tolerances.
+  O_enc        `RefEncoderPort` stock Conv1d/BatchNorm1d/ReLU/Linear stack in eval mode.
+
+Parity pinning: the reference has no golden vectors for this path; the pins are outputs of the real
+reference functions run in the build container (tests/golden/gen_golden.py -> tests/golden/*.npz).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import List, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+TIE_SQUARED = 0
+TIE_FAITHFUL = 1
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/chamfer_oracle.c -> oracle/liborc.so with the committed Makefile."""
+    so = os.path.join(_HERE, "liborc.so")
+    src = os.path.join(_HERE, "chamfer_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-B", "liborc.so"], check=True, capture_output=True)
+    return so
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liborc.so")
+        if not os.path.exists(so):
+            build()
+        L = ctypes.CDLL(so)
+        fp = ctypes.POINTER(ctypes.c_float)
+        ip = ctypes.POINTER(ctypes.c_int32)
+        dp = ctypes.POINTER(ctypes.c_double)
+        L.orc_chamfer_fwd.argtypes = [fp, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      fp, fp, ip, ip]
+        L.orc_chamfer_fwd.restype = ctypes.c_int
+        L.orc_chamfer_means.argtypes = [fp, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, fp, fp]
+        L.orc_chamfer_means.restype = ctypes.c_int
+        L.orc_chamfer_bwd.argtypes = [fp, fp, fp, fp, ip, ip, fp, fp,
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp]
+        L.orc_chamfer_bwd.restype = ctypes.c_int
+        _LIB = L
+    return _LIB
+
+
+def _f32(a) -> np.ndarray:
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a: np.ndarray, ty):
+    return a.ctypes.data_as(ctypes.POINTER(ty))
+
+
+# --------------------------------------------------------------------------------------------
+# O_direct: C restatement
+# --------------------------------------------------------------------------------------------
+def chamfer_direct(pc1, pc2, tie_rule: int = TIE_SQUARED):
+    """Direct-form nearest neighbours in fp32.  Returns (d1 (B,N), d2 (B,M), i1, i2) numpy arrays.
+
+    Follows utils/losses.py:29-33 with cdist in its direct mode."""
+    a, b = _f32(pc1), _f32(pc2)
+    B, N, _ = a.shape
+    M = b.shape[1]
+    d1 = np.empty((B, N), np.float32)
+    d2 = np.empty((B, M), np.float32)
+    i1 = np.empty((B, N), np.int32)
+    i2 = np.empty((B, M), np.int32)
+    rc = lib().orc_chamfer_fwd(_ptr(a, ctypes.c_float), _ptr(b, ctypes.c_float), B, N, M, tie_rule,
+                               _ptr(d1, ctypes.c_float), _ptr(d2, ctypes.c_float),
+                               _ptr(i1, ctypes.c_int32), _ptr(i2, ctypes.c_int32))
+    if rc != 0:
+        raise ValueError(f"orc_chamfer_fwd rc={rc}")
+    return d1, d2, i1, i2
+
+
+def chamfer_means(d1: np.ndarray, d2: np.ndarray):
+    """utils/losses.py:36-37 (double accumulation, rounded to fp32)."""
+    return (d1.astype(np.float64).mean(axis=1).astype(np.float32),
+            d2.astype(np.float64).mean(axis=1).astype(np.float32))
+
+
+def chamfer_bwd_truth(pc1, pc2, d1, d2, i1, i2, g1, g2):
+    """Closed-form gradient of (mean1, mean2) for the given indices, accumulated in float64."""
+    a, b = _f32(pc1), _f32(pc2)
+    B, N, _ = a.shape
+    M = b.shape[1]
+    d1, d2 = _f32(d1), _f32(d2)
+    i1 = np.ascontiguousarray(i1, np.int32)
+    i2 = np.ascontiguousarray(i2, np.int32)
+    g1, g2 = _f32(g1), _f32(g2)
+    ga = np.empty((B, N, 3), np.float64)
+    gb = np.empty((B, M, 3), np.float64)
+    rc = lib().orc_chamfer_bwd(_ptr(a, ctypes.c_float), _ptr(b, ctypes.c_float),
+                               _ptr(d1, ctypes.c_float), _ptr(d2, ctypes.c_float),
+                               _ptr(i1, ctypes.c_int32), _ptr(i2, ctypes.c_int32),
+                               _ptr(g1, ctypes.c_float), _ptr(g2, ctypes.c_float), B, N, M,
+                               _ptr(ga, ctypes.c_double), _ptr(gb, ctypes.c_double))
+    if rc != 0:
+        raise ValueError(f"orc_chamfer_bwd rc={rc}")
+    return ga, gb
+
+
+# --------------------------------------------------------------------------------------------
+# O_f64 (truth) and the torch direct-mode cross-check
+# --------------------------------------------------------------------------------------------
+def chamfer_f64(pc1, pc2):
+    """Float64 direct-mode distances: (d1, d2, i1, i2, D) as torch tensors; D only for small inputs."""
+    a = torch.as_tensor(pc1).double()
+    b = torch.as_tensor(pc2).double()
+    D = torch.cdist(a, b, p=2, compute_mode="donot_use_mm_for_euclid_dist")
+    d1, i1 = torch.min(D, dim=2)
+    d2, i2 = torch.min(D, dim=1)
+    return d1, d2, i1, i2, D
+
+
+def chamfer_torch_direct(pc1, pc2):
+    """fp32 torch.cdist forced into its direct mode (the branch utils/losses.py:29 takes for N,M<=25)."""
+    a = torch.as_tensor(pc1).float()
+    b = torch.as_tensor(pc2).float()
+    D = torch.cdist(a, b, p=2, compute_mode="donot_use_mm_for_euclid_dist")
+    d1, i1 = torch.min(D, dim=2)
+    d2, i2 = torch.min(D, dim=1)
+    return d1, d2, i1, i2
+
+
+# --------------------------------------------------------------------------------------------
+# O_ref_port: the reference's op sequence as written
+# --------------------------------------------------------------------------------------------
+def ref_port_chamfer_l2(pc1: torch.Tensor, pc2: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """utils/losses.py:13-39: cdist -> min over each axis -> mean over points."""
+    dm = torch.cdist(pc1, pc2, p=2)
+    near12 = torch.min(dm, dim=2)[0]
+    near21 = torch.min(dm, dim=1)[0]
+    return torch.mean(near12, dim=1), torch.mean(near21, dim=1)
+
+
+def ref_port_chamfer(pc1, pc2, bidirectional: bool = True) -> torch.Tensor:
+    """utils/losses.py:42-59."""
+    m1, m2 = ref_port_chamfer_l2(pc1, pc2)
+    return (m1 + m2) / 2.0 if bidirectional else m1
+
+
+def ref_port_chamfer_loss(pred, target, bidirectional: bool = True) -> torch.Tensor:
+    """utils/losses.py:62-75 (ChamferLoss.forward)."""
+    return torch.mean(ref_port_chamfer(pred, target, bidirectional))
+
+
+def ref_port_argmins(pc1: torch.Tensor, pc2: torch.Tensor):
+    """The indices autograd saves for MinBackward0 in the as-written reference."""
+    dm = torch.cdist(pc1, pc2, p=2)
+    return torch.min(dm, dim=2)[1], torch.min(dm, dim=1)[1]
+
+
+class RefEncoderPort(nn.Module):
+    """models/autoencoder.py:13-76 restated: [Conv1d(k=1) -> BatchNorm1d -> ReLU] x L over (B,C,N),
+    max over N, Linear -> BatchNorm1d -> ReLU.  Module/attribute names match the reference so a
+    reference state_dict loads unchanged."""
+
+    def __init__(self, input_dim: int = 3, latent_dim: int = 128,
+                 hidden_dims: Sequence[int] = (64, 128, 128, 256, 128)):
+        super().__init__()
+        self.input_dim, self.latent_dim, self.hidden_dims = input_dim, latent_dim, list(hidden_dims)
+        seq: List[nn.Module] = []
+        c_in = input_dim
+        for c_out in self.hidden_dims:
+            seq += [nn.Conv1d(c_in, c_out, 1), nn.BatchNorm1d(c_out), nn.ReLU(inplace=True)]
+            c_in = c_out
+        self.point_mlp = nn.Sequential(*seq)
+        self.global_mlp = nn.Sequential(nn.Linear(c_in, latent_dim), nn.BatchNorm1d(latent_dim),
+                                        nn.ReLU(inplace=True))
+
+    def pooled(self, x: torch.Tensor) -> torch.Tensor:
+        return torch.max(self.point_mlp(x.transpose(2, 1)), dim=2)[0]
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.global_mlp(self.pooled(x))
+
+
+def randomize_bn(module: nn.Module, seed: int = 0) -> None:
+    """Non-trivial BatchNorm statistics/affine (a fresh BN is identity-like and hides folding bugs).
+    SURVEY.md 8d: running_mean~N(0,.5), running_var~U(.3,2), gamma~N(1,.5), beta~N(0,.3)."""
+    g = torch.Generator().manual_seed(seed)
+    for m in module.modules():
+        if isinstance(m, nn.BatchNorm1d):
+            with torch.no_grad():
+                m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.5)
+                m.running_var.copy_(torch.rand(m.num_features, generator=g) * 1.7 + 0.3)
+                m.weight.copy_(1.0 + torch.randn(m.num_features, generator=g) * 0.5)
+                m.bias.copy_(torch.randn(m.num_features, generator=g) * 0.3)
+
+
+# --------------------------------------------------------------------------------------------
+# seeded synthetic inputs -- generated on the CPU so every backend sees the same bits
+# --------------------------------------------------------------------------------------------
+def make_clouds(B: int, N: int, kind: str = "sphere", seed: int = 1234) -> torch.Tensor:
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    if kind == "sphere":
+        x = torch.randn(B, N, 3, generator=g)
+        x = x / x.norm(dim=2, keepdim=True).clamp_min(1e-12)
+    elif kind == "uniform":
+        x = torch.rand(B, N, 3, generator=g) * 2.0 - 1.0
+    else:
+        raise ValueError(kind)
+    return x.contiguous()
+
+
+def pad_with_duplicates(pc: torch.Tensor, frac: float = 0.25, seed: int = 99) -> torch.Tensor:
+    """Overwrite the last `frac` of each cloud with copies of earlier points, as the reference's
+    collate does for ragged partial clouds (utils/dataset.py:398-421) -> exact-tie stress."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    B, N, _ = pc.shape
+    keep = N - int(N * frac)
+    out = pc.clone()
+    for b in range(B):
+        src = torch.randint(0, keep, (N - keep,), generator=g)
+        out[b, keep:] = pc[b, src]
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# parity-contract helpers
+# --------------------------------------------------------------------------------------------
+def idx_mismatches_are_exact_ties(pc_q, pc_c, idx_ours, idx_ref) -> Tuple[int, int]:
+    """For every query where idx_ours != idx_ref, check both candidates are at the SAME fp32 direct
+    distance (an exact tie in the reference's sqrt-ed matrix).  Returns (n_mismatch, n_not_tie)."""
+    q, c = _f32(pc_q), _f32(pc_c)
+    io = np.asarray(idx_ours).astype(np.int64)
+    ir = np.asarray(idx_ref).astype(np.int64)
+    bb, ii = np.nonzero(io != ir)
+    if len(bb) == 0:
+        return 0, 0
+
+    def dist(b, i, j):
+        d = (q[b, i] - c[b, j]).astype(np.float32)
+        t = np.float32(d[..., 0] * d[..., 0])
+        t = (t.astype(np.float64) + d[..., 1].astype(np.float64) ** 2).astype(np.float32)  # fmaf
+        t = (t.astype(np.float64) + d[..., 2].astype(np.float64) ** 2).astype(np.float32)
+        return np.sqrt(t, dtype=np.float32)
+
+    da, db = dist(bb, ii, io[bb, ii]), dist(bb, ii, ir[bb, ii])
+    return len(bb), int(np.count_nonzero(da != db))
+
+
+def idx_mismatches_are_near_ties(pc_q, pc_c, idx_ours, idx_ref, ulps: float = 8.0) -> Tuple[int, int]:
+    """vs the as-written (matmul-path) reference: a disagreement must be a near-tie in float64:
+    |d64(i,ours) - d64(i,ref)| <= ulps * eps32 * (|x|^2+|y|^2) / max(d,eps)  (SURVEY.md 8c)."""
+    q = _f32(pc_q).astype(np.float64)
+    c = _f32(pc_c).astype(np.float64)
+    io = np.asarray(idx_ours).astype(np.int64)
+    ir = np.asarray(idx_ref).astype(np.int64)
+    bb, ii = np.nonzero(io != ir)
+    if len(bb) == 0:
+        return 0, 0
+    x = q[bb, ii]
+    ya, yb = c[bb, io[bb, ii]], c[bb, ir[bb, ii]]
+    ta = ((x - ya) ** 2).sum(-1)
+    tb = ((x - yb) ** 2).sum(-1)
+    scale = (x ** 2).sum(-1) + np.maximum((ya ** 2).sum(-1), (yb ** 2).sum(-1))
+    eps32 = float(np.finfo(np.float32).eps)
+    bad = np.abs(ta - tb) > ulps * eps32 * scale          # compared on squared distances
+    return len(bb), int(np.count_nonzero(bad))
+
+
+def rel_err(a, b, floor: float = 0.0) -> float:
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))) if a.size else 0.0
+
+
+def rowwise_rel_err(g, g_truth, floor_frac: float = 1e-3) -> float:
+    """Row-wise gradient error: |g_i - t_i|_2 / max(|t_i|_2, floor_frac * max_i |t_i|_2)."""
+    g = np.asarray(g, np.float64).reshape(-1, 3)
+    t = np.asarray(g_truth, np.float64).reshape(-1, 3)
+    tn = np.linalg.norm(t, axis=1)
+    floor = floor_frac * (tn.max() if tn.size else 1.0)
+    return float(np.max(np.linalg.norm(g - t, axis=1) / np.maximum(tn, max(floor, 1e-300))))
+
+
+def gfv_close(a, b, rel: float) -> Tuple[bool, float]:
+    """Encoder tolerance with the abs-floor rule of SURVEY.md 7.2-6:
+    |a-b| <= rel * max(|b|, 1e-2 * |b|_inf)."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    floor = 1e-2 * np.abs(b).max()
+    err = np.abs(a - b) / np.maximum(np.abs(b), floor)
+    return bool(err.max() <= rel), float(err.max())

@@ -1,0 +1,123 @@
+"""Generates tests/golden/*.npz from the REAL reference (phanich004/GAN-RL_3D), imported by file path from
+/root/reference in the build container (the package import needs h5py, which is absent; utils/losses.py and
+models/autoencoder.py themselves depend only on torch/numpy).  The reference holds no golden vectors for
+this path, so these outputs are the pins.
+
+    python tests/golden/gen_golden.py            # rewrites the fixtures (CPU, torch 2.11.0, ~10 s)
+
+The fixtures carry inputs (or the seeds of oracle.make_clouds) and reference outputs, so the tests need
+neither /root/reference nor this script at run time.
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402
+
+REF = os.environ.get("RLG_REFERENCE", "/root/reference")
+
+
+def load_ref(rel, name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def chamfer_case(losses, pc1, pc2):
+    """Everything the reference computes for one input pair, plus what autograd saves/returns."""
+    a = pc1.clone().requires_grad_(True)
+    b = pc2.clone().requires_grad_(True)
+    dist1, dist2 = losses.chamfer_distance_l2(a, b)                 # utils/losses.py:13-39
+    cd = losses.chamfer_distance(a, b)                              # :42-59
+    cd_uni = losses.chamfer_distance(a, b, bidirectional=False)
+    loss = losses.ChamferLoss()(a, b)                               # :62-75
+    loss.backward()
+    with torch.no_grad():
+        D = torch.cdist(pc1, pc2, p=2)                              # :29 as written (mode picked by size)
+        d1, i1 = torch.min(D, dim=2)                                # :32
+        d2, i2 = torch.min(D, dim=1)                                # :33
+    return dict(dist1=dist1.detach().numpy(), dist2=dist2.detach().numpy(), cd=cd.detach().numpy(),
+                cd_uni=cd_uni.detach().numpy(), loss=np.float32(loss.item()),
+                g1=a.grad.numpy(), g2=b.grad.numpy(),
+                d1=d1.numpy(), d2=d2.numpy(), i1=i1.numpy().astype(np.int32), i2=i2.numpy().astype(np.int32))
+
+
+def main():
+    torch.set_num_threads(1)        # fixtures must not depend on the reduction split of a thread pool
+    losses = load_ref("utils/losses.py", "ref_losses")
+    ae = load_ref("models/autoencoder.py", "ref_autoencoder")
+    out = {}
+
+    # --- Chamfer, small shapes: the reference itself takes cdist's DIRECT path (N,M <= 25) -> bit-exact pins
+    small = [(4, 16, 25, "sphere"), (3, 1, 7, "uniform"), (2, 25, 1, "sphere"), (5, 25, 25, "uniform"),
+             (1, 2, 3, "sphere")]
+    for k, (B, N, M, kind) in enumerate(small):
+        pc1 = O.make_clouds(B, N, kind, seed=100 + k)
+        pc2 = O.make_clouds(B, M, kind, seed=200 + k)
+        if k == 3:   # exact duplicates -> exact ties
+            pc2[:, 20:] = pc2[:, :5]
+            pc1[:, 3] = pc2[:, 7]      # a zero distance -> zero-gradient rule of EuclideanDistBackward0
+        case = chamfer_case(losses, pc1, pc2)
+        for name, v in case.items():
+            out[f"small{k}_{name}"] = v
+        out[f"small{k}_pc1"] = pc1.numpy()
+        out[f"small{k}_pc2"] = pc2.numpy()
+    out["small_count"] = np.int32(len(small))
+
+    # --- Chamfer, matmul-path shapes (N or M > 25): the as-written reference is noisy here;
+    #     inputs are regenerated from seeds by the tests, outputs stored.
+    big = [(2, 300, 257, "sphere", True), (2, 2048, 2048, "sphere", False), (2, 2048, 2048, "uniform", False),
+           (2, 2048, 1400, "sphere", True)]
+    for k, (B, N, M, kind, dup) in enumerate(big):
+        pc1 = O.make_clouds(B, N, kind, seed=300 + k)
+        pc2 = O.make_clouds(B, M, kind, seed=400 + k)
+        if dup:
+            pc2 = O.pad_with_duplicates(pc2, 0.25, seed=500 + k)
+        case = chamfer_case(losses, pc1, pc2)
+        for name in ("dist1", "dist2", "cd", "loss", "i1", "i2"):
+            out[f"big{k}_{name}"] = case[name]
+        out[f"big{k}_g1"] = case["g1"].astype(np.float32)
+        out[f"big{k}_g2"] = case["g2"].astype(np.float32)
+        out[f"big{k}_meta"] = np.array([B, N, M, 300 + k, 400 + k, 500 + k if dup else -1], np.int64)
+        out[f"big{k}_kind"] = np.array(kind)
+    out["big_count"] = np.int32(len(big))
+    np.savez_compressed(os.path.join(HERE, "chamfer_ref.npz"), **out)
+
+    # --- Encoder: reference PointNetEncoder in eval mode with non-trivial BatchNorm statistics
+    enc_out = {}
+    cfgs = [([64, 128, 128, 256, 128], 128), ([64, 128, 1024], 128), ([32, 48], 16)]
+    for k, (dims, latent) in enumerate(cfgs):
+        torch.manual_seed(k)
+        enc = ae.PointNetEncoder(3, latent, dims)
+        O.randomize_bn(enc, seed=10 + k)
+        enc.eval()
+        x = O.make_clouds(3, 200, "sphere", seed=600 + k)
+        with torch.no_grad():
+            gfv = enc(x)                                                        # autoencoder.py:56-76
+            pooled = torch.max(enc.point_mlp(x.transpose(2, 1)), dim=2)[0]      # :65-71
+        sd = enc.state_dict()
+        checksum = float(sum(v.double().abs().sum().item() for v in sd.values()))
+        enc_out[f"enc{k}_dims"] = np.array(dims, np.int32)
+        enc_out[f"enc{k}_latent"] = np.int32(latent)
+        enc_out[f"enc{k}_gfv"] = gfv.numpy()
+        enc_out[f"enc{k}_pooled"] = pooled.numpy()
+        enc_out[f"enc{k}_x"] = x.numpy()
+        enc_out[f"enc{k}_state_checksum"] = np.float64(checksum)
+        enc_out[f"enc{k}_keys"] = np.array(list(sd.keys()))
+        if k == 2:   # tiny net: carry the weights themselves so the pin does not depend on torch's init RNG
+            for name, v in sd.items():
+                enc_out[f"enc{k}_sd_{name}"] = v.numpy()
+    enc_out["enc_count"] = np.int32(len(cfgs))
+    np.savez_compressed(os.path.join(HERE, "encoder_ref.npz"), **enc_out)
+    print("wrote", os.listdir(HERE))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,70 @@
+"""CPU: the C-ABI library loads and exports every symbol include/rlg_b200.h declares; host-side argument
+validation returns the documented negative codes without touching a GPU.  No compute calls here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "rlg_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import importlib
+    build = importlib.import_module("gan-rl_3d_b200.build")
+    build.build_library()
+    _lib = importlib.import_module("gan-rl_3d_b200._lib")
+    return _lib.load(), _lib
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rlg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported(lib):
+    cdll, _lib = lib
+    names = declared_functions()
+    assert {"rlg_chamfer_fwd", "rlg_chamfer_bwd", "rlg_encoder_fwd", "rlg_chamfer_ws_bytes"} <= set(names)
+    for name in names:
+        assert hasattr(cdll, name), f"{name} declared in include/rlg_b200.h but not exported"
+    assert set(names) == set(_lib.EXPORTS), "ctypes table and header disagree"
+
+
+def test_version_and_ws_bytes(lib):
+    cdll, _ = lib
+    assert cdll.rlg_version() == 1
+    assert cdll.rlg_chamfer_ws_bytes(32, 2048, 2048) == 8 * 32 * 4096
+    assert cdll.rlg_chamfer_ws_bytes(1, 1, 1) == 256            # rounded up to the 256-B granule
+    assert cdll.rlg_chamfer_ws_bytes(1, 0, 5) == 0
+
+
+def test_argument_errors_are_negative_codes_with_messages(lib):
+    cdll, _lib = lib
+    # empty clouds: the reference raises IndexError; here RLG_ERR_BAD_SHAPE before any launch
+    rc = cdll.rlg_chamfer_fwd(None, None, 2, 0, 5, None, None, None, None, None, None, None, 0, 0, None)
+    assert rc == -2 and b"bad shape" in cdll.rlg_last_error()
+    rc = cdll.rlg_chamfer_fwd(None, None, 2, 4, 5, None, None, None, None, None, None, None, 0, 0, None)
+    assert rc == -1
+    rc = cdll.rlg_chamfer_bwd(*([None] * 8), 1, 3, 0, None, None, None)
+    assert rc == -2
+    with pytest.raises(_lib.RlgError) as ei:
+        _lib.check("rlg_chamfer_bwd", rc)
+    assert ei.value.code == -2
+    # B == 0 is a no-op, like an empty batch through the reference
+    assert cdll.rlg_chamfer_fwd(None, None, 0, 4, 5, None, None, None, None, None, None, None, 0, 0, None) == 0
+    layer = (_lib.RlgLayer * 1)()
+    layer[0].c_in, layer[0].c_out = 4, 8
+    assert cdll.rlg_encoder_fwd(1, 1, 16, layer, 1, 1, None, 1, 256, None) == -4   # layer 0 must be 3 -> c
+
+
+def test_missing_library_is_loud(monkeypatch):
+    import importlib
+    _lib = importlib.import_module("gan-rl_3d_b200._lib")
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/librlg_b200.so")
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        _lib.load()

@@ -1,0 +1,219 @@
+"""GPU parity tests of the Chamfer path, through the C ABI (librlg_b200.so), against the oracle and the golden
+fixtures.  Bit-exact for distances and indices (vs the direct-form oracle); tolerances written where floating
+point sums are involved.  Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _run(rlg, pc1, pc2, simple=False):
+    d1, d2, i1, i2, m1, m2 = rlg.chamfer_nearest(pc1.to(DEV), pc2.to(DEV), simple=simple)
+    torch.cuda.synchronize()
+    return [t.cpu().numpy() for t in (d1, d2, i1, i2, m1, m2)]
+
+
+def _check_against_direct(rlg, pc1, pc2, simple=False):
+    d1, d2, i1, i2, m1, m2 = _run(rlg, pc1, pc2, simple)
+    o1, o2, j1, j2 = O.chamfer_direct(pc1, pc2, O.TIE_SQUARED)
+    assert np.array_equal(d1, o1) and np.array_equal(d2, o2), "distances not bit-equal to the direct oracle"
+    assert np.array_equal(i1, j1) and np.array_equal(i2, j2), "argmin not equal to the direct oracle"
+    w1, w2 = O.chamfer_means(o1, o2)
+    np.testing.assert_allclose(m1, w1, rtol=2e-7)
+    np.testing.assert_allclose(m2, w2, rtol=2e-7)
+    return d1, d2, i1, i2, m1, m2
+
+
+SHAPES = [(1, 1, 1), (3, 1, 7), (2, 25, 1), (4, 16, 25), (2, 31, 33), (2, 32, 32), (3, 255, 257), (2, 256, 64),
+          (1, 300, 1000), (2, 1400, 2048), (2, 2048, 2048), (1, 2049, 513), (5, 700, 90)]
+
+
+@pytest.mark.parametrize("B,N,M", SHAPES)
+@pytest.mark.parametrize("kind", ["sphere", "uniform"])
+def test_forward_bit_exact_vs_direct_oracle(rlg, B, N, M, kind):
+    pc1 = O.make_clouds(B, N, kind, 1000 + N)
+    pc2 = O.make_clouds(B, M, kind, 2000 + M)
+    _check_against_direct(rlg, pc1, pc2)
+
+
+@pytest.mark.parametrize("B,N,M", [(2, 31, 33), (2, 700, 2048), (1, 2048, 1400)])
+def test_simple_kernel_agrees_with_tile_kernel(rlg, B, N, M):
+    pc1, pc2 = O.make_clouds(B, N, "sphere", 5), O.make_clouds(B, M, "sphere", 6)
+    a = _check_against_direct(rlg, pc1, pc2, simple=True)
+    b = _check_against_direct(rlg, pc1, pc2, simple=False)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_exact_ties_pick_lowest_index(rlg):
+    """Duplicate padding of ragged partial clouds (utils/dataset.py:398-421) creates exact ties."""
+    pc1 = O.make_clouds(3, 600, "sphere", 11)
+    pc2 = O.pad_with_duplicates(O.make_clouds(3, 2048, "sphere", 12), 0.25, 13)
+    d1, d2, i1, i2, *_ = _check_against_direct(rlg, pc1, pc2)
+    t1 = O.chamfer_torch_direct(pc1, pc2)
+    assert np.array_equal(i1, t1[2].numpy()) and np.array_equal(i2, t1[3].numpy())
+    # identical clouds: zero distances, identity argmin
+    same = O.make_clouds(2, 500, "uniform", 14)
+    d1, d2, i1, i2, m1, m2 = _check_against_direct(rlg, same, same.clone())
+    assert not d1.any() and not d2.any() and np.array_equal(i1[0], np.arange(500))
+    # all points equal: every candidate ties -> index 0 everywhere
+    ones = torch.ones(1, 70, 3)
+    _, _, i1, i2, *_ = _check_against_direct(rlg, ones, ones.clone())
+    assert not i1.any() and not i2.any()
+
+
+def test_golden_small_cases_match_reference_bitwise(rlg, golden_chamfer):
+    """N,M <= 25: the reference itself runs direct-mode cdist; distances bit-equal, means to 1 ulp-ish."""
+    g = golden_chamfer
+    for k in range(int(g["small_count"])):
+        pc1, pc2 = torch.from_numpy(g[f"small{k}_pc1"]), torch.from_numpy(g[f"small{k}_pc2"])
+        d1, d2, i1, i2, m1, m2 = _run(rlg, pc1, pc2)
+        assert np.array_equal(d1, g[f"small{k}_d1"]) and np.array_equal(d2, g[f"small{k}_d2"])
+        assert O.idx_mismatches_are_exact_ties(pc1, pc2, i1, g[f"small{k}_i1"])[1] == 0
+        assert O.idx_mismatches_are_exact_ties(pc2, pc1, i2, g[f"small{k}_i2"])[1] == 0
+        np.testing.assert_allclose(m1, g[f"small{k}_dist1"], rtol=2e-7)
+        np.testing.assert_allclose(m2, g[f"small{k}_dist2"], rtol=2e-7)
+
+
+def test_golden_big_cases_contract_vs_as_written_reference(rlg, golden_chamfer):
+    """N or M > 25: the as-written reference is the noisy matmul path; the contract of SURVEY.md 8c."""
+    g = golden_chamfer
+    for k in range(int(g["big_count"])):
+        B, N, M, s1, s2, sd = [int(v) for v in g[f"big{k}_meta"]]
+        kind = str(g[f"big{k}_kind"])
+        pc1, pc2 = O.make_clouds(B, N, kind, s1), O.make_clouds(B, M, kind, s2)
+        if sd >= 0:
+            pc2 = O.pad_with_duplicates(pc2, 0.25, sd)
+        d1, d2, i1, i2, m1, m2 = _check_against_direct(rlg, pc1, pc2)
+        assert O.idx_mismatches_are_near_ties(pc1, pc2, i1, g[f"big{k}_i1"])[1] == 0
+        assert O.idx_mismatches_are_near_ties(pc2, pc1, i2, g[f"big{k}_i2"])[1] == 0
+        f1, f2, *_ = O.chamfer_f64(pc1, pc2)
+        t1, t2 = f1.mean(1).numpy(), f2.mean(1).numpy()
+        assert O.rel_err(m1, t1) < 1e-6 and O.rel_err(m2, t2) < 1e-6           # vs float64 truth
+        ref_err = max(O.rel_err(g[f"big{k}_dist1"], t1), O.rel_err(g[f"big{k}_dist2"], t2))
+        tol = max(1e-5, 2 * ref_err)                                           # vs the reference: its own error
+        assert O.rel_err(m1, g[f"big{k}_dist1"]) < tol and O.rel_err(m2, g[f"big{k}_dist2"]) < tol
+
+
+@pytest.mark.parametrize("B,N,M", [(2, 16, 25), (3, 300, 257), (2, 2048, 2048), (2, 2048, 1400)])
+def test_backward_vs_float64_truth(rlg, B, N, M):
+    pc1 = O.make_clouds(B, N, "sphere", 21)
+    pc2 = O.pad_with_duplicates(O.make_clouds(B, M, "sphere", 22), 0.25, 23) if M > 100 else O.make_clouds(B, M, "sphere", 22)
+    a = pc1.to(DEV).requires_grad_(True)
+    b = pc2.to(DEV).requires_grad_(True)
+    loss = rlg.ChamferLoss()(a, b)
+    loss.backward()
+    d1, d2, i1, i2 = O.chamfer_direct(pc1, pc2, O.TIE_SQUARED)
+    up = np.full((B,), 0.5 / B, np.float32)
+    ga, gb = O.chamfer_bwd_truth(pc1, pc2, d1, d2, i1, i2, up, up)
+    # tolerance: 1e-5 relative row-wise (north_star), rows measured against max(|row|, 1e-3 * largest row)
+    assert O.rowwise_rel_err(a.grad.cpu().numpy(), ga) < 1e-5
+    assert O.rowwise_rel_err(b.grad.cpu().numpy(), gb) < 1e-5
+    m1, m2 = O.chamfer_means(d1, d2)
+    want = float(np.mean((m1.astype(np.float64) + m2) / 2))
+    assert abs(loss.item() - want) <= 1e-6 * abs(want)
+
+
+def test_backward_matches_reference_autograd_on_small_golden(rlg, golden_chamfer):
+    g = golden_chamfer
+    for k in range(int(g["small_count"])):
+        a = torch.from_numpy(g[f"small{k}_pc1"]).to(DEV).requires_grad_(True)
+        b = torch.from_numpy(g[f"small{k}_pc2"]).to(DEV).requires_grad_(True)
+        loss = rlg.ChamferLoss()(a, b)
+        loss.backward()
+        assert abs(loss.item() - float(g[f"small{k}_loss"])) <= 1e-6 * abs(float(g[f"small{k}_loss"])) + 1e-9
+        # exact ties may route a gradient to a different (equally near) partner: compare only when indices agree
+        _, _, i1, i2, *_ = _run(rlg, a.detach().cpu(), b.detach().cpu())
+        if np.array_equal(i1, g[f"small{k}_i1"]) and np.array_equal(i2, g[f"small{k}_i2"]):
+            assert O.rowwise_rel_err(a.grad.cpu().numpy(), g[f"small{k}_g1"]) < 1e-5
+            assert O.rowwise_rel_err(b.grad.cpu().numpy(), g[f"small{k}_g2"]) < 1e-5
+
+
+def test_per_pair_upstream_and_unidirectional(rlg):
+    """chamfer_distance returns (B,) and may be weighted per pair (reward path); bidirectional=False uses
+    dist1 only, so pc2 receives gradient only through the argmin partners."""
+    B, N, M = 4, 200, 150
+    pc1, pc2 = O.make_clouds(B, N, "uniform", 31), O.make_clouds(B, M, "uniform", 32)
+    w = torch.tensor([0.5, -1.0, 2.0, 0.0])
+    a = pc1.to(DEV).requires_grad_(True)
+    b = pc2.to(DEV).requires_grad_(True)
+    cd = rlg.chamfer_distance(a, b, bidirectional=False)
+    assert cd.shape == (B,)
+    (cd * w.to(DEV)).sum().backward()
+    d1, d2, i1, i2 = O.chamfer_direct(pc1, pc2, O.TIE_SQUARED)
+    ga, gb = O.chamfer_bwd_truth(pc1, pc2, d1, d2, i1, i2, w.numpy(), np.zeros(B, np.float32))
+    assert O.rowwise_rel_err(a.grad.cpu().numpy(), ga) < 1e-5
+    assert O.rowwise_rel_err(b.grad.cpu().numpy(), gb) < 1e-5
+    assert not a.grad[3].any() and not b.grad[3].any()
+
+
+def test_no_grad_and_requires_grad_false_inputs(rlg):
+    pc1, pc2 = O.make_clouds(2, 100, "sphere", 41).to(DEV), O.make_clouds(2, 90, "sphere", 42).to(DEV)
+    with torch.no_grad():
+        v = rlg.ChamferLoss()(pc1, pc2)
+    assert v.dim() == 0 and not v.requires_grad
+    a = pc1.clone().requires_grad_(True)
+    rlg.ChamferLoss()(a, pc2).backward()           # target has no grad (the trainer's case, train:236)
+    assert a.grad is not None and pc2.grad is None
+
+
+def test_full_size_properties_cfg2(rlg):
+    """B=32, N=M=2048 (BASELINE config 2), size-independent properties: symmetry under swapping the clouds,
+    invariance of distances under a permutation of the candidates, idempotence (second call, clean workspace)."""
+    pc1, pc2 = O.make_clouds(32, 2048, "sphere", 1236), O.make_clouds(32, 2048, "sphere", 2236)
+    a, b = pc1.to(DEV), pc2.to(DEV)
+    d1, d2, i1, i2, m1, m2 = rlg.chamfer_nearest(a, b)
+    e2, e1, j2, j1, n2, n1 = rlg.chamfer_nearest(b, a)
+    assert torch.equal(d1, e1) and torch.equal(d2, e2) and torch.equal(i1, j1) and torch.equal(i2, j2)
+    assert torch.equal(m1, n1) and torch.equal(m2, n2)
+    perm = torch.randperm(2048, generator=torch.Generator().manual_seed(0)).to(DEV)
+    p1, _, pi1, *_ = rlg.chamfer_nearest(a, b[:, perm])
+    assert torch.equal(p1, d1) and torch.equal(perm[pi1.long()], i1.long())     # no exact ties in this draw
+    again = rlg.chamfer_nearest(a, b)
+    assert all(torch.equal(x, y) for x, y in zip(again, (d1, d2, i1, i2, m1, m2)))
+    # gathered partner really is at the reported distance
+    gathered = torch.gather(b, 1, i1.long().unsqueeze(-1).expand(-1, -1, 3))
+    assert torch.allclose((a - gathered).norm(dim=2), d1, rtol=1e-6, atol=1e-7)
+    # and two clouds of the oracle's budget are bit-exact
+    _check_against_direct(rlg, pc1[:2], pc2[:2])
+
+
+def test_large_cloud_16384(rlg):
+    """BASELINE config 5 shape (N=M=16384), one pair against the oracle, plus memory stays O(N+M)."""
+    pc1, pc2 = O.make_clouds(1, 16384, "sphere", 51), O.make_clouds(1, 16384, "sphere", 52)
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    _check_against_direct(rlg, pc1, pc2)
+    assert torch.cuda.max_memory_allocated() - base < 64 << 20        # the reference needs 1 GiB per (N,M) matrix here
+
+
+def test_error_paths_raise(rlg):
+    with pytest.raises(ValueError):
+        rlg.chamfer_distance_l2(torch.zeros(2, 4, 3, device=DEV), torch.zeros(3, 4, 3, device=DEV))
+    with pytest.raises(ValueError):
+        rlg.chamfer_distance_l2(torch.zeros(2, 0, 3, device=DEV), torch.zeros(2, 4, 3, device=DEV))
+    with pytest.raises(ValueError):
+        rlg.chamfer_distance_l2(torch.zeros(2, 4, 3, device=DEV, dtype=torch.float64), torch.zeros(2, 4, 3, device=DEV))
+    out = rlg.chamfer_nearest(torch.zeros(0, 4, 3, device=DEV), torch.zeros(0, 5, 3, device=DEV))
+    assert out[0].shape == (0, 4) and out[1].shape == (0, 5)
+
+
+def test_cuda_graph_capture(rlg):
+    """Every call is enqueued on the caller's stream without sync/alloc inside the library -> capturable."""
+    pc1, pc2 = O.make_clouds(4, 512, "sphere", 61).to(DEV), O.make_clouds(4, 512, "sphere", 62).to(DEV)
+    want = rlg.chamfer_nearest(pc1, pc2)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        rlg.chamfer_nearest(pc1, pc2)            # warm the per-stream workspace outside capture
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            got = rlg.chamfer_nearest(pc1, pc2)
+    graph.replay()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert all(torch.equal(x, y) for x, y in zip(got, want))

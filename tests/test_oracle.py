@@ -1,0 +1,167 @@
+"""CPU: pins the oracle (oracle/) against the golden vectors generated from the real reference, and against
+the reference itself where it is mounted.  The oracle is the checker of every GPU parity test."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+
+def _small_cases(g):
+    for k in range(int(g["small_count"])):
+        yield k, torch.from_numpy(g[f"small{k}_pc1"]), torch.from_numpy(g[f"small{k}_pc2"])
+
+
+def _big_cases(g):
+    for k in range(int(g["big_count"])):
+        B, N, M, s1, s2, sd = [int(v) for v in g[f"big{k}_meta"]]
+        kind = str(g[f"big{k}_kind"])
+        pc1 = O.make_clouds(B, N, kind, seed=s1)
+        pc2 = O.make_clouds(B, M, kind, seed=s2)
+        if sd >= 0:
+            pc2 = O.pad_with_duplicates(pc2, 0.25, seed=sd)
+        yield k, pc1, pc2
+
+
+def test_direct_oracle_is_bit_exact_on_reference_direct_path(golden_chamfer):
+    """N,M <= 25: the reference's own cdist takes the direct branch -> distances and indices bit-equal."""
+    g = golden_chamfer
+    for k, pc1, pc2 in _small_cases(g):
+        d1, d2, i1, i2 = O.chamfer_direct(pc1, pc2, O.TIE_FAITHFUL)
+        assert np.array_equal(d1, g[f"small{k}_d1"]), k
+        assert np.array_equal(d2, g[f"small{k}_d2"]), k
+        assert np.array_equal(i1, g[f"small{k}_i1"]), k
+        assert np.array_equal(i2, g[f"small{k}_i2"]), k
+        # squared-distance tie rule: same distances; indices may differ only on exact ties of the sqrt-ed value
+        s1, s2, j1, j2 = O.chamfer_direct(pc1, pc2, O.TIE_SQUARED)
+        assert np.array_equal(s1, d1) and np.array_equal(s2, d2)
+        assert O.idx_mismatches_are_exact_ties(pc1, pc2, j1, i1)[1] == 0
+        assert O.idx_mismatches_are_exact_ties(pc2, pc1, j2, i2)[1] == 0
+        m1, m2 = O.chamfer_means(d1, d2)
+        np.testing.assert_allclose(m1, g[f"small{k}_dist1"], rtol=2e-7, atol=0)
+        np.testing.assert_allclose(m2, g[f"small{k}_dist2"], rtol=2e-7, atol=0)
+        np.testing.assert_allclose((m1.astype(np.float64) + m2) / 2, g[f"small{k}_cd"], rtol=3e-7)
+        np.testing.assert_allclose(m1, g[f"small{k}_cd_uni"], rtol=2e-7)
+
+
+def test_backward_closed_form_matches_reference_autograd(golden_chamfer):
+    g = golden_chamfer
+    for k, pc1, pc2 in _small_cases(g):
+        B, N, M = pc1.shape[0], pc1.shape[1], pc2.shape[1]
+        d1, d2, i1, i2 = O.chamfer_direct(pc1, pc2, O.TIE_FAITHFUL)
+        # ChamferLoss = mean_b (mean1+mean2)/2 -> upstream of mean1, mean2 is 1/(2B)
+        up = np.full((B,), 0.5 / B, np.float32)
+        ga, gb = O.chamfer_bwd_truth(pc1, pc2, d1, d2, i1, i2, up, up)
+        assert O.rowwise_rel_err(g[f"small{k}_g1"], ga) < 2e-6, k
+        assert O.rowwise_rel_err(g[f"small{k}_g2"], gb) < 2e-6, k
+
+
+def test_port_matches_golden_everywhere(golden_chamfer):
+    """The restated op sequence reproduces the reference outputs stored in the fixtures (same torch build:
+    bit-exact; the tolerance only absorbs a different BLAS thread split on another host)."""
+    g = golden_chamfer
+    torch.set_num_threads(1)
+    for k, pc1, pc2 in list(_small_cases(g)):
+        m1, m2 = O.ref_port_chamfer_l2(pc1, pc2)
+        assert np.array_equal(m1.numpy(), g[f"small{k}_dist1"]) and np.array_equal(m2.numpy(), g[f"small{k}_dist2"])
+        assert np.float32(O.ref_port_chamfer_loss(pc1, pc2).item()) == g[f"small{k}_loss"]
+    for k, pc1, pc2 in _big_cases(g):
+        m1, m2 = O.ref_port_chamfer_l2(pc1, pc2)
+        np.testing.assert_allclose(m1.numpy(), g[f"big{k}_dist1"], rtol=1e-6)
+        np.testing.assert_allclose(m2.numpy(), g[f"big{k}_dist2"], rtol=1e-6)
+
+
+def test_port_is_bit_identical_to_mounted_reference(ref_losses):
+    torch.set_num_threads(1)
+    for (B, N, M, kind) in [(3, 16, 25, "sphere"), (2, 300, 257, "uniform"), (1, 1024, 700, "sphere")]:
+        pc1, pc2 = O.make_clouds(B, N, kind, 1), O.make_clouds(B, M, kind, 2)
+        r1, r2 = ref_losses.chamfer_distance_l2(pc1, pc2)
+        p1, p2 = O.ref_port_chamfer_l2(pc1, pc2)
+        assert torch.equal(r1, p1) and torch.equal(r2, p2)
+        assert torch.equal(ref_losses.chamfer_distance(pc1, pc2, False), O.ref_port_chamfer(pc1, pc2, False))
+        assert torch.equal(ref_losses.ChamferLoss()(pc1, pc2), O.ref_port_chamfer_loss(pc1, pc2))
+
+
+def test_direct_oracle_vs_noisy_reference_contract(golden_chamfer):
+    """N or M > 25: the as-written reference uses the matmul expansion.  Contract: index
+    disagreements are near-ties in float64; per-pair means agree to max(1e-5, the reference's own error)."""
+    g = golden_chamfer
+    for k, pc1, pc2 in _big_cases(g):
+        d1, d2, i1, i2 = O.chamfer_direct(pc1, pc2, O.TIE_SQUARED)
+        n1, bad1 = O.idx_mismatches_are_near_ties(pc1, pc2, i1, g[f"big{k}_i1"])
+        n2, bad2 = O.idx_mismatches_are_near_ties(pc2, pc1, i2, g[f"big{k}_i2"])
+        assert bad1 == 0 and bad2 == 0, (k, n1, bad1, n2, bad2)
+        f1, f2, j1, j2, _ = O.chamfer_f64(pc1, pc2)
+        # ours vs float64 truth: indices equal except exact fp32 ties, distances to 1e-6
+        assert O.idx_mismatches_are_exact_ties(pc1, pc2, i1, j1.numpy())[1] == 0
+        assert O.idx_mismatches_are_exact_ties(pc2, pc1, i2, j2.numpy())[1] == 0
+        assert O.rel_err(d1, f1.numpy(), floor=1e-30) < 1e-6 and O.rel_err(d2, f2.numpy(), floor=1e-30) < 1e-6
+        m1, m2 = O.chamfer_means(d1, d2)
+        t1, t2 = f1.mean(1).numpy(), f2.mean(1).numpy()
+        ref_err = max(O.rel_err(g[f"big{k}_dist1"], t1), O.rel_err(g[f"big{k}_dist2"], t2))
+        tol = max(1e-5, 2 * ref_err)
+        assert O.rel_err(m1, g[f"big{k}_dist1"]) < tol and O.rel_err(m2, g[f"big{k}_dist2"]) < tol
+
+
+def test_sqrt_collision_tie_rules():
+    """sqrtf is many-to-one: two squared distances one ulp apart can collide after the square root.  The
+    faithful rule (torch.min over the sqrt-ed matrix) then picks the LOWER index, the squared rule the
+    smaller t; both return the same distance (SURVEY.md 7.1 step 2 trap)."""
+    rng = np.random.default_rng(0)
+    found = 0
+    for _ in range(2000):
+        # from the origin, (r,0,0) has t = fl(r*r) in [2,4) where ulp(t) = 2^-22; adding a second coordinate
+        # s ~ 2^-11 lifts t by one ulp, and sqrt compresses that spacing below one ulp of the result.
+        r = np.float32(rng.uniform(1.42, 1.99))
+        s_ = np.float32(2.0 ** -11 * rng.uniform(0.8, 1.2))
+        tb = np.float32(r * r)
+        ta = np.float32(np.float64(s_) * np.float64(s_) + np.float64(tb))      # fmaf(s,s,t), exact in float64
+        if not (ta == np.nextafter(tb, np.float32(8), dtype=np.float32)
+                and np.sqrt(ta, dtype=np.float32) == np.sqrt(tb, dtype=np.float32)):
+            continue
+        pc1 = np.zeros((1, 1, 3), np.float32)
+        pc2 = np.array([[[r, s_, 0], [r, 0, 0]]], np.float32)     # index 0 has the LARGER squared distance
+        df, _, jf, _ = O.chamfer_direct(pc1, pc2, O.TIE_FAITHFUL)
+        ds, _, js, _ = O.chamfer_direct(pc1, pc2, O.TIE_SQUARED)
+        td, _, tj, _ = O.chamfer_torch_direct(pc1, pc2)
+        assert jf[0, 0] == 0 and js[0, 0] == 1 and int(tj[0, 0]) == 0
+        assert df[0, 0] == ds[0, 0] == td.numpy()[0, 0]
+        assert O.idx_mismatches_are_exact_ties(pc1, pc2, js, jf) == (1, 0)
+        found += 1
+        if found >= 5:
+            break
+    assert found >= 1
+
+
+def test_encoder_port_matches_golden(golden_encoder):
+    g = golden_encoder
+    torch.set_num_threads(1)
+    for k in range(int(g["enc_count"])):
+        dims, latent = [int(v) for v in g[f"enc{k}_dims"]], int(g[f"enc{k}_latent"])
+        torch.manual_seed(k)
+        enc = O.RefEncoderPort(3, latent, dims)
+        assert list(enc.state_dict().keys()) == [str(s) for s in g[f"enc{k}_keys"]]
+        if k == 2:
+            enc.load_state_dict({str(n): torch.from_numpy(g[f"enc{k}_sd_{n}"]) for n in g[f"enc{k}_keys"]})
+        else:
+            O.randomize_bn(enc, seed=10 + k)
+            chk = float(sum(v.double().abs().sum().item() for v in enc.state_dict().values()))
+            if abs(chk - float(g[f"enc{k}_state_checksum"])) > 1e-6 * abs(chk):
+                pytest.skip("torch default init differs from the fixture's torch build")
+        enc.eval()
+        x = torch.from_numpy(g[f"enc{k}_x"])
+        with torch.no_grad():
+            np.testing.assert_allclose(enc.pooled(x).numpy(), g[f"enc{k}_pooled"], rtol=1e-6, atol=1e-7)
+            np.testing.assert_allclose(enc(x).numpy(), g[f"enc{k}_gfv"], rtol=1e-6, atol=1e-7)
+
+
+def test_encoder_port_is_reference(ref_autoencoder):
+    torch.manual_seed(3)
+    ref = ref_autoencoder.PointNetEncoder(3, 32, [16, 64])
+    O.randomize_bn(ref, 5)
+    port = O.RefEncoderPort(3, 32, [16, 64])
+    port.load_state_dict(ref.state_dict())          # identical keys and shapes
+    x = O.make_clouds(2, 77, "uniform", 9)
+    for mode in ("eval", "train"):
+        getattr(ref, mode)(), getattr(port, mode)()
+        assert torch.equal(ref(x), port(x))
