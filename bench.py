@@ -186,82 +186,72 @@ def run_ours(args):
     peaks, peaks_src = load_peaks()
     K, W = args.steps, max(3, args.warmup)
 
+    P = importlib.import_module("gan-rl_3d_b200.pipeline")
     slot_bytes = (B * N + B * M) * 3 * 4
     slots = max(8, RING_BYTES // slot_bytes)
     ring_host = make_ring(rank, slots)
     ring = [(a.to(dev), b.to(dev)) for a, b in ring_host]
-    crit = rlg.ChamferLoss()
-    loss_buf = torch.zeros(64, device=dev)
-    launches = {"n": 0}
+    loss_buf = torch.zeros(1, device=dev)
 
-    def step(k, reduce_loss=True):
-        a, b = ring[k % slots]
-        a.requires_grad_(True); b.requires_grad_(True)
-        a.grad = None; b.grad = None
-        loss = crit(a, b)
-        loss.backward()
-        launches["n"] += 4                        # tile + finalize + bwd own + bwd scatter (our kernels)
-        if world > 1 and reduce_loss:
-            slot = loss_buf[k % 64: k % 64 + 1]
-            slot.copy_(loss.detach().reshape(1))
-            dist.all_reduce(slot, op=dist.ReduceOp.SUM, async_op=True)   # logged scalar, off the critical path
-        return loss
+    # The timed loop: `loss = ChamferLoss()(pred, target); loss.backward()` per batch, captured S steps at a time
+    # in a CUDA graph (the loop is launch-bound from Python: ~60 us of GPU work per step in 4 kernels).
+    full = P.ChamferStepGraph(ring)                                   # S = slots steps per replay
+    n_full, rem = divmod(K, slots)
+    tail = P.ChamferStepGraph(ring[:rem]) if rem else None
+    n_launches = n_full * full.kernel_launches_per_replay + (tail.kernel_launches_per_replay if tail else 0)
 
-    for k in range(W):
-        step(k)
+    def run_steps(n_full_, tail_):
+        for _ in range(n_full_):
+            full.replay()
+            if world > 1:      # the logged loss scalar of the last step, all-reduced off the critical path
+                loss_buf.copy_(full.losses[-1].detach().reshape(1))
+                dist.all_reduce(loss_buf, op=dist.ReduceOp.SUM, async_op=True)
+        if tail_ is not None:
+            tail_.replay()
+
+    run_steps(max(1, -(-W // slots)), None)                           # >= W warm-up steps
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches["n"] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
-    for k in range(K):
-        step(W + k)
+    run_steps(n_full, tail)
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
-    n_launches = launches["n"]
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = K * B * world / (ms * 1e-3)
+    last_loss = float((tail.losses[-1] if tail else full.losses[-1]).item())
 
-    # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region ----------------
-    pinned = [(a.pin_memory(), b.pin_memory()) for a, b in ring_host[:min(slots, 32)]]
-    nb = len(pinned)
-    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
-
-    def e2e_step(k):
-        a, b = pinned[k % nb]
-        da = a.to(dev, non_blocking=True).requires_grad_(True)
-        db = b.to(dev, non_blocking=True)
-        loss = crit(da, db)
-        loss.backward()
-        loss_host.copy_(loss.detach().reshape(1), non_blocking=False)    # what loss.item() does (train:242)
-        return loss_host
-
-    Ke = max(10, min(K, 500))
-    for k in range(3):
-        e2e_step(k)
+    # ---- e2e: host buffers through the public API, H2D + D2H of every step inside the timed region --
+    nb = min(slots, 32)
+    pinned = [(a.pin_memory(), b.pin_memory()) for a, b in ring_host[:nb]]
+    host_graph = P.HostChamferStepGraph(pinned, dev)
+    Ke_replays = max(1, min(K, 2000) // nb)
+    Ke = Ke_replays * nb
+    host_graph.replay()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    for k in range(Ke):
-        e2e_step(k)
+    for _ in range(Ke_replays):
+        host_graph.replay()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = Ke * B * world / float(t.item())
+    e2e_loss_check = float(host_graph.losses_host[0])
     if rank == 0:
         clocks = sampler.stop()
 
@@ -351,10 +341,14 @@ def run_ours(args):
         "config": {"workload": "chamfer_fwd_bwd B=32 N=M=2048 sphere (BASELINE configs[1])", "B_per_gpu": B, "N": N,
                    "M": M, "global_batch": B * world, "parallelism": f"batch-sharded dp{world}",
                    "l2_policy": f"inputs cycle through a ring of {slots} batches = {slots * slot_bytes >> 20} MiB > 126 MB L2",
-                   "step": "ChamferLoss forward + backward (autograd), loss all-reduce async when n_gpus > 1"},
+                   "step": "ChamferLoss forward + backward (autograd), captured S steps per CUDA graph; loss all-reduce async "
+                           "per replay when n_gpus > 1", "steps_per_graph": slots, "last_loss": last_loss},
         "roofline": roofline, "roofline_bwd": roofline_bwd, "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": slot_bytes, "d2h_bytes_per_step": 4,
-                "steps": Ke, "how": "pinned host clouds -> .to(device) -> ChamferLoss -> backward -> loss to host, every step"},
+                "steps": Ke, "loss_step0": e2e_loss_check,
+                "how": "HostChamferStepGraph: per step H2D of pinned (pred,target) -> ChamferLoss -> backward -> D2H of the "
+                       "loss, 32 steps per CUDA-graph replay, copies double-buffered against the previous step's kernels; "
+                       "wall clock around replays + synchronize"},
         "gpu_launches": n_launches, "clocks": clocks,
     }
     out.update(extra)

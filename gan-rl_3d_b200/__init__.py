@@ -17,14 +17,14 @@ import sys
 from typing import Optional
 
 from . import _lib
-from .chamfer import (ChamferFn, ChamferLoss, chamfer_backward, chamfer_distance, chamfer_distance_l2,
+from .chamfer import (ChamferFn, ChamferLoss, ChamferLossFn, chamfer_backward, chamfer_distance, chamfer_distance_l2,
                       chamfer_nearest)
 from .chamfer import is_hot_path_input as _chamfer_hot
 from .encoder import (EncoderTrunkFn, PointNetEncoder, encoder_pool, fold_trunk, folded_trunk_cached,
                       fused_forward)
 
 __all__ = ["install", "uninstall", "is_installed", "chamfer_distance_l2", "chamfer_distance", "ChamferLoss",
-           "ChamferFn", "chamfer_nearest", "chamfer_backward", "PointNetEncoder", "EncoderTrunkFn", "encoder_pool",
+           "ChamferFn", "ChamferLossFn", "chamfer_nearest", "chamfer_backward", "PointNetEncoder", "EncoderTrunkFn", "encoder_pool",
            "fold_trunk", "folded_trunk_cached", "fused_forward", "library_path", "abi_version"]
 
 _installed = {}

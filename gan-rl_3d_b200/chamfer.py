@@ -9,7 +9,7 @@ Inputs must be CUDA fp32 (B,N,3)/(B,M,3) with N,M >= 1; there is no CPU implemen
 """
 from __future__ import annotations
 
-from typing import Dict, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 import torch.nn as nn
@@ -56,12 +56,14 @@ class _Workspace:
         return ws
 
 
-def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = True, simple: bool = False):
+def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = True, simple: bool = False,
+                    loss_weights: Optional[Tuple[float, float]] = None):
     """Nearest neighbours in both directions (no autograd).
 
     Returns (d1 (B,N) fp32, d2 (B,M) fp32, i1 (B,N) int32, i2 (B,M) int32, mean1 (B,), mean2 (B,)):
     exactly torch.min(torch.cdist(pc1,pc2), 2) / (…, 1) of utils/losses.py:29-33 with cdist in direct mode,
-    and torch.mean(…, dim=1) of :36-37."""
+    and torch.mean(…, dim=1) of :36-37.  With loss_weights=(w1,w2) a 7th element is appended: the 0-dim
+    batch loss sum_b(w1*mean1[b] + w2*mean2[b]) reduced inside the same launch (utils/losses.py:54-59,75)."""
     _require_hot_path(pc1, pc2)
     lib = _lib.load()
     pc1 = pc1.contiguous()
@@ -75,8 +77,10 @@ def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = Tru
     i2 = torch.empty((B, M), dtype=torch.int32, device=dev)
     m1 = torch.empty((B,), dtype=torch.float32, device=dev) if want_means else None
     m2 = torch.empty((B,), dtype=torch.float32, device=dev) if want_means else None
+    loss = torch.zeros((), dtype=torch.float32, device=dev) if loss_weights is not None else None
     if B == 0:
-        return d1, d2, i1, i2, m1, m2
+        return (d1, d2, i1, i2, m1, m2) if loss is None else (d1, d2, i1, i2, m1, m2, loss)
+    w1, w2 = loss_weights if loss_weights is not None else (0.0, 0.0)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         ws = _Workspace.get(dev, stream, B, N, M)
@@ -86,13 +90,14 @@ def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = Tru
         elif ws.clean:
             flags |= _lib.CHAMFER_WS_CLEAN
         ws.clean = False
-        rc = lib.rlg_chamfer_fwd(pc1.data_ptr(), pc2.data_ptr(), B, N, M,
-                                 d1.data_ptr(), d2.data_ptr(), i1.data_ptr(), i2.data_ptr(),
-                                 m1.data_ptr() if want_means else None, m2.data_ptr() if want_means else None,
-                                 ws.buf.data_ptr(), ws.buf.numel(), flags, stream)
-        _lib.check("rlg_chamfer_fwd", rc)
+        rc = lib.rlg_chamfer_loss_fwd(pc1.data_ptr(), pc2.data_ptr(), B, N, M,
+                                      d1.data_ptr(), d2.data_ptr(), i1.data_ptr(), i2.data_ptr(),
+                                      m1.data_ptr() if want_means else None, m2.data_ptr() if want_means else None,
+                                      loss.data_ptr() if loss is not None else None, w1, w2,
+                                      ws.buf.data_ptr(), ws.buf.numel(), flags, stream)
+        _lib.check("rlg_chamfer_loss_fwd", rc)
         ws.clean = not simple
-    return d1, d2, i1, i2, m1, m2
+    return (d1, d2, i1, i2, m1, m2) if loss is None else (d1, d2, i1, i2, m1, m2, loss)
 
 
 def chamfer_backward(pc1, pc2, d1, d2, i1, i2, g1, g2) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -137,6 +142,43 @@ class ChamferFn(torch.autograd.Function):
         return (gpc1 if ctx.needs_input_grad[0] else None, gpc2 if ctx.needs_input_grad[1] else None)
 
 
+def _loss_weights(B: int, bidirectional: bool) -> Tuple[float, float]:
+    # torch.mean over the batch of (dist1+dist2)/2 (bidirectional) or dist1   (utils/losses.py:56-59, :75)
+    return (0.5 / B, 0.5 / B) if bidirectional else (1.0 / B, 0.0)
+
+
+class ChamferLossFn(torch.autograd.Function):
+    """(pred (B,N,3), target (B,M,3)) -> the 0-dim ChamferLoss of utils/losses.py:62-75 with the batch reduction
+    fused into the forward launch and its scaling fused into the backward: 2 + 2 kernel launches per
+    training step, no elementwise torch kernels in between."""
+
+    @staticmethod
+    def forward(ctx, pc1, pc2, bidirectional: bool):
+        pc1c, pc2c = pc1.contiguous(), pc2.contiguous()
+        w = _loss_weights(max(pc1c.shape[0], 1), bidirectional)
+        d1, d2, i1, i2, m1, m2, loss = chamfer_nearest(pc1c, pc2c, want_means=True, loss_weights=w)
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            ctx.save_for_backward(pc1c, pc2c, d1, d2, i1, i2)
+            ctx.w = w
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        pc1, pc2, d1, d2, i1, i2 = ctx.saved_tensors
+        lib = _lib.load()
+        B, N, _ = pc1.shape
+        M = pc2.shape[1]
+        gpc1, gpc2 = torch.empty_like(pc1), torch.empty_like(pc2)
+        gloss = gloss.contiguous().float()
+        with torch.cuda.device(pc1.device):
+            stream = torch.cuda.current_stream(pc1.device).cuda_stream
+            rc = lib.rlg_chamfer_loss_bwd(pc1.data_ptr(), pc2.data_ptr(), d1.data_ptr(), d2.data_ptr(),
+                                          i1.data_ptr(), i2.data_ptr(), gloss.data_ptr(), ctx.w[0], ctx.w[1],
+                                          B, N, M, gpc1.data_ptr(), gpc2.data_ptr(), stream)
+            _lib.check("rlg_chamfer_loss_bwd", rc)
+        return (gpc1 if ctx.needs_input_grad[0] else None, gpc2 if ctx.needs_input_grad[1] else None, None)
+
+
 # ---- mirrors of the reference API -------------------------------------------------------------------
 def chamfer_distance_l2(pc1: torch.Tensor, pc2: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """Drop-in for utils/losses.py:13-39.  Returns (dist1 (B,), dist2 (B,)): the mean over points of the
@@ -161,4 +203,7 @@ class ChamferLoss(nn.Module):
         self.bidirectional = bidirectional
 
     def forward(self, pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-        return torch.mean(chamfer_distance(pred, target, self.bidirectional))
+        _require_hot_path(pred, target)
+        if pred.shape[0] == 0:
+            return torch.mean(chamfer_distance(pred, target, self.bidirectional))   # nan, as the reference
+        return ChamferLossFn.apply(pred, target, self.bidirectional)

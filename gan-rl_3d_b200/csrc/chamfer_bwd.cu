@@ -19,7 +19,9 @@ namespace rlg {
 struct BwdArgs {
     const float *pc1, *pc2, *d1, *d2;
     const int32_t *i1, *i2;
-    const float *g1, *g2;
+    const float *g1, *g2;   // upstream of mean1 / mean2: per pair (gstride 1) or one shared scalar (gstride 0)
+    int gstride;
+    float scale1, scale2;   // multiplies the upstream (loss weights 0.5/B etc. for the fused ChamferLoss)
     float *gpc1, *gpc2;
     int N, M;
     long long n1, n2;   // B*N, B*M
@@ -36,7 +38,7 @@ __device__ __forceinline__ bool bwd_term(const BwdArgs &a, int dir, long long p,
     const float *g = dir ? a.g2 : a.g1;
     partner_flat = b * m + j;
     const float *oth = (dir ? a.pc1 : a.pc2) + 3 * partner_flat;
-    const float w = g ? g[b] / (float)n : 0.0f;
+    const float w = g ? g[b * a.gstride] * (dir ? a.scale2 : a.scale1) / (float)n : 0.0f;
     if (d == 0.0f || w == 0.0f) { ux = uy = uz = 0.0f; return false; }
     const float s = w / d;
     ux = (own[0] - oth[0]) * s;
@@ -77,15 +79,16 @@ __global__ void __launch_bounds__(256) chamfer_bwd_scatter_kernel(BwdArgs a) {
 
 using namespace rlg;
 
-extern "C" int rlg_chamfer_bwd(const float *pc1, const float *pc2, const float *d1, const float *d2,
-                               const int32_t *i1, const int32_t *i2, const float *g1, const float *g2, int B,
-                               int N, int M, float *gpc1, float *gpc2, void *stream) {
+static int bwd_launch(const float *pc1, const float *pc2, const float *d1, const float *d2, const int32_t *i1,
+                      const int32_t *i2, const float *g1, const float *g2, int gstride, float scale1, float scale2,
+                      int B, int N, int M, float *gpc1, float *gpc2, void *stream) {
     if (B < 0 || N < 1 || M < 1)
         return fail(RLG_ERR_BAD_SHAPE, "rlg_chamfer_bwd: bad shape B=%d N=%d M=%d", B, N, M);
     if (B == 0) return 0;
     if (!pc1 || !pc2 || !d1 || !d2 || !i1 || !i2 || !gpc1 || !gpc2)
         return fail(RLG_ERR_NULL_POINTER, "rlg_chamfer_bwd: null pointer");
-    BwdArgs a{pc1, pc2, d1, d2, i1, i2, g1, g2, gpc1, gpc2, N, M, (long long)B * N, (long long)B * M};
+    BwdArgs a{pc1, pc2, d1, d2, i1, i2, g1, g2, gstride, scale1, scale2, gpc1, gpc2, N, M, (long long)B * N,
+              (long long)B * M};
     const long long total = a.n1 + a.n2;
     const long long blocks = (total + 255) / 256;
     if (blocks > 0x7fffffffLL) return fail(RLG_ERR_TOO_LARGE, "rlg_chamfer_bwd: too many points");
@@ -93,4 +96,18 @@ extern "C" int rlg_chamfer_bwd(const float *pc1, const float *pc2, const float *
     chamfer_bwd_own_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
     chamfer_bwd_scatter_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
     return check_launch("chamfer_bwd kernels");
+}
+
+extern "C" int rlg_chamfer_bwd(const float *pc1, const float *pc2, const float *d1, const float *d2,
+                               const int32_t *i1, const int32_t *i2, const float *g1, const float *g2, int B,
+                               int N, int M, float *gpc1, float *gpc2, void *stream) {
+    return bwd_launch(pc1, pc2, d1, d2, i1, i2, g1, g2, 1, 1.0f, 1.0f, B, N, M, gpc1, gpc2, stream);
+}
+
+extern "C" int rlg_chamfer_loss_bwd(const float *pc1, const float *pc2, const float *d1, const float *d2,
+                                    const int32_t *i1, const int32_t *i2, const float *gloss, float w1, float w2,
+                                    int B, int N, int M, float *gpc1, float *gpc2, void *stream) {
+    if (!gloss) return fail(RLG_ERR_NULL_POINTER, "rlg_chamfer_loss_bwd: null upstream gradient");
+    return bwd_launch(pc1, pc2, d1, d2, i1, i2, gloss, w2 != 0.0f ? gloss : nullptr, 0, w1, w2, B, N, M, gpc1, gpc2,
+                      stream);
 }

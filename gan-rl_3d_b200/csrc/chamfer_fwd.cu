@@ -25,9 +25,7 @@
 
 namespace rlg {
 
-static constexpr int kGroup = 32;          // columns per group == lanes per warp
 static constexpr float kPad = 3.0e18f;     // sentinel coordinate for out-of-range rows/columns
-static constexpr u64 kKeyInit = ~0ull;
 
 // ------------------------------------------------------------------------------------------------
 // simple cross-check path: one thread per query point, candidates tiled through shared memory
@@ -94,8 +92,15 @@ struct TileCfg {
     static constexpr int kBufFloats = 3 * kStride;   // one staged group
 };
 
-template <int R>
-__global__ void __launch_bounds__(TileCfg<R>::kWarps * 32, (R <= 8 ? 3 : 2))
+template <bool MIN3>
+__device__ __forceinline__ float minacc(float acc, float a, float b) {
+    // FMNMX3 saves an issue slot but measures ~1.7 cycles next to packed FMA traffic vs ~0.6 per FMNMX
+    if (MIN3) return min3(acc, a, b);
+    return min2(min2(acc, a), b);
+}
+
+template <int R, int OCC, bool MIN3>
+__global__ void __launch_bounds__(TileCfg<R>::kWarps * 32, OCC)
 chamfer_tile_kernel(const float *__restrict__ pc1, const float *__restrict__ pc2, int N, int M,
                     int n_rb, int n_cg, long long total_units, u64 *__restrict__ rowkey,
                     u64 *__restrict__ colkey) {
@@ -211,13 +216,13 @@ chamfer_tile_kernel(const float *__restrict__ pc1, const float *__restrict__ pc2
                     tb = fma2(d2, d2, tb);
                     unpack2(ta, t[rr][0], t[rr][1]);
                     unpack2(tb, t[rr][2], t[rr][3]);
-                    rowmin[r + rr] = min3(rowmin[r + rr], t[rr][0], t[rr][1]);
-                    rowmin[r + rr] = min3(rowmin[r + rr], t[rr][2], t[rr][3]);
+                    rowmin[r + rr] = minacc<MIN3>(rowmin[r + rr], t[rr][0], t[rr][1]);
+                    rowmin[r + rr] = minacc<MIN3>(rowmin[r + rr], t[rr][2], t[rr][3]);
                 }
-                c0 = min3(c0, t[0][0], t[1][0]);
-                c1 = min3(c1, t[0][1], t[1][1]);
-                c2 = min3(c2, t[0][2], t[1][2]);
-                c3 = min3(c3, t[0][3], t[1][3]);
+                c0 = minacc<MIN3>(c0, t[0][0], t[1][0]);
+                c1 = minacc<MIN3>(c1, t[0][1], t[1][1]);
+                c2 = minacc<MIN3>(c2, t[0][2], t[1][2]);
+                c3 = minacc<MIN3>(c3, t[0][3], t[1][3]);
             }
             // warp-wide column minima; lane (4*step+q) keeps the result of column q of this step
             const float cq[4] = {c0, c1, c2, c3};
@@ -249,65 +254,7 @@ chamfer_tile_kernel(const float *__restrict__ pc1, const float *__restrict__ pc2
     flush_rows();
 }
 
-// ------------------------------------------------------------------------------------------------
-// finalize: exact index inside the winning group, sqrt, workspace reset, deterministic means.
-// One CTA per (cloud, direction).
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) chamfer_finalize_kernel(
-    const float *__restrict__ pc1, const float *__restrict__ pc2, int N, int M, int rows_per_group,
-    u64 *__restrict__ rowkey, u64 *__restrict__ colkey, float *__restrict__ d1, float *__restrict__ d2,
-    int32_t *__restrict__ i1, int32_t *__restrict__ i2, float *__restrict__ mean1,
-    float *__restrict__ mean2) {
-    __shared__ double red[512];
-    const int b = blockIdx.x, dir = blockIdx.y;
-    // dir 0: queries = pc1 rows, candidates = pc2 columns in groups of 32
-    // dir 1: queries = pc2 columns, candidates = pc1 rows in groups of rows_per_group
-    const int nq = dir ? M : N, nc = dir ? N : M;
-    const int gsz = dir ? rows_per_group : kGroup;
-    const float *q = (dir ? pc2 : pc1) + (size_t)b * nq * 3;
-    const float *c = (dir ? pc1 : pc2) + (size_t)b * nc * 3;
-    u64 *keys = (dir ? colkey : rowkey) + (size_t)b * nq;
-    float *dout = (dir ? d2 : d1) + (size_t)b * nq;
-    int32_t *iout = (dir ? i2 : i1) + (size_t)b * nq;
-
-    double acc = 0.0;
-    for (int i = threadIdx.x; i < nq; i += 512) {
-        const u64 key = keys[i];
-        keys[i] = kKeyInit;                                  // leave the workspace clean for the next call
-        float tmin = __uint_as_float((unsigned)(key >> 32));
-        const unsigned g = (unsigned)(key & 0xffffffffu);
-        const float px = q[3 * i], py = q[3 * i + 1], pz = q[3 * i + 2];
-        int found = -1;
-        if (key != kKeyInit) {
-            const int j0 = (int)g * gsz;
-            const int j1 = min(j0 + gsz, nc);
-            for (int j = j0; j < j1; ++j) {
-                const float t = sqdist(px, py, pz, c[3 * j], c[3 * j + 1], c[3 * j + 2]);
-                if (t == tmin) { found = j; break; }
-            }
-        }
-        if (found < 0) {
-            // only reachable with non-finite input (outside the contract): mirror torch.min, where the
-            // first NaN wins -> candidate 0
-            found = 0;
-            tmin = sqdist(px, py, pz, c[0], c[1], c[2]);
-        }
-        const float dist = sqrtf(tmin);
-        dout[i] = dist;
-        iout[i] = found;
-        acc += (double)dist;
-    }
-    if (mean1 == nullptr) return;
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    for (int s = 256; s > 0; s >>= 1) {
-        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) (dir ? mean2 : mean1)[b] = (float)(red[0] / (double)nq);
-}
-
-template <int R>
+template <int R, int OCC, bool MIN3>
 static int launch_tile(const float *pc1, const float *pc2, int B, int N, int M, u64 *rowkey, u64 *colkey,
                        cudaStream_t st) {
     using Cfg = TileCfg<R>;
@@ -317,14 +264,14 @@ static int launch_tile(const float *pc1, const float *pc2, int B, int N, int M, 
     const int sms = sm_count();
     if (sms <= 0) return fail((int)cudaErrorNoDevice, "rlg_chamfer_fwd: no CUDA device");
     int ctas_per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, chamfer_tile_kernel<R>,
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, chamfer_tile_kernel<R, OCC, MIN3>,
                                                                   Cfg::kWarps * 32, 0);
     if (e != cudaSuccess || ctas_per_sm < 1) ctas_per_sm = 1;
     long long grid = (long long)sms * ctas_per_sm;
     const long long max_useful = (total + Cfg::kWarps - 1) / Cfg::kWarps;   // at least one unit per warp
     if (grid > max_useful) grid = max_useful;
     if (grid < 1) grid = 1;
-    chamfer_tile_kernel<R><<<(unsigned)grid, Cfg::kWarps * 32, 0, st>>>(pc1, pc2, N, M, n_rb, n_cg, total,
+    chamfer_tile_kernel<R, OCC, MIN3><<<(unsigned)grid, Cfg::kWarps * 32, 0, st>>>(pc1, pc2, N, M, n_rb, n_cg, total,
                                                                        rowkey, colkey);
     return check_launch("chamfer_tile_kernel");
 }
@@ -335,20 +282,31 @@ using namespace rlg;
 
 extern "C" {
 
+static size_t keys_bytes(int B, int N, int M) { return align_up(sizeof(u64) * ((size_t)B * N + (size_t)B * M), 256); }
+
 size_t rlg_chamfer_ws_bytes(int B, int N, int M) {
     if (B < 0 || N < 1 || M < 1) return 0;
-    return align_up(sizeof(u64) * ((size_t)B * N + (size_t)B * M), 256);
+    return keys_bytes(B, N, M) + finalize_ws_bytes(B, N, M);   // packed (t,group) keys + finalize counters/partials
 }
 
 int rlg_chamfer_fwd(const float *pc1, const float *pc2, int B, int N, int M, float *d1, float *d2,
                     int32_t *i1, int32_t *i2, float *mean1, float *mean2, void *ws, size_t ws_bytes,
                     unsigned flags, void *stream) {
+    return rlg_chamfer_loss_fwd(pc1, pc2, B, N, M, d1, d2, i1, i2, mean1, mean2, nullptr, 0.0f, 0.0f, ws, ws_bytes,
+                                flags, stream);
+}
+
+int rlg_chamfer_loss_fwd(const float *pc1, const float *pc2, int B, int N, int M, float *d1, float *d2,
+                         int32_t *i1, int32_t *i2, float *mean1, float *mean2, float *loss, float w1, float w2,
+                         void *ws, size_t ws_bytes, unsigned flags, void *stream) {
     if (B < 0 || N < 1 || M < 1)
         return fail(RLG_ERR_BAD_SHAPE, "rlg_chamfer_fwd: bad shape B=%d N=%d M=%d (need B>=0, N>=1, M>=1)", B, N, M);
     if (B == 0) return 0;
     if (!pc1 || !pc2 || !d1 || !d2 || !i1 || !i2) return fail(RLG_ERR_NULL_POINTER, "rlg_chamfer_fwd: null pointer");
     if ((mean1 == nullptr) != (mean2 == nullptr))
         return fail(RLG_ERR_NULL_POINTER, "rlg_chamfer_fwd: mean1/mean2 must both be given or both be null");
+    if (loss != nullptr && mean1 == nullptr)
+        return fail(RLG_ERR_NULL_POINTER, "rlg_chamfer_loss_fwd: the batch loss needs the mean1/mean2 buffers");
     if ((long long)B > 65535) return fail(RLG_ERR_TOO_LARGE, "rlg_chamfer_fwd: B=%d exceeds 65535 (grid.x of the finalize)", B);
     if ((long long)N * 3 > 0x7fffffffLL || (long long)M * 3 > 0x7fffffffLL)
         return fail(RLG_ERR_TOO_LARGE, "rlg_chamfer_fwd: N or M too large for 32-bit indexing");
@@ -359,6 +317,7 @@ int rlg_chamfer_fwd(const float *pc1, const float *pc2, int B, int N, int M, flo
         chamfer_simple_kernel<<<g1, 128, 0, st>>>(pc1, pc2, N, M, d1, i1);
         chamfer_simple_kernel<<<g2, 128, 0, st>>>(pc2, pc1, M, N, d2, i2);
         if (mean1) chamfer_mean_kernel<<<dim3(B, 2), 256, 0, st>>>(d1, d2, N, M, mean1, mean2);
+        if (loss) return fail(RLG_ERR_UNSUPPORTED, "rlg_chamfer_loss_fwd: the simple cross-check path has no fused loss");
         return check_launch("chamfer_simple_kernel");
     }
 
@@ -369,19 +328,28 @@ int rlg_chamfer_fwd(const float *pc1, const float *pc2, int B, int N, int M, flo
     u64 *rowkey = (u64 *)ws;
     u64 *colkey = rowkey + (size_t)B * N;
     if (!(flags & RLG_CHAMFER_WS_CLEAN)) {
-        cudaError_t e = cudaMemsetAsync(ws, 0xff, sizeof(u64) * ((size_t)B * N + (size_t)B * M), st);
+        cudaError_t e = cudaMemsetAsync(ws, 0xff, need, st);
         if (e != cudaSuccess) {
             cudaGetLastError();
             return fail((int)e, "rlg_chamfer_fwd: cudaMemsetAsync: %s", cudaGetErrorString(e));
         }
     }
-    constexpr int R = 8;
-    int rc = launch_tile<R>(pc1, pc2, B, N, M, rowkey, colkey, st);
+    // bits 8..11 of flags select an experimental tile variant (tools/sweep_tile.py); 0 = production
+    int R = 8, rc = 0;
+    switch ((flags >> 8) & 15u) {
+        default:
+        case 0: rc = launch_tile<8, 3, false>(pc1, pc2, B, N, M, rowkey, colkey, st); break;
+        case 1: rc = launch_tile<8, 3, true>(pc1, pc2, B, N, M, rowkey, colkey, st); break;
+        case 2: rc = launch_tile<8, 4, false>(pc1, pc2, B, N, M, rowkey, colkey, st); break;
+        case 3: R = 4; rc = launch_tile<4, 5, false>(pc1, pc2, B, N, M, rowkey, colkey, st); break;
+        case 4: R = 16; rc = launch_tile<16, 2, false>(pc1, pc2, B, N, M, rowkey, colkey, st); break;
+        case 5: R = 4; rc = launch_tile<4, 4, false>(pc1, pc2, B, N, M, rowkey, colkey, st); break;
+        case 6: R = 8; rc = launch_tile<8, 2, false>(pc1, pc2, B, N, M, rowkey, colkey, st); break;
+    }
     if (rc) return rc;
     if (flags & RLG_CHAMFER_TILE_ONLY) return 0;
-    chamfer_finalize_kernel<<<dim3(B, 2), 512, 0, st>>>(pc1, pc2, N, M, R, rowkey, colkey, d1, d2, i1, i2, mean1,
-                                                       mean2);
-    return check_launch("chamfer_finalize_kernel");
+    return launch_finalize(pc1, pc2, B, N, M, R, rowkey, colkey, (char *)ws + keys_bytes(B, N, M), d1, d2, i1, i2,
+                           mean1, mean2, loss, w1, w2, st);
 }
 
 }  // extern "C"

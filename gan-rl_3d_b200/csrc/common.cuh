@@ -22,6 +22,14 @@ int sm_count();
 
 typedef unsigned long long u64;
 
+// ---- Chamfer forward: shared between the tile kernel (chamfer_fwd.cu) and the finalize (chamfer_finalize.cu)
+static constexpr int kGroup = 32;           // columns per group == lanes per warp
+static constexpr u64 kKeyInit = ~0ull;      // workspace state on entry and on exit of every forward
+size_t finalize_ws_bytes(int B, int N, int M);
+int launch_finalize(const float *pc1, const float *pc2, int B, int N, int M, int rows_per_group, u64 *rowkey,
+                    u64 *colkey, void *fin_ws, float *d1, float *d2, int32_t *i1, int32_t *i2, float *mean1,
+                    float *mean2, float *loss, float w1, float w2, cudaStream_t st);
+
 // ---- packed fp32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2) ------------------------------
 // One instruction issues two IEEE fp32 operations, halving the issue-slot cost of the distance math.
 __device__ __forceinline__ u64 pack2(float lo, float hi) {
@@ -42,6 +50,10 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
 // 3-input min (FMNMX3).  NaN operands are dropped, like fminf.
 __device__ __forceinline__ float min3(float a, float b, float c) {
     float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r;
+}
+// 2-input min kept as its own instruction (ptxas otherwise re-fuses fminf(fminf(a,b),c) into FMNMX3)
+__device__ __forceinline__ float min2(float a, float b) {
+    float r; asm("min.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r;
 }
 __device__ __forceinline__ float max3(float a, float b, float c) {
     float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r;

@@ -1,0 +1,131 @@
+"""CUDA-graph step runners for the Chamfer hot path.
+
+At the headline shape (B=32, N=M=2048) one ChamferLoss forward+backward is ~60 us of GPU work in four kernel
+launches, less than the Python/ctypes cost of enqueuing it.  These helpers capture S steps -- exactly the calls a
+user makes, `loss = ChamferLoss()(pred, target); loss.backward()` -- into one CUDA graph so the launch-bound
+loop is replayed by the driver instead of re-issued from Python (train_rl_gan_net.py:220-249 is such a loop).
+
+  ChamferStepGraph      S steps over S device-resident batches.
+  HostChamferStepGraph  S steps over S pinned host batches: every step's H2D copy of its inputs and D2H copy of
+                        its loss are inside the graph, double-buffered on a copy stream so transfers overlap
+                        the previous step's kernels.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+
+from .chamfer import ChamferLoss
+
+
+class ChamferStepGraph:
+    """Capture `for pred, target in batches: loss = crit(pred, target); loss.backward()` in one CUDA graph.
+    After replay(): self.losses[k] (0-dim tensors) and self.grads[k] (d loss / d pred) hold step k's results."""
+
+    def __init__(self, batches: Sequence[Tuple[torch.Tensor, torch.Tensor]], bidirectional: bool = True,
+                 grad_target: bool = False):
+        assert len(batches) > 0 and batches[0][0].is_cuda
+        self.crit = ChamferLoss(bidirectional)
+        self.batches = [(a.detach().requires_grad_(True), b.detach().requires_grad_(grad_target)) for a, b in batches]
+        self.device = self.batches[0][0].device
+        self.losses: List[torch.Tensor] = []
+        self.grads: List[torch.Tensor] = []
+        self.kernel_launches_per_replay = 4 * len(self.batches)    # tile + finalize + bwd own + bwd scatter
+        self.stream = torch.cuda.Stream(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        self._capture()
+
+    def _one_step(self, k: int) -> torch.Tensor:
+        a, b = self.batches[k]
+        a.grad = None
+        b.grad = None
+        loss = self.crit(a, b)
+        loss.backward()
+        return loss
+
+    def _capture(self) -> None:
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            for k in range(min(3, len(self.batches))):       # warm-up on the capture stream (workspace, allocator)
+                self._one_step(k)
+        self.stream.synchronize()
+        with torch.cuda.graph(self.graph, stream=self.stream):
+            for k in range(len(self.batches)):
+                self.losses.append(self._one_step(k))
+                self.grads.append(self.batches[k][0].grad)
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+    def replay(self) -> None:
+        self.graph.replay()
+
+
+class HostChamferStepGraph:
+    """S training steps whose inputs live in pinned HOST memory.  Per step, inside the graph: H2D copy of
+    (pred, target) into one of two device staging pairs (copy stream), ChamferLoss forward+backward (compute
+    stream), D2H copy of the loss into a pinned (S,) result vector.  The copy of step k+1 overlaps the kernels
+    of step k.  After replay() + synchronize: self.losses_host[k] is step k's loss."""
+
+    def __init__(self, host_batches: Sequence[Tuple[torch.Tensor, torch.Tensor]], device: torch.device,
+                 bidirectional: bool = True):
+        assert all(a.is_pinned() and b.is_pinned() for a, b in host_batches), "host batches must be pinned"
+        self.host = list(host_batches)
+        self.device = device
+        self.S = len(self.host)
+        self.crit = ChamferLoss(bidirectional)
+        a0, b0 = self.host[0]
+        self.stage = [(torch.empty_like(a0, device=device).requires_grad_(True), torch.empty_like(b0, device=device))
+                      for _ in range(2)]
+        self.losses_host = torch.zeros(self.S, dtype=torch.float32).pin_memory()
+        self.h2d_bytes_per_step = (a0.numel() + b0.numel()) * 4
+        self.d2h_bytes_per_step = 4
+        self.kernel_launches_per_replay = 4 * self.S
+        self.compute = torch.cuda.Stream(device)
+        self.copy = torch.cuda.Stream(device)
+        self.graph = torch.cuda.CUDAGraph()
+        self._capture()
+
+    def _copy_in(self, k: int) -> None:
+        da, db = self.stage[k % 2]
+        ha, hb = self.host[k]
+        da.detach().copy_(ha, non_blocking=True)
+        db.copy_(hb, non_blocking=True)
+
+    def _step(self, k: int) -> None:
+        da, db = self.stage[k % 2]
+        da.grad = None
+        loss = self.crit(da, db)
+        loss.backward()
+        self.losses_host[k:k + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+
+    def _capture(self) -> None:
+        cur = torch.cuda.current_stream(self.device)
+        self.compute.wait_stream(cur)
+        with torch.cuda.stream(self.compute):          # eager warm-up
+            for k in range(min(2, self.S)):
+                self._copy_in(k)
+                self._step(k)
+        self.compute.synchronize()
+        with torch.cuda.graph(self.graph, stream=self.compute):
+            copied = [None] * self.S
+            computed = [None] * self.S
+            for k in range(self.S):
+                # copy k may start once step k-2 (last user of this staging pair) has finished
+                self.copy.wait_stream(self.compute) if k < 2 else self.copy.wait_event(computed[k - 2])
+                with torch.cuda.stream(self.copy):
+                    self._copy_in(k)
+                    copied[k] = torch.cuda.Event()
+                    copied[k].record(self.copy)
+                if k >= 1:
+                    # while copy k is in flight, compute step k-1
+                    self.compute.wait_event(copied[k - 1])
+                    self._step(k - 1)
+                    computed[k - 1] = torch.cuda.Event()
+                    computed[k - 1].record(self.compute)
+            self.compute.wait_event(copied[self.S - 1])
+            self._step(self.S - 1)
+            self.compute.wait_stream(self.copy)
+        cur.wait_stream(self.compute)
+
+    def replay(self) -> None:
+        self.graph.replay()

@@ -78,6 +78,15 @@ int rlg_chamfer_fwd(const float *pc1, const float *pc2, int B, int N, int M,
                     float *mean1, float *mean2,
                     void *ws, size_t ws_bytes, unsigned flags, void *stream);
 
+/* Forward fused with the reference's loss reduction (utils/losses.py:54-59 and :75):
+ *   loss[0] = sum_b ( w1 * mean1[b] + w2 * mean2[b] ),  accumulated in a fixed order (deterministic);
+ *   ChamferLoss(bidirectional=True) is w1 = w2 = 0.5/B, bidirectional=False is w1 = 1/B, w2 = 0.
+ * loss: device fp32 scalar (nullable -> identical to rlg_chamfer_fwd); needs mean1/mean2. */
+int rlg_chamfer_loss_fwd(const float *pc1, const float *pc2, int B, int N, int M,
+                         float *d1, float *d2, int32_t *i1, int32_t *i2,
+                         float *mean1, float *mean2, float *loss, float w1, float w2,
+                         void *ws, size_t ws_bytes, unsigned flags, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Chamfer distance, backward
  *
@@ -90,6 +99,13 @@ int rlg_chamfer_bwd(const float *pc1, const float *pc2,
                     const float *d1, const float *d2, const int32_t *i1, const int32_t *i2,
                     const float *g1, const float *g2, int B, int N, int M,
                     float *gpc1, float *gpc2, void *stream);
+
+/* Backward of rlg_chamfer_loss_fwd: gloss is the device fp32 scalar upstream of loss[0]; the per-pair
+ * upstreams are gloss[0]*w1 (mean1) and gloss[0]*w2 (mean2). */
+int rlg_chamfer_loss_bwd(const float *pc1, const float *pc2,
+                         const float *d1, const float *d2, const int32_t *i1, const int32_t *i2,
+                         const float *gloss, float w1, float w2, int B, int N, int M,
+                         float *gpc1, float *gpc2, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * PointNet encoder: shared per-point MLP + global max-pool  (models/autoencoder.py:65-71), eval mode.

@@ -36,6 +36,14 @@ def _reference_shaped_modules():
     return losses, ae
 
 
+def _graph_nodes(fn, seen=None):
+    seen = set() if seen is None else seen
+    if fn is None or fn in seen:
+        return ""
+    seen.add(fn)
+    return type(fn).__name__ + " " + " ".join(_graph_nodes(n, seen) for n, _ in fn.next_functions)
+
+
 def test_install_routes_cuda_inputs_through_the_kernels(rlg):
     losses, ae = _reference_shaped_modules()
     crit_before = losses.ChamferLoss()
@@ -45,12 +53,15 @@ def test_install_routes_cuda_inputs_through_the_kernels(rlg):
     O.randomize_bn(enc, 4)
     enc.eval()
     with torch.no_grad():
-        stock_gfv = enc(pc1)
+        stock_gfv = enc(pc1)                                       # stock CUDA path: cuDNN conv, TF32 allowed by default
+        truth_gfv = ae.PointNetEncoder(3, 32, [16, 64]).double()
+        truth_gfv.load_state_dict(enc.state_dict())
+        truth_gfv = truth_gfv.eval()(pc1.cpu().double()).float()   # float64 truth of the same module on the host
     rlg.install(losses, ae)
     try:
         a = pc1.clone().requires_grad_(True)
         v = crit_before(a, pc2)                                    # created before the patch, follows it
-        assert isinstance(v.grad_fn, torch.autograd.function.BackwardCFunction) or "ChamferFn" in repr(v.grad_fn.next_functions)
+        assert "ChamferFnBackward" in _graph_nodes(v.grad_fn)        # the CUDA Function is in the autograd graph
         v.backward()
         d1, d2, i1, i2 = O.chamfer_direct(pc1.cpu(), pc2.cpu(), O.TIE_SQUARED)
         m1, m2 = O.chamfer_means(d1, d2)
@@ -59,7 +70,8 @@ def test_install_routes_cuda_inputs_through_the_kernels(rlg):
         assert abs(v.item() - stock) <= 1e-4 * want                # the stock matmul path is the noisy one
         with torch.no_grad():
             gfv = enc(pc1)
-        assert O.gfv_close(gfv.cpu().numpy(), stock_gfv.cpu().numpy(), 1e-5)[0]
+        assert O.gfv_close(gfv.cpu().numpy(), truth_gfv.numpy(), 1e-5)[0]
+        assert O.gfv_close(gfv.cpu().numpy(), stock_gfv.cpu().numpy(), 1e-2)[0]   # TF32 conv noise of the stock path
         # 4-D input (validate_joint's broadcast defect, train_rl_gan_net.py:541) is NOT the hot path: the
         # original function must see it unchanged
         four_d = torch.zeros(2, 2, 8, 3, device=DEV)

@@ -59,15 +59,30 @@ def test_golden_gfvs_from_reference(rlg, golden_encoder):
             chk = float(sum(v.double().abs().sum().item() for v in enc.state_dict().values()))
             if abs(chk - float(g[f"enc{k}_state_checksum"])) > 1e-6 * abs(chk):
                 pytest.skip("torch default init differs from the fixture's torch build")
-        enc = enc.eval().to(DEV)
-        x = torch.from_numpy(g[f"enc{k}_x"]).to(DEV)
+        enc = enc.eval()
+        x_cpu = torch.from_numpy(g[f"enc{k}_x"])
+        truth = O.RefEncoderPort(3, latent, dims).double()
+        truth.load_state_dict(enc.state_dict())
+        truth.eval()
+        with torch.no_grad():
+            t_gfv = truth(x_cpu.double()).numpy()
+            t_pool = truth.pooled(x_cpu.double()).numpy()
+        enc = enc.to(DEV)
+        x = x_cpu.to(DEV)
         with torch.no_grad():
             gfv = enc(x)
-        ok, err = O.gfv_close(gfv.cpu().numpy(), g[f"enc{k}_gfv"], FP32_TOL)
-        assert ok, (k, err)
         pooled, _ = rlg.encoder_pool(x, rlg.folded_trunk_cached(enc))
-        ok, err = O.gfv_close(pooled.cpu().numpy(), g[f"enc{k}_pooled"], FP32_TOL)
-        assert ok, (k, err)
+        # the fixture is the reference's own fp32 result; it carries fp32 rounding of its own (measured here
+        # against the float64 evaluation of the same weights), so: ours vs truth <= 1e-5, and ours vs the
+        # reference <= 1e-5 + the reference's distance from truth
+        for ours, gold, tru in ((gfv, g[f"enc{k}_gfv"], t_gfv), (pooled, g[f"enc{k}_pooled"], t_pool)):
+            ours = ours.cpu().numpy()
+            ref_err = O.gfv_close(gold, tru, 1.0)[1]
+            assert ref_err < 1e-4, (k, ref_err)                      # the fixture really is this network
+            ok, err = O.gfv_close(ours, tru, FP32_TOL)
+            assert ok, (k, err)
+            ok, err = O.gfv_close(ours, gold, FP32_TOL + ref_err)
+            assert ok, (k, err, ref_err)
 
 
 def test_train_mode_uses_stock_layers_and_updates_running_stats(rlg):
