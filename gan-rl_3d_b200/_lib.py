@@ -51,6 +51,12 @@ EXPORTS = {
     "rlg_encoder_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(RlgLayer),
                                        ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "rlg_encoder_pack_bytes": (ctypes.c_size_t, [ctypes.POINTER(RlgLayer), ctypes.c_int]),
+    "rlg_encoder_pack_bf16": (ctypes.c_int, [ctypes.POINTER(RlgLayer), ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
+                                             ctypes.c_void_p]),
+    "rlg_encoder_fwd_bf16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(RlgLayer),
+                                            ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                            ctypes.c_void_p]),
     "rlg_fp32_peak": (ctypes.c_int, [c_float_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
 }
 

@@ -71,7 +71,18 @@ def folded_trunk_cached(module: nn.Module) -> List[Tuple[torch.Tensor, torch.Ten
     if cache is None or cache[0] != ver:
         cache = (ver, fold_trunk(module.point_mlp))
         module.__dict__["_rlg_folded"] = cache
+        module.__dict__.pop("_rlg_packed", None)
     return cache[1]
+
+
+def packed_trunk_cached(module: nn.Module) -> torch.Tensor:
+    """bf16 images of the folded weights, cached next to (and invalidated with) the folded fp32 weights."""
+    layers = folded_trunk_cached(module)
+    packed = module.__dict__.get("_rlg_packed")
+    if packed is None:
+        packed = pack_bf16(layers)
+        module.__dict__["_rlg_packed"] = packed
+    return packed
 
 
 # ---- the CUDA trunk ---------------------------------------------------------------------------------
@@ -80,15 +91,24 @@ def is_hot_path_input(x) -> bool:
             and x.shape[2] == 3 and x.shape[1] >= 1)
 
 
-def encoder_pool(x: torch.Tensor, layers: List[Tuple[torch.Tensor, torch.Tensor]], want_argmax: bool = False):
-    """pooled (B, C_last) = max over points of the folded per-point MLP (ReLU after every layer), i.e.
-    torch.max(point_mlp(x.transpose(2,1)), dim=2)[0] of models/autoencoder.py:65-71 in eval mode.
-    Returns (pooled fp32, argmax int32 or None)."""
-    if not is_hot_path_input(x):
-        raise ValueError("gan-rl_3d_b200 encoder needs a CUDA float32 tensor (B,N,3) with N >= 1; there is no CPU path")
-    lib = _lib.load()
-    x = x.contiguous()
-    B, N, _ = x.shape
+_PRECISION = "fp32"
+
+
+def set_encoder_precision(precision: str) -> None:
+    """Default arithmetic of the fused trunk: "fp32" (CUDA cores, GFVs within 1e-5 of the reference) or "bf16"
+    (tcgen05/TMEM tensor-core GEMMs with fp32 accumulation, GFVs within 2e-2; widths must fit the tensor path).
+    A module can override it with an attribute `rlg_precision`."""
+    global _PRECISION
+    if precision not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    _PRECISION = precision
+
+
+def get_encoder_precision() -> str:
+    return _PRECISION
+
+
+def _layer_array(layers):
     L = len(layers)
     arr = (_lib.RlgLayer * L)()
     keep = []
@@ -100,7 +120,52 @@ def encoder_pool(x: torch.Tensor, layers: List[Tuple[torch.Tensor, torch.Tensor]
         keep += [w, b]
         arr[l].w, arr[l].b = w.data_ptr(), b.data_ptr()
         arr[l].c_out, arr[l].c_in = w.shape[0], w.shape[1]
+    return arr, keep
+
+
+def pack_bf16(layers: List[Tuple[torch.Tensor, torch.Tensor]]) -> torch.Tensor:
+    """bf16 weight images of layers >= 1 in the swizzled shared-memory layout the tcgen05 kernel loads with TMA
+    bulk copies.  Raises RlgError (RLG_ERR_UNSUPPORTED) if the widths do not fit the tensor path."""
+    lib = _lib.load()
+    arr, keep = _layer_array(layers)
+    dev = layers[0][0].device
+    with torch.cuda.device(dev):
+        nbytes = lib.rlg_encoder_pack_bytes(arr, len(layers))
+        if nbytes == 0:
+            _lib.check("rlg_encoder_pack_bytes", -4)
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        rc = lib.rlg_encoder_pack_bf16(arr, len(layers), packed.data_ptr(), packed.numel(),
+                                       torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check("rlg_encoder_pack_bf16", rc)
+    return packed
+
+
+def encoder_pool(x: torch.Tensor, layers: List[Tuple[torch.Tensor, torch.Tensor]], want_argmax: bool = False,
+                 precision: str = "fp32", packed: Optional[torch.Tensor] = None):
+    """pooled (B, C_last) = max over points of the folded per-point MLP (ReLU after every layer), i.e.
+    torch.max(point_mlp(x.transpose(2,1)), dim=2)[0] of models/autoencoder.py:65-71 in eval mode.
+    Returns (pooled fp32, argmax int32 or None).  precision="bf16" runs layers >= 1 on the tensor cores."""
+    if not is_hot_path_input(x):
+        raise ValueError("gan-rl_3d_b200 encoder needs a CUDA float32 tensor (B,N,3) with N >= 1; there is no CPU path")
+    lib = _lib.load()
+    x = x.contiguous()
+    B, N, _ = x.shape
+    L = len(layers)
+    arr, keep = _layer_array(layers)
     c_last = layers[-1][0].shape[0]
+    if precision == "bf16":
+        if want_argmax:
+            raise ValueError("the bf16 tensor-core path does not report argmax indices")
+        if packed is None:
+            packed = pack_bf16(layers)
+        pooled = torch.empty((B, c_last), dtype=torch.float32, device=x.device)
+        if B == 0:
+            return pooled, None
+        with torch.cuda.device(x.device):
+            rc = lib.rlg_encoder_fwd_bf16(x.data_ptr(), B, N, arr, L, packed.data_ptr(), packed.numel(),
+                                          pooled.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream)
+            _lib.check("rlg_encoder_fwd_bf16", rc)
+        return pooled, None
     pooled = torch.empty((B, c_last), dtype=torch.float32, device=x.device)
     argmax = torch.empty((B, c_last), dtype=torch.int32, device=x.device) if want_argmax else None
     if B == 0:
@@ -123,8 +188,7 @@ class EncoderTrunkFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, module, *params):
-        layers = folded_trunk_cached(module)
-        pooled, _ = encoder_pool(x, layers)
+        pooled = _trunk_pool(module, x)
         ctx.module = module
         ctx.n_params = len(params)
         ctx.save_for_backward(x)
@@ -145,6 +209,14 @@ class EncoderTrunkFn(torch.autograd.Function):
         return (gx, None) + gps
 
 
+def _trunk_pool(module: nn.Module, x: torch.Tensor) -> torch.Tensor:
+    precision = getattr(module, "rlg_precision", _PRECISION)
+    layers = folded_trunk_cached(module)
+    if precision == "bf16":
+        return encoder_pool(x, layers, precision="bf16", packed=packed_trunk_cached(module))[0]
+    return encoder_pool(x, layers)[0]
+
+
 def fused_forward(self: nn.Module, x: torch.Tensor, _original=None) -> torch.Tensor:
     """Drop-in for PointNetEncoder.forward (models/autoencoder.py:56-76)."""
     if self.training or not is_hot_path_input(x) or x.shape[0] == 0:
@@ -157,7 +229,7 @@ def fused_forward(self: nn.Module, x: torch.Tensor, _original=None) -> torch.Ten
     if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
         pooled = EncoderTrunkFn.apply(x, self, *params)
     else:
-        pooled, _ = encoder_pool(x, folded_trunk_cached(self))
+        pooled = _trunk_pool(self, x)
     return self.global_mlp(pooled)
 
 

@@ -120,9 +120,7 @@ int rlg_chamfer_loss_bwd(const float *pc1, const float *pc2,
  *   argmax (B, c_out of last)      device int32, nullable: a point index attaining the max
  *
  * rlg_encoder_fwd      fp32 CUDA-core path, any layer widths (c_in of layer 0 must be 3).
- * rlg_encoder_fwd_bf16 tcgen05/TMEM path: layers >= 1 run as bf16 x bf16 -> fp32 GEMMs on the 5th-gen
- *                      tensor cores; needs every width to be a multiple of 64 and the packed weights
- *                      produced by rlg_encoder_pack_bf16.
+ * rlg_encoder_fwd_bf16 tcgen05/TMEM path, see below.
  * --------------------------------------------------------------------------------------------- */
 typedef struct rlg_layer {
     const float *w;     /* device, (c_out, c_in) row-major, BatchNorm already folded */
@@ -136,6 +134,19 @@ size_t rlg_encoder_ws_bytes(int B, int N, const rlg_layer *layers, int L);
 int rlg_encoder_fwd(const float *x, int B, int N, const rlg_layer *layers, int L,
                     float *pooled, int32_t *argmax,
                     void *ws, size_t ws_bytes, void *stream);
+
+/* tcgen05 / TMEM path (bf16 operands, fp32 accumulation).  Layer 0 (3 -> c1) stays fp32 on the CUDA cores; layers
+ * >= 1 are tensor-core GEMMs whose accumulators live in TMEM; the last layer's bias+ReLU+max-pool is the epilogue,
+ * so the (B, C_last, N) activation never leaves the SM.  Supported widths: every hidden width 64 or 128, last width
+ * a multiple of 128, L >= 2 (anything else: RLG_ERR_UNSUPPORTED -> use rlg_encoder_fwd).
+ *   rlg_encoder_pack_bytes  size of the packed bf16 weight image (0 if the layer list is unsupported)
+ *   rlg_encoder_pack_bf16   folded fp32 layers -> bf16 images in the swizzled shared-memory layout (device, 256-B
+ *                           aligned); repack whenever the weights change
+ *   rlg_encoder_fwd_bf16    pooled (B, C_last) fp32, fully overwritten; `layers` still supplies layer 0 and biases */
+size_t rlg_encoder_pack_bytes(const rlg_layer *layers, int L);
+int rlg_encoder_pack_bf16(const rlg_layer *layers, int L, void *packed, size_t packed_bytes, void *stream);
+int rlg_encoder_fwd_bf16(const float *x, int B, int N, const rlg_layer *layers, int L,
+                         const void *packed, size_t packed_bytes, float *pooled, void *stream);
 
 /* FP32 CUDA-core peak microbenchmark (measurement helper, not on the hot path; it synchronises).
  * Fills host array out[0..5]:

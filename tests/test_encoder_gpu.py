@@ -125,3 +125,51 @@ def test_unsupported_widths_fail_loudly(rlg):
     w = torch.zeros(4, 5, device=DEV)
     with pytest.raises(RuntimeError, match="c_in == 3"):
         rlg.encoder_pool(x, [(w, torch.zeros(4, device=DEV))])
+
+
+BF16_TOL = 2e-2      # north_star: 2e-2 relative for the bf16 encoder GEMMs (abs-floor rule of SURVEY.md 7.2-6)
+
+
+@pytest.mark.parametrize("dims", [[64, 128, 1024], [64, 128, 256], [128, 128], [64, 64, 64, 128], [64, 384], [128, 64, 640]])
+@pytest.mark.parametrize("B,N", [(2, 200), (1, 1), (3, 128), (2, 2048), (5, 1300)])
+def test_bf16_tensor_core_path_vs_float64_stack(rlg, dims, B, N):
+    enc = _port(dims, 32, len(dims) + 3)
+    x = O.make_clouds(B, N, "sphere", 900 + N)
+    with torch.no_grad():
+        want = enc.double().pooled(x.double()).float().numpy()
+    enc = enc.float().to(DEV)
+    layers = rlg.fold_trunk(enc.point_mlp)
+    pooled, _ = rlg.encoder_pool(x.to(DEV), layers, precision="bf16")
+    torch.cuda.synchronize()
+    got = pooled.cpu().numpy()
+    ok, err = O.gfv_close(got, want, BF16_TOL)
+    assert ok, err
+    # norm-wise the bf16 path is far tighter than the element-wise bound (~5e-4 measured)
+    assert np.linalg.norm(got - want) <= 5e-3 * np.linalg.norm(want)
+    # and it agrees with this repo's own fp32 CUDA-core path to the same tolerance
+    fp32, _ = rlg.encoder_pool(x.to(DEV), layers)
+    assert O.gfv_close(got, fp32.cpu().numpy(), BF16_TOL)[0]
+
+
+def test_bf16_module_switch_and_cache(rlg):
+    enc = _port([64, 128, 1024], 128, 9).to(DEV)
+    x = O.make_clouds(4, 700, "uniform", 10).to(DEV)
+    with torch.no_grad():
+        ref = rlg.fused_forward(enc, x)                       # fp32 default
+        enc.rlg_precision = "bf16"
+        out = rlg.fused_forward(enc, x)
+        packed = enc.__dict__["_rlg_packed"]
+        assert rlg.fused_forward(enc, x) is not None and enc.__dict__["_rlg_packed"] is packed     # cache hit
+        enc.point_mlp[3].weight.mul_(1.25)                    # optimizer-like update -> repack
+        out2 = rlg.fused_forward(enc, x)
+        assert enc.__dict__["_rlg_packed"] is not packed
+    assert O.gfv_close(out.cpu().numpy(), ref.cpu().numpy(), BF16_TOL)[0]
+    assert not torch.equal(out, out2)
+    assert "_rlg_packed" not in enc.state_dict()
+
+
+def test_bf16_unsupported_widths_fail_loudly(rlg):
+    enc = _port([64, 128, 128, 256, 128], 128, 4).to(DEV)     # the reference's default config: 256-wide hidden layer
+    layers = rlg.fold_trunk(enc.point_mlp)
+    with pytest.raises(RuntimeError, match="hidden width"):
+        rlg.encoder_pool(torch.zeros(1, 64, 3, device=DEV), layers, precision="bf16")
