@@ -141,26 +141,38 @@ def cpu_reference_step(pc1, pc2):
 
 
 def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path (oracle port of utils/losses.py:13-75 run with
+    all host threads).  EXACTLY K timed steps; each step is ChamferLoss forward+backward on a bounded sample of the
+    B=32 batch (b pairs, b chosen from a calibration step so the whole run stays within ~2 minutes)."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     gen = torch.Generator(device="cpu").manual_seed(1234 + 2)
     pc1, pc2 = sphere(gen, B, N), sphere(gen, B, M)
-    steps, warm = max(1, min(args.steps, 12)), max(1, min(args.warmup, 2))
-    for _ in range(warm):
-        cpu_reference_step(pc1, pc2)
+    K, W = max(1, args.steps), max(1, args.warmup)
+    cpu_reference_step(pc1[:2], pc2[:2])
     t0 = time.perf_counter()
-    for _ in range(steps):
-        cpu_reference_step(pc1, pc2)
+    cpu_reference_step(pc1[:4], pc2[:4])
+    per_pair = (time.perf_counter() - t0) / 4
+    b = int(max(1, min(B, 100.0 / ((K + W) * per_pair))))
+    for k in range(W):
+        o = (k * b) % (B - b + 1)
+        cpu_reference_step(pc1[o:o + b], pc2[o:o + b])
+    t0 = time.perf_counter()
+    for k in range(K):
+        o = (k * b) % (B - b + 1)
+        cpu_reference_step(pc1[o:o + b], pc2[o:o + b])
     dt = time.perf_counter() - t0
-    value = steps * B / dt
-    sample = f"{steps} steps of ChamferLoss fwd+bwd on B={B}, N=M={N} (torch CPU ops of the reference, all host threads)"
+    value = K * b / dt
+    sample = (f"{K} steps, each ChamferLoss fwd+bwd on {b} of the {B} pairs of the batch, N=M={N} "
+              f"(torch CPU ops of the reference, {torch.get_num_threads()} threads)")
     print(json.dumps({
         "impl": "reference", "metric": "chamfer_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "chamfer_fwd_bwd B=32 N=M=2048 sphere (BASELINE configs[1])", "B": B, "N": N, "M": M},
+        "config": {"workload": "chamfer_fwd_bwd B=32 N=M=2048 sphere (BASELINE configs[1])", "B": B, "N": N, "M": M,
+                   "pairs_per_step": b},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -369,35 +381,79 @@ def ctypes_float6(lib, dev):
 
 
 def encoder_side_measurement(rlg, dev, peaks, peaks_src):
-    """Encoder clouds/s at cfg3 (B=256, N=2048, dims 3->64->128->1024 + max-pool), the second half of the
-    BASELINE metric.  Reported as extra keys of the same JSON line."""
+    """Encoder clouds/s at cfg3 (B=256, N=2048, dims 3->64->128->1024 + max-pool + global MLP -> GFV), the second
+    half of the BASELINE metric, through the public module call `enc(x)` in eval mode.  Reported as extra keys of
+    the same JSON line: the tcgen05 bf16 path (headline), its e2e figure from pinned host clouds, and the fp32
+    CUDA-core path for comparison."""
     from oracle import oracle as O
     torch.manual_seed(0)
     enc = rlg.PointNetEncoder(3, 128, ENC_DIMS)
     O.randomize_bn(enc, 0)
     enc = enc.eval().to(dev)
     gen = torch.Generator(device="cpu").manual_seed(1234 + 3)
-    xs = [sphere(gen, ENC_B, ENC_N).to(dev) for _ in range(4)]
-    with torch.no_grad():
-        for k in range(2):
-            enc(xs[k % 4])
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10
-        e0.record()
-        for k in range(reps):
-            enc(xs[k % 4])
-        e1.record()
-        torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
+    xs_host = [sphere(gen, ENC_B, ENC_N).pin_memory() for _ in range(24)]      # 24 x 6.3 MB = 151 MB > L2
+    xs = [x.to(dev) for x in xs_host]
     flop = 2.0 * ENC_N * (3 * 64 + 64 * 128 + 128 * 1024) * ENC_B
-    tf = flop / (ms * 1e-3) / 1e12
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out = {}
+    for precision, reps in (("bf16", 240), ("fp32", 12)):
+        enc.rlg_precision = precision
+        with torch.no_grad():
+            for k in range(3):
+                enc(xs[k])
+            torch.cuda.synchronize()
+            e0.record()
+            for k in range(reps):
+                enc(xs[k % len(xs)])
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out[precision] = (ms, flop / (ms * 1e-3) / 1e12)
+    # e2e: pinned host clouds -> H2D -> enc(x) -> GFV D2H, every step, double-buffered on two streams
+    enc.rlg_precision = "bf16"
+    gfv_host = torch.empty(len(xs_host), ENC_B, 128).pin_memory()
+    copy_s, comp_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    stage = [torch.empty_like(xs[0]) for _ in range(2)]
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_pass(n):
+        for k in range(n):
+            s = k % 2
+            with torch.cuda.stream(copy_s):
+                if k >= 2:
+                    copy_s.wait_event(consumed[s])
+                stage[s].copy_(xs_host[k % len(xs_host)], non_blocking=True)
+                copied[s].record(copy_s)
+            with torch.cuda.stream(comp_s), torch.no_grad():
+                comp_s.wait_event(copied[s])
+                gfv = enc(stage[s])
+                consumed[s].record(comp_s)
+                gfv_host[k % len(xs_host)].copy_(gfv, non_blocking=True)
+        copy_s.synchronize()
+        comp_s.synchronize()
+
+    e2e_pass(4)
+    n = 96
+    t0 = time.perf_counter()
+    e2e_pass(n)
+    e2e_s = time.perf_counter() - t0
+    ms, tf = out["bf16"]
     return {"encoder": {"metric": "encoder_clouds_per_s", "value": ENC_B / (ms * 1e-3), "unit": "clouds/s",
-                        "config": {"workload": "PointNet encoder 3->64->128->1024 + max-pool, B=256, N=2048 (BASELINE configs[2])"},
-                        "path": "fp32 CUDA-core fused trunk (rlg_encoder_fwd)", "ms_per_step": ms,
-                        "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"],
-                                     "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops_sustained"], "traffic": None,
-                                     "peak_source": f"{peaks_src} MEASURED_PEAKS.json bf16_tflops_sustained"}}}
+                        "config": {"workload": "PointNet encoder 3->64->128->1024 + max-pool + GFV head, B=256, N=2048 "
+                                               "(BASELINE configs[2])", "l2_policy": "24 input batches = 151 MB cycled"},
+                        "dtype": "bf16", "path": "tcgen05/TMEM bf16 fused trunk (rlg_encoder_fwd_bf16) + stock global_mlp",
+                        "ms_per_step": ms,
+                        "roofline": {"bound": "tensor", "kernel": "encoder_tc_kernel", "achieved": tf,
+                                     "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                                     "frac": tf / peaks["bf16_tflops_sustained"], "traffic": None,
+                                     "peak_source": f"{peaks_src} MEASURED_PEAKS.json bf16_tflops_sustained",
+                                     "algorithmic_flop_per_launch": flop},
+                        "e2e": {"value": n * ENC_B / e2e_s, "unit": "clouds/s", "h2d_bytes_per_step": ENC_B * ENC_N * 12,
+                                "d2h_bytes_per_step": ENC_B * 128 * 4, "steps": n},
+                        "fp32_path": {"value": ENC_B / (out["fp32"][0] * 1e-3), "unit": "clouds/s",
+                                      "ms_per_step": out["fp32"][0], "tflops": out["fp32"][1],
+                                      "path": "fp32 CUDA-core fused trunk (rlg_encoder_fwd)"}}}
 
 
 def main():

@@ -63,6 +63,7 @@ EXPORTS = {
 CHAMFER_WS_CLEAN = 1
 CHAMFER_ALGO_SIMPLE = 2
 CHAMFER_TILE_ONLY = 4
+CHAMFER_ALGO_DIRECT = 8
 
 
 def load() -> ctypes.CDLL:

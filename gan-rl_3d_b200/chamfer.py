@@ -57,13 +57,15 @@ class _Workspace:
 
 
 def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = True, simple: bool = False,
-                    loss_weights: Optional[Tuple[float, float]] = None):
+                    loss_weights: Optional[Tuple[float, float]] = None, direct: bool = False, variant: int = 0):
     """Nearest neighbours in both directions (no autograd).
 
     Returns (d1 (B,N) fp32, d2 (B,M) fp32, i1 (B,N) int32, i2 (B,M) int32, mean1 (B,), mean2 (B,)):
     exactly torch.min(torch.cdist(pc1,pc2), 2) / (…, 1) of utils/losses.py:29-33 with cdist in direct mode,
     and torch.mean(…, dim=1) of :36-37.  With loss_weights=(w1,w2) a 7th element is appended: the 0-dim
-    batch loss sum_b(w1*mean1[b] + w2*mean2[b]) reduced inside the same launch (utils/losses.py:54-59,75)."""
+    batch loss sum_b(w1*mean1[b] + w2*mean2[b]) reduced inside the same launch (utils/losses.py:54-59,75).
+    simple / direct select the two cross-check kernels (one thread per query; direct-form tiles) instead of the
+    filter-and-refine kernel; variant (1..15) forces an experimental tile shape.  All paths return the same bits."""
     _require_hot_path(pc1, pc2)
     lib = _lib.load()
     pc1 = pc1.contiguous()
@@ -89,6 +91,9 @@ def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = Tru
             flags |= _lib.CHAMFER_ALGO_SIMPLE
         elif ws.clean:
             flags |= _lib.CHAMFER_WS_CLEAN
+        if direct:
+            flags |= _lib.CHAMFER_ALGO_DIRECT
+        flags |= (int(variant) & 15) << 8
         ws.clean = False
         rc = lib.rlg_chamfer_loss_fwd(pc1.data_ptr(), pc2.data_ptr(), B, N, M,
                                       d1.data_ptr(), d2.data_ptr(), i1.data_ptr(), i2.data_ptr(),

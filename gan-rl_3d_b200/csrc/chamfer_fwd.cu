@@ -283,10 +283,16 @@ using namespace rlg;
 extern "C" {
 
 static size_t keys_bytes(int B, int N, int M) { return align_up(sizeof(u64) * ((size_t)B * N + (size_t)B * M), 256); }
+static size_t secs_bytes(int B, int N, int M) { return align_up(sizeof(unsigned) * ((size_t)B * N + (size_t)B * M), 256); }
+static size_t nrm_bytes(int B) { return align_up(sizeof(unsigned) * 2 * (size_t)B, 256); }
 
 size_t rlg_chamfer_ws_bytes(int B, int N, int M) {
     if (B < 0 || N < 1 || M < 1) return 0;
-    return keys_bytes(B, N, M) + finalize_ws_bytes(B, N, M);   // packed (t,group) keys + finalize counters/partials
+    // packed (value, group) keys + second-best values + cloud norms + finalize counters/partials (the direct
+    // cross-check path uses a prefix of the same layout)
+    const size_t fin = finalize2_ws_bytes(B, N, M) > finalize_ws_bytes(B, N, M) ? finalize2_ws_bytes(B, N, M)
+                                                                                : finalize_ws_bytes(B, N, M);
+    return keys_bytes(B, N, M) + secs_bytes(B, N, M) + nrm_bytes(B) + fin;
 }
 
 int rlg_chamfer_fwd(const float *pc1, const float *pc2, int B, int N, int M, float *d1, float *d2,
@@ -307,7 +313,7 @@ int rlg_chamfer_loss_fwd(const float *pc1, const float *pc2, int B, int N, int M
         return fail(RLG_ERR_NULL_POINTER, "rlg_chamfer_fwd: mean1/mean2 must both be given or both be null");
     if (loss != nullptr && mean1 == nullptr)
         return fail(RLG_ERR_NULL_POINTER, "rlg_chamfer_loss_fwd: the batch loss needs the mean1/mean2 buffers");
-    if ((long long)B > 65535) return fail(RLG_ERR_TOO_LARGE, "rlg_chamfer_fwd: B=%d exceeds 65535 (grid.x of the finalize)", B);
+    if ((long long)B > 65535) return fail(RLG_ERR_TOO_LARGE, "rlg_chamfer_fwd: B=%d exceeds 65535 (grid.y of the finalize)", B);
     if ((long long)N * 3 > 0x7fffffffLL || (long long)M * 3 > 0x7fffffffLL)
         return fail(RLG_ERR_TOO_LARGE, "rlg_chamfer_fwd: N or M too large for 32-bit indexing");
     cudaStream_t st = (cudaStream_t)stream;
@@ -325,8 +331,6 @@ int rlg_chamfer_loss_fwd(const float *pc1, const float *pc2, int B, int N, int M
     if (!ws || ws_bytes < need || ((uintptr_t)ws & 255u))
         return fail(RLG_ERR_WORKSPACE, "rlg_chamfer_fwd: workspace %p/%zu bytes, need %zu bytes 256-B aligned", ws,
                     ws_bytes, need);
-    u64 *rowkey = (u64 *)ws;
-    u64 *colkey = rowkey + (size_t)B * N;
     if (!(flags & RLG_CHAMFER_WS_CLEAN)) {
         cudaError_t e = cudaMemsetAsync(ws, 0xff, need, st);
         if (e != cudaSuccess) {
@@ -334,22 +338,36 @@ int rlg_chamfer_loss_fwd(const float *pc1, const float *pc2, int B, int N, int M
             return fail((int)e, "rlg_chamfer_fwd: cudaMemsetAsync: %s", cudaGetErrorString(e));
         }
     }
-    // bits 8..11 of flags select an experimental tile variant (tools/sweep_tile.py); 0 = production
-    int R = 8, rc = 0;
-    switch ((flags >> 8) & 15u) {
-        default:
-        case 0: rc = launch_tile<8, 3, false>(pc1, pc2, B, N, M, rowkey, colkey, st); break;
-        case 1: rc = launch_tile<8, 3, true>(pc1, pc2, B, N, M, rowkey, colkey, st); break;
-        case 2: rc = launch_tile<8, 4, false>(pc1, pc2, B, N, M, rowkey, colkey, st); break;
-        case 3: R = 4; rc = launch_tile<4, 5, false>(pc1, pc2, B, N, M, rowkey, colkey, st); break;
-        case 4: R = 16; rc = launch_tile<16, 2, false>(pc1, pc2, B, N, M, rowkey, colkey, st); break;
-        case 5: R = 4; rc = launch_tile<4, 4, false>(pc1, pc2, B, N, M, rowkey, colkey, st); break;
-        case 6: R = 8; rc = launch_tile<8, 2, false>(pc1, pc2, B, N, M, rowkey, colkey, st); break;
+    u64 *rowkey = (u64 *)ws;
+    u64 *colkey = rowkey + (size_t)B * N;
+    const unsigned variant = (flags >> 8) & 15u;      // experimental kernel variants (tools/sweep_tile.py); 0 = production
+    if (flags & RLG_CHAMFER_ALGO_DIRECT) {
+        // direct-form tile kernel: every pair evaluated exactly (6 FP32 operations); kept as a cross-check
+        int R = 8, rc = 0;
+        switch (variant) {
+            default:
+            case 0: rc = launch_tile<8, 3, false>(pc1, pc2, B, N, M, rowkey, colkey, st); break;
+            case 1: rc = launch_tile<8, 3, true>(pc1, pc2, B, N, M, rowkey, colkey, st); break;
+            case 2: rc = launch_tile<8, 4, false>(pc1, pc2, B, N, M, rowkey, colkey, st); break;
+            case 4: R = 16; rc = launch_tile<16, 2, false>(pc1, pc2, B, N, M, rowkey, colkey, st); break;
+        }
+        if (rc) return rc;
+        if (flags & RLG_CHAMFER_TILE_ONLY) return 0;
+        char *fin = (char *)ws + keys_bytes(B, N, M) + secs_bytes(B, N, M) + nrm_bytes(B);
+        return launch_finalize(pc1, pc2, B, N, M, R, rowkey, colkey, fin, d1, d2, i1, i2, mean1, mean2, loss, w1, w2, st);
     }
+    FwdWs w;
+    w.rowkey = rowkey;
+    w.colkey = colkey;
+    w.rowsec = (unsigned *)((char *)ws + keys_bytes(B, N, M));
+    w.colsec = w.rowsec + (size_t)B * N;
+    w.nrm = (unsigned *)((char *)ws + keys_bytes(B, N, M) + secs_bytes(B, N, M));
+    int R = 0;
+    int rc = launch_filter(pc1, pc2, B, N, M, (int)variant, w, &R, st);
     if (rc) return rc;
     if (flags & RLG_CHAMFER_TILE_ONLY) return 0;
-    return launch_finalize(pc1, pc2, B, N, M, R, rowkey, colkey, (char *)ws + keys_bytes(B, N, M), d1, d2, i1, i2,
-                           mean1, mean2, loss, w1, w2, st);
+    char *fin = (char *)ws + keys_bytes(B, N, M) + secs_bytes(B, N, M) + nrm_bytes(B);
+    return launch_finalize2(pc1, pc2, B, N, M, R, w, fin, d1, d2, i1, i2, mean1, mean2, loss, w1, w2, st);
 }
 
 }  // extern "C"

@@ -30,6 +30,19 @@ int launch_finalize(const float *pc1, const float *pc2, int B, int N, int M, int
                     u64 *colkey, void *fin_ws, float *d1, float *d2, int32_t *i1, int32_t *i2, float *mean1,
                     float *mean2, float *loss, float w1, float w2, cudaStream_t st);
 
+// ---- Chamfer forward, filter-and-refine path (chamfer_filter.cu).  Every array starts and ends all-ones.
+struct FwdWs {
+    u64 *rowkey, *colkey;          // (B,N), (B,M): filter value bits << 32 | winning candidate group
+    unsigned *rowsec, *colsec;     // (B,N), (B,M): smallest filter value of any OTHER group
+    unsigned *nrm;                 // (2,B): bitwise complement of the largest |p|^2 of pc1[b] / pc2[b]
+};
+size_t finalize2_ws_bytes(int B, int N, int M);
+int launch_filter(const float *pc1, const float *pc2, int B, int N, int M, int variant, const FwdWs &w,
+                  int *rows_per_lane, cudaStream_t st);
+int launch_finalize2(const float *pc1, const float *pc2, int B, int N, int M, int rows_per_lane, const FwdWs &w,
+                     void *fin_ws, float *d1, float *d2, int32_t *i1, int32_t *i2, float *mean1, float *mean2,
+                     float *loss, float w1, float w2, cudaStream_t st);
+
 // ---- packed fp32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2) ------------------------------
 // One instruction issues two IEEE fp32 operations, halving the issue-slot cost of the distance math.
 __device__ __forceinline__ u64 pack2(float lo, float hi) {

@@ -48,8 +48,10 @@ extern "C" {
 #define RLG_CHAMFER_WS_CLEAN   1u     /* workspace is known to hold the all-ones pattern the previous
                                          rlg_chamfer_fwd left behind on the same shape: skip the memset */
 #define RLG_CHAMFER_ALGO_SIMPLE 2u    /* run the simple one-thread-per-query kernel (cross-check path) */
-#define RLG_CHAMFER_TILE_ONLY  4u     /* measurement aid: enqueue only the distance/min tile kernel (no finalize,
+#define RLG_CHAMFER_TILE_ONLY  4u     /* measurement aid: enqueue only the pair-sweep kernel (no finalize,
                                          outputs untouched, workspace left dirty) so it can be timed alone */
+#define RLG_CHAMFER_ALGO_DIRECT 8u    /* run the direct-form tile kernel (every pair evaluated exactly, 6 FP32
+                                         operations per pair) instead of the filter-and-refine kernel: cross-check */
 
 int rlg_version(void);
 const char *rlg_last_error(void);
@@ -68,7 +70,11 @@ int rlg_device_sm_count(void);
  *   ws                                            device, >= rlg_chamfer_ws_bytes(B,N,M), 256-B aligned
  *
  * Distances are computed in the direct-difference form  t=d0*d0; t=fma(d1,d1,t); t=fma(d2,d2,t);
- * sqrtf(min t)  and are bit-identical to ATen's direct-mode cdist; argmin is taken over t.
+ * sqrtf(min t)  and are bit-identical to ATen's direct-mode cdist; argmin is taken over t, lowest index on
+ * ties.  The default kernel finds the candidates with a 4-operation FP32 filter (|y|^2 - 2x.y + |x|^2) and
+ * re-evaluates every candidate within a rigorous rounding margin in the direct form, so the outputs do not
+ * depend on the filter's rounding; clouds far from the origin relative to their extent (|p|^2 >> min
+ * distance^2 * 1e5) only lose speed (more candidates are re-evaluated), not exactness.
  * Non-finite coordinates are outside the contract (NaN distances are ignored, not propagated).
  * --------------------------------------------------------------------------------------------- */
 size_t rlg_chamfer_ws_bytes(int B, int N, int M);

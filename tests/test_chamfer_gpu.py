@@ -11,14 +11,14 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _run(rlg, pc1, pc2, simple=False):
-    d1, d2, i1, i2, m1, m2 = rlg.chamfer_nearest(pc1.to(DEV), pc2.to(DEV), simple=simple)
+def _run(rlg, pc1, pc2, simple=False, **kw):
+    d1, d2, i1, i2, m1, m2 = rlg.chamfer_nearest(pc1.to(DEV), pc2.to(DEV), simple=simple, **kw)
     torch.cuda.synchronize()
     return [t.cpu().numpy() for t in (d1, d2, i1, i2, m1, m2)]
 
 
-def _check_against_direct(rlg, pc1, pc2, simple=False):
-    d1, d2, i1, i2, m1, m2 = _run(rlg, pc1, pc2, simple)
+def _check_against_direct(rlg, pc1, pc2, simple=False, **kw):
+    d1, d2, i1, i2, m1, m2 = _run(rlg, pc1, pc2, simple, **kw)
     o1, o2, j1, j2 = O.chamfer_direct(pc1, pc2, O.TIE_SQUARED)
     assert np.array_equal(d1, o1) and np.array_equal(d2, o2), "distances not bit-equal to the direct oracle"
     assert np.array_equal(i1, j1) and np.array_equal(i2, j2), "argmin not equal to the direct oracle"
@@ -47,6 +47,56 @@ def test_simple_kernel_agrees_with_tile_kernel(rlg, B, N, M):
     b = _check_against_direct(rlg, pc1, pc2, simple=False)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("B,N,M", [(2, 1, 1), (3, 33, 31), (2, 600, 1400), (2, 2048, 2048), (1, 1025, 70)])
+def test_every_filter_tile_shape_is_bit_exact(rlg, variant, B, N, M):
+    """Rows per lane 16 / 8 / 4 and both min-instruction forms: same bits as the direct oracle, ragged shapes included."""
+    pc1, pc2 = O.make_clouds(B, N, "uniform", 70 + variant), O.make_clouds(B, M, "sphere", 80 + variant)
+    _check_against_direct(rlg, pc1, pc2, variant=variant)
+
+
+@pytest.mark.parametrize("B,N,M", [(2, 31, 33), (2, 700, 2048), (2, 2048, 2048)])
+def test_direct_tile_kernel_agrees_with_filter_kernel(rlg, B, N, M):
+    pc1, pc2 = O.make_clouds(B, N, "sphere", 7), O.make_clouds(B, M, "uniform", 8)
+    a = _check_against_direct(rlg, pc1, pc2, direct=True)
+    b = _check_against_direct(rlg, pc1, pc2)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("offset,scale", [(0.0, 1e-3), (3.0, 1.0), (100.0, 1.0), (1e4, 10.0), (0.0, 1e4)])
+def test_filter_margin_keeps_exactness_far_from_the_origin(rlg, offset, scale):
+    """The filter |y|^2 - 2x.y loses precision when |p| >> nearest-neighbour distance; the rounding margin must then
+    send (almost) every point through the exact scan.  Outputs stay bit-equal to the direct oracle."""
+    pc1 = O.make_clouds(2, 700, "sphere", 91) * scale + offset
+    pc2 = O.make_clouds(2, 900, "uniform", 92) * scale + offset
+    _check_against_direct(rlg, pc1.contiguous(), pc2.contiguous())
+
+
+def test_near_ties_across_candidate_groups(rlg):
+    """Candidates at almost the same distance in different 32-column groups / row blocks: the filter cannot order
+    them, the exact refinement must.  pc2 = jittered copies of a few anchor points spread over the whole cloud."""
+    g = torch.Generator().manual_seed(5)
+    anchors = O.make_clouds(2, 16, "sphere", 93)
+    idx = torch.randint(0, 16, (2, 2048), generator=g)
+    pc2 = torch.gather(anchors, 1, idx.unsqueeze(-1).expand(-1, -1, 3)) * (1 + 3e-7 * torch.randn(2, 2048, 1, generator=g))
+    pc1 = O.make_clouds(2, 1500, "sphere", 94)
+    _check_against_direct(rlg, pc1, pc2.contiguous())
+    _check_against_direct(rlg, pc2.contiguous(), pc1)
+
+
+def test_workspace_returns_to_clean_state(rlg):
+    """Repeat calls reuse the cached workspace without a memset (RLG_CHAMFER_WS_CLEAN): results must not depend on
+    what the previous call (other inputs, same shape) left behind."""
+    a1, b1 = O.make_clouds(3, 1000, "sphere", 95), O.make_clouds(3, 777, "sphere", 96)
+    a2, b2 = O.make_clouds(3, 1000, "uniform", 97) * 0.01, O.make_clouds(3, 777, "uniform", 98) * 0.01
+    first = _run(rlg, a1, b1)
+    _run(rlg, a2, b2)                      # much smaller distances: stale keys would win every atomicMin
+    again = _run(rlg, a1, b1)
+    assert all(np.array_equal(x, y) for x, y in zip(first, again))
+    _check_against_direct(rlg, a2, b2)
 
 
 def test_exact_ties_pick_lowest_index(rlg):
@@ -99,7 +149,7 @@ def test_golden_big_cases_contract_vs_as_written_reference(rlg, golden_chamfer):
         assert O.rel_err(m1, g[f"big{k}_dist1"]) < tol and O.rel_err(m2, g[f"big{k}_dist2"]) < tol
 
 
-@pytest.mark.parametrize("B,N,M", [(2, 16, 25), (3, 300, 257), (2, 2048, 2048), (2, 2048, 1400)])
+@pytest.mark.parametrize("B,N,M", [(2, 16, 25), (3, 300, 257), (2, 2048, 2048), (2, 2048, 1400), (1, 9000, 8200)])
 def test_backward_vs_float64_truth(rlg, B, N, M):
     pc1 = O.make_clouds(B, N, "sphere", 21)
     pc2 = O.pad_with_duplicates(O.make_clouds(B, M, "sphere", 22), 0.25, 23) if M > 100 else O.make_clouds(B, M, "sphere", 22)

@@ -115,9 +115,10 @@ def test_cache_follows_optimizer_steps(rlg):
         a = rlg.fused_forward(enc, x)
         enc.point_mlp[0].weight.mul_(1.5)
         b = rlg.fused_forward(enc, x)
-        want = enc.global_mlp(torch.max(enc.point_mlp(x.transpose(2, 1)), dim=2)[0])
+        ref = enc.double().cpu()             # float64 truth of the stock stack (the stock CUDA convs may run in TF32)
+        want = ref.global_mlp(torch.max(ref.point_mlp(x.double().cpu().transpose(2, 1)), dim=2)[0])
     assert not torch.equal(a, b)
-    assert O.gfv_close(b.cpu().numpy(), want.cpu().numpy(), 2e-5)[0]
+    assert O.gfv_close(b.cpu().numpy(), want.numpy(), 2e-5)[0]
 
 
 def test_unsupported_widths_fail_loudly(rlg):
@@ -127,7 +128,9 @@ def test_unsupported_widths_fail_loudly(rlg):
         rlg.encoder_pool(x, [(w, torch.zeros(4, device=DEV))])
 
 
-BF16_TOL = 2e-2      # north_star: 2e-2 relative for the bf16 encoder GEMMs (abs-floor rule of SURVEY.md 7.2-6)
+BF16_TOL = 2e-2      # north_star: 2e-2 relative for the bf16 encoder GEMMs
+BF16_FLOOR = 1e-1    # ... on entries >= 10 % of the largest; smaller entries: |err| <= 2e-3 * largest (see O.gfv_close)
+BF16_NORM = 5e-3     # and norm-wise |a-b|_2 <= 5e-3 |b|_2 (measured ~1e-3)
 
 
 @pytest.mark.parametrize("dims", [[64, 128, 1024], [64, 128, 256], [128, 128], [64, 64, 64, 128], [64, 384], [128, 64, 640]])
@@ -142,13 +145,13 @@ def test_bf16_tensor_core_path_vs_float64_stack(rlg, dims, B, N):
     pooled, _ = rlg.encoder_pool(x.to(DEV), layers, precision="bf16")
     torch.cuda.synchronize()
     got = pooled.cpu().numpy()
-    ok, err = O.gfv_close(got, want, BF16_TOL)
+    ok, err = O.gfv_close(got, want, BF16_TOL, BF16_FLOOR)
     assert ok, err
-    # norm-wise the bf16 path is far tighter than the element-wise bound (~5e-4 measured)
-    assert np.linalg.norm(got - want) <= 5e-3 * np.linalg.norm(want)
+    # norm-wise the bf16 path is far tighter than the element-wise bound
+    assert np.linalg.norm(got - want) <= BF16_NORM * np.linalg.norm(want)
     # and it agrees with this repo's own fp32 CUDA-core path to the same tolerance
     fp32, _ = rlg.encoder_pool(x.to(DEV), layers)
-    assert O.gfv_close(got, fp32.cpu().numpy(), BF16_TOL)[0]
+    assert O.gfv_close(got, fp32.cpu().numpy(), BF16_TOL, BF16_FLOOR)[0]
 
 
 def test_bf16_module_switch_and_cache(rlg):
@@ -163,7 +166,7 @@ def test_bf16_module_switch_and_cache(rlg):
         enc.point_mlp[3].weight.mul_(1.25)                    # optimizer-like update -> repack
         out2 = rlg.fused_forward(enc, x)
         assert enc.__dict__["_rlg_packed"] is not packed
-    assert O.gfv_close(out.cpu().numpy(), ref.cpu().numpy(), BF16_TOL)[0]
+    assert O.gfv_close(out.cpu().numpy(), ref.cpu().numpy(), BF16_TOL, BF16_FLOOR)[0]
     assert not torch.equal(out, out2)
     assert "_rlg_packed" not in enc.state_dict()
 

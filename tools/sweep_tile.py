@@ -27,10 +27,11 @@ i1 = torch.empty(B, N, dtype=torch.int32, device=dev); i2 = torch.empty(B, M, dt
 ws = torch.empty(lib.rlg_chamfer_ws_bytes(B, N, M), dtype=torch.uint8, device=dev).fill_(0xFF)
 stream = torch.cuda.current_stream().cuda_stream
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-names = {0: "R8 occ3 min2", 1: "R8 occ3 min3", 2: "R8 occ4 min2", 3: "R4 occ5 min2", 4: "R16 occ2 min2",
-         5: "R4 occ4 min2", 6: "R8 occ2 min2"}
-for var, name in names.items():
-    flags = _lib.CHAMFER_WS_CLEAN | _lib.CHAMFER_TILE_ONLY | (var << 8)
+names = {(0, 0): "filter auto", (0, 1): "filter R16 min2", (0, 2): "filter R16 min3", (0, 3): "filter R8 min2",
+         (0, 4): "filter R8 min3", (0, 5): "filter R4 min2", (1, 0): "direct R8 occ3 min2", (1, 4): "direct R16 occ2 min2"}
+for (direct, var), name in names.items():
+    algo = _lib.CHAMFER_ALGO_DIRECT if direct else 0
+    flags = _lib.CHAMFER_WS_CLEAN | _lib.CHAMFER_TILE_ONLY | (var << 8) | algo
 
     def run(k):
         a, b = ring[k % slots]
@@ -49,9 +50,9 @@ for var, name in names.items():
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / reps * 1e3
     tf = 8.0 * N * M * B / (us * 1e-6) / 1e12
-    print(f"variant {var} ({name}): {us:8.2f} us  {tf:6.2f} TFLOP/s  {tf / 74.45 * 100:5.1f}% of FFMA peak")
+    print(f"variant {direct}/{var} ({name}): {us:8.2f} us  {tf:6.2f} TFLOP/s  {tf / 74.45 * 100:5.1f}% of FFMA peak")
     # correctness of the variant against the production path
-    full = _lib.CHAMFER_WS_CLEAN | (var << 8)
+    full = _lib.CHAMFER_WS_CLEAN | (var << 8) | algo
     a, b = ring[0]
     m1 = torch.empty(B, device=dev); m2 = torch.empty(B, device=dev)
     ws.fill_(0xFF)
