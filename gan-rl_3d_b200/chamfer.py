@@ -57,7 +57,8 @@ class _Workspace:
 
 
 def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = True, simple: bool = False,
-                    loss_weights: Optional[Tuple[float, float]] = None, direct: bool = False, variant: int = 0):
+                    loss_weights: Optional[Tuple[float, float]] = None, direct: bool = False, variant: int = 0,
+                    zero_grads: Optional[Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]] = None):
     """Nearest neighbours in both directions (no autograd).
 
     Returns (d1 (B,N) fp32, d2 (B,M) fp32, i1 (B,N) int32, i2 (B,M) int32, mean1 (B,), mean2 (B,)):
@@ -65,7 +66,9 @@ def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = Tru
     and torch.mean(…, dim=1) of :36-37.  With loss_weights=(w1,w2) a 7th element is appended: the 0-dim
     batch loss sum_b(w1*mean1[b] + w2*mean2[b]) reduced inside the same launch (utils/losses.py:54-59,75).
     simple / direct select the two cross-check kernels (one thread per query; direct-form tiles) instead of the
-    filter-and-refine kernel; variant (1..15) forces an experimental tile shape.  All paths return the same bits."""
+    filter-and-refine kernel; variant (1..15) forces an experimental tile shape.  All paths return the same bits.
+    zero_grads=(g1, g2): (B,N,3)/(B,M,3) buffers (each may be None) the forward zero-fills in its last launch, so
+    chamfer_backward(..., out=(g1, g2), accumulate=True) is a single launch."""
     _require_hot_path(pc1, pc2)
     lib = _lib.load()
     pc1 = pc1.contiguous()
@@ -83,6 +86,7 @@ def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = Tru
     if B == 0:
         return (d1, d2, i1, i2, m1, m2) if loss is None else (d1, d2, i1, i2, m1, m2, loss)
     w1, w2 = loss_weights if loss_weights is not None else (0.0, 0.0)
+    gz1, gz2 = zero_grads if zero_grads is not None else (None, None)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         ws = _Workspace.get(dev, stream, B, N, M)
@@ -99,19 +103,22 @@ def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = Tru
                                       d1.data_ptr(), d2.data_ptr(), i1.data_ptr(), i2.data_ptr(),
                                       m1.data_ptr() if want_means else None, m2.data_ptr() if want_means else None,
                                       loss.data_ptr() if loss is not None else None, w1, w2,
+                                      gz1.data_ptr() if gz1 is not None else None,
+                                      gz2.data_ptr() if gz2 is not None else None,
                                       ws.buf.data_ptr(), ws.buf.numel(), flags, stream)
         _lib.check("rlg_chamfer_loss_fwd", rc)
         ws.clean = not simple
     return (d1, d2, i1, i2, m1, m2) if loss is None else (d1, d2, i1, i2, m1, m2, loss)
 
 
-def chamfer_backward(pc1, pc2, d1, d2, i1, i2, g1, g2) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Gradient of (mean1, mean2) w.r.t. (pc1, pc2) for upstream (g1 (B,), g2 (B,)); None = zero."""
+def chamfer_backward(pc1, pc2, d1, d2, i1, i2, g1, g2, out=None, accumulate: bool = False
+                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Gradient of (mean1, mean2) w.r.t. (pc1, pc2) for upstream (g1 (B,), g2 (B,)); None = zero.
+    out=(gpc1, gpc2) with accumulate=True adds into buffers that already hold zeros (or a gradient)."""
     lib = _lib.load()
     B, N, _ = pc1.shape
     M = pc2.shape[1]
-    gpc1 = torch.empty_like(pc1)
-    gpc2 = torch.empty_like(pc2)
+    gpc1, gpc2 = out if out is not None else (torch.empty_like(pc1), torch.empty_like(pc2))
     if B == 0:
         return gpc1, gpc2
     g1 = g1.contiguous().float() if g1 is not None else None
@@ -122,7 +129,8 @@ def chamfer_backward(pc1, pc2, d1, d2, i1, i2, g1, g2) -> Tuple[torch.Tensor, to
                                  i1.data_ptr(), i2.data_ptr(),
                                  g1.data_ptr() if g1 is not None else None,
                                  g2.data_ptr() if g2 is not None else None,
-                                 B, N, M, gpc1.data_ptr(), gpc2.data_ptr(), stream)
+                                 B, N, M, gpc1.data_ptr(), gpc2.data_ptr(),
+                                 _lib.CHAMFER_BWD_ACCUMULATE if (accumulate and out is not None) else 0, stream)
         _lib.check("rlg_chamfer_bwd", rc)
     return gpc1, gpc2
 
@@ -135,15 +143,19 @@ class ChamferFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pc1, pc2):
         pc1c, pc2c = pc1.contiguous(), pc2.contiguous()
-        d1, d2, i1, i2, m1, m2 = chamfer_nearest(pc1c, pc2c, want_means=True)
-        if any(ctx.needs_input_grad):
+        need = any(ctx.needs_input_grad)
+        gbuf = (torch.empty_like(pc1c), torch.empty_like(pc2c)) if need else None   # zero-filled by the forward
+        d1, d2, i1, i2, m1, m2 = chamfer_nearest(pc1c, pc2c, want_means=True, zero_grads=gbuf)
+        if need:
             ctx.save_for_backward(pc1c, pc2c, d1, d2, i1, i2)
+            ctx.gbuf = gbuf
         return m1, m2
 
     @staticmethod
     def backward(ctx, g1, g2):
         pc1, pc2, d1, d2, i1, i2 = ctx.saved_tensors
-        gpc1, gpc2 = chamfer_backward(pc1, pc2, d1, d2, i1, i2, g1, g2)
+        gbuf, ctx.gbuf = ctx.gbuf, None          # a second backward through the same graph allocates afresh
+        gpc1, gpc2 = chamfer_backward(pc1, pc2, d1, d2, i1, i2, g1, g2, out=gbuf, accumulate=True)
         return (gpc1 if ctx.needs_input_grad[0] else None, gpc2 if ctx.needs_input_grad[1] else None)
 
 
@@ -154,17 +166,20 @@ def _loss_weights(B: int, bidirectional: bool) -> Tuple[float, float]:
 
 class ChamferLossFn(torch.autograd.Function):
     """(pred (B,N,3), target (B,M,3)) -> the 0-dim ChamferLoss of utils/losses.py:62-75 with the batch reduction
-    fused into the forward launch and its scaling fused into the backward: 2 + 2 kernel launches per
-    training step, no elementwise torch kernels in between."""
+    fused into the forward launch and its scaling fused into the backward: 2 + 1 kernel launches per
+    training step (the forward also zero-fills the gradient buffers), no elementwise torch kernels in between."""
 
     @staticmethod
     def forward(ctx, pc1, pc2, bidirectional: bool):
         pc1c, pc2c = pc1.contiguous(), pc2.contiguous()
         w = _loss_weights(max(pc1c.shape[0], 1), bidirectional)
-        d1, d2, i1, i2, m1, m2, loss = chamfer_nearest(pc1c, pc2c, want_means=True, loss_weights=w)
-        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        gbuf = (torch.empty_like(pc1c), torch.empty_like(pc2c)) if need else None   # zero-filled by the forward
+        d1, d2, i1, i2, m1, m2, loss = chamfer_nearest(pc1c, pc2c, want_means=True, loss_weights=w, zero_grads=gbuf)
+        if need:
             ctx.save_for_backward(pc1c, pc2c, d1, d2, i1, i2)
             ctx.w = w
+            ctx.gbuf = gbuf
         return loss
 
     @staticmethod
@@ -173,13 +188,15 @@ class ChamferLossFn(torch.autograd.Function):
         lib = _lib.load()
         B, N, _ = pc1.shape
         M = pc2.shape[1]
-        gpc1, gpc2 = torch.empty_like(pc1), torch.empty_like(pc2)
+        gbuf, ctx.gbuf = ctx.gbuf, None          # a second backward through the same graph allocates afresh
+        flags = _lib.CHAMFER_BWD_ACCUMULATE if gbuf is not None else 0
+        gpc1, gpc2 = gbuf if gbuf is not None else (torch.empty_like(pc1), torch.empty_like(pc2))
         gloss = gloss.contiguous().float()
         with torch.cuda.device(pc1.device):
             stream = torch.cuda.current_stream(pc1.device).cuda_stream
             rc = lib.rlg_chamfer_loss_bwd(pc1.data_ptr(), pc2.data_ptr(), d1.data_ptr(), d2.data_ptr(),
                                           i1.data_ptr(), i2.data_ptr(), gloss.data_ptr(), ctx.w[0], ctx.w[1],
-                                          B, N, M, gpc1.data_ptr(), gpc2.data_ptr(), stream)
+                                          B, N, M, gpc1.data_ptr(), gpc2.data_ptr(), flags, stream)
             _lib.check("rlg_chamfer_loss_bwd", rc)
         return (gpc1 if ctx.needs_input_grad[0] else None, gpc2 if ctx.needs_input_grad[1] else None, None)
 

@@ -349,41 +349,42 @@ size_t finalize2_ws_bytes(int B, int N, int M) {
     return fin2_counter_bytes(B) + align_up(sizeof(double) * 2 * (size_t)B * cm, 256);
 }
 
-// exact direct-form scan of candidates [lane, lane+32, ...) of c for query (px,py,pz): this lane's smallest t and
-// the lowest index attaining it
-__device__ __forceinline__ void scan_all(const float *c, int nc, int lane, float px, float py, float pz, float &lt,
-                                         int &lj) {
+// exact direct-form scan of candidates [first, first+step, ...) of c for query (px,py,pz): this thread's smallest t
+// and the lowest index attaining it (four independent candidates in flight)
+__device__ __forceinline__ void scan_strided(const float *__restrict__ c, int nc, int first, int step, float px, float py,
+                                             float pz, float &lt, int &lj) {
     lt = INFINITY;
     lj = 0x7fffffff;
-    int j = lane;
-    for (; j + 96 < nc; j += 128) {                   // four independent candidates in flight
+    int j = first;
+    for (; j + 3 * step < nc; j += 4 * step) {
+        const int j1 = j + step, j2 = j + 2 * step, j3 = j + 3 * step;
         const float t0 = sqdist(px, py, pz, c[3 * j], c[3 * j + 1], c[3 * j + 2]);
-        const float t1 = sqdist(px, py, pz, c[3 * j + 96], c[3 * j + 97], c[3 * j + 98]);
-        const float t2 = sqdist(px, py, pz, c[3 * j + 192], c[3 * j + 193], c[3 * j + 194]);
-        const float t3 = sqdist(px, py, pz, c[3 * j + 288], c[3 * j + 289], c[3 * j + 290]);
+        const float t1 = sqdist(px, py, pz, c[3 * j1], c[3 * j1 + 1], c[3 * j1 + 2]);
+        const float t2 = sqdist(px, py, pz, c[3 * j2], c[3 * j2 + 1], c[3 * j2 + 2]);
+        const float t3 = sqdist(px, py, pz, c[3 * j3], c[3 * j3 + 1], c[3 * j3 + 2]);
         if (t0 < lt) { lt = t0; lj = j; }
-        if (t1 < lt) { lt = t1; lj = j + 32; }
-        if (t2 < lt) { lt = t2; lj = j + 64; }
-        if (t3 < lt) { lt = t3; lj = j + 96; }
+        if (t1 < lt) { lt = t1; lj = j1; }
+        if (t2 < lt) { lt = t2; lj = j2; }
+        if (t3 < lt) { lt = t3; lj = j3; }
     }
-    for (; j < nc; j += 32) {
+    for (; j < nc; j += step) {
         const float t = sqdist(px, py, pz, c[3 * j], c[3 * j + 1], c[3 * j + 2]);
         if (t < lt) { lt = t; lj = j; }
     }
 }
 
+template <bool SMEM>
 __global__ void __launch_bounds__(kFin2Threads) chamfer_finalize2_kernel(
     const float *__restrict__ pc1, const float *__restrict__ pc2, int N, int M, int rows_per_lane, FwdWs w, Fin2Ws fw,
     float *__restrict__ d1, float *__restrict__ d2, int32_t *__restrict__ i1, int32_t *__restrict__ i2,
     float *__restrict__ mean1, float *__restrict__ mean2, float *__restrict__ loss, float loss_w1, float loss_w2,
-    int cand_in_smem) {
+    float *__restrict__ zero1, float *__restrict__ zero2) {
     extern __shared__ __align__(16) float s_cand[];
     __shared__ double red[kFin2Warps];
     __shared__ float s_q[3][kFin2Threads];            // query coordinates of the CTA's points
-    __shared__ float s_bt[kFin2Threads];              // results of the ambiguous points (written by the scanning warp)
-    __shared__ int s_bj[kFin2Threads];
     __shared__ short s_list[kFin2Threads];            // ambiguous points of the CTA, in thread order
     __shared__ int s_wcount[kFin2Warps];
+    __shared__ u64 s_wbest[kFin2Warps];               // per-warp (t bits << 32 | index) of the point being scanned
     const int chunk = blockIdx.x, b = blockIdx.y, dir = blockIdx.z;
     const int B = gridDim.y;
     // dir 0: queries = pc1 rows; a candidate group = 32 consecutive columns of pc2
@@ -413,8 +414,8 @@ __global__ void __launch_bounds__(kFin2Threads) chamfer_finalize2_kernel(
     // largest squared norm of the OTHER cloud (the filter kernel published its bitwise complement)
     const float onrm = __uint_as_float(~w.nrm[dir ? b : B + b]);
 
-    const float *c = cglob;
-    if (cand_in_smem) {
+    const float *__restrict__ c = cglob;
+    if (SMEM) {
         const int nf = nc * 3;
         if ((reinterpret_cast<uintptr_t>(cglob) & 15u) == 0) {
             const int n4 = nf >> 2;
@@ -430,6 +431,11 @@ __global__ void __launch_bounds__(kFin2Threads) chamfer_finalize2_kernel(
     if (live) {
         keys[i] = kKeyInit;
         secs[i] = 0xffffffffu;
+        float *z = dir ? zero2 : zero1;                 // optional: zero-fill the gradient rows of this point
+        if (z != nullptr) {
+            z += ((size_t)b * nq + i) * 3;
+            z[0] = 0.0f; z[1] = 0.0f; z[2] = 0.0f;
+        }
     }
     s_q[0][tid] = qx; s_q[1][tid] = qy; s_q[2][tid] = qz;
 
@@ -450,38 +456,45 @@ __global__ void __launch_bounds__(kFin2Threads) chamfer_finalize2_kernel(
     }
     if (amb) s_list[my_off + __popc(am & ((1u << lane) - 1u))] = (short)tid;
 
-    // ---- fast path: the exact winner lies in the best group; lane-serial over its <= 32 candidates
+    // ---- fast path: the exact winner lies in the best group; lane-serial over its <= 32 candidates.  Indices past
+    // the end are clamped to the last point: a real candidate with the highest index, so it never wins a tie it
+    // should not, and it cannot beat the group's winner unless it is the true nearest point anyway.
     float bt = INFINITY;
-    int bj = 0;
+    int bj = 0x7fffffff;
     if (live && !amb) {
         const unsigned grp = (unsigned)(key & 0xffffffffu);
         const int base = dir ? (int)(grp >> 5) * (32 * R) + (int)(grp & 31u) : (int)grp * kGroup;
         const int stride = dir ? 32 : 1;
 #pragma unroll 4
         for (int k = 0; k < gsz; ++k) {
-            const int j = base + ((k + lane) & (gsz - 1)) * stride;     // rotated per lane: conflict-free shared reads
-            if (j < nc) {
-                const float t = sqdist(qx, qy, qz, c[3 * j], c[3 * j + 1], c[3 * j + 2]);
-                if (t < bt || (t == bt && j < bj)) { bt = t; bj = j; }
-            }
+            const int j = min(base + ((k + lane) & (gsz - 1)) * stride, nc - 1);   // rotated per lane: conflict-free
+            const float t = sqdist(qx, qy, qz, c[3 * j], c[3 * j + 1], c[3 * j + 2]);
+            if (t < bt || (t == bt && j < bj)) { bt = t; bj = j; }
         }
     }
     __syncthreads();                                    // s_list complete
-    // ---- ambiguous points: the CTA's warps take them in turn and scan every candidate exactly
-    for (int a = wid; a < n_amb; a += kFin2Warps) {
+    // ---- ambiguous points, one after the other: all 256 threads scan the candidates exactly
+    for (int a = 0; a < n_amb; ++a) {
         const int t_a = s_list[a];
         float lt;
         int lj;
-        scan_all(c, nc, lane, s_q[0][t_a], s_q[1][t_a], s_q[2][t_a], lt, lj);
+        scan_strided(c, nc, tid, kFin2Threads, s_q[0][t_a], s_q[1][t_a], s_q[2][t_a], lt, lj);
         const unsigned tb = __float_as_uint(lt);                     // lt >= 0 or +inf: orders as unsigned
         const unsigned mt = __reduce_min_sync(0xffffffffu, tb);
         const int mj = __reduce_min_sync(0xffffffffu, tb == mt ? lj : 0x7fffffff);
-        if (lane == 0) { s_bt[t_a] = __uint_as_float(mt); s_bj[t_a] = mj; }
+        if (lane == 0) s_wbest[wid] = ((u64)mt << 32) | (unsigned)mj;
+        __syncthreads();
+        if (tid == t_a) {
+            u64 m = s_wbest[0];
+#pragma unroll
+            for (int k = 1; k < kFin2Warps; ++k) m = s_wbest[k] < m ? s_wbest[k] : m;
+            bt = __uint_as_float((unsigned)(m >> 32));
+            bj = (int)(unsigned)(m & 0xffffffffu);
+        }
+        __syncthreads();
     }
-    __syncthreads();
     double dist_d = 0.0;
     if (live) {
-        if (amb) { bt = s_bt[tid]; bj = s_bj[tid]; }
         if (!(bt < INFINITY)) {
             // only reachable with non-finite input (outside the contract): mirror torch.min, where the first
             // NaN wins -> candidate 0
@@ -533,7 +546,7 @@ __global__ void __launch_bounds__(kFin2Threads) chamfer_finalize2_kernel(
 
 int launch_finalize2(const float *pc1, const float *pc2, int B, int N, int M, int rows_per_lane, const FwdWs &w,
                      void *fin_ws, float *d1, float *d2, int32_t *i1, int32_t *i2, float *mean1, float *mean2,
-                     float *loss, float w1, float w2, cudaStream_t st) {
+                     float *loss, float w1, float w2, float *zero1, float *zero2, cudaStream_t st) {
     Fin2Ws fw;
     fw.global_counter = (unsigned *)fin_ws;
     fw.cloud_counter = fw.global_counter + 1;
@@ -541,16 +554,21 @@ int launch_finalize2(const float *pc1, const float *pc2, int B, int N, int M, in
     fw.chunks_max = fin2_chunks(N > M ? N : M);
     // the candidate cloud of a (cloud, direction) is staged in shared memory when it fits (<= 200 KB)
     const size_t cand_bytes = (size_t)(N > M ? N : M) * 3 * sizeof(float);
-    const int in_smem = cand_bytes <= 200u * 1024u;
-    const size_t dyn = in_smem ? align_up(cand_bytes, 16) : 0;
-    if (dyn > 40u * 1024u) {
-        cudaError_t e = cudaFuncSetAttribute(chamfer_finalize2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(200u * 1024u));
-        if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "rlg_chamfer_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
-    }
+    const bool in_smem = cand_bytes <= 200u * 1024u;
     dim3 grid(fw.chunks_max, B, 2);
-    chamfer_finalize2_kernel<<<grid, kFin2Threads, dyn, st>>>(pc1, pc2, N, M, rows_per_lane, w, fw, d1, d2, i1, i2,
-                                                              mean1, mean2, loss, w1, w2, in_smem);
+    if (in_smem) {
+        const size_t dyn = align_up(cand_bytes, 16);
+        if (dyn > 40u * 1024u) {
+            cudaError_t e = cudaFuncSetAttribute(chamfer_finalize2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)(200u * 1024u));
+            if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "rlg_chamfer_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
+        }
+        chamfer_finalize2_kernel<true><<<grid, kFin2Threads, dyn, st>>>(pc1, pc2, N, M, rows_per_lane, w, fw, d1, d2, i1, i2,
+                                                                        mean1, mean2, loss, w1, w2, zero1, zero2);
+    } else {
+        chamfer_finalize2_kernel<false><<<grid, kFin2Threads, 0, st>>>(pc1, pc2, N, M, rows_per_lane, w, fw, d1, d2, i1, i2,
+                                                                       mean1, mean2, loss, w1, w2, zero1, zero2);
+    }
     return check_launch("chamfer_finalize2_kernel");
 }
 

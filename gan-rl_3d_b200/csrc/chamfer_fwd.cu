@@ -298,13 +298,13 @@ size_t rlg_chamfer_ws_bytes(int B, int N, int M) {
 int rlg_chamfer_fwd(const float *pc1, const float *pc2, int B, int N, int M, float *d1, float *d2,
                     int32_t *i1, int32_t *i2, float *mean1, float *mean2, void *ws, size_t ws_bytes,
                     unsigned flags, void *stream) {
-    return rlg_chamfer_loss_fwd(pc1, pc2, B, N, M, d1, d2, i1, i2, mean1, mean2, nullptr, 0.0f, 0.0f, ws, ws_bytes,
-                                flags, stream);
+    return rlg_chamfer_loss_fwd(pc1, pc2, B, N, M, d1, d2, i1, i2, mean1, mean2, nullptr, 0.0f, 0.0f, nullptr, nullptr,
+                                ws, ws_bytes, flags, stream);
 }
 
 int rlg_chamfer_loss_fwd(const float *pc1, const float *pc2, int B, int N, int M, float *d1, float *d2,
                          int32_t *i1, int32_t *i2, float *mean1, float *mean2, float *loss, float w1, float w2,
-                         void *ws, size_t ws_bytes, unsigned flags, void *stream) {
+                         float *gz1, float *gz2, void *ws, size_t ws_bytes, unsigned flags, void *stream) {
     if (B < 0 || N < 1 || M < 1)
         return fail(RLG_ERR_BAD_SHAPE, "rlg_chamfer_fwd: bad shape B=%d N=%d M=%d (need B>=0, N>=1, M>=1)", B, N, M);
     if (B == 0) return 0;
@@ -317,6 +317,11 @@ int rlg_chamfer_loss_fwd(const float *pc1, const float *pc2, int B, int N, int M
     if ((long long)N * 3 > 0x7fffffffLL || (long long)M * 3 > 0x7fffffffLL)
         return fail(RLG_ERR_TOO_LARGE, "rlg_chamfer_fwd: N or M too large for 32-bit indexing");
     cudaStream_t st = (cudaStream_t)stream;
+    const bool fused_zero = !(flags & (RLG_CHAMFER_ALGO_SIMPLE | RLG_CHAMFER_ALGO_DIRECT | RLG_CHAMFER_TILE_ONLY));
+    if (!fused_zero) {              // the cross-check paths have no fused zero-fill: plain memsets
+        if (gz1) cudaMemsetAsync(gz1, 0, sizeof(float) * 3 * (size_t)B * N, st);
+        if (gz2) cudaMemsetAsync(gz2, 0, sizeof(float) * 3 * (size_t)B * M, st);
+    }
 
     if (flags & RLG_CHAMFER_ALGO_SIMPLE) {
         dim3 g1((N + 127) / 128, B), g2((M + 127) / 128, B);
@@ -367,7 +372,7 @@ int rlg_chamfer_loss_fwd(const float *pc1, const float *pc2, int B, int N, int M
     if (rc) return rc;
     if (flags & RLG_CHAMFER_TILE_ONLY) return 0;
     char *fin = (char *)ws + keys_bytes(B, N, M) + secs_bytes(B, N, M) + nrm_bytes(B);
-    return launch_finalize2(pc1, pc2, B, N, M, R, w, fin, d1, d2, i1, i2, mean1, mean2, loss, w1, w2, st);
+    return launch_finalize2(pc1, pc2, B, N, M, R, w, fin, d1, d2, i1, i2, mean1, mean2, loss, w1, w2, gz1, gz2, st);
 }
 
 }  // extern "C"

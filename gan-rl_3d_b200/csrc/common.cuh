@@ -41,7 +41,7 @@ int launch_filter(const float *pc1, const float *pc2, int B, int N, int M, int v
                   int *rows_per_lane, cudaStream_t st);
 int launch_finalize2(const float *pc1, const float *pc2, int B, int N, int M, int rows_per_lane, const FwdWs &w,
                      void *fin_ws, float *d1, float *d2, int32_t *i1, int32_t *i2, float *mean1, float *mean2,
-                     float *loss, float w1, float w2, cudaStream_t st);
+                     float *loss, float w1, float w2, float *zero1, float *zero2, cudaStream_t st);
 
 // ---- packed fp32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2) ------------------------------
 // One instruction issues two IEEE fp32 operations, halving the issue-slot cost of the distance math.

@@ -31,7 +31,7 @@ class ChamferStepGraph:
         self.device = self.batches[0][0].device
         self.losses: List[torch.Tensor] = []
         self.grads: List[torch.Tensor] = []
-        self.kernel_launches_per_replay = 4 * len(self.batches)    # tile + finalize + bwd own + bwd scatter
+        self.kernel_launches_per_replay = 3 * len(self.batches)    # pair sweep + finalize + backward
         self.stream = torch.cuda.Stream(self.device)
         self.graph = torch.cuda.CUDAGraph()
         self._capture()
@@ -79,7 +79,7 @@ class HostChamferStepGraph:
         self.losses_host = torch.zeros(self.S, dtype=torch.float32).pin_memory()
         self.h2d_bytes_per_step = (a0.numel() + b0.numel()) * 4
         self.d2h_bytes_per_step = 4
-        self.kernel_launches_per_replay = 4 * self.S
+        self.kernel_launches_per_replay = 3 * self.S
         self.compute = torch.cuda.Stream(device)
         self.copy = torch.cuda.Stream(device)
         self.graph = torch.cuda.CUDAGraph()

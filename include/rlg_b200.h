@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define RLG_ABI_VERSION 1
+#define RLG_ABI_VERSION 2
 
 #define RLG_ERR_NULL_POINTER   (-1)
 #define RLG_ERR_BAD_SHAPE      (-2)   /* B < 0, N < 1, M < 1 (the reference raises IndexError for empty clouds) */
@@ -87,31 +87,38 @@ int rlg_chamfer_fwd(const float *pc1, const float *pc2, int B, int N, int M,
 /* Forward fused with the reference's loss reduction (utils/losses.py:54-59 and :75):
  *   loss[0] = sum_b ( w1 * mean1[b] + w2 * mean2[b] ),  accumulated in a fixed order (deterministic);
  *   ChamferLoss(bidirectional=True) is w1 = w2 = 0.5/B, bidirectional=False is w1 = 1/B, w2 = 0.
- * loss: device fp32 scalar (nullable -> identical to rlg_chamfer_fwd); needs mean1/mean2. */
+ * loss: device fp32 scalar (nullable); needs mean1/mean2.
+ * gz1 (B,N,3), gz2 (B,M,3): device fp32, each nullable: buffers the forward zero-fills on the way (for free, in its
+ * last launch) so that the backward can run as ONE launch with RLG_CHAMFER_BWD_ACCUMULATE into them. */
 int rlg_chamfer_loss_fwd(const float *pc1, const float *pc2, int B, int N, int M,
                          float *d1, float *d2, int32_t *i1, int32_t *i2,
                          float *mean1, float *mean2, float *loss, float w1, float w2,
+                         float *gz1, float *gz2,
                          void *ws, size_t ws_bytes, unsigned flags, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Chamfer distance, backward
  *
  *   g1 (B), g2 (B)      device, fp32: upstream gradients of mean1, mean2 (nullable individually = 0)
- *   gpc1 (B,N,3), gpc2 (B,M,3)   device, fp32, fully overwritten:
+ *   gpc1 (B,N,3), gpc2 (B,M,3)   device, fp32, fully overwritten (or added to, with RLG_CHAMFER_BWD_ACCUMULATE):
  *       gpc1[b,i] = g1[b]/N * (pc1[b,i]-pc2[b,i1])/d1[b,i]  -  sum_{j: i2[b,j]==i} g2[b]/M * (pc2[b,j]-pc1[b,i])/d2[b,j]
  *       (and symmetrically for gpc2); a term is 0 where its distance is 0 (EuclideanDistBackward0).
+ *   flags   RLG_CHAMFER_BWD_ACCUMULATE: gpc1/gpc2 already hold zeros (see rlg_chamfer_loss_fwd's gz1/gz2) or a
+ *           gradient to add to: one launch of fire-and-forget float atomics.  Without it the library zero-fills
+ *           them first (a memset node + the same launch).
  * --------------------------------------------------------------------------------------------- */
+#define RLG_CHAMFER_BWD_ACCUMULATE 1u
 int rlg_chamfer_bwd(const float *pc1, const float *pc2,
                     const float *d1, const float *d2, const int32_t *i1, const int32_t *i2,
                     const float *g1, const float *g2, int B, int N, int M,
-                    float *gpc1, float *gpc2, void *stream);
+                    float *gpc1, float *gpc2, unsigned flags, void *stream);
 
 /* Backward of rlg_chamfer_loss_fwd: gloss is the device fp32 scalar upstream of loss[0]; the per-pair
  * upstreams are gloss[0]*w1 (mean1) and gloss[0]*w2 (mean2). */
 int rlg_chamfer_loss_bwd(const float *pc1, const float *pc2,
                          const float *d1, const float *d2, const int32_t *i1, const int32_t *i2,
                          const float *gloss, float w1, float w2, int B, int N, int M,
-                         float *gpc1, float *gpc2, void *stream);
+                         float *gpc1, float *gpc2, unsigned flags, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * PointNet encoder: shared per-point MLP + global max-pool  (models/autoencoder.py:65-71), eval mode.

@@ -36,7 +36,7 @@ def test_header_symbols_are_exported(lib):
 
 def test_version_and_ws_bytes(lib):
     cdll, _ = lib
-    assert cdll.rlg_version() == 1
+    assert cdll.rlg_version() == 2
     big = cdll.rlg_chamfer_ws_bytes(32, 2048, 2048)   # 8-byte keys + 4-byte second-best values per point + counters
     assert 12 * 32 * 4096 < big <= 12 * 32 * 4096 + 16384 and big % 256 == 0
     assert 0 < cdll.rlg_chamfer_ws_bytes(1, 1, 1) <= 2048
@@ -50,7 +50,7 @@ def test_argument_errors_are_negative_codes_with_messages(lib):
     assert rc == -2 and b"bad shape" in cdll.rlg_last_error()
     rc = cdll.rlg_chamfer_fwd(None, None, 2, 4, 5, None, None, None, None, None, None, None, 0, 0, None)
     assert rc == -1
-    rc = cdll.rlg_chamfer_bwd(*([None] * 8), 1, 3, 0, None, None, None)
+    rc = cdll.rlg_chamfer_bwd(*([None] * 8), 1, 3, 0, None, None, 0, None)
     assert rc == -2
     with pytest.raises(_lib.RlgError) as ei:
         _lib.check("rlg_chamfer_bwd", rc)

@@ -129,7 +129,7 @@ def test_unsupported_widths_fail_loudly(rlg):
 
 
 BF16_TOL = 2e-2      # north_star: 2e-2 relative for the bf16 encoder GEMMs
-BF16_FLOOR = 1e-1    # ... on entries >= 10 % of the largest; smaller entries: |err| <= 2e-3 * largest (see O.gfv_close)
+BF16_FLOOR = 0.25    # ... on entries >= 25 % of the largest; smaller entries: |err| <= 5e-3 * largest (see O.gfv_close)
 BF16_NORM = 5e-3     # and norm-wise |a-b|_2 <= 5e-3 |b|_2 (measured ~1e-3)
 
 

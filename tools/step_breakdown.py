@@ -35,7 +35,7 @@ def fwd(a, b, flags):
 
 def bwd(a, b):
     rc = lib.rlg_chamfer_bwd(a.data_ptr(), b.data_ptr(), d1.data_ptr(), d2.data_ptr(), i1.data_ptr(), i2.data_ptr(),
-                             g.data_ptr(), g.data_ptr(), B, N, M, ga.data_ptr(), gb.data_ptr(), st)
+                             g.data_ptr(), g.data_ptr(), B, N, M, ga.data_ptr(), gb.data_ptr(), 0, st)
     _lib.check("bwd", rc)
 
 
