@@ -38,7 +38,7 @@ struct TcPlan {
     const float *bias[kTcMaxLayers];    // fp32 biases of layers >= 1
     const unsigned char *img[kTcMaxLayers];   // packed bf16 images of layers >= 1 (global)
     uint32_t smem_w[kTcMaxLayers];      // shared-memory byte offsets (1024-B aligned)
-    uint32_t smem_act[2], smem_bias[kTcMaxLayers], smem_w0, smem_bar, smem_total;
+    uint32_t smem_act[2], smem_x[2], smem_bias[kTcMaxLayers], smem_w0, smem_bar, smem_total;
     int split, nblk;                    // last layer: channel groups over CTAs, 128-channel blocks per CTA
     int n_pchunks, tiles_per_chunk;     // point chunks per cloud, 128-point tiles per chunk
 };
@@ -120,26 +120,60 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_smem, int
     }
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1) encoder_tc_kernel(const float *__restrict__ x, int B, int N, TcPlan p,
-                                                                  float *__restrict__ pooled) {
+// ---- warp-specialised pipeline ------------------------------------------------------------------------------
+//   warps 0-3  FE   one thread per point of the 128-point tile: layer 0 on the CUDA cores, then the bias+ReLU+bf16
+//                   epilogue of every hidden layer (TMEM -> registers -> swizzled operand tile of the next GEMM)
+//   warp  4    MMA  one elected thread issues every tcgen05.mma; owns the TMEM allocation and the weight TMA loads
+//   warps 5-8  EP   last-layer epilogue: tcgen05.ld of a 128-channel x 128-point accumulator, running max per channel
+// Hand-offs are mbarriers; the MMA thread interleaves the hidden GEMM of tile n+1 between the last-layer blocks of
+// tile n, so the front end of the next tile runs under the tensor-core time of the current one.
+//   TMEM columns: [0,128) hidden accumulator H, [128,512) three last-layer accumulators.
+static constexpr int kFeThreads = 128, kEpThreads = 128;
+static constexpr int kTcThreads2 = kFeThreads + 32 + kEpThreads;
+static constexpr int kAccBufs = 3;
+static constexpr uint32_t kColH = 0, kColAcc = 128;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded wait: a protocol bug must trap, not hang the GPU
+__device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    for (uint32_t spin = 0;; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (spin > (1u << 26)) __trap();
+    }
+}
+
+__global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float *__restrict__ x, int B, int N, TcPlan p,
+                                                                   float *__restrict__ pooled) {
     extern __shared__ unsigned char smem_raw[];
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // SWIZZLE_128B operand tiles need a 1024-byte aligned base: realign inside the 1 KB of slack the launch adds
     const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
     unsigned char *smem = smem_raw + pad;
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t bar_w = sbase + p.smem_bar, bar_h = bar_w + 8, bar_d0 = bar_w + 16, bar_d1 = bar_w + 24;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + p.smem_bar + 32);
+    const uint32_t bars = sbase + p.smem_bar;
+    const uint32_t bar_w = bars, bar_fe = bars + 8, bar_h = bars + 16;
+    const uint32_t bar_xfull = bars + 24, bar_xempty = bars + 40;               // [2] each
+    const uint32_t bar_accfull = bars + 56, bar_accempty = bars + 80;           // [3] each
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + p.smem_bar + 104);
     const int L = p.L, c_last = p.c[L], k_last = p.c[L - 1];
     const int g = blockIdx.x % p.split, cta_in_group = blockIdx.x / p.split, ctas_per_group = gridDim.x / p.split;
     const int blk0 = g * p.nblk;
     const int nblk = min(p.nblk, c_last / 128 - blk0);
+    const int n_tasks = (nblk > 0) ? B * p.n_pchunks : 0;
+    const int n_hidden = L - 2;                                                 // tensor-core layers before the last
 
     if (tid == 0) {
-        mbar_init(bar_w, 1); mbar_init(bar_h, 1); mbar_init(bar_d0, 1); mbar_init(bar_d1, 1);
+        mbar_init(bar_w, 1); mbar_init(bar_fe, kFeThreads); mbar_init(bar_h, 1);
+        for (int k = 0; k < 2; ++k) { mbar_init(bar_xfull + 8 * k, kFeThreads); mbar_init(bar_xempty + 8 * k, 1); }
+        for (int k = 0; k < kAccBufs; ++k) { mbar_init(bar_accfull + 8 * k, 1); mbar_init(bar_accempty + 8 * k, kEpThreads); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
+    if (warp == 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -149,164 +183,203 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_tc_kernel(const float *
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    // resident weights: one TMA bulk load per layer (the last layer: this CTA's channel slice)
-    if (tid == 0 && nblk > 0) {
-        uint32_t total = 0;
-        for (int l = 1; l < L - 1; ++l) total += (uint32_t)p.c[l + 1] * p.c[l] * 2;
-        total += (uint32_t)nblk * 128 * k_last * 2;
-        mbar_arrive_expect_tx(bar_w, total);
-        for (int l = 1; l < L; ++l) {
-            const bool last = (l == L - 1);
-            uint32_t bytes = last ? (uint32_t)nblk * 128 * k_last * 2 : (uint32_t)p.c[l + 1] * p.c[l] * 2;
-            const unsigned char *src = p.img[l] + (last ? (size_t)blk0 * 128 * k_last * 2 : 0);
-            uint32_t dst = sbase + p.smem_w[l];
-            while (bytes) {                                  // <= 32 KB per bulk copy
-                const uint32_t n = bytes < 32768u ? bytes : 32768u;
-                bulk_g2s(dst, src, n, bar_w);
-                dst += n; src += n; bytes -= n;
+    if (warp == 4) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0 && n_tasks > 0) {
+            // resident weights: one TMA bulk load per layer (the last layer: this CTA's channel slice)
+            uint32_t total = 0;
+            for (int l = 1; l < L - 1; ++l) total += (uint32_t)p.c[l + 1] * p.c[l] * 2;
+            total += (uint32_t)nblk * 128 * k_last * 2;
+            mbar_arrive_expect_tx(bar_w, total);
+            for (int l = 1; l < L; ++l) {
+                const bool last = (l == L - 1);
+                uint32_t bytes = last ? (uint32_t)nblk * 128 * k_last * 2 : (uint32_t)p.c[l + 1] * p.c[l] * 2;
+                const unsigned char *src = p.img[l] + (last ? (size_t)blk0 * 128 * k_last * 2 : 0);
+                uint32_t dst = sbase + p.smem_w[l];
+                while (bytes) {                                  // <= 32 KB per bulk copy
+                    const uint32_t n = bytes < 32768u ? bytes : 32768u;
+                    bulk_g2s(dst, src, n, bar_w);
+                    dst += n; src += n; bytes -= n;
+                }
+            }
+            // how many tiles this CTA will see
+            int T = 0;
+            for (int task = cta_in_group; task < n_tasks; task += ctas_per_group) {
+                const int pc = task % p.n_pchunks;
+                for (int t = 0; t < p.tiles_per_chunk; ++t)
+                    if ((pc * p.tiles_per_chunk + t) * kTileP < N) ++T;
+            }
+            mbar_wait_wd(bar_w, 0);
+            uint32_t fe_ph = 0;
+            int kb = 0;                                           // running last-layer block counter -> accumulator ring
+            const uint32_t wl = sbase + p.smem_w[L - 1];
+            auto hidden_step = [&](int l) {
+                mbar_wait_wd(bar_fe, fe_ph);
+                fe_ph ^= 1;
+                tc_fence_after();
+                const uint32_t in = sbase + (((l - 1) & 1) ? p.smem_act[1] : p.smem_act[0]);
+                issue_gemm(tmem + kColH, in, kTileP, sbase + p.smem_w[l], p.c[l + 1], kTileP, p.c[l + 1], p.c[l]);
+                tc_commit(bar_h);
+            };
+            auto last_block = [&](int blk, uint32_t act) {
+                const int a = kb % kAccBufs, use = kb / kAccBufs;
+                mbar_wait_wd(bar_accempty + 8 * a, (uint32_t)((use & 1) ^ 1));
+                tc_fence_after();
+                issue_gemm(tmem + kColAcc + (uint32_t)a * 128u, wl + (uint32_t)blk * 128 * k_last * 2, 128, act, kTileP, 128,
+                           kTileP, k_last);
+                tc_commit(bar_accfull + 8 * a);
+                ++kb;
+            };
+            if (T > 0)
+                for (int l = 1; l <= n_hidden; ++l) hidden_step(l);   // prologue: the first tile's hidden chain
+            for (int n = 0; n < T; ++n) {
+                const int s = n & 1;
+                mbar_wait_wd(bar_xfull + 8 * s, (uint32_t)((n >> 1) & 1));
+                tc_fence_after();
+                int blk = 0;
+                last_block(blk++, sbase + p.smem_x[s]);
+                if (n + 1 < T) {
+                    for (int l = 1; l <= n_hidden; ++l) {         // next tile's hidden GEMMs ride between the blocks
+                        hidden_step(l);
+                        if (blk < nblk && l < n_hidden) last_block(blk++, sbase + p.smem_x[s]);
+                    }
+                }
+                while (blk < nblk) last_block(blk++, sbase + p.smem_x[s]);
+                tc_commit(bar_xempty + 8 * s);                    // X[s] may be overwritten once these MMAs are done
             }
         }
-    }
-    // layer-0 weights and hidden biases: plain loads
-    float *w0s = reinterpret_cast<float *>(smem + p.smem_w0);
-    const int c1 = p.c[1];
-    for (int e = tid; e < c1 * 4; e += kTcThreads) {
-        const int o = e >> 2, k = e & 3;
-        w0s[e] = (k < 3) ? __ldg(p.w0 + o * 3 + k) : __ldg(p.b0 + o);
-    }
-    for (int l = 1; l < L - 1; ++l) {
-        float *bs = reinterpret_cast<float *>(smem + p.smem_bias[l]);
-        for (int e = tid; e < p.c[l + 1]; e += kTcThreads) bs[e] = __ldg(p.bias[l] + e);
-    }
-    __syncthreads();
-    if (nblk > 0) mbar_wait(bar_w, 0);
-
-    uint32_t ph_h = 0, ph_d0 = 0, ph_d1 = 0;
-    const uint32_t lane_base = ((uint32_t)(warp & 3) * 32u) << 16;     // this warp's TMEM lane quarter
-    const int n_tasks = (nblk > 0) ? B * p.n_pchunks : 0;
-
-    for (int task = cta_in_group; task < n_tasks; task += ctas_per_group) {
-        const int b = task / p.n_pchunks, pc = task - b * p.n_pchunks;
-        const float *xb = x + (size_t)b * N * 3;
-        float runmax[kMaxBlk];
-#pragma unroll
-        for (int k = 0; k < kMaxBlk; ++k) runmax[k] = -INFINITY;
-
-        for (int t = 0; t < p.tiles_per_chunk; ++t) {
-            const int n0 = (pc * p.tiles_per_chunk + t) * kTileP;
-            if (n0 >= N) break;
-            // ---- layer 0 on CUDA cores; rows past the end repeat the last valid point (max is unaffected)
-            {
-                const int n = min(n0 + tid, N - 1);
-                const float px = __ldg(xb + 3 * n), py = __ldg(xb + 3 * n + 1), pz = __ldg(xb + 3 * n + 2);
-                unsigned char *dst = smem + p.smem_act[0];
-                for (int k8 = 0; k8 < c1 / 8; ++k8) {
-                    uint32_t pk[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float v[2];
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const float4 w = *reinterpret_cast<const float4 *>(w0s + (k8 * 8 + q * 2 + h) * 4);
-                            v[h] = fmaxf(fmaf(w.x, px, fmaf(w.y, py, fmaf(w.z, pz, w.w))), 0.0f);
-                        }
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[0], v[1]);
-                        pk[q] = *reinterpret_cast<uint32_t *>(&h2);
-                    }
-                    *reinterpret_cast<uint4 *>(dst + sw128_chunk_off(kTileP, tid, k8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                }
-            }
-            fence_async_proxy();
-            tc_fence_before();
-            __syncthreads();
-            int cur = 0;
-            // ---- hidden layers on the tensor cores: points on the TMEM lanes
-            for (int l = 1; l < L - 1; ++l) {
-                const int cin = p.c[l], cout = p.c[l + 1];
-                if (tid == 0) {
-                    tc_fence_after();
-                    issue_gemm(tmem + kColHidden, sbase + p.smem_act[cur], kTileP, sbase + p.smem_w[l], cout, kTileP, cout, cin);
-                    tc_commit(bar_h);
-                }
-                mbar_wait(bar_h, ph_h);
-                ph_h ^= 1;
-                tc_fence_after();
-                const float *bs = reinterpret_cast<const float *>(smem + p.smem_bias[l]);
-                unsigned char *dst = smem + p.smem_act[cur ^ 1];
-                for (int c0 = 0; c0 < cout; c0 += 32) {
-                    float v[32];
-                    tc_ld32(tmem + lane_base + kColHidden + c0, v);
-#pragma unroll
-                    for (int q8 = 0; q8 < 4; ++q8) {
+    } else if (warp < 4) {
+        // =========================== front end ===========================
+        float *w0s = reinterpret_cast<float *>(smem + p.smem_w0);
+        const int c1 = p.c[1];
+        for (int e = tid; e < c1 * 4; e += kFeThreads) {
+            const int o = e >> 2, k = e & 3;
+            w0s[e] = (k < 3) ? __ldg(p.w0 + o * 3 + k) : __ldg(p.b0 + o);
+        }
+        for (int l = 1; l < L - 1; ++l) {
+            float *bs = reinterpret_cast<float *>(smem + p.smem_bias[l]);
+            for (int e = tid; e < p.c[l + 1]; e += kFeThreads) bs[e] = __ldg(p.bias[l] + e);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kFeThreads) : "memory");
+        const uint32_t lane_base = ((uint32_t)warp * 32u) << 16;      // this warp's TMEM lane quarter
+        uint32_t h_ph = 0;
+        int n = 0;
+        for (int task = cta_in_group; task < n_tasks; task += ctas_per_group) {
+            const int b = task / p.n_pchunks, pc = task - b * p.n_pchunks;
+            const float *xb = x + (size_t)b * N * 3;
+            for (int t = 0; t < p.tiles_per_chunk; ++t) {
+                const int n0 = (pc * p.tiles_per_chunk + t) * kTileP;
+                if (n0 >= N) break;
+                const int s = n & 1;
+                const uint32_t xempty_par = (uint32_t)(((n >> 1) & 1) ^ 1);
+                // ---- layer 0 on CUDA cores; rows past the end repeat the last valid point (the max is unaffected)
+                {
+                    const int pt = min(n0 + tid, N - 1);
+                    const float px = __ldg(xb + 3 * pt), py = __ldg(xb + 3 * pt + 1), pz = __ldg(xb + 3 * pt + 2);
+                    if (n_hidden == 0) mbar_wait_wd(bar_xempty + 8 * s, xempty_par);
+                    unsigned char *dst = smem + (n_hidden == 0 ? p.smem_x[s] : p.smem_act[0]);
+                    for (int k8 = 0; k8 < c1 / 8; ++k8) {
                         uint32_t pk[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const int ch = q8 * 8 + q * 2;
-                            const float a = fmaxf(v[ch] + bs[c0 + ch], 0.0f), bb = fmaxf(v[ch + 1] + bs[c0 + ch + 1], 0.0f);
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
+                            float v[2];
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const float4 w = *reinterpret_cast<const float4 *>(w0s + (k8 * 8 + q * 2 + h) * 4);
+                                v[h] = fmaxf(fmaf(w.x, px, fmaf(w.y, py, fmaf(w.z, pz, w.w))), 0.0f);
+                            }
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[0], v[1]);
                             pk[q] = *reinterpret_cast<uint32_t *>(&h2);
                         }
-                        *reinterpret_cast<uint4 *>(dst + sw128_chunk_off(kTileP, tid, (c0 >> 3) + q8)) =
-                            make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4 *>(dst + sw128_chunk_off(kTileP, tid, k8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                    fence_async_proxy();
+                    mbar_arrive(n_hidden == 0 ? bar_xfull + 8 * s : bar_fe);
+                }
+                // ---- hidden layers: accumulator H (points on the TMEM lanes) -> bias + ReLU -> bf16 operand tile
+                for (int l = 1; l <= n_hidden; ++l) {
+                    const int cout = p.c[l + 1];
+                    const bool last_hidden = (l == n_hidden);
+                    mbar_wait_wd(bar_h, h_ph);
+                    h_ph ^= 1;
+                    tc_fence_after();
+                    if (last_hidden) mbar_wait_wd(bar_xempty + 8 * s, xempty_par);
+                    const float *bs = reinterpret_cast<const float *>(smem + p.smem_bias[l]);
+                    unsigned char *dst = smem + (last_hidden ? p.smem_x[s] : ((l & 1) ? p.smem_act[1] : p.smem_act[0]));
+                    for (int c0 = 0; c0 < cout; c0 += 32) {
+                        float v[32];
+                        tc_ld32(tmem + lane_base + kColH + c0, v);
+#pragma unroll
+                        for (int q8 = 0; q8 < 4; ++q8) {
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int ch = q8 * 8 + q * 2;
+                                const float a = fmaxf(v[ch] + bs[c0 + ch], 0.0f), bb = fmaxf(v[ch + 1] + bs[c0 + ch + 1], 0.0f);
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
+                                pk[q] = *reinterpret_cast<uint32_t *>(&h2);
+                            }
+                            *reinterpret_cast<uint4 *>(dst + sw128_chunk_off(kTileP, tid, (c0 >> 3) + q8)) =
+                                make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
+                    }
+                    fence_async_proxy();
+                    tc_fence_before();
+                    mbar_arrive(last_hidden ? bar_xfull + 8 * s : bar_fe);
+                }
+                ++n;
+            }
+        }
+    } else {
+        // =========================== last-layer epilogue ===========================
+        const int q = warp & 3;                                        // TMEM lane quarter this warp may read
+        const uint32_t lane_base = ((uint32_t)q * 32u) << 16;
+        const int ch_in_blk = q * 32 + lane;
+        const float *bl = p.bias[L - 1];
+        int kb = 0;
+        for (int task = cta_in_group; task < n_tasks; task += ctas_per_group) {
+            const int b = task / p.n_pchunks, pc = task - b * p.n_pchunks;
+            float runmax[kMaxBlk];
+#pragma unroll
+            for (int k = 0; k < kMaxBlk; ++k) runmax[k] = -INFINITY;
+            for (int t = 0; t < p.tiles_per_chunk; ++t) {
+                if ((pc * p.tiles_per_chunk + t) * kTileP >= N) break;
+#pragma unroll
+                for (int blk = 0; blk < kMaxBlk; ++blk) {
+                    if (blk < nblk) {
+                        const int a = kb % kAccBufs, use = kb / kAccBufs;
+                        mbar_wait_wd(bar_accfull + 8 * a, (uint32_t)(use & 1));
+                        tc_fence_after();
+                        float m = runmax[blk];
+                        const uint32_t col = kColAcc + (uint32_t)a * 128u;
+#pragma unroll
+                        for (int c0 = 0; c0 < kTileP; c0 += 32) {
+                            float v[32];
+                            tc_ld32(tmem + lane_base + col + c0, v);
+#pragma unroll
+                            for (int i = 0; i < 32; i += 2) m = max3(m, v[i], v[i + 1]);
+                        }
+                        runmax[blk] = m;
+                        tc_fence_before();
+                        mbar_arrive(bar_accempty + 8 * a);
+                        ++kb;
                     }
                 }
-                fence_async_proxy();
-                tc_fence_before();
-                __syncthreads();
-                cur ^= 1;
             }
-            // ---- last layer: channels on the TMEM lanes, two accumulators alternate
-            const uint32_t act = sbase + p.smem_act[cur];
-            const uint32_t wl = sbase + p.smem_w[L - 1];
-            auto issue_blk = [&](int blk) {
-                if (tid == 0) {
-                    tc_fence_after();
-                    issue_gemm(tmem + ((blk & 1) ? kColLast1 : kColLast0), wl + (uint32_t)blk * 128 * k_last * 2, 128, act,
-                               kTileP, 128, kTileP, k_last);
-                    tc_commit((blk & 1) ? bar_d1 : bar_d0);
-                }
-            };
-            issue_blk(0);
-            if (nblk > 1) issue_blk(1);
+            // task result: bias + ReLU commute with the max; merge the point chunks of a cloud with atomicMax
 #pragma unroll
             for (int blk = 0; blk < kMaxBlk; ++blk) {
                 if (blk < nblk) {
-                    if (blk & 1) { mbar_wait(bar_d1, ph_d1); ph_d1 ^= 1; } else { mbar_wait(bar_d0, ph_d0); ph_d0 ^= 1; }
-                    tc_fence_after();
-                    float m = runmax[blk];
-                    const uint32_t col = (blk & 1) ? kColLast1 : kColLast0;
-#pragma unroll
-                    for (int c0 = 0; c0 < kTileP; c0 += 32) {
-                        float v[32];
-                        tc_ld32(tmem + lane_base + col + c0, v);
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2) m = max3(m, v[i], v[i + 1]);
-                    }
-                    runmax[blk] = m;
-                    if (blk + 2 < nblk) {                   // accumulator is free again: start block blk+2 into it
-                        tc_fence_before();
-                        __syncthreads();
-                        issue_blk(blk + 2);
-                    }
+                    const int ch = (blk0 + blk) * 128 + ch_in_blk;
+                    const float v = fmaxf(runmax[blk] + __ldg(bl + ch), 0.0f);
+                    atomicMax(reinterpret_cast<int *>(pooled) + (size_t)b * c_last + ch, __float_as_int(v));
                 }
-            }
-            tc_fence_before();
-            __syncthreads();    // every thread is done with TMEM and the operand tiles before the next tile reuses them
-        }
-        // ---- task result: bias + ReLU commute with the max; merge point chunks of a cloud with atomicMax
-        const float *bl = p.bias[L - 1];
-#pragma unroll
-        for (int blk = 0; blk < kMaxBlk; ++blk) {
-            if (blk < nblk) {
-                const int ch = (blk0 + blk) * 128 + tid;
-                const float v = fmaxf(runmax[blk] + __ldg(bl + ch), 0.0f);
-                atomicMax(reinterpret_cast<int *>(pooled) + (size_t)b * c_last + ch, __float_as_int(v));
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
+    if (warp == 4) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
     }
 }
@@ -350,13 +423,18 @@ static int tc_plan(const rlg_layer *layers, int L, int N, TcPlan &p, size_t img_
     const int k_last = p.c[L - 1], nblk_total = p.c[L] / 128;
     uint32_t fixed = 0;
     for (int l = 1; l < L - 1; ++l) { p.smem_w[l] = fixed; fixed += (uint32_t)align_up((size_t)p.c[l + 1] * p.c[l] * 2, 1024); }
-    p.smem_act[0] = fixed; fixed += kTileP * 128 * 2;
-    p.smem_act[1] = fixed; fixed += kTileP * 128 * 2;
+    // operand tiles: A0/A1 alternate along the hidden chain (only as wide as their users), X[2] feeds the last layer
+    uint32_t wa0 = 0, wa1 = 0;
+    for (int l = 1; l <= L - 2; ++l) { uint32_t &wdt = ((l - 1) & 1) ? wa1 : wa0; if ((uint32_t)p.c[l] > wdt) wdt = (uint32_t)p.c[l]; }
+    p.smem_act[0] = fixed; fixed += kTileP * wa0 * 2;
+    p.smem_act[1] = fixed; fixed += kTileP * wa1 * 2;
+    p.smem_x[0] = fixed; fixed += kTileP * (uint32_t)p.c[L - 1] * 2;
+    p.smem_x[1] = fixed; fixed += kTileP * (uint32_t)p.c[L - 1] * 2;
     p.smem_w[L - 1] = fixed;
     const uint32_t blk_bytes = 128u * k_last * 2u;
     uint32_t tail = 0;
     for (int l = 1; l < L - 1; ++l) { p.smem_bias[l] = tail; tail += (uint32_t)align_up((size_t)p.c[l + 1] * 4, 16); }
-    const uint32_t w0_bytes = (uint32_t)p.c[1] * 16, bar_bytes = 64;
+    const uint32_t w0_bytes = (uint32_t)p.c[1] * 16, bar_bytes = 128;
     const uint32_t budget = 226u * 1024u;          // 227 KB per CTA minus the 1 KB alignment slack
     if (fixed + tail + w0_bytes + bar_bytes + blk_bytes > budget)
         return fail(RLG_ERR_UNSUPPORTED, "rlg_encoder bf16: resident weights do not fit in shared memory");
@@ -434,7 +512,7 @@ int rlg_encoder_fwd_bf16(const float *x, int B, int N, const rlg_layer *layers, 
     if (per_group < 1) per_group = 1;
     if (per_group > tasks) per_group = tasks;
     const unsigned grid = (unsigned)(per_group * p.split);
-    encoder_tc_kernel<<<grid, kTcThreads, smem_bytes, st>>>(x, B, N, p, pooled);
+    encoder_tc_kernel<<<grid, kTcThreads2, smem_bytes, st>>>(x, B, N, p, pooled);
     return check_launch("encoder_tc_kernel");
 }
 
