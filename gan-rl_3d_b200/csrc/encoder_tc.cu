@@ -78,15 +78,38 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                  "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
+                 "tcgen05.wait::ld.sync.aligned;"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
                    "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                  : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 32 lanes x 64 consecutive fp32 columns in one instruction (the wait is part of the same statement, so no use of
+// the registers can be scheduled ahead of it)
+__device__ __forceinline__ void tc_ld64(uint32_t taddr, float (&v)[64]) {
+    uint32_t r[64];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+                 "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,"
+                 "%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];\n\t"
+                 "tcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
+                   "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+                   "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]),
+                   "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]),
+                   "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address and offsets
@@ -120,15 +143,47 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_smem, int
     }
 }
 
+// one lane of a converged warp (the same one every time)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// Same GEMM as issue_gemm, written so that every operand is warp-uniform (descriptors advance by constant
+// increments): called by ALL lanes of the MMA warp, the elected lane issues.  Keeping the descriptor arithmetic on
+// the uniform datapath avoids a register->uniform-register move per tcgen05.mma operand.
+__device__ __forceinline__ void issue_gemm_uniform(bool leader, uint32_t d_tmem, uint32_t a_smem, int a_rows,
+                                                   uint32_t b_smem, int b_rows, int M, int N, int K) {
+    const uint32_t idesc = umma_idesc(M, N);
+    uint64_t ad = umma_desc(a_smem), bd = umma_desc(b_smem);
+    const uint64_t a_inc = (uint64_t)((uint32_t)a_rows * 128u >> 4), b_inc = (uint64_t)((uint32_t)b_rows * 128u >> 4);
+    uint32_t acc = 0;
+    for (int kb = 0; kb < K / 64; ++kb) {
+        if (leader) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {              // 16 bf16 = 32 bytes per MMA along K
+                tc_mma_bf16(d_tmem, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), idesc, acc);
+                acc = 1;
+            }
+        }
+        acc = 1;
+        ad += a_inc;
+        bd += b_inc;
+    }
+}
+
 // ---- warp-specialised pipeline ------------------------------------------------------------------------------
-//   warps 0-3  FE   one thread per point of the 128-point tile: layer 0 on the CUDA cores, then the bias+ReLU+bf16
-//                   epilogue of every hidden layer (TMEM -> registers -> swizzled operand tile of the next GEMM)
-//   warp  4    MMA  one elected thread issues every tcgen05.mma; owns the TMEM allocation and the weight TMA loads
-//   warps 5-8  EP   last-layer epilogue: tcgen05.ld of a 128-channel x 128-point accumulator, running max per channel
+//   warps 0-7   FE   two threads per point of the 128-point tile (each half of the channels): layer 0 on the CUDA
+//                    cores, then the bias+ReLU+bf16 epilogue of every hidden layer (TMEM -> registers -> swizzled
+//                    operand tile of the next GEMM)
+//   warp  8     MMA  one elected thread issues every tcgen05.mma; owns the TMEM allocation and the weight TMA loads
+//   warps 9-16  EP   last-layer epilogue: tcgen05.ld of a 128-channel x 128-point accumulator (two warps per TMEM lane
+//                    quarter, 64 columns each), running max per channel
 // Hand-offs are mbarriers; the MMA thread interleaves the hidden GEMM of tile n+1 between the last-layer blocks of
 // tile n, so the front end of the next tile runs under the tensor-core time of the current one.
 //   TMEM columns: [0,128) hidden accumulator H, [128,512) three last-layer accumulators.
-static constexpr int kFeThreads = 128, kEpThreads = 128;
+static constexpr int kFeThreads = 256, kEpThreads = 256;
+static constexpr int kMmaWarp = kFeThreads / 32;
 static constexpr int kTcThreads2 = kFeThreads + 32 + kEpThreads;
 static constexpr int kAccBufs = 3;
 static constexpr uint32_t kColH = 0, kColAcc = 128;
@@ -173,7 +228,7 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
         for (int k = 0; k < kAccBufs; ++k) { mbar_init(bar_accfull + 8 * k, 1); mbar_init(bar_accempty + 8 * k, kEpThreads); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -183,25 +238,30 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == kMmaWarp) {
         // =========================== MMA issuer ===========================
-        if (lane == 0 && n_tasks > 0) {
-            // resident weights: one TMA bulk load per layer (the last layer: this CTA's channel slice)
-            uint32_t total = 0;
-            for (int l = 1; l < L - 1; ++l) total += (uint32_t)p.c[l + 1] * p.c[l] * 2;
-            total += (uint32_t)nblk * 128 * k_last * 2;
-            mbar_arrive_expect_tx(bar_w, total);
-            for (int l = 1; l < L; ++l) {
-                const bool last = (l == L - 1);
-                uint32_t bytes = last ? (uint32_t)nblk * 128 * k_last * 2 : (uint32_t)p.c[l + 1] * p.c[l] * 2;
-                const unsigned char *src = p.img[l] + (last ? (size_t)blk0 * 128 * k_last * 2 : 0);
-                uint32_t dst = sbase + p.smem_w[l];
-                while (bytes) {                                  // <= 32 KB per bulk copy
-                    const uint32_t n = bytes < 32768u ? bytes : 32768u;
-                    bulk_g2s(dst, src, n, bar_w);
-                    dst += n; src += n; bytes -= n;
+        // All 32 lanes run this (warp-uniform) code; one elected lane issues the tcgen05 instructions.
+        if (n_tasks > 0) {
+            const bool leader = elect_one();
+            if (leader) {
+                // resident weights: one TMA bulk load per layer (the last layer: this CTA's channel slice)
+                uint32_t total = 0;
+                for (int l = 1; l < L - 1; ++l) total += (uint32_t)p.c[l + 1] * p.c[l] * 2;
+                total += (uint32_t)nblk * 128 * k_last * 2;
+                mbar_arrive_expect_tx(bar_w, total);
+                for (int l = 1; l < L; ++l) {
+                    const bool last = (l == L - 1);
+                    uint32_t bytes = last ? (uint32_t)nblk * 128 * k_last * 2 : (uint32_t)p.c[l + 1] * p.c[l] * 2;
+                    const unsigned char *src = p.img[l] + (last ? (size_t)blk0 * 128 * k_last * 2 : 0);
+                    uint32_t dst = sbase + p.smem_w[l];
+                    while (bytes) {                                  // <= 32 KB per bulk copy
+                        const uint32_t n = bytes < 32768u ? bytes : 32768u;
+                        bulk_g2s(dst, src, n, bar_w);
+                        dst += n; src += n; bytes -= n;
+                    }
                 }
             }
+            __syncwarp();
             // how many tiles this CTA will see
             int T = 0;
             for (int task = cta_in_group; task < n_tasks; task += ctas_per_group) {
@@ -218,16 +278,18 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
                 fe_ph ^= 1;
                 tc_fence_after();
                 const uint32_t in = sbase + (((l - 1) & 1) ? p.smem_act[1] : p.smem_act[0]);
-                issue_gemm(tmem + kColH, in, kTileP, sbase + p.smem_w[l], p.c[l + 1], kTileP, p.c[l + 1], p.c[l]);
-                tc_commit(bar_h);
+                issue_gemm_uniform(leader, tmem + kColH, in, kTileP, sbase + p.smem_w[l], p.c[l + 1], kTileP, p.c[l + 1], p.c[l]);
+                if (leader) tc_commit(bar_h);
+                __syncwarp();
             };
             auto last_block = [&](int blk, uint32_t act) {
                 const int a = kb % kAccBufs, use = kb / kAccBufs;
                 mbar_wait_wd(bar_accempty + 8 * a, (uint32_t)((use & 1) ^ 1));
                 tc_fence_after();
-                issue_gemm(tmem + kColAcc + (uint32_t)a * 128u, wl + (uint32_t)blk * 128 * k_last * 2, 128, act, kTileP, 128,
-                           kTileP, k_last);
-                tc_commit(bar_accfull + 8 * a);
+                issue_gemm_uniform(leader, tmem + kColAcc + (uint32_t)a * 128u, wl + (uint32_t)blk * 128 * k_last * 2, 128,
+                                   act, kTileP, 128, kTileP, k_last);
+                if (leader) tc_commit(bar_accfull + 8 * a);
+                __syncwarp();
                 ++kb;
             };
             if (T > 0)
@@ -245,10 +307,11 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
                     }
                 }
                 while (blk < nblk) last_block(blk++, sbase + p.smem_x[s]);
-                tc_commit(bar_xempty + 8 * s);                    // X[s] may be overwritten once these MMAs are done
+                if (leader) tc_commit(bar_xempty + 8 * s);        // X[s] may be overwritten once these MMAs are done
+                __syncwarp();
             }
         }
-    } else if (warp < 4) {
+    } else if (warp < kMmaWarp) {
         // =========================== front end ===========================
         float *w0s = reinterpret_cast<float *>(smem + p.smem_w0);
         const int c1 = p.c[1];
@@ -261,24 +324,50 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
             for (int e = tid; e < p.c[l + 1]; e += kFeThreads) bs[e] = __ldg(p.bias[l] + e);
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kFeThreads) : "memory");
-        const uint32_t lane_base = ((uint32_t)warp * 32u) << 16;      // this warp's TMEM lane quarter
+        const int row = (warp & 3) * 32 + lane;                        // point of the tile == TMEM lane
+        const int half = warp >> 2;                                    // which half of the channels this thread does
+        const uint32_t lane_base = ((uint32_t)(warp & 3) * 32u) << 16; // this warp's TMEM lane quarter
         uint32_t h_ph = 0;
         int n = 0;
+        // coordinates of the first tile's point; every later tile's are fetched one tile ahead
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (cta_in_group < n_tasks) {
+            const int b = cta_in_group / p.n_pchunks, pc = cta_in_group - b * p.n_pchunks;
+            const int pt = min(pc * p.tiles_per_chunk * kTileP + row, N - 1);
+            const float *src = x + ((size_t)b * N + pt) * 3;
+            px = __ldg(src); py = __ldg(src + 1); pz = __ldg(src + 2);
+        }
         for (int task = cta_in_group; task < n_tasks; task += ctas_per_group) {
             const int b = task / p.n_pchunks, pc = task - b * p.n_pchunks;
-            const float *xb = x + (size_t)b * N * 3;
             for (int t = 0; t < p.tiles_per_chunk; ++t) {
                 const int n0 = (pc * p.tiles_per_chunk + t) * kTileP;
                 if (n0 >= N) break;
                 const int s = n & 1;
                 const uint32_t xempty_par = (uint32_t)(((n >> 1) & 1) ^ 1);
+                // prefetch the next tile's point (same task, or the first tile of this CTA's next task)
+                float qx = 0.f, qy = 0.f, qz = 0.f;
+                {
+                    int nb = b, nn0 = n0 + kTileP;
+                    bool have = (t + 1 < p.tiles_per_chunk) && (nn0 < N);
+                    if (!have && task + ctas_per_group < n_tasks) {
+                        const int nt = task + ctas_per_group;
+                        nb = nt / p.n_pchunks;
+                        nn0 = (nt - nb * p.n_pchunks) * p.tiles_per_chunk * kTileP;
+                        have = true;
+                    }
+                    if (have) {
+                        const float *src = x + ((size_t)nb * N + min(nn0 + row, N - 1)) * 3;
+                        qx = __ldg(src); qy = __ldg(src + 1); qz = __ldg(src + 2);
+                    }
+                }
                 // ---- layer 0 on CUDA cores; rows past the end repeat the last valid point (the max is unaffected)
                 {
-                    const int pt = min(n0 + tid, N - 1);
-                    const float px = __ldg(xb + 3 * pt), py = __ldg(xb + 3 * pt + 1), pz = __ldg(xb + 3 * pt + 2);
                     if (n_hidden == 0) mbar_wait_wd(bar_xempty + 8 * s, xempty_par);
                     unsigned char *dst = smem + (n_hidden == 0 ? p.smem_x[s] : p.smem_act[0]);
-                    for (int k8 = 0; k8 < c1 / 8; ++k8) {
+                    const int k8n = c1 / 16;                           // 16-byte chunks (8 channels) per thread
+#pragma unroll 2
+                    for (int kk = 0; kk < k8n; ++kk) {
+                        const int k8 = half * k8n + kk;
                         uint32_t pk[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
@@ -291,7 +380,7 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
                             __nv_bfloat162 h2 = __floats2bfloat162_rn(v[0], v[1]);
                             pk[q] = *reinterpret_cast<uint32_t *>(&h2);
                         }
-                        *reinterpret_cast<uint4 *>(dst + sw128_chunk_off(kTileP, tid, k8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4 *>(dst + sw128_chunk_off(kTileP, row, k8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
                     fence_async_proxy();
                     mbar_arrive(n_hidden == 0 ? bar_xfull + 8 * s : bar_fe);
@@ -299,27 +388,35 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
                 // ---- hidden layers: accumulator H (points on the TMEM lanes) -> bias + ReLU -> bf16 operand tile
                 for (int l = 1; l <= n_hidden; ++l) {
                     const int cout = p.c[l + 1];
+                    const int ncol = cout >> 1, col0 = half * ncol;    // this thread's channels: 32 or 64 of them
                     const bool last_hidden = (l == n_hidden);
                     mbar_wait_wd(bar_h, h_ph);
                     h_ph ^= 1;
                     tc_fence_after();
                     if (last_hidden) mbar_wait_wd(bar_xempty + 8 * s, xempty_par);
-                    const float *bs = reinterpret_cast<const float *>(smem + p.smem_bias[l]);
+                    const float *bs = reinterpret_cast<const float *>(smem + p.smem_bias[l]) + col0;
                     unsigned char *dst = smem + (last_hidden ? p.smem_x[s] : ((l & 1) ? p.smem_act[1] : p.smem_act[0]));
-                    for (int c0 = 0; c0 < cout; c0 += 32) {
-                        float v[32];
-                        tc_ld32(tmem + lane_base + kColH + c0, v);
+                    float v[64];
+                    if (ncol == 64) {
+                        tc_ld64(tmem + lane_base + kColH + col0, v);
+                    } else {
+                        float v32[32];
+                        tc_ld32(tmem + lane_base + kColH + col0, v32);
 #pragma unroll
-                        for (int q8 = 0; q8 < 4; ++q8) {
+                        for (int i = 0; i < 32; ++i) v[i] = v32[i];
+                    }
+#pragma unroll
+                    for (int q8 = 0; q8 < 8; ++q8) {
+                        if (q8 * 8 < ncol) {
                             uint32_t pk[4];
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 const int ch = q8 * 8 + q * 2;
-                                const float a = fmaxf(v[ch] + bs[c0 + ch], 0.0f), bb = fmaxf(v[ch + 1] + bs[c0 + ch + 1], 0.0f);
+                                const float a = fmaxf(v[ch] + bs[ch], 0.0f), bb = fmaxf(v[ch + 1] + bs[ch + 1], 0.0f);
                                 __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
                                 pk[q] = *reinterpret_cast<uint32_t *>(&h2);
                             }
-                            *reinterpret_cast<uint4 *>(dst + sw128_chunk_off(kTileP, tid, (c0 >> 3) + q8)) =
+                            *reinterpret_cast<uint4 *>(dst + sw128_chunk_off(kTileP, row, (col0 >> 3) + q8)) =
                                 make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         }
                     }
@@ -327,12 +424,14 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
                     tc_fence_before();
                     mbar_arrive(last_hidden ? bar_xfull + 8 * s : bar_fe);
                 }
+                px = qx; py = qy; pz = qz;
                 ++n;
             }
         }
     } else {
         // =========================== last-layer epilogue ===========================
         const int q = warp & 3;                                        // TMEM lane quarter this warp may read
+        const int half = (warp - kMmaWarp - 1) >> 2;                   // which 64 of the 128 points (columns)
         const uint32_t lane_base = ((uint32_t)q * 32u) << 16;
         const int ch_in_blk = q * 32 + lane;
         const float *bl = p.bias[L - 1];
@@ -350,18 +449,19 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
                         const int a = kb % kAccBufs, use = kb / kAccBufs;
                         mbar_wait_wd(bar_accfull + 8 * a, (uint32_t)(use & 1));
                         tc_fence_after();
-                        float m = runmax[blk];
-                        const uint32_t col = kColAcc + (uint32_t)a * 128u;
-#pragma unroll
-                        for (int c0 = 0; c0 < kTileP; c0 += 32) {
-                            float v[32];
-                            tc_ld32(tmem + lane_base + col + c0, v);
-#pragma unroll
-                            for (int i = 0; i < 32; i += 2) m = max3(m, v[i], v[i + 1]);
-                        }
-                        runmax[blk] = m;
+                        float v[64];
+                        tc_ld64(tmem + lane_base + kColAcc + (uint32_t)a * 128u + (uint32_t)half * 64u, v);
                         tc_fence_before();
-                        mbar_arrive(bar_accempty + 8 * a);
+                        mbar_arrive(bar_accempty + 8 * a);             // the accumulator is free as soon as it is in registers
+                        float m0 = runmax[blk], m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+                        for (int i = 0; i < 64; i += 8) {
+                            m0 = max3(m0, v[i], v[i + 1]);
+                            m1 = max3(m1, v[i + 2], v[i + 3]);
+                            m2 = max3(m2, v[i + 4], v[i + 5]);
+                            m3 = max3(m3, v[i + 6], v[i + 7]);
+                        }
+                        runmax[blk] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                         ++kb;
                     }
                 }
@@ -379,7 +479,7 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
     }
 }
