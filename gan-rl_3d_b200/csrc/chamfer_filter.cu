@@ -43,10 +43,6 @@ static constexpr int kFWarps = 4;                      // warps per CTA; each wa
 static constexpr float kMarginC = 96.0f / 16777216.0f; // 96 u
 static constexpr float kMarginQ = 1.0f / 65536.0f;     // column keys: 2 x 32 ulp of quantisation, with slack
 
-__device__ __forceinline__ u64 add2(u64 a, u64 b) {
-    u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
-}
-
 template <bool MIN3>
 __device__ __forceinline__ float facc(float acc, float a, float b) {
     if (MIN3) return min3(acc, a, b);

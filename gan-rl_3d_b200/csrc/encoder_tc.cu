@@ -21,6 +21,7 @@
 // (post-ReLU values are >= 0, so their bit patterns order like ints).
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <type_traits>
 
 namespace rlg {
 
@@ -181,13 +182,20 @@ __device__ __forceinline__ void issue_gemm_uniform(bool leader, uint32_t d_tmem,
 //                    quarter, 64 columns each), running max per channel
 // Hand-offs are mbarriers; the MMA thread interleaves the hidden GEMM of tile n+1 between the last-layer blocks of
 // tile n, so the front end of the next tile runs under the tensor-core time of the current one.
-//   TMEM columns: [0,128) hidden accumulator H, [128,512) three last-layer accumulators.
+//   TMEM columns: [0,256) two hidden accumulators H[tile parity], [256,512) two last-layer accumulators.
 static constexpr int kFeThreads = 256, kEpThreads = 256;
 static constexpr int kMmaWarp = kFeThreads / 32;
 static constexpr int kTcThreads2 = kFeThreads + 32 + kEpThreads;
-static constexpr int kAccBufs = 3;
-static constexpr uint32_t kColH = 0, kColAcc = 128;
+static constexpr int kAccBufs = 2;
+static constexpr uint32_t kColH = 0, kColAcc = 256;      // H[2] at columns 0 / 128, accumulators at 256 / 384
 
+// two fp32 -> packed bf16x2 with ReLU folded into the conversion (round-to-nearest-even, negative -> +0): the same
+// bits as fmaxf(.,0) followed by the conversion, in one instruction per pair
+__device__ __forceinline__ uint32_t relu_pack_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -195,10 +203,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     for (uint32_t spin = 0;; ++spin) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        // the hint lets the hardware park the thread (up to ~2 us) instead of re-issuing the poll
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(2000u) : "memory");
         if (ok) return;
-        if (spin > (1u << 26)) __trap();
+        if (spin > (1u << 24)) __trap();
     }
 }
 
@@ -211,9 +220,10 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
     unsigned char *smem = smem_raw + pad;
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bars = sbase + p.smem_bar;
-    const uint32_t bar_w = bars, bar_fe = bars + 8, bar_h = bars + 16;
-    const uint32_t bar_xfull = bars + 24, bar_xempty = bars + 40;               // [2] each
-    const uint32_t bar_accfull = bars + 56, bar_accempty = bars + 80;           // [3] each
+    // every pair below is indexed by tile parity (n & 1) resp. accumulator buffer
+    const uint32_t bar_w = bars, bar_fe = bars + 8, bar_h = bars + 24;
+    const uint32_t bar_xfull = bars + 40, bar_xempty = bars + 56;
+    const uint32_t bar_accfull = bars + 72, bar_accempty = bars + 88;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + p.smem_bar + 104);
     const int L = p.L, c_last = p.c[L], k_last = p.c[L - 1];
     const int g = blockIdx.x % p.split, cta_in_group = blockIdx.x / p.split, ctas_per_group = gridDim.x / p.split;
@@ -221,11 +231,17 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
     const int nblk = min(p.nblk, c_last / 128 - blk0);
     const int n_tasks = (nblk > 0) ? B * p.n_pchunks : 0;
     const int n_hidden = L - 2;                                                 // tensor-core layers before the last
+    // With <= 2 hidden layers the front end computes layer 0 of tile n+1 BEFORE the epilogue of tile n, so the hidden
+    // GEMM of tile n+1 runs under that epilogue (deeper chains would overwrite a live operand tile: plain order).
+    const bool early = n_hidden >= 1 && n_hidden <= 2;
 
     if (tid == 0) {
-        mbar_init(bar_w, 1); mbar_init(bar_fe, kFeThreads); mbar_init(bar_h, 1);
-        for (int k = 0; k < 2; ++k) { mbar_init(bar_xfull + 8 * k, kFeThreads); mbar_init(bar_xempty + 8 * k, 1); }
-        for (int k = 0; k < kAccBufs; ++k) { mbar_init(bar_accfull + 8 * k, 1); mbar_init(bar_accempty + 8 * k, kEpThreads); }
+        mbar_init(bar_w, 1);
+        for (int k = 0; k < 2; ++k) {
+            mbar_init(bar_fe + 8 * k, kFeThreads); mbar_init(bar_h + 8 * k, 1);
+            mbar_init(bar_xfull + 8 * k, kFeThreads); mbar_init(bar_xempty + 8 * k, 1);
+            mbar_init(bar_accfull + 8 * k, 1); mbar_init(bar_accempty + 8 * k, kEpThreads);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) {
@@ -238,10 +254,18 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
+    // tiles this CTA will see (same count in every role)
+    int T = 0;
+    for (int task = cta_in_group; task < n_tasks; task += ctas_per_group) {
+        const int pc = task % p.n_pchunks;
+        for (int t = 0; t < p.tiles_per_chunk; ++t)
+            if ((pc * p.tiles_per_chunk + t) * kTileP < N) ++T;
+    }
+
     if (warp == kMmaWarp) {
         // =========================== MMA issuer ===========================
         // All 32 lanes run this (warp-uniform) code; one elected lane issues the tcgen05 instructions.
-        if (n_tasks > 0) {
+        if (T > 0) {
             const bool leader = elect_one();
             if (leader) {
                 // resident weights: one TMA bulk load per layer (the last layer: this CTA's channel slice)
@@ -262,24 +286,19 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
                 }
             }
             __syncwarp();
-            // how many tiles this CTA will see
-            int T = 0;
-            for (int task = cta_in_group; task < n_tasks; task += ctas_per_group) {
-                const int pc = task % p.n_pchunks;
-                for (int t = 0; t < p.tiles_per_chunk; ++t)
-                    if ((pc * p.tiles_per_chunk + t) * kTileP < N) ++T;
-            }
             mbar_wait_wd(bar_w, 0);
-            uint32_t fe_ph = 0;
+            uint32_t fe_ph[2] = {0, 0};
             int kb = 0;                                           // running last-layer block counter -> accumulator ring
             const uint32_t wl = sbase + p.smem_w[L - 1];
-            auto hidden_step = [&](int l) {
-                mbar_wait_wd(bar_fe, fe_ph);
-                fe_ph ^= 1;
+            auto hidden_step = [&](int n, int l) {                // hidden GEMM l of tile n into H[n & 1]
+                const int par = n & 1;
+                mbar_wait_wd(bar_fe + 8 * par, par ? fe_ph[1] : fe_ph[0]);
+                if (par) fe_ph[1] ^= 1; else fe_ph[0] ^= 1;
                 tc_fence_after();
                 const uint32_t in = sbase + (((l - 1) & 1) ? p.smem_act[1] : p.smem_act[0]);
-                issue_gemm_uniform(leader, tmem + kColH, in, kTileP, sbase + p.smem_w[l], p.c[l + 1], kTileP, p.c[l + 1], p.c[l]);
-                if (leader) tc_commit(bar_h);
+                issue_gemm_uniform(leader, tmem + kColH + (uint32_t)par * 128u, in, kTileP, sbase + p.smem_w[l], p.c[l + 1],
+                                   kTileP, p.c[l + 1], p.c[l]);
+                if (leader) tc_commit(bar_h + 8 * par);
                 __syncwarp();
             };
             auto last_block = [&](int blk, uint32_t act) {
@@ -292,20 +311,16 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
                 __syncwarp();
                 ++kb;
             };
-            if (T > 0)
-                for (int l = 1; l <= n_hidden; ++l) hidden_step(l);   // prologue: the first tile's hidden chain
+            if (n_hidden >= 1) hidden_step(0, 1);                 // prologue: first hidden GEMM of the first tile
             for (int n = 0; n < T; ++n) {
                 const int s = n & 1;
+                if (early && n + 1 < T) hidden_step(n + 1, 1);    // runs under the front end's epilogue of tile n
+                for (int l = 2; l <= n_hidden; ++l) hidden_step(n, l);
                 mbar_wait_wd(bar_xfull + 8 * s, (uint32_t)((n >> 1) & 1));
                 tc_fence_after();
                 int blk = 0;
                 last_block(blk++, sbase + p.smem_x[s]);
-                if (n + 1 < T) {
-                    for (int l = 1; l <= n_hidden; ++l) {         // next tile's hidden GEMMs ride between the blocks
-                        hidden_step(l);
-                        if (blk < nblk && l < n_hidden) last_block(blk++, sbase + p.smem_x[s]);
-                    }
-                }
+                if (!early && n_hidden >= 1 && n + 1 < T) hidden_step(n + 1, 1);
                 while (blk < nblk) last_block(blk++, sbase + p.smem_x[s]);
                 if (leader) tc_commit(bar_xempty + 8 * s);        // X[s] may be overwritten once these MMAs are done
                 __syncwarp();
@@ -315,8 +330,9 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
         // =========================== front end ===========================
         float *w0s = reinterpret_cast<float *>(smem + p.smem_w0);
         const int c1 = p.c[1];
+        // layer-0 weights per channel PAIR (2k, 2k+1): (wx,wx', wy,wy' | wz,wz', b,b') -- FFMA2 operands
         for (int e = tid; e < c1 * 4; e += kFeThreads) {
-            const int o = e >> 2, k = e & 3;
+            const int pr = e >> 3, j = e & 7, o = 2 * pr + (j & 1), k = j >> 1;
             w0s[e] = (k < 3) ? __ldg(p.w0 + o * 3 + k) : __ldg(p.b0 + o);
         }
         for (int l = 1; l < L - 1; ++l) {
@@ -325,108 +341,133 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kFeThreads) : "memory");
         const int row = (warp & 3) * 32 + lane;                        // point of the tile == TMEM lane
+        const uint32_t row_off = (uint32_t)row * 128u, row_x = (uint32_t)(row & 7);   // swizzled store address parts
         const int half = warp >> 2;                                    // which half of the channels this thread does
         const uint32_t lane_base = ((uint32_t)(warp & 3) * 32u) << 16; // this warp's TMEM lane quarter
-        uint32_t h_ph = 0;
-        int n = 0;
-        // coordinates of the first tile's point; every later tile's are fetched one tile ahead
-        float px = 0.f, py = 0.f, pz = 0.f;
-        if (cta_in_group < n_tasks) {
-            const int b = cta_in_group / p.n_pchunks, pc = cta_in_group - b * p.n_pchunks;
-            const int pt = min(pc * p.tiles_per_chunk * kTileP + row, N - 1);
-            const float *src = x + ((size_t)b * N + pt) * 3;
-            px = __ldg(src); py = __ldg(src + 1); pz = __ldg(src + 2);
-        }
-        for (int task = cta_in_group; task < n_tasks; task += ctas_per_group) {
-            const int b = task / p.n_pchunks, pc = task - b * p.n_pchunks;
-            for (int t = 0; t < p.tiles_per_chunk; ++t) {
-                const int n0 = (pc * p.tiles_per_chunk + t) * kTileP;
-                if (n0 >= N) break;
-                const int s = n & 1;
-                const uint32_t xempty_par = (uint32_t)(((n >> 1) & 1) ^ 1);
-                // prefetch the next tile's point (same task, or the first tile of this CTA's next task)
-                float qx = 0.f, qy = 0.f, qz = 0.f;
-                {
-                    int nb = b, nn0 = n0 + kTileP;
-                    bool have = (t + 1 < p.tiles_per_chunk) && (nn0 < N);
-                    if (!have && task + ctas_per_group < n_tasks) {
-                        const int nt = task + ctas_per_group;
-                        nb = nt / p.n_pchunks;
-                        nn0 = (nt - nb * p.n_pchunks) * p.tiles_per_chunk * kTileP;
-                        have = true;
-                    }
-                    if (have) {
-                        const float *src = x + ((size_t)nb * N + min(nn0 + row, N - 1)) * 3;
-                        qx = __ldg(src); qy = __ldg(src + 1); qz = __ldg(src + 2);
-                    }
-                }
-                // ---- layer 0 on CUDA cores; rows past the end repeat the last valid point (the max is unaffected)
-                {
-                    if (n_hidden == 0) mbar_wait_wd(bar_xempty + 8 * s, xempty_par);
-                    unsigned char *dst = smem + (n_hidden == 0 ? p.smem_x[s] : p.smem_act[0]);
-                    const int k8n = c1 / 16;                           // 16-byte chunks (8 channels) per thread
-#pragma unroll 2
-                    for (int kk = 0; kk < k8n; ++kk) {
-                        const int k8 = half * k8n + kk;
-                        uint32_t pk[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float v[2];
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                const float4 w = *reinterpret_cast<const float4 *>(w0s + (k8 * 8 + q * 2 + h) * 4);
-                                v[h] = fmaxf(fmaf(w.x, px, fmaf(w.y, py, fmaf(w.z, pz, w.w))), 0.0f);
-                            }
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[0], v[1]);
-                            pk[q] = *reinterpret_cast<uint32_t *>(&h2);
-                        }
-                        *reinterpret_cast<uint4 *>(dst + sw128_chunk_off(kTileP, row, k8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    }
-                    fence_async_proxy();
-                    mbar_arrive(n_hidden == 0 ? bar_xfull + 8 * s : bar_fe);
-                }
-                // ---- hidden layers: accumulator H (points on the TMEM lanes) -> bias + ReLU -> bf16 operand tile
-                for (int l = 1; l <= n_hidden; ++l) {
-                    const int cout = p.c[l + 1];
-                    const int ncol = cout >> 1, col0 = half * ncol;    // this thread's channels: 32 or 64 of them
-                    const bool last_hidden = (l == n_hidden);
-                    mbar_wait_wd(bar_h, h_ph);
-                    h_ph ^= 1;
-                    tc_fence_after();
-                    if (last_hidden) mbar_wait_wd(bar_xempty + 8 * s, xempty_par);
-                    const float *bs = reinterpret_cast<const float *>(smem + p.smem_bias[l]) + col0;
-                    unsigned char *dst = smem + (last_hidden ? p.smem_x[s] : ((l & 1) ? p.smem_act[1] : p.smem_act[0]));
-                    float v[64];
-                    if (ncol == 64) {
-                        tc_ld64(tmem + lane_base + kColH + col0, v);
-                    } else {
-                        float v32[32];
-                        tc_ld32(tmem + lane_base + kColH + col0, v32);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = v32[i];
-                    }
-#pragma unroll
-                    for (int q8 = 0; q8 < 8; ++q8) {
-                        if (q8 * 8 < ncol) {
-                            uint32_t pk[4];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const int ch = q8 * 8 + q * 2;
-                                const float a = fmaxf(v[ch] + bs[ch], 0.0f), bb = fmaxf(v[ch + 1] + bs[ch + 1], 0.0f);
-                                __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
-                                pk[q] = *reinterpret_cast<uint32_t *>(&h2);
-                            }
-                            *reinterpret_cast<uint4 *>(dst + sw128_chunk_off(kTileP, row, (col0 >> 3) + q8)) =
-                                make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        }
-                    }
-                    fence_async_proxy();
-                    tc_fence_before();
-                    mbar_arrive(last_hidden ? bar_xfull + 8 * s : bar_fe);
-                }
-                px = qx; py = qy; pz = qz;
-                ++n;
+        uint32_t h_ph[2] = {0, 0};
+
+        // tile cursor with one tile of look-ahead
+        struct Cursor { int task, t, b, n0; bool valid; };
+        auto first = [&]() {
+            Cursor c{cta_in_group, 0, 0, 0, cta_in_group < n_tasks};
+            if (c.valid) { c.b = c.task / p.n_pchunks; c.n0 = (c.task - c.b * p.n_pchunks) * p.tiles_per_chunk * kTileP; }
+            return c;
+        };
+        auto advance = [&](Cursor c) {
+            ++c.t;
+            c.n0 += kTileP;
+            if (c.t >= p.tiles_per_chunk || c.n0 >= N) {
+                c.task += ctas_per_group;
+                c.t = 0;
+                c.valid = c.task < n_tasks;
+                if (c.valid) { c.b = c.task / p.n_pchunks; c.n0 = (c.task - c.b * p.n_pchunks) * p.tiles_per_chunk * kTileP; }
             }
+            return c;
+        };
+        auto load_point = [&](const Cursor &c, float &ox, float &oy, float &oz) {
+            const float *src = x + ((size_t)c.b * N + min(c.n0 + row, N - 1)) * 3;    // rows past the end repeat the last
+            // volatile: keeps the loads where they are written (one tile ahead of their use)
+            asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(ox) : "l"(src));
+            asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(oy) : "l"(src + 1));
+            asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(oz) : "l"(src + 2));
+        };
+        // 16-byte chunk k8 (8 channels) of this thread's row in a [128 x K] K-major SW128 tile
+        auto chunk_ptr = [&](unsigned char *tile, int k8) {
+            return reinterpret_cast<uint4 *>(tile + (uint32_t)(k8 >> 3) * (kTileP * 128u) + row_off +
+                                             ((((uint32_t)k8 & 7u) ^ row_x) << 4));
+        };
+        // layer 0 on the CUDA cores for this thread's point and half of the channels -> bf16 operand tile.
+        // Packed FFMA2: two channels per instruction (same IEEE fma per lane as the scalar form).
+        auto layer0 = [&](float px, float py, float pz, unsigned char *dst) {
+            const u64 px2 = pack2(px, px), py2 = pack2(py, py), pz2 = pack2(pz, pz);
+            const int k8n = c1 / 16;                                   // 16-byte chunks (8 channels) per thread
+#pragma unroll 2
+            for (int kk = 0; kk < k8n; ++kk) {
+                const int k8 = half * k8n + kk;
+                const ulonglong2 *wp = reinterpret_cast<const ulonglong2 *>(w0s) + k8 * 8;   // 4 pairs x 2 vectors
+                uint32_t pk[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const ulonglong2 wa = wp[2 * q], wb = wp[2 * q + 1];
+                    const u64 r = fma2(wa.x, px2, fma2(wa.y, py2, fma2(wb.x, pz2, wb.y)));
+                    float lo, hi;
+                    unpack2(r, lo, hi);
+                    pk[q] = relu_pack_bf16(lo, hi);
+                }
+                *chunk_ptr(dst, k8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            fence_async_proxy();
+        };
+        // epilogue of hidden layer l of tile n: H[n & 1] -> bias + ReLU -> bf16 -> dst (NCOL = 32 or 64 channels)
+        auto epilogue_cols = [&](auto ncol_tag, int n, int l, unsigned char *dst) {
+            constexpr int NCOL = decltype(ncol_tag)::value;
+            const int col0 = half * NCOL;
+            const ulonglong2 *bs = reinterpret_cast<const ulonglong2 *>(reinterpret_cast<const float *>(smem + p.smem_bias[l]) + col0);
+            const uint32_t taddr = tmem + lane_base + kColH + (uint32_t)(n & 1) * 128u + (uint32_t)col0;
+            float v[NCOL];
+            if constexpr (NCOL == 64) tc_ld64(taddr, v); else tc_ld32(taddr, v);
+#pragma unroll
+            for (int q8 = 0; q8 < NCOL / 8; ++q8) {
+                const ulonglong2 b0 = bs[2 * q8], b1 = bs[2 * q8 + 1];        // 8 biases as 4 pairs
+                const u64 s0 = add2(pack2(v[8 * q8], v[8 * q8 + 1]), b0.x), s1 = add2(pack2(v[8 * q8 + 2], v[8 * q8 + 3]), b0.y);
+                const u64 s2 = add2(pack2(v[8 * q8 + 4], v[8 * q8 + 5]), b1.x), s3 = add2(pack2(v[8 * q8 + 6], v[8 * q8 + 7]), b1.y);
+                float a0, a1, a2, a3, a4, a5, a6, a7;
+                unpack2(s0, a0, a1); unpack2(s1, a2, a3); unpack2(s2, a4, a5); unpack2(s3, a6, a7);
+                *chunk_ptr(dst, (col0 >> 3) + q8) = make_uint4(relu_pack_bf16(a0, a1), relu_pack_bf16(a2, a3),
+                                                               relu_pack_bf16(a4, a5), relu_pack_bf16(a6, a7));
+            }
+            fence_async_proxy();
+            tc_fence_before();
+        };
+        auto hidden_epilogue = [&](int n, int l, unsigned char *dst) {
+            if (p.c[l + 1] == 128) epilogue_cols(std::integral_constant<int, 64>{}, n, l, dst);
+            else epilogue_cols(std::integral_constant<int, 32>{}, n, l, dst);
+        };
+
+        Cursor cur = first();
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (cur.valid) load_point(cur, px, py, pz);
+        if (n_hidden >= 1 && cur.valid) {                              // prologue: layer 0 of the first tile
+            layer0(px, py, pz, smem + p.smem_act[0]);
+            mbar_arrive(bar_fe);
+        }
+        for (int n = 0; cur.valid; ++n) {
+            const int s = n & 1;
+            const uint32_t xempty_par = (uint32_t)(((n >> 1) & 1) ^ 1);
+            const Cursor nxt = advance(cur);
+            float qx = 0.f, qy = 0.f, qz = 0.f;
+            if (nxt.valid) load_point(nxt, qx, qy, qz);                // next tile's point, one tile ahead
+            if (n_hidden == 0) {
+                mbar_wait_wd(bar_xempty + 8 * s, xempty_par);
+                layer0(px, py, pz, smem + p.smem_x[s]);
+                mbar_arrive(bar_xfull + 8 * s);
+            } else {
+                // hidden GEMM 1 of this tile is done: H[s] holds it and the layer-0 tile A0 is free again
+                mbar_wait_wd(bar_h + 8 * s, s ? h_ph[1] : h_ph[0]);
+                if (s) h_ph[1] ^= 1; else h_ph[0] ^= 1;
+                tc_fence_after();
+                if (early && nxt.valid) {
+                    layer0(qx, qy, qz, smem + p.smem_act[0]);
+                    mbar_arrive(bar_fe + 8 * (s ^ 1));
+                }
+                for (int l = 1; l <= n_hidden; ++l) {
+                    const bool last_hidden = (l == n_hidden);
+                    if (l > 1) {
+                        mbar_wait_wd(bar_h + 8 * s, s ? h_ph[1] : h_ph[0]);
+                        if (s) h_ph[1] ^= 1; else h_ph[0] ^= 1;
+                        tc_fence_after();
+                    }
+                    if (last_hidden) mbar_wait_wd(bar_xempty + 8 * s, xempty_par);
+                    hidden_epilogue(n, l, smem + (last_hidden ? p.smem_x[s] : ((l & 1) ? p.smem_act[1] : p.smem_act[0])));
+                    mbar_arrive(last_hidden ? bar_xfull + 8 * s : bar_fe + 8 * s);
+                }
+                if (!early && nxt.valid) {
+                    layer0(qx, qy, qz, smem + p.smem_act[0]);
+                    mbar_arrive(bar_fe + 8 * (s ^ 1));
+                }
+            }
+            px = qx; py = qy; pz = qz;
+            cur = nxt;
         }
     } else {
         // =========================== last-layer epilogue ===========================
