@@ -177,15 +177,20 @@ __device__ __forceinline__ void issue_gemm_uniform(bool leader, uint32_t d_tmem,
 //   warps 0-7   FE   two threads per point of the 128-point tile (each half of the channels): layer 0 on the CUDA
 //                    cores, then the bias+ReLU+bf16 epilogue of every hidden layer (TMEM -> registers -> swizzled
 //                    operand tile of the next GEMM)
-//   warp  8     MMA  one elected thread issues every tcgen05.mma; owns the TMEM allocation and the weight TMA loads
+//   warps 8,17  MMA  two issuers, one elected thread each.  A tcgen05.mma blocks its issuing thread until the tensor
+//                    pipe takes it (measured with tools/umma_bench.cu: the queue is about one instruction deep, so every
+//                    cycle the issuer spends on barrier waits, fences and commits is a tensor-pipe bubble).  Two issuers
+//                    alternate last-layer blocks -- each owns one TMEM accumulator -- so one's bookkeeping runs under
+//                    the other's MMAs.  Warp 8 also owns the TMEM allocation, the weight TMA loads and the hidden GEMMs.
 //   warps 9-16  EP   last-layer epilogue: tcgen05.ld of a 128-channel x 128-point accumulator (two warps per TMEM lane
 //                    quarter, 64 columns each), running max per channel
 // Hand-offs are mbarriers; the MMA thread interleaves the hidden GEMM of tile n+1 between the last-layer blocks of
 // tile n, so the front end of the next tile runs under the tensor-core time of the current one.
 //   TMEM columns: [0,256) two hidden accumulators H[tile parity], [256,512) two last-layer accumulators.
 static constexpr int kFeThreads = 256, kEpThreads = 256;
-static constexpr int kMmaWarp = kFeThreads / 32;
-static constexpr int kTcThreads2 = kFeThreads + 32 + kEpThreads;
+static constexpr int kMmaWarp = kFeThreads / 32;                        // issuer A (+ TMEM owner, weight loads, hidden GEMMs)
+static constexpr int kMmaWarpB = (kFeThreads + 32 + kEpThreads) / 32;   // issuer B: the last warp
+static constexpr int kTcThreads2 = kFeThreads + 32 + kEpThreads + 32;
 static constexpr int kAccBufs = 2;
 static constexpr uint32_t kColH = 0, kColAcc = 256;      // H[2] at columns 0 / 128, accumulators at 256 / 384
 
@@ -239,7 +244,7 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
         mbar_init(bar_w, 1);
         for (int k = 0; k < 2; ++k) {
             mbar_init(bar_fe + 8 * k, kFeThreads); mbar_init(bar_h + 8 * k, 1);
-            mbar_init(bar_xfull + 8 * k, kFeThreads); mbar_init(bar_xempty + 8 * k, 1);
+            mbar_init(bar_xfull + 8 * k, kFeThreads); mbar_init(bar_xempty + 8 * k, 2);   // both issuers commit
             mbar_init(bar_accfull + 8 * k, 1); mbar_init(bar_accempty + 8 * k, kEpThreads);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -262,12 +267,13 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
             if ((pc * p.tiles_per_chunk + t) * kTileP < N) ++T;
     }
 
-    if (warp == kMmaWarp) {
-        // =========================== MMA issuer ===========================
+    if (warp == kMmaWarp || warp == kMmaWarpB) {
+        // =========================== MMA issuers ===========================
         // All 32 lanes run this (warp-uniform) code; one elected lane issues the tcgen05 instructions.
+        const int me = (warp == kMmaWarp) ? 0 : 1;
         if (T > 0) {
             const bool leader = elect_one();
-            if (leader) {
+            if (me == 0 && leader) {
                 // resident weights: one TMA bulk load per layer (the last layer: this CTA's channel slice)
                 uint32_t total = 0;
                 for (int l = 1; l < L - 1; ++l) total += (uint32_t)p.c[l + 1] * p.c[l] * 2;
@@ -288,9 +294,9 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
             __syncwarp();
             mbar_wait_wd(bar_w, 0);
             uint32_t fe_ph[2] = {0, 0};
-            int kb = 0;                                           // running last-layer block counter -> accumulator ring
+            int kb = 0;                                           // running last-layer block counter (both issuers count)
             const uint32_t wl = sbase + p.smem_w[L - 1];
-            auto hidden_step = [&](int n, int l) {                // hidden GEMM l of tile n into H[n & 1]
+            auto hidden_step = [&](int n, int l) {                // hidden GEMM l of tile n into H[n & 1]  (issuer A)
                 const int par = n & 1;
                 mbar_wait_wd(bar_fe + 8 * par, par ? fe_ph[1] : fe_ph[0]);
                 if (par) fe_ph[1] ^= 1; else fe_ph[0] ^= 1;
@@ -301,28 +307,33 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
                 if (leader) tc_commit(bar_h + 8 * par);
                 __syncwarp();
             };
+            // block kb goes to accumulator kb & 1, which belongs to issuer kb & 1
             auto last_block = [&](int blk, uint32_t act) {
-                const int a = kb % kAccBufs, use = kb / kAccBufs;
-                mbar_wait_wd(bar_accempty + 8 * a, (uint32_t)((use & 1) ^ 1));
-                tc_fence_after();
-                issue_gemm_uniform(leader, tmem + kColAcc + (uint32_t)a * 128u, wl + (uint32_t)blk * 128 * k_last * 2, 128,
-                                   act, kTileP, 128, kTileP, k_last);
-                if (leader) tc_commit(bar_accfull + 8 * a);
-                __syncwarp();
+                const int a = kb & 1, use = kb >> 1;
+                if (a == me) {
+                    mbar_wait_wd(bar_accempty + 8 * a, (uint32_t)((use & 1) ^ 1));
+                    tc_fence_after();
+                    issue_gemm_uniform(leader, tmem + kColAcc + (uint32_t)a * 128u, wl + (uint32_t)blk * 128 * k_last * 2, 128,
+                                       act, kTileP, 128, kTileP, k_last);
+                    if (leader) tc_commit(bar_accfull + 8 * a);
+                    __syncwarp();
+                }
                 ++kb;
             };
-            if (n_hidden >= 1) hidden_step(0, 1);                 // prologue: first hidden GEMM of the first tile
+            if (me == 0 && n_hidden >= 1) hidden_step(0, 1);      // prologue: first hidden GEMM of the first tile
             for (int n = 0; n < T; ++n) {
                 const int s = n & 1;
-                if (early && n + 1 < T) hidden_step(n + 1, 1);    // runs under the front end's epilogue of tile n
-                for (int l = 2; l <= n_hidden; ++l) hidden_step(n, l);
+                if (me == 0) {
+                    if (early && n + 1 < T) hidden_step(n + 1, 1);    // runs under the front end's epilogue of tile n
+                    for (int l = 2; l <= n_hidden; ++l) hidden_step(n, l);
+                }
                 mbar_wait_wd(bar_xfull + 8 * s, (uint32_t)((n >> 1) & 1));
                 tc_fence_after();
                 int blk = 0;
                 last_block(blk++, sbase + p.smem_x[s]);
-                if (!early && n_hidden >= 1 && n + 1 < T) hidden_step(n + 1, 1);
+                if (me == 0 && !early && n_hidden >= 1 && n + 1 < T) hidden_step(n + 1, 1);
                 while (blk < nblk) last_block(blk++, sbase + p.smem_x[s]);
-                if (leader) tc_commit(bar_xempty + 8 * s);        // X[s] may be overwritten once these MMAs are done
+                if (leader) tc_commit(bar_xempty + 8 * s);        // X[s] may be overwritten once BOTH issuers' MMAs are done
                 __syncwarp();
             }
         }
