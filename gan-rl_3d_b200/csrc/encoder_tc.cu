@@ -186,13 +186,14 @@ __device__ __forceinline__ void issue_gemm_uniform(bool leader, uint32_t d_tmem,
 //                    quarter, 64 columns each), running max per channel
 // Hand-offs are mbarriers; the MMA thread interleaves the hidden GEMM of tile n+1 between the last-layer blocks of
 // tile n, so the front end of the next tile runs under the tensor-core time of the current one.
-//   TMEM columns: [0,256) two hidden accumulators H[tile parity], [256,512) two last-layer accumulators.
+//   TMEM columns: [0,128) the hidden accumulator H, [128,512) three last-layer accumulators (a ring shared by the two
+//   issuers: block kb goes to accumulator kb % 3 and is issued by issuer kb % 2).
 static constexpr int kFeThreads = 256, kEpThreads = 256;
 static constexpr int kMmaWarp = kFeThreads / 32;                        // issuer A (+ TMEM owner, weight loads, hidden GEMMs)
 static constexpr int kMmaWarpB = (kFeThreads + 32 + kEpThreads) / 32;   // issuer B: the last warp
 static constexpr int kTcThreads2 = kFeThreads + 32 + kEpThreads + 32;
-static constexpr int kAccBufs = 2;
-static constexpr uint32_t kColH = 0, kColAcc = 256;      // H[2] at columns 0 / 128, accumulators at 256 / 384
+static constexpr int kAccBufs = 3;
+static constexpr uint32_t kColH = 0, kColAcc = 128;      // H at columns [0,128), three accumulators at 128 / 256 / 384
 
 // two fp32 -> packed bf16x2 with ReLU folded into the conversion (round-to-nearest-even, negative -> +0): the same
 // bits as fmaxf(.,0) followed by the conversion, in one instruction per pair
@@ -228,16 +229,17 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
     // every pair below is indexed by tile parity (n & 1) resp. accumulator buffer
     const uint32_t bar_w = bars, bar_fe = bars + 8, bar_h = bars + 24;
     const uint32_t bar_xfull = bars + 40, bar_xempty = bars + 56;
-    const uint32_t bar_accfull = bars + 72, bar_accempty = bars + 88;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + p.smem_bar + 104);
+    const uint32_t bar_accfull = bars + 72, bar_accempty = bars + 96;           // [3] each
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + p.smem_bar + 120);
     const int L = p.L, c_last = p.c[L], k_last = p.c[L - 1];
     const int g = blockIdx.x % p.split, cta_in_group = blockIdx.x / p.split, ctas_per_group = gridDim.x / p.split;
     const int blk0 = g * p.nblk;
     const int nblk = min(p.nblk, c_last / 128 - blk0);
     const int n_tasks = (nblk > 0) ? B * p.n_pchunks : 0;
     const int n_hidden = L - 2;                                                 // tensor-core layers before the last
-    // With <= 2 hidden layers the front end computes layer 0 of tile n+1 BEFORE the epilogue of tile n, so the hidden
-    // GEMM of tile n+1 runs under that epilogue (deeper chains would overwrite a live operand tile: plain order).
+    // With <= 2 hidden layers the front end computes layer 0 of tile n+1 BEFORE the epilogue of tile n (the layer-0 tile
+    // is free once the first hidden GEMM of tile n is done), so issuer A can start the next tile's hidden GEMM the
+    // moment this tile's epilogue has drained H.  Deeper chains would overwrite a live operand tile: plain order.
     const bool early = n_hidden >= 1 && n_hidden <= 2;
 
     if (tid == 0) {
@@ -245,8 +247,8 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
         for (int k = 0; k < 2; ++k) {
             mbar_init(bar_fe + 8 * k, kFeThreads); mbar_init(bar_h + 8 * k, 1);
             mbar_init(bar_xfull + 8 * k, kFeThreads); mbar_init(bar_xempty + 8 * k, 2);   // both issuers commit
-            mbar_init(bar_accfull + 8 * k, 1); mbar_init(bar_accempty + 8 * k, kEpThreads);
         }
+        for (int k = 0; k < kAccBufs; ++k) { mbar_init(bar_accfull + 8 * k, 1); mbar_init(bar_accempty + 8 * k, kEpThreads); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) {
@@ -302,15 +304,14 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
                 if (par) fe_ph[1] ^= 1; else fe_ph[0] ^= 1;
                 tc_fence_after();
                 const uint32_t in = sbase + (((l - 1) & 1) ? p.smem_act[1] : p.smem_act[0]);
-                issue_gemm_uniform(leader, tmem + kColH + (uint32_t)par * 128u, in, kTileP, sbase + p.smem_w[l], p.c[l + 1],
-                                   kTileP, p.c[l + 1], p.c[l]);
+                issue_gemm_uniform(leader, tmem + kColH, in, kTileP, sbase + p.smem_w[l], p.c[l + 1], kTileP, p.c[l + 1], p.c[l]);
                 if (leader) tc_commit(bar_h + 8 * par);
                 __syncwarp();
             };
-            // block kb goes to accumulator kb & 1, which belongs to issuer kb & 1
+            // block kb goes to accumulator kb % 3 and is issued by issuer kb & 1
             auto last_block = [&](int blk, uint32_t act) {
-                const int a = kb & 1, use = kb >> 1;
-                if (a == me) {
+                const int a = kb % kAccBufs, use = kb / kAccBufs;
+                if ((kb & 1) == me) {
                     mbar_wait_wd(bar_accempty + 8 * a, (uint32_t)((use & 1) ^ 1));
                     tc_fence_after();
                     issue_gemm_uniform(leader, tmem + kColAcc + (uint32_t)a * 128u, wl + (uint32_t)blk * 128 * k_last * 2, 128,
@@ -323,16 +324,13 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
             if (me == 0 && n_hidden >= 1) hidden_step(0, 1);      // prologue: first hidden GEMM of the first tile
             for (int n = 0; n < T; ++n) {
                 const int s = n & 1;
-                if (me == 0) {
-                    if (early && n + 1 < T) hidden_step(n + 1, 1);    // runs under the front end's epilogue of tile n
+                if (me == 0)
                     for (int l = 2; l <= n_hidden; ++l) hidden_step(n, l);
-                }
-                mbar_wait_wd(bar_xfull + 8 * s, (uint32_t)((n >> 1) & 1));
+                mbar_wait_wd(bar_xfull + 8 * s, (uint32_t)((n >> 1) & 1));    // X[s] is ready, and H has been drained
                 tc_fence_after();
-                int blk = 0;
-                last_block(blk++, sbase + p.smem_x[s]);
-                if (me == 0 && !early && n_hidden >= 1 && n + 1 < T) hidden_step(n + 1, 1);
-                while (blk < nblk) last_block(blk++, sbase + p.smem_x[s]);
+                // first hidden GEMM of the next tile ahead of this tile's blocks: the front end gets H back early
+                if (me == 0 && n_hidden >= 1 && n + 1 < T) hidden_step(n + 1, 1);
+                for (int blk = 0; blk < nblk; ++blk) last_block(blk, sbase + p.smem_x[s]);
                 if (leader) tc_commit(bar_xempty + 8 * s);        // X[s] may be overwritten once BOTH issuers' MMAs are done
                 __syncwarp();
             }
@@ -414,7 +412,7 @@ __global__ void __launch_bounds__(kTcThreads2, 1) encoder_tc_kernel(const float 
             constexpr int NCOL = decltype(ncol_tag)::value;
             const int col0 = half * NCOL;
             const ulonglong2 *bs = reinterpret_cast<const ulonglong2 *>(reinterpret_cast<const float *>(smem + p.smem_bias[l]) + col0);
-            const uint32_t taddr = tmem + lane_base + kColH + (uint32_t)(n & 1) * 128u + (uint32_t)col0;
+            const uint32_t taddr = tmem + lane_base + kColH + (uint32_t)col0;
             float v[NCOL];
             if constexpr (NCOL == 64) tc_ld64(taddr, v); else tc_ld32(taddr, v);
 #pragma unroll

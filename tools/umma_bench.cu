@@ -258,6 +258,110 @@ __global__ void __launch_bounds__(128, 1) k_tmem_read(int iters, long long *cycl
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(slot), "r"(512) : "memory");
 }
 
+
+// Handshake with warp-uniform issue: NI issuer warps (elect.sync), 4 epilogue warps (tcgen05.ld x64 x2 per block), nacc
+// accumulators; block g goes to accumulator g % nacc and is issued by issuer (g % nacc) % NI.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+template <int NI, bool LOADS>
+__global__ void __launch_bounds__(128 + 32 * NI, 1) k_pipe(int nacc, int groups, long long *cycles_out) {
+    extern __shared__ unsigned char raw[];
+    const uint32_t pad = (1024u - (smem_u32(raw) & 1023u)) & 1023u;
+    unsigned char *smem = raw + pad;
+    const uint32_t sA = smem_u32(smem), sB = sA + 32768;
+    __shared__ uint64_t full[4], empty[4];
+    __shared__ uint32_t slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int e = tid; e < (32768 + 65536) / 4; e += 128 + 32 * NI) reinterpret_cast<uint32_t *>(smem)[e] = 0;
+    if (tid == 0) {
+        for (int k = 0; k < 4; ++k) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&full[k])), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&empty[k])), "r"(128));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = slot;
+    if (warp >= 4) {
+        const int me = warp - 4;
+        const bool leader = elect_one();
+        const uint32_t idesc = umma_idesc(128, 128);
+        const long long t0 = clock64();
+        for (int g = 0; g < groups; ++g) {
+            const int a = g % nacc, use = g / nacc;
+            if (a % NI != me) continue;
+            bar_wait(smem_u32(&empty[a]), (uint32_t)((use & 1) ^ 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d = tmem + (uint32_t)(a * 128);
+            uint64_t ad = umma_desc(sA), bd = umma_desc(sB);
+            uint32_t acc = 0;
+            for (int kb = 0; kb < 2; ++kb) {
+                if (leader) {
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) { mma_ss(d, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), idesc, acc); acc = 1; }
+                }
+                acc = 1;
+                ad += (128 * 128) >> 4;
+                bd += (128 * 128) >> 4;
+            }
+            if (leader) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&full[a])) : "memory");
+            __syncwarp();
+        }
+        if (me == 0) {
+            for (int a = 0; a < nacc; ++a) {          // drain: every accumulator's last use released
+                int last = -1;
+                for (int g = groups - 1; g >= 0; --g) if (g % nacc == a) { last = g; break; }
+                if (last >= 0) bar_wait(smem_u32(&empty[a]), (uint32_t)((last / nacc) & 1));
+            }
+            const long long t1 = clock64();
+            if (blockIdx.x == 0 && leader) *cycles_out = t1 - t0;
+        }
+    } else {
+        const uint32_t lane_base = ((uint32_t)warp * 32u) << 16;
+        float keep = 0.f;
+        for (int g = 0; g < groups; ++g) {
+            const int a = g % nacc, use = g / nacc;
+            bar_wait(smem_u32(&full[a]), (uint32_t)(use & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (LOADS) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t r[64];
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+                                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+                                 "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];\n\t"
+                                 "tcgen05.wait::ld.sync.aligned;"
+                                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+                                   "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+                                   "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+                                   "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]),
+                                   "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]),
+                                   "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+                                 : "r"(tmem + lane_base + (uint32_t)(a * 128 + h * 64)) : "memory");
+                    keep += __uint_as_float(r[0]) + __uint_as_float(r[63]);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[a])) : "memory");
+        }
+        if (keep == 123.456f) cycles_out[1] = 1;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
 int main() {
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
@@ -307,6 +411,22 @@ int main() {
         run(k_umma<false, 256>, "256 cyc");
         run(k_umma<false, 384>, "384 cyc");
         run(k_umma<false, 512>, "512 cyc");
+    }
+    {
+        auto runp = [&](auto kern, int threads, int nacc, const char *name) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            for (int rep = 0; rep < 2; ++rep) { kern<<<sms, threads, smem>>>(nacc, 4000, d_cyc); cudaDeviceSynchronize(); }
+            long long cyc = 0; cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost);
+            cudaError_t e = cudaGetLastError();
+            printf("pipe %-28s nacc=%d : %7.1f cycles per 128x128x128 block (512 = MMA bound) %s\n", name, nacc, (double)cyc / 4000.0,
+                   e == cudaSuccess ? "" : cudaGetErrorString(e));
+        };
+        for (int nacc : {2, 3, 4}) {
+            runp(k_pipe<1, false>, 160, nacc, "1 issuer, no TMEM loads");
+            runp(k_pipe<1, true>, 160, nacc, "1 issuer, ld x64 x2");
+            runp(k_pipe<2, false>, 192, nacc, "2 issuers, no TMEM loads");
+            runp(k_pipe<2, true>, 192, nacc, "2 issuers, ld x64 x2");
+        }
     }
     for (int shape = 0; shape < 2; ++shape) {
         const int iters = 2000;
