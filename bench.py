@@ -206,7 +206,7 @@ def run_ours(args):
     loss_buf = torch.zeros(1, device=dev)
 
     # The timed loop: `loss = ChamferLoss()(pred, target); loss.backward()` per batch, captured S steps at a time
-    # in a CUDA graph (the loop is launch-bound from Python: ~60 us of GPU work per step in 4 kernels).
+    # in a CUDA graph (the loop is launch-bound from Python: ~55 us of GPU work per step in 3 kernels).
     full = P.ChamferStepGraph(ring)                                   # S = slots steps per replay
     n_full, rem = divmod(K, slots)
     tail = P.ChamferStepGraph(ring[:rem]) if rem else None
@@ -302,11 +302,13 @@ def run_ours(args):
 
     peak = (ctypes_float6(lib, dev))
     fp32_theory = peak[2]
-    roofline = {"bound": "fp32", "kernel": "chamfer_tile_kernel<8>", "achieved": achieved_tflops, "peak": fp32_theory,
+    roofline = {"bound": "fp32", "kernel": "chamfer_filter_kernel<16>", "achieved": achieved_tflops, "peak": fp32_theory,
                 "unit": "TFLOP/s", "frac": achieved_tflops / fp32_theory, "traffic": None,
                 "peak_source": f"theoretical FP32 FMA: {int(peak[3])} SMs x 128 lanes x 2 flop x {peak[1]:.0f} MHz "
                                "(MEASURED_PEAKS.json has no FP32 entry; north_star names the FFMA peak)",
-                "peak_measured_ffma": peak[0], "peak_measured_ffma2": peak[4], "mix_ceiling_tflops": peak[5],
+                "peak_measured_ffma": peak[0], "peak_measured_ffma2": peak[4],
+                "fp32_pipe_ops_per_pair": 4, "note": "algorithmic 8 flop per pair; the filter spends 4 FP32-pipe operations "
+                "(3 FFMA + 1 FADD) per pair, the exact direct form (6) only on candidates within the rounding margin",
                 "frac_of_measured_ffma": achieved_tflops / peak[0] if peak[0] else None,
                 "launch_us": tile_ms * 1e3, "algorithmic_flop_per_launch": FLOP_PER_PAIR * B}
 
@@ -322,10 +324,11 @@ def run_ours(args):
     torch.cuda.synchronize()
     bwd_ms = e0.elapsed_time(e1) / reps
     bwd_gbs = BWD_BYTES_PER_PAIR * B / (bwd_ms * 1e-3) / 1e9
-    roofline_bwd = {"bound": "hbm", "kernel": "chamfer_bwd_own_kernel+chamfer_bwd_scatter_kernel", "achieved": bwd_gbs,
+    roofline_bwd = {"bound": "hbm", "kernel": "memset x2 + chamfer_bwd_kernel (stand-alone call; inside a training step the "
+                    "forward zero-fills and the backward is the single kernel)", "achieved": bwd_gbs,
                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": bwd_gbs / peaks["hbm_gbs"], "traffic": None,
                     "peak_source": f"{peaks_src} MEASURED_PEAKS.json hbm_gbs", "launch_us": bwd_ms * 1e3,
-                    "note": "7.3 MB per call: launch-latency bound at this shape"}
+                    "note": "7.3 MB per call: launch-latency bound at this shape; timed through Python (ctypes) calls"}
 
     extra = {}
     if not args.no_encoder:
