@@ -303,7 +303,8 @@ def run_ours(args):
     peak = (ctypes_float6(lib, dev))
     fp32_theory = peak[2]
     roofline = {"bound": "fp32", "kernel": "chamfer_filter_kernel<16>", "achieved": achieved_tflops, "peak": fp32_theory,
-                "unit": "TFLOP/s", "frac": achieved_tflops / fp32_theory, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved_tflops / fp32_theory,
+                "traffic": 3174656,    # dram__bytes_read+write per launch, profiles/r1_chamfer_kernels_ncu.txt (ncu --set full)
                 "peak_source": f"theoretical FP32 FMA: {int(peak[3])} SMs x 128 lanes x 2 flop x {peak[1]:.0f} MHz "
                                "(MEASURED_PEAKS.json has no FP32 entry; north_star names the FFMA peak)",
                 "peak_measured_ffma": peak[0], "peak_measured_ffma2": peak[4],

@@ -82,9 +82,9 @@ def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = Tru
     i2 = torch.empty((B, M), dtype=torch.int32, device=dev)
     m1 = torch.empty((B,), dtype=torch.float32, device=dev) if want_means else None
     m2 = torch.empty((B,), dtype=torch.float32, device=dev) if want_means else None
-    loss = torch.zeros((), dtype=torch.float32, device=dev) if loss_weights is not None else None
+    loss = torch.empty((), dtype=torch.float32, device=dev) if loss_weights is not None else None   # fully written
     if B == 0:
-        return (d1, d2, i1, i2, m1, m2) if loss is None else (d1, d2, i1, i2, m1, m2, loss)
+        return (d1, d2, i1, i2, m1, m2) if loss is None else (d1, d2, i1, i2, m1, m2, loss.zero_())
     w1, w2 = loss_weights if loss_weights is not None else (0.0, 0.0)
     gz1, gz2 = zero_grads if zero_grads is not None else (None, None)
     with torch.cuda.device(dev):
