@@ -334,6 +334,7 @@ def run_ours(args):
     extra = {}
     if not args.no_encoder:
         extra.update(encoder_side_measurement(rlg, dev, peaks, peaks_src))
+        extra.update(reward_side_measurement(rlg, dev, fp32_theory))
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
@@ -458,6 +459,33 @@ def encoder_side_measurement(rlg, dev, peaks, peaks_src):
                         "fp32_path": {"value": ENC_B / (out["fp32"][0] * 1e-3), "unit": "clouds/s",
                                       "ms_per_step": out["fp32"][0], "tflops": out["fp32"][1],
                                       "path": "fp32 CUDA-core fused trunk (rlg_encoder_fwd)"}}}
+
+
+def reward_side_measurement(rlg, dev, fp32_peak):
+    """BASELINE configs[3]: reward evaluation for E=1024 episodes (decoder output vs complete cloud, N=M=2048) in one
+    batched forward-only pass (rlg.batched_rewards; the reference loops B=1 with a host sync per episode)."""
+    E, n = 1024, 2048
+    gen = torch.Generator(device="cpu").manual_seed(1234 + 4)
+    batches = []
+    for _ in range(3):                                   # 3 x 50 MB of clouds > L2
+        batches.append((sphere(gen, E, n).to(dev), sphere(gen, E, n).to(dev), torch.rand(E, 128, generator=gen).to(dev),
+                        torch.rand(E, 128, generator=gen).to(dev), torch.randn(E, 1, generator=gen).to(dev)))
+    for k in range(3):
+        rlg.batched_rewards(*batches[k])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 12
+    e0.record()
+    for k in range(reps):
+        r = rlg.batched_rewards(*batches[k % 3])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    tf = 8.0 * n * n * E / (ms * 1e-3) / 1e12
+    return {"reward_loop": {"metric": "reward_evals_per_s", "value": E / (ms * 1e-3), "unit": "episodes/s", "ms_per_step": ms,
+                            "config": {"workload": "RewardFunction for E=1024 episodes, Chamfer N=M=2048 forward only + GFV MSE + "
+                                                   "discriminator term (BASELINE configs[3])"},
+                            "chamfer_tflops": tf, "frac_of_fp32_peak": tf / fp32_peak, "last_reward_mean": float(r.mean().item())}}
 
 
 def main():

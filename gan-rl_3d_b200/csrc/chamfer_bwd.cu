@@ -52,6 +52,8 @@ __device__ __forceinline__ bool bwd_term(const BwdArgs &a, int dir, int b, int i
 static constexpr int kBwdThreads = 256;
 
 __global__ void __launch_bounds__(kBwdThreads) chamfer_bwd_kernel(BwdArgs a, int B) {
+    pdl_launch_dependents();
+    pdl_wait();                       // distances, indices and the upstream gradient come from the kernels before
     const int per_cloud = a.N + a.M;
     const long long t = (long long)blockIdx.x * kBwdThreads + threadIdx.x;
     const int b = (int)(t / per_cloud);
@@ -89,7 +91,8 @@ static int bwd_launch(const float *pc1, const float *pc2, const float *d1, const
     const long long total = (long long)B * ((long long)N + M);
     const long long blocks = (total + kBwdThreads - 1) / kBwdThreads;
     if (blocks > 0x7fffffffLL) return fail(RLG_ERR_TOO_LARGE, "rlg_chamfer_bwd: too many points");
-    chamfer_bwd_kernel<<<(unsigned)blocks, kBwdThreads, 0, st>>>(a, B);
+    cudaError_t le = launch_pdl(chamfer_bwd_kernel, dim3((unsigned)blocks), dim3(kBwdThreads), 0, st, a, B);
+    if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "chamfer_bwd_kernel: %s", cudaGetErrorString(le)); }
     return check_launch("chamfer_bwd_kernel");
 }
 

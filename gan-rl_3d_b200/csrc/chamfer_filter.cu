@@ -52,8 +52,8 @@ __device__ __forceinline__ float facc(float acc, float a, float b) {
 // |p|^2 in a fixed operation order (used by the filter and by the finalize's margin; not part of the outputs)
 __device__ __forceinline__ float norm2(float x, float y, float z) { return fmaf(z, z, fmaf(y, y, x * x)); }
 
-template <int R, bool MIN3>
-__global__ void __launch_bounds__(kFWarps * 32, (R >= 16 ? 2 : 3))
+template <int R, int OCC, bool PP>          // rows per lane, CTAs per SM the register budget is cut for, operand ping-pong
+__global__ void __launch_bounds__(kFWarps * 32, OCC)
 chamfer_filter_kernel(const float *__restrict__ pc1, const float *__restrict__ pc2, int B, int N, int M, int n_rb,
                       int n_cg, long long total_units, FwdWs w) {
     constexpr int P = R / 2;                      // row pairs per lane
@@ -69,6 +69,8 @@ chamfer_filter_kernel(const float *__restrict__ pc1, const float *__restrict__ p
     const long long n_warps = (long long)gridDim.x * kFWarps;
     const long long u0 = total_units * warp / n_warps;
     const long long u1 = total_units * (warp + 1) / n_warps;
+    pdl_launch_dependents();
+    pdl_wait();                       // the clouds may come from the kernel right before this one; the workspace does
     if (u0 >= u1) return;
     const int n_units = (int)(u1 - u0);
 
@@ -211,24 +213,30 @@ chamfer_filter_kernel(const float *__restrict__ pc1, const float *__restrict__ p
                 float gAl, gAh, gBl, gBh, tAl, tAh, tBl, tBh;
                 unpack2(gA, gAl, gAh); unpack2(gB, gBl, gBh);
                 unpack2(tA, tAl, tAh); unpack2(tB, tBl, tBh);
-                rowmin[2 * p] = facc<MIN3>(rowmin[2 * p], gAl, gBl);
-                rowmin[2 * p + 1] = facc<MIN3>(rowmin[2 * p + 1], gAh, gBh);
-                cA = facc<MIN3>(cA, tAl, tAh);
-                cB = facc<MIN3>(cB, tBl, tBh);
+                rowmin[2 * p] = facc<true>(rowmin[2 * p], gAl, gBl);
+                rowmin[2 * p + 1] = facc<true>(rowmin[2 * p + 1], gAh, gBh);
+                cA = facc<true>(cA, tAl, tAh);
+                cB = facc<true>(cB, tBl, tBh);
             }
             s_cmin[wic][2 * cp][lane] = (__float_as_int(cA) & ~31) | lane;
             s_cmin[wic][2 * cp + 1][lane] = (__float_as_int(cB) & ~31) | lane;
         };
-        ulonglong2 pa0 = s_col[wic][0][0], pa1 = s_col[wic][0][1], pb0 = s_col[wic][1][0], pb1 = s_col[wic][1][1];
+        if (PP) {
+            ulonglong2 pa0 = s_col[wic][0][0], pa1 = s_col[wic][0][1], pb0 = s_col[wic][1][0], pb1 = s_col[wic][1][1];
 #pragma unroll 1
-        for (int cp = 0; cp < kGroup / 2; cp += 2) {
-            const ulonglong2 qa0 = s_col[wic][2 * cp + 2][0], qa1 = s_col[wic][2 * cp + 2][1];
-            const ulonglong2 qb0 = s_col[wic][2 * cp + 3][0], qb1 = s_col[wic][2 * cp + 3][1];
-            sweep_pair(pa0, pa1, pb0, pb1, cp);
-            const int nx = cp + 2 < kGroup / 2 ? 2 * cp + 4 : 0;      // the last prefetch re-reads pair 0 (unused)
-            pa0 = s_col[wic][nx][0]; pa1 = s_col[wic][nx][1];
-            pb0 = s_col[wic][nx + 1][0]; pb1 = s_col[wic][nx + 1][1];
-            sweep_pair(qa0, qa1, qb0, qb1, cp + 1);
+            for (int cp = 0; cp < kGroup / 2; cp += 2) {
+                const ulonglong2 qa0 = s_col[wic][2 * cp + 2][0], qa1 = s_col[wic][2 * cp + 2][1];
+                const ulonglong2 qb0 = s_col[wic][2 * cp + 3][0], qb1 = s_col[wic][2 * cp + 3][1];
+                sweep_pair(pa0, pa1, pb0, pb1, cp);
+                const int nx = cp + 2 < kGroup / 2 ? 2 * cp + 4 : 0;      // the last prefetch re-reads pair 0 (unused)
+                pa0 = s_col[wic][nx][0]; pa1 = s_col[wic][nx][1];
+                pb0 = s_col[wic][nx + 1][0]; pb1 = s_col[wic][nx + 1][1];
+                sweep_pair(qa0, qa1, qb0, qb1, cp + 1);
+            }
+        } else {
+#pragma unroll 1
+            for (int cp = 0; cp < kGroup / 2; ++cp)
+                sweep_pair(s_col[wic][2 * cp][0], s_col[wic][2 * cp][1], s_col[wic][2 * cp + 1][0], s_col[wic][2 * cp + 1][1], cp);
         }
         __syncwarp();
         // lane j reduces column j over the 32 lanes' entries (rotated start: conflict-free): smallest key (its low
@@ -275,7 +283,7 @@ chamfer_filter_kernel(const float *__restrict__ pc1, const float *__restrict__ p
     }
 }
 
-template <int R, bool MIN3>
+template <int R, int OCC, bool PP>
 static int launch_filter_t(const float *pc1, const float *pc2, int B, int N, int M, const FwdWs &w, cudaStream_t st) {
     const int rows = 32 * R;
     const int n_rb = (N + rows - 1) / rows;
@@ -284,14 +292,16 @@ static int launch_filter_t(const float *pc1, const float *pc2, int B, int N, int
     const int sms = sm_count();
     if (sms <= 0) return fail((int)cudaErrorNoDevice, "rlg_chamfer_fwd: no CUDA device");
     int ctas_per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, chamfer_filter_kernel<R, MIN3>,
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, chamfer_filter_kernel<R, OCC, PP>,
                                                                   kFWarps * 32, 0);
     if (e != cudaSuccess || ctas_per_sm < 1) { cudaGetLastError(); ctas_per_sm = 1; }
     long long grid = (long long)sms * ctas_per_sm;
     const long long max_useful = (total + kFWarps - 1) / kFWarps;      // at least one unit per warp
     if (grid > max_useful) grid = max_useful;
     if (grid < 1) grid = 1;
-    chamfer_filter_kernel<R, MIN3><<<(unsigned)grid, kFWarps * 32, 0, st>>>(pc1, pc2, B, N, M, n_rb, n_cg, total, w);
+    cudaError_t le = launch_pdl(chamfer_filter_kernel<R, OCC, PP>, dim3((unsigned)grid), dim3(kFWarps * 32), 0, st, pc1, pc2, B, N, M,
+                                n_rb, n_cg, total, w);
+    if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "chamfer_filter_kernel: %s", cudaGetErrorString(le)); }
     return check_launch("chamfer_filter_kernel");
 }
 
@@ -308,20 +318,21 @@ int filter_pick_rows(int N) {
 
 int launch_filter(const float *pc1, const float *pc2, int B, int N, int M, int variant, const FwdWs &w, int *rows_per_lane,
                   cudaStream_t st) {
-    int R = filter_pick_rows(N);
-    bool min3 = false;
+    const int R = (variant >= 7 && variant <= 8) ? 8 : (variant == 9 ? 4 : (variant >= 1 && variant <= 6 ? 16 : filter_pick_rows(N)));
+    *rows_per_lane = R;
     switch (variant) {           // experimental overrides (tools/sweep_tile.py); 0 = automatic
-        case 1: R = 16; min3 = false; break;
-        case 2: R = 16; min3 = true; break;
-        case 3: R = 8; min3 = false; break;
-        case 4: R = 8; min3 = true; break;
-        case 5: R = 4; min3 = false; break;
+        case 1: return launch_filter_t<16, 2, true>(pc1, pc2, B, N, M, w, st);
+        case 2: return launch_filter_t<16, 2, false>(pc1, pc2, B, N, M, w, st);
+        case 3: return launch_filter_t<16, 3, true>(pc1, pc2, B, N, M, w, st);
+        case 4: return launch_filter_t<16, 3, false>(pc1, pc2, B, N, M, w, st);
+        case 7: return launch_filter_t<8, 3, true>(pc1, pc2, B, N, M, w, st);
+        case 8: return launch_filter_t<8, 4, false>(pc1, pc2, B, N, M, w, st);
+        case 9: return launch_filter_t<4, 4, true>(pc1, pc2, B, N, M, w, st);
         default: break;
     }
-    *rows_per_lane = R;
-    if (R == 16) return min3 ? launch_filter_t<16, true>(pc1, pc2, B, N, M, w, st) : launch_filter_t<16, false>(pc1, pc2, B, N, M, w, st);
-    if (R == 8) return min3 ? launch_filter_t<8, true>(pc1, pc2, B, N, M, w, st) : launch_filter_t<8, false>(pc1, pc2, B, N, M, w, st);
-    return launch_filter_t<4, false>(pc1, pc2, B, N, M, w, st);
+    if (R == 16) return launch_filter_t<16, 2, true>(pc1, pc2, B, N, M, w, st);
+    if (R == 8) return launch_filter_t<8, 3, true>(pc1, pc2, B, N, M, w, st);
+    return launch_filter_t<4, 4, true>(pc1, pc2, B, N, M, w, st);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -396,19 +407,15 @@ __global__ void __launch_bounds__(kFin2Threads) chamfer_finalize2_kernel(
     unsigned *secs = (dir ? w.colsec : w.rowsec) + (size_t)b * nq;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
-    // this thread's point: issue its loads before the candidate staging so their latencies overlap
+    // Everything up to pdl_wait() reads only the clouds, which were complete before the pair sweep started: under a
+    // programmatic dependent launch it overlaps the tail of the pair sweep.
+    pdl_launch_dependents();
     const int i = chunk * kFin2Threads + tid;
     const bool live = i < nq;
     u64 key = kKeyInit;
     unsigned sec = 0xffffffffu;
     float qx = 0.f, qy = 0.f, qz = 0.f;
-    if (live) {
-        key = keys[i];
-        sec = secs[i];
-        qx = __ldg(q + 3 * (size_t)i); qy = __ldg(q + 3 * (size_t)i + 1); qz = __ldg(q + 3 * (size_t)i + 2);
-    }
-    // largest squared norm of the OTHER cloud (the filter kernel published its bitwise complement)
-    const float onrm = __uint_as_float(~w.nrm[dir ? b : B + b]);
+    if (live) { qx = __ldg(q + 3 * (size_t)i); qy = __ldg(q + 3 * (size_t)i + 1); qz = __ldg(q + 3 * (size_t)i + 2); }
 
     const float *__restrict__ c = cglob;
     if (SMEM) {
@@ -424,6 +431,13 @@ __global__ void __launch_bounds__(kFin2Threads) chamfer_finalize2_kernel(
         }
         c = s_cand;
     }
+    pdl_wait();                                         // from here on: results of the pair sweep
+    if (live) {
+        key = keys[i];
+        sec = secs[i];
+    }
+    // largest squared norm of the OTHER cloud (the filter kernel published its bitwise complement)
+    const float onrm = __uint_as_float(~w.nrm[dir ? b : B + b]);
     if (live) {
         keys[i] = kKeyInit;
         secs[i] = 0xffffffffu;
@@ -559,11 +573,13 @@ int launch_finalize2(const float *pc1, const float *pc2, int B, int N, int M, in
                                                  (int)(200u * 1024u));
             if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "rlg_chamfer_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
         }
-        chamfer_finalize2_kernel<true><<<grid, kFin2Threads, dyn, st>>>(pc1, pc2, N, M, rows_per_lane, w, fw, d1, d2, i1, i2,
-                                                                        mean1, mean2, loss, w1, w2, zero1, zero2);
+        cudaError_t le = launch_pdl(chamfer_finalize2_kernel<true>, grid, dim3(kFin2Threads), dyn, st, pc1, pc2, N, M, rows_per_lane,
+                                    w, fw, d1, d2, i1, i2, mean1, mean2, loss, w1, w2, zero1, zero2);
+        if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "chamfer_finalize2_kernel: %s", cudaGetErrorString(le)); }
     } else {
-        chamfer_finalize2_kernel<false><<<grid, kFin2Threads, 0, st>>>(pc1, pc2, N, M, rows_per_lane, w, fw, d1, d2, i1, i2,
-                                                                       mean1, mean2, loss, w1, w2, zero1, zero2);
+        cudaError_t le = launch_pdl(chamfer_finalize2_kernel<false>, grid, dim3(kFin2Threads), 0, st, pc1, pc2, N, M, rows_per_lane,
+                                    w, fw, d1, d2, i1, i2, mean1, mean2, loss, w1, w2, zero1, zero2);
+        if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "chamfer_finalize2_kernel: %s", cudaGetErrorString(le)); }
     }
     return check_launch("chamfer_finalize2_kernel");
 }

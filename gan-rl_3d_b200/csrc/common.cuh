@@ -22,6 +22,30 @@ int sm_count();
 
 typedef unsigned long long u64;
 
+// ---- programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while its predecessor in the
+// stream is still running; it must call pdl_wait() before touching anything the predecessor (or anything before it)
+// wrote.  Every kernel calls pdl_launch_dependents() early, so its successor's CTAs can take over SM slots as they
+// free up and run their independent prologue under this kernel's tail.  Outside a PDL launch both are no-ops.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 // ---- Chamfer forward: shared between the tile kernel (chamfer_fwd.cu) and the finalize (chamfer_finalize.cu)
 static constexpr int kGroup = 32;           // columns per group == lanes per warp
 static constexpr u64 kKeyInit = ~0ull;      // workspace state on entry and on exit of every forward

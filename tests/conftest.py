@@ -65,6 +65,11 @@ def golden_encoder():
 
 
 @pytest.fixture(scope="session")
+def golden_reward():
+    return np.load(os.path.join(GOLDEN, "reward_ref.npz"))
+
+
+@pytest.fixture(scope="session")
 def rlg():
     import gan_rl_3d_b200
     return gan_rl_3d_b200

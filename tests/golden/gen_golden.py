@@ -116,6 +116,29 @@ def main():
                 enc_out[f"enc{k}_sd_{name}"] = v.numpy()
     enc_out["enc_count"] = np.int32(len(cfgs))
     np.savez_compressed(os.path.join(HERE, "encoder_ref.npz"), **enc_out)
+
+    # --- Reward: the reference's RewardFunction (utils/losses.py:209-246) called episode by episode
+    #     with B=1 tensors, exactly as RLGANNetEnvironment.step does (models/rl_gan_net.py:316-324)
+    rw_out = {}
+    rf = losses.RewardFunction()
+    shapes = [(6, 25, 25, "sphere"), (5, 2048, 2048, "sphere"), (4, 2048, 1400, "uniform")]
+    for k, (E, N, M, kind) in enumerate(shapes):
+        pred = O.make_clouds(E, N, kind, seed=700 + k)
+        target = O.make_clouds(E, M, kind, seed=800 + k)
+        g = torch.Generator().manual_seed(900 + k)
+        pred_gfv, target_gfv = torch.rand(E, 128, generator=g), torch.rand(E, 128, generator=g)
+        disc = torch.randn(E, 1, generator=g)
+        with torch.no_grad():
+            rewards = torch.stack([rf.compute_reward(pred[e:e + 1], target[e:e + 1], pred_gfv[e:e + 1], target_gfv[e:e + 1],
+                                                     disc[e:e + 1]) for e in range(E)])
+        rw_out[f"rw{k}_meta"] = np.array([E, N, M, 700 + k, 800 + k], np.int64)
+        rw_out[f"rw{k}_kind"] = np.array(kind)
+        rw_out[f"rw{k}_pred_gfv"] = pred_gfv.numpy()
+        rw_out[f"rw{k}_target_gfv"] = target_gfv.numpy()
+        rw_out[f"rw{k}_disc"] = disc.numpy()
+        rw_out[f"rw{k}_rewards"] = rewards.numpy()
+    rw_out["rw_count"] = np.int32(len(shapes))
+    np.savez_compressed(os.path.join(HERE, "reward_ref.npz"), **rw_out)
     print("wrote", os.listdir(HERE))
 
 

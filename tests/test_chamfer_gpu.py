@@ -49,10 +49,10 @@ def test_simple_kernel_agrees_with_tile_kernel(rlg, B, N, M):
         assert np.array_equal(x, y)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 7, 8, 9])
 @pytest.mark.parametrize("B,N,M", [(2, 1, 1), (3, 33, 31), (2, 600, 1400), (2, 2048, 2048), (1, 1025, 70)])
 def test_every_filter_tile_shape_is_bit_exact(rlg, variant, B, N, M):
-    """Rows per lane 16 / 8 / 4 and both min-instruction forms: same bits as the direct oracle, ragged shapes included."""
+    """Rows per lane 16 / 8 / 4, every occupancy / operand-prefetch variant: same bits as the direct oracle, ragged shapes included."""
     pc1, pc2 = O.make_clouds(B, N, "uniform", 70 + variant), O.make_clouds(B, M, "sphere", 80 + variant)
     _check_against_direct(rlg, pc1, pc2, variant=variant)
 

@@ -165,3 +165,17 @@ def test_encoder_port_is_reference(ref_autoencoder):
     for mode in ("eval", "train"):
         getattr(ref, mode)(), getattr(port, mode)()
         assert torch.equal(ref(x), port(x))
+
+
+def test_reward_golden_is_the_reference_formula(golden_reward):
+    """The reward fixture (generated from the reference's RewardFunction) equals the closed form the batched API
+    implements, evaluated in float64 -- within the reference's own cdist noise."""
+    g = golden_reward
+    for k in range(int(g["rw_count"])):
+        E, N, M, s1, s2 = [int(v) for v in g[f"rw{k}_meta"]]
+        pred, target = O.make_clouds(E, N, str(g[f"rw{k}_kind"]), s1), O.make_clouds(E, M, str(g[f"rw{k}_kind"]), s2)
+        f1, f2, *_ = O.chamfer_f64(pred, target)
+        cd = (f1.mean(1) + f2.mean(1)).numpy() / 2.0
+        gfv = ((g[f"rw{k}_pred_gfv"].astype(np.float64) - g[f"rw{k}_target_gfv"]) ** 2).mean(1)
+        truth = -(100.0 * cd + 10.0 * gfv + 0.01 * (-g[f"rw{k}_disc"].astype(np.float64).reshape(E)))
+        assert O.rel_err(g[f"rw{k}_rewards"], truth) < 5e-5

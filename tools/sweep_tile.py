@@ -27,8 +27,9 @@ i1 = torch.empty(B, N, dtype=torch.int32, device=dev); i2 = torch.empty(B, M, dt
 ws = torch.empty(lib.rlg_chamfer_ws_bytes(B, N, M), dtype=torch.uint8, device=dev).fill_(0xFF)
 stream = torch.cuda.current_stream().cuda_stream
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-names = {(0, 0): "filter auto", (0, 1): "filter R16 min2", (0, 2): "filter R16 min3", (0, 3): "filter R8 min2",
-         (0, 4): "filter R8 min3", (0, 5): "filter R4 min2", (1, 0): "direct R8 occ3 min2", (1, 4): "direct R16 occ2 min2"}
+names = {(0, 0): "filter auto", (0, 1): "filter R16 occ2 pp", (0, 2): "filter R16 occ2 nopp", (0, 3): "filter R16 occ3 pp",
+         (0, 4): "filter R16 occ3 nopp", (0, 7): "filter R8 occ3 pp", (0, 8): "filter R8 occ4 nopp", (0, 9): "filter R4 occ4",
+         (1, 0): "direct R8 occ3 min2"}
 for (direct, var), name in names.items():
     algo = _lib.CHAMFER_ALGO_DIRECT if direct else 0
     flags = _lib.CHAMFER_WS_CLEAN | _lib.CHAMFER_TILE_ONLY | (var << 8) | algo
