@@ -65,10 +65,12 @@ chamfer_filter_kernel(const float *__restrict__ pc1, const float *__restrict__ p
 
     const int lane = threadIdx.x & 31;
     const int wic = threadIdx.x >> 5;
+    // even split of the unit range over all warps: the first `rem` warps take one unit more
     const long long warp = (long long)blockIdx.x * kFWarps + wic;
     const long long n_warps = (long long)gridDim.x * kFWarps;
-    const long long u0 = total_units * warp / n_warps;
-    const long long u1 = total_units * (warp + 1) / n_warps;
+    const long long per = total_units / n_warps, rem = total_units - per * n_warps;
+    const long long u0 = warp * per + (warp < rem ? warp : rem);
+    const long long u1 = u0 + per + (warp < rem ? 1 : 0);
     pdl_launch_dependents();
     pdl_wait();                       // the clouds may come from the kernel right before this one; the workspace does
     if (u0 >= u1) return;
@@ -242,13 +244,27 @@ chamfer_filter_kernel(const float *__restrict__ pc1, const float *__restrict__ p
         // lane j reduces column j over the 32 lanes' entries (rotated start: conflict-free): smallest key (its low
         // 5 bits name the lane, i.e. which rows r*32+lane) and the runner-up.  Signed order: a rounding residue below
         // zero sorts first, which is what we want.
-        int2 mm = make_int2(0x7fffffff, 0x7fffffff);
-#pragma unroll 8
-        for (int l = 0; l < 32; ++l) {
-            const int k = s_cmin[wic][lane][(l + lane) & 31];
-            mm.y = min(mm.y, max(mm.x, k));
-            mm.x = min(mm.x, k);
+        // four independent (best, runner-up) chains of 8 entries each, then a 2-level merge: short dependency chains
+        int bst[4], snd[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { bst[c] = 0x7fffffff; snd[c] = 0x7fffffff; }
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int k = s_cmin[wic][lane][(8 * c + l + lane) & 31];
+                snd[c] = min(snd[c], max(bst[c], k));
+                bst[c] = min(bst[c], k);
+            }
         }
+        auto merge2 = [](int &b0, int &s0, int b1, int s1) {
+            s0 = min(max(b0, b1), min(s0, s1));
+            b0 = min(b0, b1);
+        };
+        merge2(bst[0], snd[0], bst[1], snd[1]);
+        merge2(bst[2], snd[2], bst[3], snd[3]);
+        merge2(bst[0], snd[0], bst[2], snd[2]);
+        const int2 mm = make_int2(bst[0], snd[0]);
         __syncwarp();            // s_cmin and s_col may be rewritten by the next unit from here on
 
         // ---- rows: best / second-best group minimum (strict < keeps the earliest group on ties)
