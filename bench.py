@@ -246,7 +246,7 @@ def run_ours(args):
 
     # ---- e2e: host buffers through the public API, H2D + D2H of every step inside the timed region --
     nb = min(slots, 32)
-    pinned = [(a.pin_memory(), b.pin_memory()) for a, b in ring_host[:nb]]
+    pinned = [P.pin_pair(a, b) for a, b in ring_host[:nb]]      # (pred, target) of a step: one pinned buffer, one transfer
     host_graph = P.HostChamferStepGraph(pinned, dev)
     Ke_replays = max(1, min(K, 2000) // nb)
     Ke = Ke_replays * nb
@@ -363,9 +363,9 @@ def run_ours(args):
         "roofline": roofline, "roofline_bwd": roofline_bwd, "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": slot_bytes, "d2h_bytes_per_step": 4,
                 "steps": Ke, "loss_step0": e2e_loss_check,
-                "how": "HostChamferStepGraph: per step H2D of pinned (pred,target) -> ChamferLoss -> backward -> D2H of the "
-                       "loss, 32 steps per CUDA-graph replay, copies double-buffered against the previous step's kernels; "
-                       "wall clock around replays + synchronize"},
+                "how": "HostChamferStepGraph: per step ONE H2D transfer of the pinned (pred,target) buffer -> ChamferLoss -> "
+                       "backward -> D2H of the loss (own stream), 32 steps per CUDA-graph replay, copies double-buffered "
+                       "against the previous step's kernels; wall clock around replays + synchronize"},
         "gpu_launches": n_launches, "clocks": clocks,
     }
     out.update(extra)

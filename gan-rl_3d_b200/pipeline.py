@@ -61,11 +61,27 @@ class ChamferStepGraph:
         self.graph.replay()
 
 
+def pin_pair(a: torch.Tensor, b: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Copies of (a, b) as two views of ONE pinned host buffer, so a step's inputs cross PCIe as a single transfer."""
+    flat = torch.empty(a.numel() + b.numel(), dtype=a.dtype).pin_memory()
+    va, vb = flat[:a.numel()].view_as(a), flat[a.numel():].view_as(b)
+    va.copy_(a)
+    vb.copy_(b)
+    return va, vb
+
+
+def _adjacent(a: torch.Tensor, b: torch.Tensor) -> bool:
+    return (a.is_contiguous() and b.is_contiguous() and a.dtype == b.dtype
+            and a.data_ptr() + a.numel() * a.element_size() == b.data_ptr())
+
+
 class HostChamferStepGraph:
     """S training steps whose inputs live in pinned HOST memory.  Per step, inside the graph: H2D copy of
-    (pred, target) into one of two device staging pairs (copy stream), ChamferLoss forward+backward (compute
-    stream), D2H copy of the loss into a pinned (S,) result vector.  The copy of step k+1 overlaps the kernels
-    of step k.  After replay() + synchronize: self.losses_host[k] is step k's loss."""
+    (pred, target) into one of two device staging slots (copy stream; ONE transfer when the two host tensors are
+    adjacent views of one pinned buffer, see pin_pair), ChamferLoss forward+backward (compute stream), D2H copy of the
+    loss into a pinned (S,) result vector (its own stream, so it neither waits behind the next H2D nor holds up the
+    next step).  The copy of step k+1 overlaps the kernels of step k.  After replay() + synchronize:
+    self.losses_host[k] is step k's loss."""
 
     def __init__(self, host_batches: Sequence[Tuple[torch.Tensor, torch.Tensor]], device: torch.device,
                  bidirectional: bool = True):
@@ -75,8 +91,9 @@ class HostChamferStepGraph:
         self.S = len(self.host)
         self.crit = ChamferLoss(bidirectional)
         a0, b0 = self.host[0]
-        self.stage = [(torch.empty_like(a0, device=device).requires_grad_(True), torch.empty_like(b0, device=device))
-                      for _ in range(2)]
+        self.flat = [torch.empty(a0.numel() + b0.numel(), dtype=a0.dtype, device=device) for _ in range(2)]
+        self.stage = [(f[:a0.numel()].view_as(a0).requires_grad_(True), f[a0.numel():].view_as(b0)) for f in self.flat]
+        self.single_copy = all(_adjacent(a, b) for a, b in self.host)
         self.losses_host = torch.zeros(self.S, dtype=torch.float32).pin_memory()
         self.h2d_bytes_per_step = (a0.numel() + b0.numel()) * 4
         self.d2h_bytes_per_step = 4
@@ -84,21 +101,27 @@ class HostChamferStepGraph:
         self._one = torch.ones((), dtype=torch.float32, device=device)
         self.compute = torch.cuda.Stream(device)
         self.copy = torch.cuda.Stream(device)
+        self.readback = torch.cuda.Stream(device)
         self.graph = torch.cuda.CUDAGraph()
         self._capture()
 
     def _copy_in(self, k: int) -> None:
-        da, db = self.stage[k % 2]
         ha, hb = self.host[k]
-        da.detach().copy_(ha, non_blocking=True)
-        db.copy_(hb, non_blocking=True)
+        if self.single_copy:
+            n = ha.numel() + hb.numel()
+            host_flat = torch.as_strided(ha, (n,), (1,))          # the pinned buffer both views live in
+            self.flat[k % 2].copy_(host_flat, non_blocking=True)
+        else:
+            da, db = self.stage[k % 2]
+            da.detach().copy_(ha, non_blocking=True)
+            db.copy_(hb, non_blocking=True)
 
-    def _step(self, k: int) -> None:
+    def _step(self, k: int) -> torch.Tensor:
         da, db = self.stage[k % 2]
         da.grad = None
         loss = self.crit(da, db)
         loss.backward(gradient=self._one)
-        self.losses_host[k:k + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        return loss.detach().reshape(1)
 
     def _capture(self) -> None:
         cur = torch.cuda.current_stream(self.device)
@@ -106,27 +129,33 @@ class HostChamferStepGraph:
         with torch.cuda.stream(self.compute):          # eager warm-up
             for k in range(min(2, self.S)):
                 self._copy_in(k)
-                self._step(k)
+                self.losses_host[k:k + 1].copy_(self._step(k), non_blocking=True)
         self.compute.synchronize()
         with torch.cuda.graph(self.graph, stream=self.compute):
             copied = [None] * self.S
             computed = [None] * self.S
+
+            def step_and_read_back(j: int) -> None:
+                self.compute.wait_event(copied[j])
+                loss = self._step(j)
+                computed[j] = torch.cuda.Event()
+                computed[j].record(self.compute)
+                self.readback.wait_event(computed[j])
+                with torch.cuda.stream(self.readback):
+                    self.losses_host[j:j + 1].copy_(loss, non_blocking=True)
+
             for k in range(self.S):
-                # copy k may start once step k-2 (last user of this staging pair) has finished
+                # copy k may start once step k-2 (last user of this staging slot) has finished
                 self.copy.wait_stream(self.compute) if k < 2 else self.copy.wait_event(computed[k - 2])
                 with torch.cuda.stream(self.copy):
                     self._copy_in(k)
                     copied[k] = torch.cuda.Event()
                     copied[k].record(self.copy)
                 if k >= 1:
-                    # while copy k is in flight, compute step k-1
-                    self.compute.wait_event(copied[k - 1])
-                    self._step(k - 1)
-                    computed[k - 1] = torch.cuda.Event()
-                    computed[k - 1].record(self.compute)
-            self.compute.wait_event(copied[self.S - 1])
-            self._step(self.S - 1)
+                    step_and_read_back(k - 1)          # while copy k is in flight
+            step_and_read_back(self.S - 1)
             self.compute.wait_stream(self.copy)
+            self.compute.wait_stream(self.readback)
         cur.wait_stream(self.compute)
 
     def replay(self) -> None:
