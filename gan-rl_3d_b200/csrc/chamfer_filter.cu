@@ -52,7 +52,10 @@ __device__ __forceinline__ float facc(float acc, float a, float b) {
 // |p|^2 in a fixed operation order (used by the filter and by the finalize's margin; not part of the outputs)
 __device__ __forceinline__ float norm2(float x, float y, float z) { return fmaf(z, z, fmaf(y, y, x * x)); }
 
-template <int R, int OCC, bool PP>          // rows per lane, CTAs per SM the register budget is cut for, operand ping-pong
+// KO: timing experiments only (tools/sweep_tile.py variants 10..15; results are WRONG with bits 0,1,3 set):
+//   1 skip the column scan, 2 skip the row second-best bookkeeping, 4 integer min3 on t for both directions,
+//   8 stage the columns only for a warp's first unit
+template <int R, int OCC, bool PP, int KO = 0>   // rows per lane, CTAs per SM the register budget is cut for, operand ping-pong
 __global__ void __launch_bounds__(kFWarps * 32, OCC)
 chamfer_filter_kernel(const float *__restrict__ pc1, const float *__restrict__ pc2, int B, int N, int M, int n_rb,
                       int n_cg, long long total_units, FwdWs w) {
@@ -112,8 +115,9 @@ chamfer_filter_kernel(const float *__restrict__ pc1, const float *__restrict__ p
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             // t = g + |x|^2 for both rows of the pair at once (nxp is only ever used as a packed operand)
-            const u64 tb2 = add2(pack2(best[2 * p], best[2 * p + 1]), nxp[p]);
-            const u64 ts2 = add2(pack2(s_second[wic][2 * p][lane], s_second[wic][2 * p + 1][lane]), nxp[p]);
+            const u64 rowoff = (KO & 4) ? pack2(0.0f, 0.0f) : nxp[p];       // KO&4 keeps the rows in t already
+            const u64 tb2 = add2(pack2(best[2 * p], best[2 * p + 1]), rowoff);
+            const u64 ts2 = add2(pack2(s_second[wic][2 * p][lane], s_second[wic][2 * p + 1][lane]), rowoff);
             float tb[2], ts[2];
             unpack2(tb2, tb[0], tb[1]);
             unpack2(ts2, ts[0], ts[1]);
@@ -172,7 +176,7 @@ chamfer_filter_kernel(const float *__restrict__ pc1, const float *__restrict__ p
         }
 
         // ---- stage this group's 32 columns as FFMA2 operands; start fetching the next group
-        {
+        if (!(KO & 8) || it == 0) {
             const bool cvalid = cg * kGroup + lane < M;
             const float y0 = pre[0], y1 = pre[1], y2 = pre[2];
             const float ny = cvalid ? norm2(y0, y1, y2) : kBig;
@@ -215,10 +219,17 @@ chamfer_filter_kernel(const float *__restrict__ pc1, const float *__restrict__ p
                 float gAl, gAh, gBl, gBh, tAl, tAh, tBl, tBh;
                 unpack2(gA, gAl, gAh); unpack2(gB, gBl, gBh);
                 unpack2(tA, tAl, tAh); unpack2(tB, tBl, tBh);
+                if (KO & 4) {
+                    rowmin[2 * p] = __int_as_float(__vimin3_s32(__float_as_int(rowmin[2 * p]), __float_as_int(tAl), __float_as_int(tBl)));
+                    rowmin[2 * p + 1] = __int_as_float(__vimin3_s32(__float_as_int(rowmin[2 * p + 1]), __float_as_int(tAh), __float_as_int(tBh)));
+                    cA = __int_as_float(__vimin3_s32(__float_as_int(cA), __float_as_int(tAl), __float_as_int(tAh)));
+                    cB = __int_as_float(__vimin3_s32(__float_as_int(cB), __float_as_int(tBl), __float_as_int(tBh)));
+                } else {
                 rowmin[2 * p] = facc<true>(rowmin[2 * p], gAl, gBl);
                 rowmin[2 * p + 1] = facc<true>(rowmin[2 * p + 1], gAh, gBh);
                 cA = facc<true>(cA, tAl, tAh);
                 cB = facc<true>(cB, tBl, tBh);
+                }
             }
             s_cmin[wic][2 * cp][lane] = (__float_as_int(cA) & ~31) | lane;
             s_cmin[wic][2 * cp + 1][lane] = (__float_as_int(cB) & ~31) | lane;
@@ -248,8 +259,9 @@ chamfer_filter_kernel(const float *__restrict__ pc1, const float *__restrict__ p
         int bst[4], snd[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) { bst[c] = 0x7fffffff; snd[c] = 0x7fffffff; }
+        if (KO & 1) { bst[0] = s_cmin[wic][lane][lane]; snd[0] = s_cmin[wic][lane][(lane + 1) & 31]; }
 #pragma unroll
-        for (int l = 0; l < 8; ++l) {
+        for (int l = 0; l < ((KO & 1) ? 0 : 8); ++l) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int k = s_cmin[wic][lane][(8 * c + l + lane) & 31];
@@ -271,6 +283,7 @@ chamfer_filter_kernel(const float *__restrict__ pc1, const float *__restrict__ p
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const float v = rowmin[r];
+            if (KO & 2) { best[r] = fminf(best[r], v); continue; }
             s_second[wic][r][lane] = fminf(s_second[wic][r][lane], fmaxf(best[r], v));
             if (v < best[r]) { best[r] = v; s_bgrp[wic][r][lane] = cg; }
         }
@@ -299,7 +312,7 @@ chamfer_filter_kernel(const float *__restrict__ pc1, const float *__restrict__ p
     }
 }
 
-template <int R, int OCC, bool PP>
+template <int R, int OCC, bool PP, int KO = 0>
 static int launch_filter_t(const float *pc1, const float *pc2, int B, int N, int M, const FwdWs &w, cudaStream_t st) {
     const int rows = 32 * R;
     const int n_rb = (N + rows - 1) / rows;
@@ -308,14 +321,14 @@ static int launch_filter_t(const float *pc1, const float *pc2, int B, int N, int
     const int sms = sm_count();
     if (sms <= 0) return fail((int)cudaErrorNoDevice, "rlg_chamfer_fwd: no CUDA device");
     int ctas_per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, chamfer_filter_kernel<R, OCC, PP>,
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, chamfer_filter_kernel<R, OCC, PP, KO>,
                                                                   kFWarps * 32, 0);
     if (e != cudaSuccess || ctas_per_sm < 1) { cudaGetLastError(); ctas_per_sm = 1; }
     long long grid = (long long)sms * ctas_per_sm;
     const long long max_useful = (total + kFWarps - 1) / kFWarps;      // at least one unit per warp
     if (grid > max_useful) grid = max_useful;
     if (grid < 1) grid = 1;
-    cudaError_t le = launch_pdl(chamfer_filter_kernel<R, OCC, PP>, dim3((unsigned)grid), dim3(kFWarps * 32), 0, st, pc1, pc2, B, N, M,
+    cudaError_t le = launch_pdl(chamfer_filter_kernel<R, OCC, PP, KO>, dim3((unsigned)grid), dim3(kFWarps * 32), 0, st, pc1, pc2, B, N, M,
                                 n_rb, n_cg, total, w);
     if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "chamfer_filter_kernel: %s", cudaGetErrorString(le)); }
     return check_launch("chamfer_filter_kernel");
@@ -334,7 +347,7 @@ int filter_pick_rows(int N) {
 
 int launch_filter(const float *pc1, const float *pc2, int B, int N, int M, int variant, const FwdWs &w, int *rows_per_lane,
                   cudaStream_t st) {
-    const int R = (variant >= 7 && variant <= 8) ? 8 : (variant == 9 ? 4 : (variant >= 1 && variant <= 6 ? 16 : filter_pick_rows(N)));
+    const int R = (variant >= 7 && variant <= 8) ? 8 : (variant == 9 ? 4 : ((variant >= 1 && variant <= 6) || variant >= 10 ? 16 : filter_pick_rows(N)));
     *rows_per_lane = R;
     switch (variant) {           // experimental overrides (tools/sweep_tile.py); 0 = automatic
         case 1: return launch_filter_t<16, 2, true>(pc1, pc2, B, N, M, w, st);
@@ -344,6 +357,12 @@ int launch_filter(const float *pc1, const float *pc2, int B, int N, int M, int v
         case 7: return launch_filter_t<8, 3, true>(pc1, pc2, B, N, M, w, st);
         case 8: return launch_filter_t<8, 4, false>(pc1, pc2, B, N, M, w, st);
         case 9: return launch_filter_t<4, 4, true>(pc1, pc2, B, N, M, w, st);
+        case 10: return launch_filter_t<16, 2, false, 1>(pc1, pc2, B, N, M, w, st);
+        case 11: return launch_filter_t<16, 2, false, 2>(pc1, pc2, B, N, M, w, st);
+        case 12: return launch_filter_t<16, 2, false, 3>(pc1, pc2, B, N, M, w, st);
+        case 13: return launch_filter_t<16, 2, false, 4>(pc1, pc2, B, N, M, w, st);
+        case 14: return launch_filter_t<16, 2, false, 11>(pc1, pc2, B, N, M, w, st);
+        case 15: return launch_filter_t<16, 2, false, 15>(pc1, pc2, B, N, M, w, st);
         default: break;
     }
     if (R == 16) return launch_filter_t<16, 2, true>(pc1, pc2, B, N, M, w, st);

@@ -29,7 +29,11 @@ stream = torch.cuda.current_stream().cuda_stream
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 names = {(0, 0): "filter auto", (0, 1): "filter R16 occ2 pp", (0, 2): "filter R16 occ2 nopp", (0, 3): "filter R16 occ3 pp",
          (0, 4): "filter R16 occ3 nopp", (0, 7): "filter R8 occ3 pp", (0, 8): "filter R8 occ4 nopp", (0, 9): "filter R4 occ4",
-         (1, 0): "direct R8 occ3 min2"}
+         (1, 0): "direct R8 occ3 min2", (0, 10): "KO col scan", (0, 11): "KO row bookkeeping", (0, 12): "KO scan+rows",
+         (0, 13): "integer min3 on t", (0, 14): "KO scan+rows+staging", (0, 15): "KO scan+rows+staging, int min"}
+if os.environ.get("SWEEP_VARIANTS"):
+    keep = {int(v) for v in os.environ["SWEEP_VARIANTS"].split(",")}
+    names = {k: v for k, v in names.items() if k[0] == 0 and k[1] in keep}
 for (direct, var), name in names.items():
     algo = _lib.CHAMFER_ALGO_DIRECT if direct else 0
     flags = _lib.CHAMFER_WS_CLEAN | _lib.CHAMFER_TILE_ONLY | (var << 8) | algo
@@ -52,6 +56,8 @@ for (direct, var), name in names.items():
     us = e0.elapsed_time(e1) / reps * 1e3
     tf = 8.0 * N * M * B / (us * 1e-6) / 1e12
     print(f"variant {direct}/{var} ({name}): {us:8.2f} us  {tf:6.2f} TFLOP/s  {tf / 74.45 * 100:5.1f}% of FFMA peak")
+    if var in (10, 11, 12, 14, 15):
+        continue                      # knock-out timing experiments: results are wrong by construction
     # correctness of the variant against the production path
     full = _lib.CHAMFER_WS_CLEAN | (var << 8) | algo
     a, b = ring[0]
