@@ -65,6 +65,7 @@ CHAMFER_WS_CLEAN = 1
 CHAMFER_ALGO_SIMPLE = 2
 CHAMFER_TILE_ONLY = 4
 CHAMFER_ALGO_DIRECT = 8
+CHAMFER_ALGO_TENSOR = 16
 CHAMFER_BWD_ACCUMULATE = 1
 
 

@@ -11,6 +11,8 @@ from __future__ import annotations
 
 from typing import Dict, Optional, Tuple
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -56,9 +58,21 @@ class _Workspace:
         return ws
 
 
+_DEFAULT_TENSOR = os.environ.get("RLG_CHAMFER_SWEEP", "fp32").lower() in ("tensor", "tc", "tcgen05")
+
+
+def set_default_sweep(kind: str) -> None:
+    """'fp32': pair sweep on the FP32 pipe (chamfer_filter.cu); 'tensor': contraction on tcgen05 (chamfer_tcfilter.cu).
+    Both feed the same exact refinement; outputs are bit-identical."""
+    global _DEFAULT_TENSOR
+    if kind not in ("fp32", "tensor"):
+        raise ValueError("kind must be 'fp32' or 'tensor'")
+    _DEFAULT_TENSOR = kind == "tensor"
+
+
 def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = True, simple: bool = False,
                     loss_weights: Optional[Tuple[float, float]] = None, direct: bool = False, variant: int = 0,
-                    zero_grads: Optional[Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]] = None):
+                    tensor: Optional[bool] = None, zero_grads: Optional[Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]] = None):
     """Nearest neighbours in both directions (no autograd).
 
     Returns (d1 (B,N) fp32, d2 (B,M) fp32, i1 (B,N) int32, i2 (B,M) int32, mean1 (B,), mean2 (B,)):
@@ -66,7 +80,9 @@ def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = Tru
     and torch.mean(…, dim=1) of :36-37.  With loss_weights=(w1,w2) a 7th element is appended: the 0-dim
     batch loss sum_b(w1*mean1[b] + w2*mean2[b]) reduced inside the same launch (utils/losses.py:54-59,75).
     simple / direct select the two cross-check kernels (one thread per query; direct-form tiles) instead of the
-    filter-and-refine kernel; variant (1..15) forces an experimental tile shape.  All paths return the same bits.
+    filter-and-refine kernel; variant (1..15) forces an experimental tile shape; tensor=True/False selects the
+    pair sweep with the contraction on the tensor cores (tcgen05, split-tf32) or on the FP32 pipe (None: the module
+    default, see set_default_sweep).  All paths return the same bits.
     zero_grads=(g1, g2): (B,N,3)/(B,M,3) buffers (each may be None) the forward zero-fills in its last launch, so
     chamfer_backward(..., out=(g1, g2), accumulate=True) is a single launch."""
     _require_hot_path(pc1, pc2)
@@ -97,6 +113,8 @@ def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = Tru
             flags |= _lib.CHAMFER_WS_CLEAN
         if direct:
             flags |= _lib.CHAMFER_ALGO_DIRECT
+        elif not simple and (_DEFAULT_TENSOR if tensor is None else tensor) and not variant:
+            flags |= _lib.CHAMFER_ALGO_TENSOR
         flags |= (int(variant) & 15) << 8
         ws.clean = False
         rc = lib.rlg_chamfer_loss_fwd(pc1.data_ptr(), pc2.data_ptr(), B, N, M,

@@ -42,6 +42,7 @@ static constexpr float kBig = 1.0e30f;                 // |x|^2 or |y|^2 of a pa
 static constexpr int kFWarps = 4;                      // warps per CTA; each warp works alone (no __syncthreads)
 static constexpr float kMarginC = 96.0f / 16777216.0f; // 96 u
 static constexpr float kMarginQ = 1.0f / 65536.0f;     // column keys: 2 x 32 ulp of quantisation, with slack
+static constexpr float kMarginT = 128.0f / 16777216.0f; // 128 u: the tensor-core filter (chamfer_tcfilter.cu)
 
 template <bool MIN3>
 __device__ __forceinline__ float facc(float acc, float a, float b) {
@@ -434,8 +435,9 @@ __global__ void __launch_bounds__(kFin2Threads) chamfer_finalize2_kernel(
     const int nq = dir ? M : N, nc = dir ? N : M;
     const int n_chunks = (nq + kFin2Threads - 1) / kFin2Threads;
     if (chunk >= n_chunks) return;                      // grid.x is sized for the longer direction
-    const int R = rows_per_lane;
-    const int gsz = dir ? R : kGroup;                   // a power of two <= 32
+    const int R = rows_per_lane;                        // 0: tensor-core filter, groups of 32 consecutive candidates both ways
+    const bool strided = dir && R > 0;
+    const int gsz = strided ? R : kGroup;               // a power of two <= 32
     const float *q = (dir ? pc2 : pc1) + (size_t)b * nq * 3;
     const float *cglob = (dir ? pc1 : pc2) + (size_t)b * nc * 3;
     u64 *keys = (dir ? w.colkey : w.rowkey) + (size_t)b * nq;
@@ -486,7 +488,7 @@ __global__ void __launch_bounds__(kFin2Threads) chamfer_finalize2_kernel(
 
     const float val = __uint_as_float((unsigned)(key >> 32));
     const float sv = __uint_as_float(sec);
-    const float margin = kMarginC * (norm2(qx, qy, qz) + onrm) + (dir ? kMarginQ * val : 0.0f);
+    const float margin = (R > 0 ? kMarginC : kMarginT) * (norm2(qx, qy, qz) + onrm) + (strided ? kMarginQ * val : 0.0f);
     // any NaN (untouched key, non-finite input) makes the comparison false -> treated as ambiguous
     const bool amb = live && !(sv > val + margin);
     // deterministic list of the CTA's ambiguous points
@@ -508,8 +510,8 @@ __global__ void __launch_bounds__(kFin2Threads) chamfer_finalize2_kernel(
     int bj = 0x7fffffff;
     if (live && !amb) {
         const unsigned grp = (unsigned)(key & 0xffffffffu);
-        const int base = dir ? (int)(grp >> 5) * (32 * R) + (int)(grp & 31u) : (int)grp * kGroup;
-        const int stride = dir ? 32 : 1;
+        const int base = strided ? (int)(grp >> 5) * (32 * R) + (int)(grp & 31u) : (int)grp * kGroup;
+        const int stride = strided ? 32 : 1;
 #pragma unroll 4
         for (int k = 0; k < gsz; ++k) {
             const int j = min(base + ((k + lane) & (gsz - 1)) * stride, nc - 1);   // rotated per lane: conflict-free

@@ -368,7 +368,8 @@ int rlg_chamfer_loss_fwd(const float *pc1, const float *pc2, int B, int N, int M
     w.colsec = w.rowsec + (size_t)B * N;
     w.nrm = (unsigned *)((char *)ws + keys_bytes(B, N, M) + secs_bytes(B, N, M));
     int R = 0;
-    int rc = launch_filter(pc1, pc2, B, N, M, (int)variant, w, &R, st);
+    int rc = (flags & RLG_CHAMFER_ALGO_TENSOR) ? launch_tcfilter(pc1, pc2, B, N, M, w, st)
+                                                : launch_filter(pc1, pc2, B, N, M, (int)variant, w, &R, st);
     if (rc) return rc;
     if (flags & RLG_CHAMFER_TILE_ONLY) return 0;
     char *fin = (char *)ws + keys_bytes(B, N, M) + secs_bytes(B, N, M) + nrm_bytes(B);

@@ -63,6 +63,9 @@ struct FwdWs {
 size_t finalize2_ws_bytes(int B, int N, int M);
 int launch_filter(const float *pc1, const float *pc2, int B, int N, int M, int variant, const FwdWs &w,
                   int *rows_per_lane, cudaStream_t st);
+// tensor-core pair sweep (chamfer_tcfilter.cu): groups are 32 consecutive candidates in BOTH directions; the finalize is
+// told so by rows_per_lane == 0
+int launch_tcfilter(const float *pc1, const float *pc2, int B, int N, int M, const FwdWs &w, cudaStream_t st);
 int launch_finalize2(const float *pc1, const float *pc2, int B, int N, int M, int rows_per_lane, const FwdWs &w,
                      void *fin_ws, float *d1, float *d2, int32_t *i1, int32_t *i2, float *mean1, float *mean2,
                      float *loss, float w1, float w2, float *zero1, float *zero2, cudaStream_t st);

@@ -52,6 +52,9 @@ extern "C" {
                                          outputs untouched, workspace left dirty) so it can be timed alone */
 #define RLG_CHAMFER_ALGO_DIRECT 8u    /* run the direct-form tile kernel (every pair evaluated exactly, 6 FP32
                                          operations per pair) instead of the filter-and-refine kernel: cross-check */
+#define RLG_CHAMFER_ALGO_TENSOR 16u   /* pair sweep with the 3-term contraction on the tensor cores (tcgen05, split-tf32
+                                         operands, fp32 accumulation in TMEM) and only the minima on the CUDA cores;
+                                         same exact refinement, same outputs bit for bit (chamfer_tcfilter.cu) */
 
 int rlg_version(void);
 const char *rlg_last_error(void);
