@@ -281,37 +281,62 @@ def run_ours(args):
     ws.fill_(0xFF)
     stream = torch.cuda.current_stream().cuda_stream
 
-    def tile_only(x, y):
-        rc = lib.rlg_chamfer_fwd(x.data_ptr(), y.data_ptr(), B, N, M, d1.data_ptr(), d2.data_ptr(), i1.data_ptr(),
-                                 i2.data_ptr(), None, None, ws.data_ptr(), ws.numel(),
-                                 _lib.CHAMFER_WS_CLEAN | _lib.CHAMFER_TILE_ONLY, stream)
-        _lib.check("rlg_chamfer_fwd", rc)
+    def time_sweep(algo_flag):
+        def tile_only(x, y):
+            rc = lib.rlg_chamfer_fwd(x.data_ptr(), y.data_ptr(), B, N, M, d1.data_ptr(), d2.data_ptr(), i1.data_ptr(),
+                                     i2.data_ptr(), None, None, ws.data_ptr(), ws.numel(),
+                                     _lib.CHAMFER_WS_CLEAN | _lib.CHAMFER_TILE_ONLY | algo_flag, stream)
+            _lib.check("rlg_chamfer_fwd", rc)
 
-    for k in range(20):
-        tile_only(*[t_.detach() for t_ in ring[k % slots]])
-    torch.cuda.synchronize()
+        ws.fill_(0xFF)
+        for k in range(20):
+            tile_only(*[t_.detach() for t_ in ring[k % slots]])
+        torch.cuda.synchronize()
+        reps_ = 400
+        e0.record()
+        for k in range(reps_):
+            x, y = ring[k % slots]
+            tile_only(x.detach(), y.detach())
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps_
+
     reps = 400
-    e0.record()
-    for k in range(reps):
-        x, y = ring[k % slots]
-        tile_only(x.detach(), y.detach())
-    e1.record()
-    torch.cuda.synchronize()
-    tile_ms = e0.elapsed_time(e1) / reps
+    use_tensor = rlg.get_default_sweep() == "tensor" or (rlg.get_default_sweep() == "auto" and N >= 64 and M >= 64)
+    tc_ms = time_sweep(_lib.CHAMFER_ALGO_TENSOR)
+    fp_ms = time_sweep(0)
+    ws.fill_(0xFF)
+    tile_ms = tc_ms if use_tensor else fp_ms
     achieved_tflops = FLOP_PER_PAIR * B / (tile_ms * 1e-3) / 1e12
+    fp_tflops = FLOP_PER_PAIR * B / (fp_ms * 1e-3) / 1e12
 
     peak = (ctypes_float6(lib, dev))
     fp32_theory = peak[2]
-    roofline = {"bound": "fp32", "kernel": "chamfer_filter_kernel<16>", "achieved": achieved_tflops, "peak": fp32_theory,
-                "unit": "TFLOP/s", "frac": achieved_tflops / fp32_theory,
-                "traffic": 3174656,    # dram__bytes_read+write per launch, profiles/r1_chamfer_kernels_ncu.txt (ncu --set full)
-                "peak_source": f"theoretical FP32 FMA: {int(peak[3])} SMs x 128 lanes x 2 flop x {peak[1]:.0f} MHz "
-                               "(MEASURED_PEAKS.json has no FP32 entry; north_star names the FFMA peak)",
-                "peak_measured_ffma": peak[0], "peak_measured_ffma2": peak[4],
-                "fp32_pipe_ops_per_pair": 4, "note": "algorithmic 8 flop per pair; the filter spends 4 FP32-pipe operations "
-                "(3 FFMA + 1 FADD) per pair, the exact direct form (6) only on candidates within the rounding margin",
-                "frac_of_measured_ffma": achieved_tflops / peak[0] if peak[0] else None,
-                "launch_us": tile_ms * 1e3, "algorithmic_flop_per_launch": FLOP_PER_PAIR * B}
+    peak_src = (f"theoretical FP32 FMA: {int(peak[3])} SMs x 128 lanes x 2 flop x {peak[1]:.0f} MHz "
+                "(MEASURED_PEAKS.json has no FP32 entry; north_star names the FFMA peak)")
+    fp32_sweep = {"bound": "fp32", "kernel": "chamfer_filter_kernel<16>", "achieved": fp_tflops, "peak": fp32_theory,
+                  "unit": "TFLOP/s", "frac": fp_tflops / fp32_theory,
+                  "traffic": 3174656,   # dram__bytes_read+write per launch, profiles/r1_chamfer_kernels_ncu.txt (ncu --set full)
+                  "peak_source": peak_src, "fp32_pipe_ops_per_pair": 4, "launch_us": fp_ms * 1e3,
+                  "note": "the FP32-pipe sweep (RLG_CHAMFER_SWEEP=fp32): 3 FFMA + 1 FADD + 2 min slots per pair through one "
+                          "dispatch port per SM sub-partition caps the FFMA pipe near 60 % (tools/ubench2.cu, DESIGN.md 3.1)"}
+    if use_tensor:
+        roofline = {"bound": "fp32", "kernel": "chamfer_tcfilter_kernel", "achieved": achieved_tflops, "peak": fp32_theory,
+                    "unit": "TFLOP/s", "frac": achieved_tflops / fp32_theory,
+                    "traffic": None,
+                    "peak_source": peak_src, "peak_measured_ffma": peak[0], "peak_measured_ffma2": peak[4],
+                    "note": "algorithmic 8 flop per point pair against the FP32 FFMA peak north_star names.  This kernel "
+                            "runs the 3-term contraction on the tensor pipe (tcgen05 kind::tf32, split-tf32 operands, "
+                            "2 x 128x128x8 MMAs per 128x128 pairs: 2*16 flop per pair on a pipe with ~1.1 PFLOP/s) and "
+                            "only the minima on the CUDA cores (~1.4 issue slots per pair and direction); its bound is "
+                            "the SM issue rate of the min reduction, not the FFMA pipe",
+                    "frac_of_measured_ffma": achieved_tflops / peak[0] if peak[0] else None,
+                    "launch_us": tile_ms * 1e3, "algorithmic_flop_per_launch": FLOP_PER_PAIR * B,
+                    "fp32_sweep": fp32_sweep}
+    else:
+        roofline = dict(fp32_sweep, peak_measured_ffma=peak[0], peak_measured_ffma2=peak[4],
+                        frac_of_measured_ffma=fp_tflops / peak[0] if peak[0] else None,
+                        algorithmic_flop_per_launch=FLOP_PER_PAIR * B)
 
     # backward: HBM-bound by bytes, launch-bound at this size
     g = torch.full((B,), 0.5 / B, device=dev)
@@ -359,7 +384,8 @@ def run_ours(args):
                    "M": M, "global_batch": B * world, "parallelism": f"batch-sharded dp{world}",
                    "l2_policy": f"inputs cycle through a ring of {slots} batches = {slots * slot_bytes >> 20} MiB > 126 MB L2",
                    "step": "ChamferLoss forward + backward (autograd), captured S steps per CUDA graph; loss all-reduce async "
-                           "per replay when n_gpus > 1", "steps_per_graph": slots, "last_loss": last_loss},
+                           "per replay when n_gpus > 1", "steps_per_graph": slots, "last_loss": last_loss,
+                   "pair_sweep": "tensor (tcgen05 kind::tf32 contraction + CUDA-core minima)" if use_tensor else "fp32 (FFMA pipe)"},
         "roofline": roofline, "roofline_bwd": roofline_bwd, "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": slot_bytes, "d2h_bytes_per_step": 4,
                 "steps": Ke, "loss_step0": e2e_loss_check,

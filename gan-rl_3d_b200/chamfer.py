@@ -58,16 +58,32 @@ class _Workspace:
         return ws
 
 
-_DEFAULT_TENSOR = os.environ.get("RLG_CHAMFER_SWEEP", "fp32").lower() in ("tensor", "tc", "tcgen05")
+_DEFAULT_SWEEP = os.environ.get("RLG_CHAMFER_SWEEP", "auto").lower()
+if _DEFAULT_SWEEP not in ("fp32", "tensor", "auto"):
+    raise ValueError("RLG_CHAMFER_SWEEP must be fp32, tensor or auto")
 
 
 def set_default_sweep(kind: str) -> None:
-    """'fp32': pair sweep on the FP32 pipe (chamfer_filter.cu); 'tensor': contraction on tcgen05 (chamfer_tcfilter.cu).
-    Both feed the same exact refinement; outputs are bit-identical."""
-    global _DEFAULT_TENSOR
-    if kind not in ("fp32", "tensor"):
-        raise ValueError("kind must be 'fp32' or 'tensor'")
-    _DEFAULT_TENSOR = kind == "tensor"
+    """Which kernel sweeps the N x M pairs when chamfer_nearest() is not told explicitly:
+    'fp32'   the FP32-pipe filter (chamfer_filter.cu),
+    'tensor' the contraction on tcgen05 with split-tf32 operands (chamfer_tcfilter.cu),
+    'auto'   (default) tensor when both clouds have at least 64 points, else fp32 (a 128 x 256 tensor tile is mostly
+             padding for tiny clouds).
+    Both feed the same exact refinement; the outputs are bit-identical."""
+    global _DEFAULT_SWEEP
+    if kind not in ("fp32", "tensor", "auto"):
+        raise ValueError("kind must be 'fp32', 'tensor' or 'auto'")
+    _DEFAULT_SWEEP = kind
+
+
+def get_default_sweep() -> str:
+    return _DEFAULT_SWEEP
+
+
+def _use_tensor(tensor: Optional[bool], n: int, m: int) -> bool:
+    if tensor is not None:
+        return bool(tensor)
+    return _DEFAULT_SWEEP == "tensor" or (_DEFAULT_SWEEP == "auto" and n >= 64 and m >= 64)
 
 
 def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = True, simple: bool = False,
@@ -113,7 +129,7 @@ def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = Tru
             flags |= _lib.CHAMFER_WS_CLEAN
         if direct:
             flags |= _lib.CHAMFER_ALGO_DIRECT
-        elif not simple and (_DEFAULT_TENSOR if tensor is None else tensor) and not variant:
+        elif not simple and not variant and _use_tensor(tensor, N, M):
             flags |= _lib.CHAMFER_ALGO_TENSOR
         flags |= (int(variant) & 15) << 8
         ws.clean = False

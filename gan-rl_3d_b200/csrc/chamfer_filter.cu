@@ -416,7 +416,9 @@ __device__ __forceinline__ void scan_strided(const float *__restrict__ c, int nc
     }
 }
 
-template <bool SMEM>
+// TWO: the sweep also reported the runner-up group and the third-smallest group minimum (tensor-core sweep on large
+// candidate clouds, rows_per_lane == 0): ambiguous points are refined on two groups when the third is out of reach
+template <bool SMEM, bool TWO>
 __global__ void __launch_bounds__(kFin2Threads) chamfer_finalize2_kernel(
     const float *__restrict__ pc1, const float *__restrict__ pc2, int N, int M, int rows_per_lane, FwdWs w, Fin2Ws fw,
     float *__restrict__ d1, float *__restrict__ d2, int32_t *__restrict__ i1, int32_t *__restrict__ i2,
@@ -450,7 +452,7 @@ __global__ void __launch_bounds__(kFin2Threads) chamfer_finalize2_kernel(
     const int i = chunk * kFin2Threads + tid;
     const bool live = i < nq;
     u64 key = kKeyInit;
-    unsigned sec = 0xffffffffu;
+    unsigned sec = 0xffffffffu, sgrp = 0, third = 0xffffffffu;
     float qx = 0.f, qy = 0.f, qz = 0.f;
     if (live) { qx = __ldg(q + 3 * (size_t)i); qy = __ldg(q + 3 * (size_t)i + 1); qz = __ldg(q + 3 * (size_t)i + 2); }
 
@@ -472,6 +474,10 @@ __global__ void __launch_bounds__(kFin2Threads) chamfer_finalize2_kernel(
     if (live) {
         key = keys[i];
         sec = secs[i];
+        if (TWO) {
+            sgrp = (dir ? w.colsg : w.rowsg)[(size_t)b * nq + i];
+            third = (dir ? w.colth : w.rowth)[(size_t)b * nq + i];
+        }
     }
     // largest squared norm of the OTHER cloud (the filter kernel published its bitwise complement)
     const float onrm = __uint_as_float(~w.nrm[dir ? b : B + b]);
@@ -490,7 +496,11 @@ __global__ void __launch_bounds__(kFin2Threads) chamfer_finalize2_kernel(
     const float sv = __uint_as_float(sec);
     const float margin = (R > 0 ? kMarginC : kMarginT) * (norm2(qx, qy, qz) + onrm) + (strided ? kMarginQ * val : 0.0f);
     // any NaN (untouched key, non-finite input) makes the comparison false -> treated as ambiguous
-    const bool amb = live && !(sv > val + margin);
+    const bool amb2 = live && !(sv > val + margin);     // a second group is within the margin of the best one
+    // the tensor-core sweep also reports WHICH group that is and the third-smallest group minimum: if the third is out of
+    // reach, the exact winner lies in one of two known groups (64 candidates instead of the whole cloud)
+    const bool two = TWO && amb2 && (__uint_as_float(third) > val + margin);
+    const bool amb = amb2 && !two;
     // deterministic list of the CTA's ambiguous points
     const unsigned am = __ballot_sync(0xffffffffu, amb);
     if (lane == 0) s_wcount[wid] = __popc(am);
@@ -517,6 +527,14 @@ __global__ void __launch_bounds__(kFin2Threads) chamfer_finalize2_kernel(
             const int j = min(base + ((k + lane) & (gsz - 1)) * stride, nc - 1);   // rotated per lane: conflict-free
             const float t = sqdist(qx, qy, qz, c[3 * j], c[3 * j + 1], c[3 * j + 2]);
             if (t < bt || (t == bt && j < bj)) { bt = t; bj = j; }
+        }
+        if (TWO && two) {
+            const int base2 = (int)sgrp * kGroup;
+            for (int k = 0; k < kGroup; ++k) {
+                const int j = min(base2 + ((k + lane) & (kGroup - 1)), nc - 1);
+                const float t = sqdist(qx, qy, qz, c[3 * j], c[3 * j + 1], c[3 * j + 2]);
+                if (t < bt || (t == bt && j < bj)) { bt = t; bj = j; }
+            }
         }
     }
     __syncthreads();                                    // s_list complete
@@ -603,21 +621,22 @@ int launch_finalize2(const float *pc1, const float *pc2, int B, int N, int M, in
     const size_t cand_bytes = (size_t)(N > M ? N : M) * 3 * sizeof(float);
     const bool in_smem = cand_bytes <= 200u * 1024u;
     dim3 grid(fw.chunks_max, B, 2);
-    if (in_smem) {
-        const size_t dyn = align_up(cand_bytes, 16);
+    const bool two = rows_per_lane == 0;
+    auto launch = [&](auto kernel, size_t dyn) -> int {
         if (dyn > 40u * 1024u) {
-            cudaError_t e = cudaFuncSetAttribute(chamfer_finalize2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)(200u * 1024u));
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200u * 1024u));
             if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "rlg_chamfer_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
         }
-        cudaError_t le = launch_pdl(chamfer_finalize2_kernel<true>, grid, dim3(kFin2Threads), dyn, st, pc1, pc2, N, M, rows_per_lane,
-                                    w, fw, d1, d2, i1, i2, mean1, mean2, loss, w1, w2, zero1, zero2);
+        cudaError_t le = launch_pdl(kernel, grid, dim3(kFin2Threads), dyn, st, pc1, pc2, N, M, rows_per_lane, w, fw, d1, d2, i1, i2,
+                                    mean1, mean2, loss, w1, w2, zero1, zero2);
         if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "chamfer_finalize2_kernel: %s", cudaGetErrorString(le)); }
-    } else {
-        cudaError_t le = launch_pdl(chamfer_finalize2_kernel<false>, grid, dim3(kFin2Threads), 0, st, pc1, pc2, N, M, rows_per_lane,
-                                    w, fw, d1, d2, i1, i2, mean1, mean2, loss, w1, w2, zero1, zero2);
-        if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "chamfer_finalize2_kernel: %s", cudaGetErrorString(le)); }
-    }
+        return 0;
+    };
+    const size_t dyn = in_smem ? align_up(cand_bytes, 16) : 0;
+    int rc;
+    if (in_smem) rc = two ? launch(chamfer_finalize2_kernel<true, true>, dyn) : launch(chamfer_finalize2_kernel<true, false>, dyn);
+    else rc = two ? launch(chamfer_finalize2_kernel<false, true>, dyn) : launch(chamfer_finalize2_kernel<false, false>, dyn);
+    if (rc) return rc;
     return check_launch("chamfer_finalize2_kernel");
 }
 

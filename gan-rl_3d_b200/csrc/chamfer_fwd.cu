@@ -292,7 +292,8 @@ size_t rlg_chamfer_ws_bytes(int B, int N, int M) {
     // cross-check path uses a prefix of the same layout)
     const size_t fin = finalize2_ws_bytes(B, N, M) > finalize_ws_bytes(B, N, M) ? finalize2_ws_bytes(B, N, M)
                                                                                 : finalize_ws_bytes(B, N, M);
-    return keys_bytes(B, N, M) + secs_bytes(B, N, M) + nrm_bytes(B) + fin;
+    // + second group / third value of the tensor-core sweep (two more arrays shaped like the second-best values)
+    return keys_bytes(B, N, M) + secs_bytes(B, N, M) + nrm_bytes(B) + fin + 2 * secs_bytes(B, N, M);
 }
 
 int rlg_chamfer_fwd(const float *pc1, const float *pc2, int B, int N, int M, float *d1, float *d2,
@@ -367,8 +368,12 @@ int rlg_chamfer_loss_fwd(const float *pc1, const float *pc2, int B, int N, int M
     w.rowsec = (unsigned *)((char *)ws + keys_bytes(B, N, M));
     w.colsec = w.rowsec + (size_t)B * N;
     w.nrm = (unsigned *)((char *)ws + keys_bytes(B, N, M) + secs_bytes(B, N, M));
+    w.rowsg = (unsigned *)((char *)ws + need - 2 * secs_bytes(B, N, M));
+    w.colsg = w.rowsg + (size_t)B * N;
+    w.rowth = (unsigned *)((char *)ws + need - secs_bytes(B, N, M));
+    w.colth = w.rowth + (size_t)B * N;
     int R = 0;
-    int rc = (flags & RLG_CHAMFER_ALGO_TENSOR) ? launch_tcfilter(pc1, pc2, B, N, M, w, st)
+    int rc = (flags & RLG_CHAMFER_ALGO_TENSOR) ? launch_tcfilter(pc1, pc2, B, N, M, w, &R, st)
                                                 : launch_filter(pc1, pc2, B, N, M, (int)variant, w, &R, st);
     if (rc) return rc;
     if (flags & RLG_CHAMFER_TILE_ONLY) return 0;

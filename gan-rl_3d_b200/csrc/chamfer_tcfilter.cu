@@ -21,14 +21,20 @@
 //   with the roles of the clouds swapped (the tensor pipe has the headroom), so a "group" is 32 consecutive candidates
 //   in either direction.
 //
-// Error bound of the filter (u = 2^-24, a = |x_i|, b = |y_j|):
-//   dropped / residual split terms      <= 3 * 2^-22 * 2 a b          <= 12 u (a^2 + b^2)
-//   accumulation inside the tensor core  15 terms, each <= a^2 + b^2; the hardware's fp32 accumulation is not
-//                                        specified bit for bit -- budgeted at 4 u per term       <= 64 u (a^2 + b^2)
-//   computed norms                                                                        <=  3 u (a^2 + b^2)
-//   => |t~ - t| <= 80 u (a^2 + b^2); with the direct form's 5 u t two candidates can swap only within
-//   2 * (80 + 10) u (a^2 + b^2) = 180 u.  kMarginT = 256 u (chamfer_filter.cu, finalize).  tests/test_chamfer_gpu.py
-//   measures the actual filter error against float64 (it is ~10x smaller) and the parity suite runs on this path.
+// Error bound of the filter (u = 2^-24, a = |x_i|, b = |y_j|, S = a^2 + b^2):
+//   dropped / residual split terms       3 * 2^-22 * 2 a b                                        <= 12 u S
+//   accumulation inside the tensor core  not specified bit for bit; modelled as truncation to an fp32 significand
+//                                        (1 ulp = 2 u of the running sum, which never exceeds S) at every one of the
+//                                        16 product additions and the 2 accumulator updates                <= 36 u S
+//   computed norms                                                                                <=  3 u S
+//   => |t~ - t| <= 51 u S; with the direct form's <= 10 u S two candidates can swap only within 2 * 61 u S = 122 u S.
+//   kMarginT = 128 u (chamfer_filter.cu, finalize).  tests/test_chamfer_gpu.py measures the filter against float64: the
+//   largest error seen is ~4.5 u S, and the whole parity suite runs on this path as well as on the FP32 one.
+//
+// Besides the best group and the runner-up VALUE (what the FP32 sweep reports), this sweep also reports the runner-up's
+// group and the third-smallest group minimum: a point whose runner-up is within the margin but whose third is not is
+// refined exactly on two groups (64 candidates) instead of the whole candidate cloud -- at N = 16384 that is the
+// difference between a finalize of ~1.6 ms and one that is a fraction of the sweep.
 //
 // Roles (one CTA per SM, persistent over (direction, cloud, 128-query block) tasks):
 //   A CTA owns a contiguous range of the tasks and walks it in segments of up to 8 query blocks of one (direction,
@@ -48,7 +54,7 @@ namespace rlg {
 
 static constexpr int kTQ = 128;                       // queries per block (UMMA M)
 static constexpr int kTC = 256;                       // candidates per tile (UMMA N)
-static constexpr int kQmax = 7;                       // query blocks that share one pass over the candidate tiles
+static constexpr int kQmax = 8;                       // query blocks that share one pass over the candidate tiles
 static constexpr int kTfEpGroups = 4;                 // epilogue warp groups == 128-column TMEM accumulators
 static constexpr int kTfEpWarps = 4 * kTfEpGroups, kTfPrWarps = 2;
 static constexpr int kTfMmaWarp = kTfEpWarps + kTfPrWarps;
@@ -56,9 +62,12 @@ static constexpr int kTfThreads = (kTfEpWarps + kTfPrWarps + 1) * 32;
 static constexpr int kTfPrThreads = kTfPrWarps * 32;
 static constexpr int kARows = kTQ / kTfPrThreads, kBRows = kTC / kTfPrThreads;   // rows per producer thread
 static constexpr uint32_t kTfABytes = kTQ * 128, kTfBBytes = kTC * 128;
-static constexpr uint32_t kTfOffB = kQmax * kTfABytes;                         // two candidate tiles
-static constexpr uint32_t kTfOffState = kTfOffB + 2 * kTfBBytes;               // [groups][kQmax][128] x (best, second, group)
-static constexpr uint32_t kTfStateBytes = (uint32_t)kTfEpGroups * kQmax * kTQ * 3u * 4u;
+// A rows carry K = 16 tf32 = 64 bytes, half of a SWIZZLE_128B row: two query blocks share one 16 KB tile (block q sits in
+// 16-byte chunks 4*(q&1) .. 4*(q&1)+3 of tile q>>1; the descriptor's start address selects the half)
+static constexpr uint32_t kTfOffB = (kQmax / 2) * kTfABytes;                   // two candidate tiles follow the A tiles
+static constexpr int kStW = 5;                                                 // state words: best, second, third, best grp, second grp
+static constexpr uint32_t kTfOffState = kTfOffB + 2 * kTfBBytes;               // [groups][kQmax][kStW][128]
+static constexpr uint32_t kTfStateBytes = (uint32_t)kTfEpGroups * kQmax * kTQ * kStW * 4u;
 static constexpr uint32_t kTfOffBar = kTfOffState + kTfStateBytes;
 static constexpr uint32_t kTfSmem = kTfOffBar + 256 + 1024;                    // + barriers + alignment slack
 static constexpr float kTfBig = 1.0e30f;
@@ -79,11 +88,11 @@ __device__ __forceinline__ void tf32_split3(float v, float &h, float &m, float &
     l = r - m;                                         // exact, at most 3 significant bits
 }
 // row `row` of a K-major SW128 tile: 16 floats as four 16-byte chunks
-__device__ __forceinline__ void tf_store_row(unsigned char *tile, int row, const float (&e)[16]) {
+__device__ __forceinline__ void tf_store_row(unsigned char *tile, int row, const float (&e)[16], uint32_t chunk0 = 0) {
     const uint32_t base = (uint32_t)row * 128u, x = (uint32_t)row & 7u;
 #pragma unroll
     for (uint32_t c = 0; c < 4; ++c)
-        *reinterpret_cast<float4 *>(tile + base + ((c ^ x) << 4)) = make_float4(e[4 * c], e[4 * c + 1], e[4 * c + 2], e[4 * c + 3]);
+        *reinterpret_cast<float4 *>(tile + base + (((chunk0 + c) ^ x) << 4)) = make_float4(e[4 * c], e[4 * c + 1], e[4 * c + 2], e[4 * c + 3]);
 }
 __device__ __forceinline__ float norm2_tf(float x, float y, float z) { return fmaf(z, z, fmaf(y, y, x * x)); }
 
@@ -105,6 +114,9 @@ __device__ unsigned long long g_tf_dbg[16];
 #define TF_ACC(slot, v) do { if (dbg) dbg_acc[(slot) & 3] += (unsigned long long)(clock64() - (v)); } while (0)
 #define TF_FLUSH(base) do { if (dbg) { for (int z = 0; z < 4; ++z) g_tf_dbg[(base) + z] = dbg_acc[z]; } } while (0)
 
+// TOP3: also track the runner-up's group and the third-smallest group minimum (5 more issue slots per 32 candidates;
+// pays off when ambiguous points would otherwise rescan a large candidate cloud -- see launch_tcfilter)
+template <bool TOP3>
 __global__ void __launch_bounds__(kTfThreads, 1)
 chamfer_tcfilter_kernel(const float *__restrict__ pc1, const float *__restrict__ pc2, int B, int N, int M, int n_tasks,
                         int qb1, int qb2, FwdWs w, int ko) {
@@ -186,7 +198,7 @@ chamfer_tcfilter_kernel(const float *__restrict__ pc1, const float *__restrict__
                         { TF_T0(t0); mbar_wait_spin(bar_accempty + 8 * ab, ((gt >> 2) & 1u) ^ 1u); TF_ACC(3, t0); }
                         tc_fence_after();
                         if (leader) {
-                            const uint64_t ad = ad0 + (uint64_t)q * a_inc;
+                            const uint64_t ad = ad0 + (uint64_t)(q >> 1) * a_inc + (uint64_t)((q & 1) * 4);
                             const uint64_t bh = bd + (uint64_t)hf * (b_inc >> 1);
                             const uint32_t d = tmem + ab * (uint32_t)(kTC / 2);
                             tc_mma_tf32(d, ad, bh, idesc, 0u);                  // K columns 0..7  (32 bytes)
@@ -251,7 +263,7 @@ chamfer_tcfilter_kernel(const float *__restrict__ pc1, const float *__restrict__
                         tf32_split3(nx, e[9], e[10], e[11]);
                         e[12] = 1.0f; e[13] = 1.0f; e[14] = 1.0f;
                     }
-                    tf_store_row(tileA0 + (uint32_t)q * kTfABytes, r, e);
+                    tf_store_row(tileA0 + (uint32_t)(q >> 1) * kTfABytes, r, e, 4u * (uint32_t)(q & 1));
                 }
                 // largest |q|^2 of the query cloud, for the finalize's margin (bitwise complement, atomicMin)
                 const unsigned wx = __reduce_max_sync(0xffffffffu, __float_as_uint(nmax));
@@ -318,15 +330,18 @@ chamfer_tcfilter_kernel(const float *__restrict__ pc1, const float *__restrict__
         const uint32_t lane_base = ((uint32_t)(warp & 3) * 32u) << 16;
         const uint32_t taddr = tmem + lane_base + (uint32_t)grp_id * (uint32_t)(kTC / 2);
         // this thread's running (best, second-best group minimum, best group) per query block of the segment
-        float *st_best = reinterpret_cast<float *>(smem + kTfOffState) + (grp_id * kQmax) * kTQ * 3 + row;
-        float *st_second = st_best + kTQ;
-        int *st_grp = reinterpret_cast<int *>(st_best + 2 * kTQ);
+        float *st = reinterpret_cast<float *>(smem + kTfOffState) + (grp_id * kQmax) * kTQ * kStW + row;
+        constexpr int kStQ = kTQ * kStW;                                // words per query block of one group
         uint32_t ht0 = 0;                                               // running half-visit index at the segment start
         TF_T0(t_alle);
         for (int task = t_begin; task < t_end;) {
             const TfSeg sg = seg_at(task);
             task = sg.next;
-            for (int q = 0; q < sg.Q; ++q) { st_best[q * kTQ * 3] = INFINITY; st_second[q * kTQ * 3] = INFINITY; st_grp[q * kTQ * 3] = 0; }
+            for (int q = 0; q < sg.Q; ++q) {
+                float *sq = st + q * kStQ;
+                sq[0] = INFINITY; sq[kTQ] = INFINITY; sq[2 * kTQ] = INFINITY;
+                reinterpret_cast<int *>(sq)[3 * kTQ] = 0; reinterpret_cast<int *>(sq)[4 * kTQ] = 0;
+            }
             // half-visits of the segment in issue order: (tile k, query block q, half hf); this group takes every fourth one
             const uint32_t n_hv = (uint32_t)sg.n_ct * (uint32_t)sg.Q * 2u;
             uint32_t hv = ((uint32_t)grp_id - ht0) & 3u;                // first local index with (ht0 + hv) % 4 == grp_id
@@ -335,13 +350,26 @@ chamfer_tcfilter_kernel(const float *__restrict__ pc1, const float *__restrict__
             while (q >= sg.Q) { q -= sg.Q; ++k; }
             for (; hv < n_hv; hv += 4u) {
                 const uint32_t use = (ht0 + hv) >> 2;
-                float best = st_best[q * kTQ * 3], second = st_second[q * kTQ * 3];
-                int bgrp = st_grp[q * kTQ * 3];
+                float *sq = st + q * kStQ;
+                float best = sq[0], second = sq[kTQ], third = TOP3 ? sq[2 * kTQ] : INFINITY;
+                int bgrp = reinterpret_cast<int *>(sq)[3 * kTQ], sgrp = TOP3 ? reinterpret_cast<int *>(sq)[4 * kTQ] : 0;
+                // running three smallest group minima (strict <: the earliest group keeps a tie) and the groups of the first two
                 auto group_done = [&](const float *v, int G) {
                     if (ko & 2) { best = fminf(best, v[0] + v[31]); return; }
                     const float m = min32(v);
-                    second = fminf(second, fmaxf(best, m));
-                    if (m < best) { best = m; bgrp = G; }                   // strict: the earliest group keeps a tie
+                    if (!TOP3) {
+                        second = fminf(second, fmaxf(best, m));
+                        if (m < best) { best = m; bgrp = G; }
+                        return;
+                    }
+                    const bool p1 = m < best;
+                    const float c1 = fmaxf(best, m);                    // what drops out of first place
+                    const bool p2 = c1 < second;
+                    third = fminf(third, fmaxf(second, c1));
+                    second = fminf(second, c1);
+                    sgrp = p2 ? (p1 ? bgrp : G) : sgrp;
+                    best = fminf(best, m);
+                    bgrp = p1 ? G : bgrp;
                 };
                 { TF_T0(t0); mbar_wait_spin(bar_accfull + 8 * grp_id, use & 1u); TF_ACC(9, t0); }
                 tc_fence_after();
@@ -364,7 +392,9 @@ chamfer_tcfilter_kernel(const float *__restrict__ pc1, const float *__restrict__
                 tc_fence_before();
                 mbar_arrive(bar_accempty + 8 * grp_id);
                 group_done(vb, G0 + 3);
-                st_best[q * kTQ * 3] = best; st_second[q * kTQ * 3] = second; st_grp[q * kTQ * 3] = bgrp;
+                sq[0] = best; sq[kTQ] = second;
+                reinterpret_cast<int *>(sq)[3 * kTQ] = bgrp;
+                if (TOP3) { sq[2 * kTQ] = third; reinterpret_cast<int *>(sq)[4 * kTQ] = sgrp; }
                 TF_ACC(10, t_ep);
                 q += 2;
                 while (q >= sg.Q) { q -= sg.Q; ++k; }
@@ -376,22 +406,38 @@ chamfer_tcfilter_kernel(const float *__restrict__ pc1, const float *__restrict__
             asm volatile("bar.sync 1, %0;" ::"n"(kTfEpWarps * 32) : "memory");
             u64 *keys = (sg.dir ? w.colkey : w.rowkey) + (size_t)sg.b * sg.nq;
             unsigned *secs = (sg.dir ? w.colsec : w.rowsec) + (size_t)sg.b * sg.nq;
-            const float *all_best = reinterpret_cast<const float *>(smem + kTfOffState) + row;
+            unsigned *sgs = (sg.dir ? w.colsg : w.rowsg) + (size_t)sg.b * sg.nq;
+            unsigned *ths = (sg.dir ? w.colth : w.rowth) + (size_t)sg.b * sg.nq;
+            const float *all_st = reinterpret_cast<const float *>(smem + kTfOffState) + row;
             for (int qq = grp_id; qq < sg.Q; qq += kTfEpGroups) {
                 const int i = (sg.qb0 + qq) * kTQ + row;
-                u64 kbest = kKeyInit;
-                float fsec = INFINITY;
+                // three smallest (value, group) keys over the four groups' top-two lists, third value also over their thirds
+                u64 k1 = kKeyInit, k2 = kKeyInit;
+                float t3 = INFINITY;
+                auto insert = [&](u64 key) {
+                    const u64 c1 = key > k1 ? key : k1;
+                    k1 = key < k1 ? key : k1;
+                    const u64 c2 = c1 > k2 ? c1 : k2;
+                    k2 = c1 < k2 ? c1 : k2;
+                    t3 = fminf(t3, __uint_as_float((unsigned)(c2 >> 32) & 0x7fffffffu));    // all-ones init -> NaN: ignored
+                };
 #pragma unroll
                 for (int g = 0; g < kTfEpGroups; ++g) {
-                    const float *sp = all_best + ((g * kQmax + qq) * 3) * kTQ;
-                    const float gb = sp[0], gs = sp[kTQ];
-                    const int gg = reinterpret_cast<const int *>(sp)[2 * kTQ];
-                    const u64 key = ((u64)__float_as_uint(fmaxf(gb, 0.0f)) << 32) | (unsigned)gg;   // +inf if the group saw nothing
-                    const u64 loser = key > kbest ? key : kbest;
-                    kbest = key < kbest ? key : kbest;
-                    fsec = fminf(fsec, fminf(fmaxf(gs, 0.0f), __uint_as_float((unsigned)(loser >> 32) & 0x7fffffffu)));
+                    const float *sp = all_st + (g * kQmax + qq) * kStQ;
+                    const int *ip = reinterpret_cast<const int *>(sp);
+                    insert(((u64)__float_as_uint(fmaxf(sp[0], 0.0f)) << 32) | (unsigned)ip[3 * kTQ]);       // +inf if nothing seen
+                    insert(((u64)__float_as_uint(fmaxf(sp[kTQ], 0.0f)) << 32) | (unsigned)ip[4 * kTQ]);
+                    t3 = fminf(t3, fmaxf(sp[2 * kTQ], 0.0f));
                 }
-                if (i < sg.nq) { keys[i] = kbest; secs[i] = __float_as_uint(fsec); }
+                if (i < sg.nq) {
+                    keys[i] = k1;
+                    const bool has2 = k2 != kKeyInit;                   // a single candidate group: no runner-up
+                    secs[i] = has2 ? (unsigned)(k2 >> 32) : 0x7f800000u;
+                    if (TOP3) {
+                        sgs[i] = has2 ? (unsigned)(k2 & 0xffffffffu) : 0u;
+                        ths[i] = __float_as_uint(t3);
+                    }
+                }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kTfEpWarps * 32) : "memory");
             TF_ACC(11, t_fl);
@@ -407,21 +453,31 @@ chamfer_tcfilter_kernel(const float *__restrict__ pc1, const float *__restrict__
     }
 }
 
-int launch_tcfilter(const float *pc1, const float *pc2, int B, int N, int M, const FwdWs &w, cudaStream_t st) {
+// rows_per_lane tells the finalize what the sweep reported: 0 = consecutive groups + runner-up group + third value,
+// -1 = consecutive groups only
+int launch_tcfilter(const float *pc1, const float *pc2, int B, int N, int M, const FwdWs &w, int *rows_per_lane, cudaStream_t st) {
     const int qb1 = (N + kTQ - 1) / kTQ, qb2 = (M + kTQ - 1) / kTQ;
     const long long n_tasks = (long long)B * (qb1 + qb2);
     if (n_tasks > 0x7fffffffLL) return fail(RLG_ERR_TOO_LARGE, "rlg_chamfer_fwd: too many query blocks");
     const int sms = sm_count();
     if (sms <= 0) return fail((int)cudaErrorNoDevice, "rlg_chamfer_fwd: no CUDA device");
+    // Ambiguous points (runner-up group within the margin) cost a rescan of the whole candidate cloud unless the sweep
+    // tracks three groups; their share grows with the point density.  Break-even is around 4096 candidates.
+    const bool top3 = getenv("RLG_TF_TOP3") ? atoi(getenv("RLG_TF_TOP3")) != 0 : (N > 4096 || M > 4096);
+    *rows_per_lane = top3 ? 0 : -1;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(chamfer_tcfilter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTfSmem);
+        cudaError_t e = cudaFuncSetAttribute(chamfer_tcfilter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTfSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(chamfer_tcfilter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTfSmem);
         if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "chamfer_tcfilter_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
         attr_set = true;
     }
     const int grid = (int)(n_tasks < sms ? n_tasks : sms);
-    cudaError_t le = launch_pdl(chamfer_tcfilter_kernel, dim3((unsigned)grid), dim3(kTfThreads), (size_t)kTfSmem, st, pc1, pc2, B, N, M,
-                                (int)n_tasks, qb1, qb2, w, (getenv("RLG_TF_KO") ? atoi(getenv("RLG_TF_KO")) : 0) | (getenv("RLG_TF_DEBUG") ? 16 : 0));
+    const int ko = (getenv("RLG_TF_KO") ? atoi(getenv("RLG_TF_KO")) : 0) | (getenv("RLG_TF_DEBUG") ? 16 : 0);
+    cudaError_t le = top3 ? launch_pdl(chamfer_tcfilter_kernel<true>, dim3((unsigned)grid), dim3(kTfThreads), (size_t)kTfSmem, st, pc1,
+                                       pc2, B, N, M, (int)n_tasks, qb1, qb2, w, ko)
+                          : launch_pdl(chamfer_tcfilter_kernel<false>, dim3((unsigned)grid), dim3(kTfThreads), (size_t)kTfSmem, st, pc1,
+                                       pc2, B, N, M, (int)n_tasks, qb1, qb2, w, ko);
     if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "chamfer_tcfilter_kernel: %s", cudaGetErrorString(le)); }
     if (getenv("RLG_TF_DEBUG")) {
         cudaStreamSynchronize(st);

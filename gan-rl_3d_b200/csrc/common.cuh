@@ -59,13 +59,17 @@ struct FwdWs {
     u64 *rowkey, *colkey;          // (B,N), (B,M): filter value bits << 32 | winning candidate group
     unsigned *rowsec, *colsec;     // (B,N), (B,M): smallest filter value of any OTHER group
     unsigned *nrm;                 // (2,B): bitwise complement of the largest |p|^2 of pc1[b] / pc2[b]
+    // tensor-core sweep only (plain stores, no all-ones invariant): the group holding the second-smallest group minimum
+    // and the third-smallest group minimum -- an ambiguous point is refined on two groups instead of the whole cloud
+    unsigned *rowsg, *colsg;       // (B,N), (B,M)
+    unsigned *rowth, *colth;       // (B,N), (B,M)
 };
 size_t finalize2_ws_bytes(int B, int N, int M);
 int launch_filter(const float *pc1, const float *pc2, int B, int N, int M, int variant, const FwdWs &w,
                   int *rows_per_lane, cudaStream_t st);
 // tensor-core pair sweep (chamfer_tcfilter.cu): groups are 32 consecutive candidates in BOTH directions; the finalize is
-// told so by rows_per_lane == 0
-int launch_tcfilter(const float *pc1, const float *pc2, int B, int N, int M, const FwdWs &w, cudaStream_t st);
+// told so by rows_per_lane <= 0 (0: the runner-up group and the third value are reported too, -1: not)
+int launch_tcfilter(const float *pc1, const float *pc2, int B, int N, int M, const FwdWs &w, int *rows_per_lane, cudaStream_t st);
 int launch_finalize2(const float *pc1, const float *pc2, int B, int N, int M, int rows_per_lane, const FwdWs &w,
                      void *fin_ws, float *d1, float *d2, int32_t *i1, int32_t *i2, float *mean1, float *mean2,
                      float *loss, float w1, float w2, float *zero1, float *zero2, cudaStream_t st);

@@ -103,6 +103,9 @@ class HostChamferStepGraph:
         self.copy = torch.cuda.Stream(device)
         self.readback = torch.cuda.Stream(device)
         self.graph = torch.cuda.CUDAGraph()
+        # device loss scalars of the captured steps, kept alive: each is read by a D2H copy on ANOTHER stream, so its
+        # block must not go back to the capture pool (where the next step's outputs would overwrite it early)
+        self._losses_dev: List[torch.Tensor] = []
         self._capture()
 
     def _copy_in(self, k: int) -> None:
@@ -138,6 +141,7 @@ class HostChamferStepGraph:
             def step_and_read_back(j: int) -> None:
                 self.compute.wait_event(copied[j])
                 loss = self._step(j)
+                self._losses_dev.append(loss)
                 computed[j] = torch.cuda.Event()
                 computed[j].record(self.compute)
                 self.readback.wait_event(computed[j])

@@ -11,6 +11,19 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True, params=["fp32", "tensor", "tensor_top3"])
+def sweep(request, rlg, monkeypatch):
+    """Every test of this module runs once per pair-sweep kernel: the FP32-pipe filter (chamfer_filter.cu) and the
+    tensor-core filter (chamfer_tcfilter.cu), the latter with and without the runner-up-group / third-value report
+    the library otherwise enables by cloud size.  All must give the same bits."""
+    old = rlg.get_default_sweep()
+    rlg.set_default_sweep("fp32" if request.param == "fp32" else "tensor")
+    if request.param != "fp32":
+        monkeypatch.setenv("RLG_TF_TOP3", "1" if request.param == "tensor_top3" else "0")
+    yield request.param
+    rlg.set_default_sweep(old)
+
+
 def _run(rlg, pc1, pc2, simple=False, **kw):
     d1, d2, i1, i2, m1, m2 = rlg.chamfer_nearest(pc1.to(DEV), pc2.to(DEV), simple=simple, **kw)
     torch.cuda.synchronize()
@@ -267,3 +280,35 @@ def test_cuda_graph_capture(rlg):
     graph.replay()
     torch.cuda.synchronize()
     assert all(torch.equal(x, y) for x, y in zip(got, want))
+
+
+def test_tensor_filter_error_is_far_inside_its_margin(rlg):
+    """The tensor-core filter's value for the best candidate vs float64, in units of u (a^2 + b^2): the finalize's
+    margin (128 u) budgets 61 u for it (chamfer_tcfilter.cu); the measured error is an order of magnitude smaller."""
+    import importlib
+    _lib = importlib.import_module("gan-rl_3d_b200._lib")
+    lib = _lib.load()
+    B, N, M = 3, 1400, 2048
+    worst = 0.0
+    for kind, scale, shift in (("sphere", 1.0, 0.0), ("uniform", 1.0, 0.0), ("sphere", 0.1, 2.0), ("uniform", 50.0, 0.0)):
+        a = (torch.as_tensor(O.make_clouds(B, N, kind, 11)) * scale + shift).to(DEV)
+        b = (torch.as_tensor(O.make_clouds(B, M, kind, 12)) * scale + shift).to(DEV)
+        d1 = torch.empty(B, N, device=DEV); d2 = torch.empty(B, M, device=DEV)
+        i1 = torch.empty(B, N, dtype=torch.int32, device=DEV); i2 = torch.empty(B, M, dtype=torch.int32, device=DEV)
+        ws = torch.empty(lib.rlg_chamfer_ws_bytes(B, N, M), dtype=torch.uint8, device=DEV).fill_(0xFF)
+        flags = _lib.CHAMFER_WS_CLEAN | _lib.CHAMFER_TILE_ONLY | _lib.CHAMFER_ALGO_TENSOR
+        rc = lib.rlg_chamfer_fwd(a.data_ptr(), b.data_ptr(), B, N, M, d1.data_ptr(), d2.data_ptr(), i1.data_ptr(),
+                                 i2.data_ptr(), None, None, ws.data_ptr(), ws.numel(), flags,
+                                 torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, lib.rlg_last_error()
+        torch.cuda.synchronize()
+        keys = ws[: 8 * B * (N + M)].view(torch.int64)
+        a64, b64 = a.double(), b.double()
+        D = ((a64[:, :, None, :] - b64[:, None, :, :]) ** 2).sum(-1)
+        na, nb = (a64 ** 2).sum(-1), (b64 ** 2).sum(-1)
+        u = 2.0 ** -24
+        for key, truth, nq, nmax in ((keys[: B * N].view(B, N), D.min(2).values, na, nb.max(1, keepdim=True).values),
+                                     (keys[B * N:].view(B, M), D.min(1).values, nb, na.max(1, keepdim=True).values)):
+            val = (key >> 32).to(torch.int32).view(torch.float32).double()
+            worst = max(worst, float(((val - truth).abs() / (u * (nq + nmax))).max()))
+    assert worst < 16.0, f"tensor filter error {worst:.1f} u(a^2+b^2): the 128 u margin assumes < 61 u"

@@ -52,8 +52,12 @@ def test_install_routes_cuda_inputs_through_the_kernels(rlg):
     enc = ae.PointNetEncoder(3, 32, [16, 64]).to(DEV)
     O.randomize_bn(enc, 4)
     enc.eval()
+    tf32_conv, tf32_mm = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False                        # TF32 convolutions make the stock path itself 1e-2 noisy
+    torch.backends.cuda.matmul.allow_tf32 = False                  # (and cuDNN's algorithm choice varies run to run)
     with torch.no_grad():
-        stock_gfv = enc(pc1)                                       # stock CUDA path: cuDNN conv, TF32 allowed by default
+        stock_gfv = enc(pc1)                                       # stock CUDA path in true fp32
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32_conv, tf32_mm
         truth_gfv = ae.PointNetEncoder(3, 32, [16, 64]).double()
         truth_gfv.load_state_dict(enc.state_dict())
         truth_gfv = truth_gfv.eval()(pc1.cpu().double()).float()   # float64 truth of the same module on the host
@@ -71,7 +75,7 @@ def test_install_routes_cuda_inputs_through_the_kernels(rlg):
         with torch.no_grad():
             gfv = enc(pc1)
         assert O.gfv_close(gfv.cpu().numpy(), truth_gfv.numpy(), 1e-5)[0]
-        assert O.gfv_close(gfv.cpu().numpy(), stock_gfv.cpu().numpy(), 1e-2)[0]   # TF32 conv noise of the stock path
+        assert O.gfv_close(gfv.cpu().numpy(), stock_gfv.cpu().numpy(), 1e-4)[0]   # fp32 summation-order noise of the stock path
         # 4-D input (validate_joint's broadcast defect, train_rl_gan_net.py:541) is NOT the hot path: the
         # original function must see it unchanged
         four_d = torch.zeros(2, 2, 8, 3, device=DEV)

@@ -65,13 +65,16 @@ def timed(fn, reps=200):
     return e0.elapsed_time(e1) * 1e3 / (n * len(ring))
 
 
-t_tile = timed(lambda a, b: fwd(a, b, _lib.CHAMFER_WS_CLEAN | _lib.CHAMFER_TILE_ONLY))
-ws.fill_(0xFF)
-torch.cuda.synchronize()
-t_fwd = timed(lambda a, b: fwd(a, b, _lib.CHAMFER_WS_CLEAN))
-t_fwd_memset = timed(lambda a, b: fwd(a, b, 0))
-t_bwd = timed(bwd)
-t_all = timed(lambda a, b: (fwd(a, b, _lib.CHAMFER_WS_CLEAN), bwd(a, b)))
 flop = 8.0 * N * M * B
-print(f"B={B} N={N} M={M} (graph replay, per call): tile {t_tile:.2f} us ({flop / t_tile / 1e6:.2f} TFLOP/s)  "
-      f"fwd(tile+finalize) {t_fwd:.2f} us  fwd+memset {t_fwd_memset:.2f} us  bwd {t_bwd:.2f} us  fwd+bwd {t_all:.2f} us")
+for name, algo in (("fp32 sweep  ", 0), ("tensor sweep", _lib.CHAMFER_ALGO_TENSOR)):
+    ws.fill_(0xFF)
+    torch.cuda.synchronize()
+    t_tile = timed(lambda a, b: fwd(a, b, _lib.CHAMFER_WS_CLEAN | _lib.CHAMFER_TILE_ONLY | algo))
+    ws.fill_(0xFF)
+    torch.cuda.synchronize()
+    t_fwd = timed(lambda a, b: fwd(a, b, _lib.CHAMFER_WS_CLEAN | algo))
+    t_fwd_memset = timed(lambda a, b: fwd(a, b, algo))
+    t_bwd = timed(bwd)
+    t_all = timed(lambda a, b: (fwd(a, b, _lib.CHAMFER_WS_CLEAN | algo), bwd(a, b)))
+    print(f"B={B} N={N} M={M} {name} (graph replay, per call): sweep {t_tile:.2f} us ({flop / t_tile / 1e6:.2f} TFLOP/s)  "
+          f"fwd(sweep+finalize) {t_fwd:.2f} us  fwd+memset {t_fwd_memset:.2f} us  bwd {t_bwd:.2f} us  fwd+bwd {t_all:.2f} us")
