@@ -110,6 +110,8 @@ struct TfSeg { int dir, b, qb0, Q, nq, nc, n_ct, next; };
 
 // RLG_TF_DEBUG=1: cycle counters of CTA 0 (one lane per role), printed by launch_tcfilter after a synchronize
 __device__ unsigned long long g_tf_dbg[16];
+__device__ unsigned long long g_tf_span[160][6];      // per CTA: globaltimer at entry, after setup, MMA loop end, exit
+__device__ __forceinline__ unsigned long long tf_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define TF_T0(v) const long long v = dbg ? clock64() : 0
 #define TF_ACC(slot, v) do { if (dbg) dbg_acc[(slot) & 3] += (unsigned long long)(clock64() - (v)); } while (0)
 #define TF_FLUSH(base) do { if (dbg) { for (int z = 0; z < 4; ++z) g_tf_dbg[(base) + z] = dbg_acc[z]; } } while (0)
@@ -119,9 +121,10 @@ __device__ unsigned long long g_tf_dbg[16];
 template <bool TOP3>
 __global__ void __launch_bounds__(kTfThreads, 1)
 chamfer_tcfilter_kernel(const float *__restrict__ pc1, const float *__restrict__ pc2, int B, int N, int M, int n_tasks,
-                        int qb1, int qb2, FwdWs w, int ko) {
+                        int qb1, int qb2, int split, FwdWs w, int ko) {
     extern __shared__ unsigned char tf_smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if ((ko & 16) && tid == 0 && blockIdx.x < 160) g_tf_span[blockIdx.x][0] = tf_gtime();
     const uint32_t pad = (1024u - (smem_u32(tf_smem_raw) & 1023u)) & 1023u;
     unsigned char *smem = tf_smem_raw + pad;
     const uint32_t sbase = smem_u32(smem);
@@ -153,12 +156,34 @@ chamfer_tcfilter_kernel(const float *__restrict__ pc1, const float *__restrict__
     const bool dbg = (ko & 16) && blockIdx.x == 0 && lane == 0 && (warp == kTfMmaWarp || warp == kTfEpWarps || warp == 0);
     pdl_launch_dependents();
     pdl_wait();                                   // clouds and workspace may come from the kernels right before this one
+    if ((ko & 16) && tid == 0 && blockIdx.x < 160) g_tf_span[blockIdx.x][1] = tf_gtime();
 
     // Tasks (direction, cloud, 128-query block) in direction-major order; a CTA owns a contiguous range and walks it in
     // SEGMENTS of up to kQmax query blocks of one (direction, cloud): they share every converted candidate tile.
-    const int per = n_tasks / (int)gridDim.x, rem = n_tasks - per * (int)gridDim.x;
-    const int t_begin = (int)blockIdx.x * per + min((int)blockIdx.x, rem);
-    const int t_end = t_begin + per + ((int)blockIdx.x < rem ? 1 : 0);
+    //   split 0: even contiguous split of the task list (a CTA may straddle two clouds: two segments)
+    //   split 1: at most as many (direction, cloud) units as CTAs: every unit is cut into equal chunks, one per CTA, so
+    //            no CTA pays the per-segment costs (a pass of candidate conversions, a pipeline refill) twice
+    //   split 2: many more units than CTAs: whole units per CTA
+    const int G = (int)gridDim.x, cta = (int)blockIdx.x, U = 2 * B;
+    auto unit_start = [&](int u) { return u < B ? u * qb1 : B * qb1 + (u - B) * qb2; };
+    int t_begin, t_end;
+    if (split == 1) {
+        const int c_lo = G / U, extra = G - c_lo * U;                // the first `extra` units get one chunk more
+        int u, ci, c;
+        if (cta < extra * (c_lo + 1)) { u = cta / (c_lo + 1); ci = cta - u * (c_lo + 1); c = c_lo + 1; }
+        else { const int r = cta - extra * (c_lo + 1); u = extra + r / c_lo; ci = r - (u - extra) * c_lo; c = c_lo; }
+        const int T = u < B ? qb1 : qb2, s0 = unit_start(u);
+        t_begin = s0 + (int)((long long)ci * T / c);
+        t_end = s0 + (int)((long long)(ci + 1) * T / c);
+    } else if (split == 2) {
+        t_begin = unit_start((int)((long long)cta * U / G));
+        t_end = unit_start((int)((long long)(cta + 1) * U / G));
+    } else {
+        const int per = n_tasks / G, rem = n_tasks - per * G;
+        t_begin = cta * per + min(cta, rem);
+        t_end = t_begin + per + (cta < rem ? 1 : 0);
+    }
+    if ((ko & 16) && tid == 0 && blockIdx.x < 160) { g_tf_span[blockIdx.x][4] = (unsigned long long)(t_end - t_begin); g_tf_span[blockIdx.x][5] = (unsigned long long)t_begin; }
     auto seg_at = [&](int task) {
         TfSeg sg;
         const int n0 = B * qb1;
@@ -217,6 +242,7 @@ chamfer_tcfilter_kernel(const float *__restrict__ pc1, const float *__restrict__
         }
         TF_ACC(0, t_all);
         TF_FLUSH(0);
+        if ((ko & 16) && lane == 0 && blockIdx.x < 160) g_tf_span[blockIdx.x][2] = tf_gtime();
     } else if (warp >= kTfEpWarps) {
         // =========================== producers ===========================
         const int ptid = tid - kTfEpWarps * 32;                         // 0..kTfPrThreads-1
@@ -447,6 +473,7 @@ chamfer_tcfilter_kernel(const float *__restrict__ pc1, const float *__restrict__
     }
     tc_fence_before();
     __syncthreads();
+    if ((ko & 16) && tid == 0 && blockIdx.x < 160) g_tf_span[blockIdx.x][3] = tf_gtime();
     if (warp == kTfMmaWarp) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
@@ -473,16 +500,42 @@ int launch_tcfilter(const float *pc1, const float *pc2, int B, int N, int M, con
         attr_set = true;
     }
     const int grid = (int)(n_tasks < sms ? n_tasks : sms);
+    const int units = 2 * B;
+    // measured (B=32, N=M=2048): unit-aligned chunks (split 1: 8-task chunks, one segment) tie with the even split (7 tasks,
+    // two segments for a third of the CTAs); at 128 units over 148 CTAs they lose badly.  The even split stays the default.
+    int split = 0;
+    if (getenv("RLG_TF_SPLIT")) split = atoi(getenv("RLG_TF_SPLIT"));
+    if ((split == 1 && units > grid) || split < 0 || split > 2) split = 0;
     const int ko = (getenv("RLG_TF_KO") ? atoi(getenv("RLG_TF_KO")) : 0) | (getenv("RLG_TF_DEBUG") ? 16 : 0);
     cudaError_t le = top3 ? launch_pdl(chamfer_tcfilter_kernel<true>, dim3((unsigned)grid), dim3(kTfThreads), (size_t)kTfSmem, st, pc1,
-                                       pc2, B, N, M, (int)n_tasks, qb1, qb2, w, ko)
+                                       pc2, B, N, M, (int)n_tasks, qb1, qb2, split, w, ko)
                           : launch_pdl(chamfer_tcfilter_kernel<false>, dim3((unsigned)grid), dim3(kTfThreads), (size_t)kTfSmem, st, pc1,
-                                       pc2, B, N, M, (int)n_tasks, qb1, qb2, w, ko);
+                                       pc2, B, N, M, (int)n_tasks, qb1, qb2, split, w, ko);
     if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "chamfer_tcfilter_kernel: %s", cudaGetErrorString(le)); }
     if (getenv("RLG_TF_DEBUG")) {
         cudaStreamSynchronize(st);
         unsigned long long c[16];
         cudaMemcpyFromSymbol(c, g_tf_dbg, sizeof(c));
+        {
+            static unsigned long long sp[160][6];
+            cudaMemcpyFromSymbol(sp, g_tf_span, sizeof(sp));
+            unsigned long long t0 = ~0ull, t3 = 0, setup_max = 0, loop_min = ~0ull, loop_max = 0, tail_max = 0, last_start = 0;
+            for (int c = 0; c < grid && c < 160; ++c) {
+                if (sp[c][0] < t0) t0 = sp[c][0];
+                if (sp[c][3] > t3) t3 = sp[c][3];
+                if (sp[c][0] > last_start) last_start = sp[c][0];
+                if (sp[c][1] - sp[c][0] > setup_max) setup_max = sp[c][1] - sp[c][0];
+                const unsigned long long lp = sp[c][2] - sp[c][1];
+                if (lp < loop_min) loop_min = lp;
+                if (lp > loop_max) loop_max = lp;
+                if (sp[c][3] - sp[c][2] > tail_max) tail_max = sp[c][3] - sp[c][2];
+            }
+            if (getenv("RLG_TF_DEBUG")[0] == '2')
+                for (int c = 0; c < grid && c < 160; ++c)
+                    fprintf(stderr, "  cta %3d tasks %2llu from %4llu  start +%5llu  loop %6llu ns\n", c, sp[c][4], sp[c][5], sp[c][0] - t0, sp[c][2] - sp[c][1]);
+            fprintf(stderr, "tcfilter span (ns): first entry -> last exit %llu | entries spread %llu | setup max %llu | MMA loop min %llu max %llu | loop end -> exit max %llu\n",
+                    t3 - t0, last_start - t0, setup_max, loop_min, loop_max, tail_max);
+        }
         fprintf(stderr, "tcfilter CTA0 cycles: mma total %llu wait_afull %llu wait_bfull %llu wait_accempty %llu | producer total %llu "
                 "wait_bempty %llu wait_aempty %llu convert+store %llu | epilogue total %llu wait_accfull %llu ld+min %llu flush %llu\n",
                 c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8], c[9], c[10], c[11]);

@@ -57,10 +57,10 @@ def test_install_routes_cuda_inputs_through_the_kernels(rlg):
     torch.backends.cuda.matmul.allow_tf32 = False                  # (and cuDNN's algorithm choice varies run to run)
     with torch.no_grad():
         stock_gfv = enc(pc1)                                       # stock CUDA path in true fp32
-    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32_conv, tf32_mm
         truth_gfv = ae.PointNetEncoder(3, 32, [16, 64]).double()
         truth_gfv.load_state_dict(enc.state_dict())
         truth_gfv = truth_gfv.eval()(pc1.cpu().double()).float()   # float64 truth of the same module on the host
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32_conv, tf32_mm
     rlg.install(losses, ae)
     try:
         a = pc1.clone().requires_grad_(True)

@@ -1,8 +1,8 @@
 #!/bin/bash
-for ko in 0; do
-echo "== RLG_TF_KO=$ko"
-RLG_TF_DEBUG=1 RLG_TF_KO=$ko timeout 120 python - <<'PY'
-import sys, os, importlib
+for sp in 0 1; do
+echo "== split $sp"
+RLG_TF_SPLIT=$sp RLG_TF_DEBUG=2 timeout 120 python - <<'PY'
+import sys, os
 sys.path.insert(0, os.getcwd())
 import torch
 import gan_rl_3d_b200 as rlg
@@ -11,7 +11,7 @@ def sphere(b, n):
     x = torch.randn(b, n, 3, generator=g)
     return (x / x.norm(dim=2, keepdim=True)).cuda()
 a, b = sphere(32, 2048), sphere(32, 2048)
-for _ in range(3):
+for _ in range(2):
     rlg.chamfer_nearest(a, b, tensor=True)
 torch.cuda.synchronize()
 PY
