@@ -323,7 +323,7 @@ def run_ours(args):
     if use_tensor:
         roofline = {"bound": "fp32", "kernel": "chamfer_tcfilter_kernel", "achieved": achieved_tflops, "peak": fp32_theory,
                     "unit": "TFLOP/s", "frac": achieved_tflops / fp32_theory,
-                    "traffic": None,
+                    "traffic": 1634048,   # dram__bytes_read+write per launch, profiles/r1b_chamfer_kernels_ncu.txt (inputs: 1.57 MB)
                     "peak_source": peak_src, "peak_measured_ffma": peak[0], "peak_measured_ffma2": peak[4],
                     "note": "algorithmic 8 flop per point pair against the FP32 FFMA peak north_star names.  This kernel "
                             "runs the 3-term contraction on the tensor pipe (tcgen05 kind::tf32, split-tf32 operands, "
