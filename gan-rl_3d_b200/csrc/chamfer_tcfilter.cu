@@ -381,7 +381,8 @@ chamfer_tcfilter_kernel(const float *__restrict__ pc1, const float *__restrict__
                 int bgrp = reinterpret_cast<int *>(sq)[3 * kTQ], sgrp = TOP3 ? reinterpret_cast<int *>(sq)[4 * kTQ] : 0;
                 // running three smallest group minima (strict <: the earliest group keeps a tie) and the groups of the first two
                 auto group_done = [&](const float *v, int G) {
-                    if (ko & 2) { best = fminf(best, v[0] + v[31]); return; }
+                    if (ko & 2) return;                                 // timing experiment; the branch also keeps ptxas from
+                                                                        // interleaving the four reductions (which spills)
                     const float m = min32(v);
                     if (!TOP3) {
                         second = fminf(second, fmaxf(best, m));
@@ -403,7 +404,8 @@ chamfer_tcfilter_kernel(const float *__restrict__ pc1, const float *__restrict__
                 // 4 groups of 32 columns, two register sets: the load of group g+1 is in flight while g is reduced; the
                 // accumulator goes back to the MMA warp as soon as its last load has landed
                 float va[32], vb[32];
-                const int G0 = k * (kTC / 32) + hf * 4;
+                int G0 = k * (kTC / 32) + hf * 4;
+                asm volatile("mov.s32 %0, %0;" : "+r"(G0));             // pinned: otherwise recomputed under every predicate
                 tc_ld32_nowait(taddr, va);
                 tc_wait_ld(va);
                 tc_ld32_nowait(taddr + 32u, vb);
