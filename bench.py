@@ -360,6 +360,7 @@ def run_ours(args):
     if not args.no_encoder:
         extra.update(encoder_side_measurement(rlg, dev, peaks, peaks_src))
         extra.update(reward_side_measurement(rlg, dev, fp32_theory))
+        extra.update(large_cloud_measurement(rlg, dev, fp32_theory))
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
@@ -512,6 +513,44 @@ def reward_side_measurement(rlg, dev, fp32_peak):
                             "config": {"workload": "RewardFunction for E=1024 episodes, Chamfer N=M=2048 forward only + GFV MSE + "
                                                    "discriminator term (BASELINE configs[3])"},
                             "chamfer_tflops": tf, "frac_of_fp32_peak": tf / fp32_peak, "last_reward_mean": float(r.mean().item())}}
+
+
+def large_cloud_measurement(rlg, dev, fp32_peak):
+    """BASELINE configs[4] as it lands on ONE GPU of the 8-GPU box: 8 of the 64 pairs, N=M=16384, ChamferLoss forward +
+    backward.  Reported as an extra key (parity at this size is tests/test_chamfer_gpu.py::test_large_cloud_16384)."""
+    B, N, M = 8, 16384, 16384
+    g = torch.Generator().manual_seed(1238)
+
+    def sphere(b, n):
+        x = torch.randn(b, n, 3, generator=g)
+        return (x / x.norm(dim=2, keepdim=True)).to(dev)
+
+    ring = [(sphere(B, N).requires_grad_(True), sphere(B, M)) for _ in range(4)]
+    crit = rlg.ChamferLoss()
+    one = torch.ones((), device=dev)
+
+    def step(k):
+        a, b = ring[k % len(ring)]
+        a.grad = None
+        loss = crit(a, b)
+        loss.backward(gradient=one)
+        return loss
+
+    for k in range(3):
+        step(k)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    e0.record()
+    for k in range(reps):
+        loss = step(k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    tf = 8.0 * N * M * B / (ms * 1e-3) / 1e12
+    return {"large_cloud": {"metric": "chamfer_pairs_per_s", "value": B / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
+                            "config": {"workload": "ChamferLoss fwd+bwd, 8 pairs per GPU of B=64, N=M=16384 (BASELINE configs[4])"},
+                            "algorithmic_tflops": tf, "frac_of_fp32_peak": tf / fp32_peak, "last_loss": float(loss.item())}}
 
 
 def main():

@@ -15,9 +15,9 @@
 //   where vh = tf32(v), vl = tf32(v - vh) (so v = vh + vl to 2^-22 relative) and the squared norms are split three ways
 //   (exactly).  Every tf32 x tf32 product is exact in fp32; only the vl x vl terms are dropped.
 //
-//   D[128 queries x 256 candidates] (fp32, TMEM) = A[128 x 16] . B[256 x 16]^T : two tcgen05.mma (M=128, N=256, K=8).
-//   Each query sits on one TMEM lane, so its minimum over the candidates is a per-thread reduction of tcgen05.ld
-//   registers: no shuffles, no shared memory, no atomics inside the sweep.  Both directions run as the same problem
+//   D[128 queries x 128 candidates] (fp32, TMEM) = A[128 x 16] . B[128 x 16]^T : two tcgen05.mma (M=128, N=128, K=8)
+//   per half of a 256-candidate tile.  Each query sits on one TMEM lane, so its minimum over the candidates is a
+//   per-thread reduction of tcgen05.ld registers: no shuffles, no shared-memory traffic, no atomics inside the sweep.  Both directions run as the same problem
 //   with the roles of the clouds swapped (the tensor pipe has the headroom), so a "group" is 32 consecutive candidates
 //   in either direction.
 //
@@ -31,8 +31,8 @@
 //   kMarginT = 128 u (chamfer_filter.cu, finalize).  tests/test_chamfer_gpu.py measures the filter against float64: the
 //   largest error seen is ~4.5 u S, and the whole parity suite runs on this path as well as on the FP32 one.
 //
-// Besides the best group and the runner-up VALUE (what the FP32 sweep reports), this sweep also reports the runner-up's
-// group and the third-smallest group minimum: a point whose runner-up is within the margin but whose third is not is
+// Besides the best group and the runner-up VALUE (what the FP32 sweep reports), this sweep can also report (TOP3, chosen
+// by launch_tcfilter for candidate clouds beyond 4096 points) the runner-up's group and the third-smallest group minimum: a point whose runner-up is within the margin but whose third is not is
 // refined exactly on two groups (64 candidates) instead of the whole candidate cloud -- at N = 16384 that is the
 // difference between a finalize of ~1.6 ms and one that is a fraction of the sweep.
 //
@@ -41,9 +41,15 @@
 //   cloud): each converted candidate tile is multiplied against all of them (a "visit" = one query block x one tile).
 //   warps 0-15  four epilogue groups of four warps; a visit is issued as two 128-column halves and half-visit h goes to
 //               TMEM accumulator h % 4 == group h % 4                  thread = query = TMEM lane
-//   warps 16-17 producers: convert 256 candidates per tile (four per thread; and the task's 128 queries) to the split-tf32
+//   warps 16-17 producers: convert 256 candidates per tile (four per thread; and the segment's queries) to the split-tf32
 //               rows above, written straight into the K-major SWIZZLE_128B operand tiles
 //   warp 18     MMA issuer (one elected lane), TMEM owner
+//   At the end of a segment the four groups' running results are merged per query in shared memory and published with
+//   plain stores: every candidate of these queries was seen by this CTA, so the workspace needs no atomics here.
+//
+// Environment (measurement only): RLG_TF_DEBUG=1|2 prints per-role cycle counters and per-CTA time spans after a
+// synchronize; RLG_TF_TOP3=0|1 and RLG_TF_SPLIT=0|1|2 override the runner-up report and the work split; RLG_TF_KO=2
+// skips the minima (timing experiment, wrong results).
 #include "common.cuh"
 #include "tcgen05.cuh"
 #include <math.h>

@@ -46,3 +46,21 @@ def test_host_step_graph_matches_eager(rlg, one_transfer):
             loss, _ = _eager(rlg, a, b)
             assert g.losses_host[k].item() == loss.item()
     assert g.h2d_bytes_per_step == (2 * 300 * 3 + 2 * 257 * 3) * 4 and g.d2h_bytes_per_step == 4
+
+
+def test_host_step_graph_read_back_survives_reuse_of_the_capture_pool(rlg):
+    """Regression: every step's loss is read back by a D2H copy on its own stream.  Its device scalar must stay
+    allocated, or the capture pool hands the block to the next step's outputs and the copy reads garbage now and then.
+    Fresh data per trial and a poisoned allocator make a stale or overwritten read visible."""
+    P = importlib.import_module("gan-rl_3d_b200.pipeline")
+    for trial in range(4):
+        junk = [torch.randn(1 << 18, device=DEV) * 3 for _ in range(8)]
+        del junk
+        raw = [(O.make_clouds(2, 300, "uniform", 500 + 10 * trial + k), O.make_clouds(2, 257, "uniform", 700 + 10 * trial + k))
+               for k in range(5)]
+        g = P.HostChamferStepGraph([P.pin_pair(a, b) for a, b in raw], DEV)
+        want = [_eager(rlg, a, b)[0].item() for a, b in raw]
+        for _ in range(3):
+            g.replay()
+            torch.cuda.synchronize()
+            assert [g.losses_host[k].item() for k in range(5)] == want
