@@ -37,9 +37,10 @@ def test_header_symbols_are_exported(lib):
 def test_version_and_ws_bytes(lib):
     cdll, _ = lib
     assert cdll.rlg_version() == 3
-    big = cdll.rlg_chamfer_ws_bytes(32, 2048, 2048)   # 8-byte keys + 4-byte second-best values per point + counters
-    assert 12 * 32 * 4096 < big <= 12 * 32 * 4096 + 16384 and big % 256 == 0
-    assert 0 < cdll.rlg_chamfer_ws_bytes(1, 1, 1) <= 2048
+    # per point: 8-byte key + 4-byte runner-up value + (tensor sweep) 4-byte runner-up group + 4-byte third value; + counters
+    big = cdll.rlg_chamfer_ws_bytes(32, 2048, 2048)
+    assert 20 * 32 * 4096 < big <= 20 * 32 * 4096 + 16384 and big % 256 == 0
+    assert 0 < cdll.rlg_chamfer_ws_bytes(1, 1, 1) <= 4096
     assert cdll.rlg_chamfer_ws_bytes(1, 0, 5) == 0
 
 
