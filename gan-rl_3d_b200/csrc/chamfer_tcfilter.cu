@@ -500,12 +500,12 @@ int launch_tcfilter(const float *pc1, const float *pc2, int B, int N, int M, con
     // tracks three groups; their share grows with the point density.  Break-even is around 4096 candidates.
     const bool top3 = getenv("RLG_TF_TOP3") ? atoi(getenv("RLG_TF_TOP3")) != 0 : (N > 4096 || M > 4096);
     *rows_per_lane = top3 ? 0 : -1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(chamfer_tcfilter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTfSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(chamfer_tcfilter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTfSmem);
+    // per launch (a host-side attribute write, no device work): the setting is per device and this library keeps no
+    // per-device state of its own
+    {
+        cudaError_t e = top3 ? cudaFuncSetAttribute(chamfer_tcfilter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTfSmem)
+                             : cudaFuncSetAttribute(chamfer_tcfilter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTfSmem);
         if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "chamfer_tcfilter_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
-        attr_set = true;
     }
     const int grid = (int)(n_tasks < sms ? n_tasks : sms);
     const int units = 2 * B;
