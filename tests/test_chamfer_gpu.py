@@ -42,7 +42,9 @@ def _check_against_direct(rlg, pc1, pc2, simple=False, **kw):
 
 
 SHAPES = [(1, 1, 1), (3, 1, 7), (2, 25, 1), (4, 16, 25), (2, 31, 33), (2, 32, 32), (3, 255, 257), (2, 256, 64),
-          (1, 300, 1000), (2, 1400, 2048), (2, 2048, 2048), (1, 2049, 513), (5, 700, 90)]
+          (1, 300, 1000), (2, 1400, 2048), (2, 2048, 2048), (1, 2049, 513), (5, 700, 90),
+          # many clouds per CTA of the tensor sweep (several segments, ragged last query block / candidate tile)
+          (300, 130, 70), (50, 257, 129), (7, 1030, 2050), (161, 64, 64)]
 
 
 @pytest.mark.parametrize("B,N,M", SHAPES)
@@ -312,3 +314,29 @@ def test_tensor_filter_error_is_far_inside_its_margin(rlg):
             val = (key >> 32).to(torch.int32).view(torch.float32).double()
             worst = max(worst, float(((val - truth).abs() / (u * (nq + nmax))).max()))
     assert worst < 16.0, f"tensor filter error {worst:.1f} u(a^2+b^2): the 128 u margin assumes < 61 u"
+
+
+@pytest.mark.parametrize("case", ["identical", "apart", "mixed_scale", "collinear"])
+def test_degenerate_geometries(rlg, case):
+    """Zero distances everywhere, clouds far from each other (every filter value is large), three decades of scale in
+    one cloud, points on a line (many near-ties): same bits as the direct oracle on every sweep."""
+    g = torch.Generator().manual_seed(77)
+    B, N, M = 2, 700, 900
+    if case == "identical":
+        pc1 = O.make_clouds(B, N, "sphere", 5)
+        pc2 = pc1.clone()
+    elif case == "apart":
+        pc1 = O.make_clouds(B, N, "uniform", 6) + 5.0
+        pc2 = O.make_clouds(B, M, "uniform", 7) - 5.0
+    elif case == "mixed_scale":
+        s1 = 10.0 ** torch.randint(-2, 2, (B, N, 1), generator=g).float()
+        s2 = 10.0 ** torch.randint(-2, 2, (B, M, 1), generator=g).float()
+        pc1 = O.make_clouds(B, N, "sphere", 8) * s1
+        pc2 = O.make_clouds(B, M, "sphere", 9) * s2
+    else:
+        t1 = torch.rand(B, N, 1, generator=g)
+        t2 = torch.rand(B, M, 1, generator=g)
+        d = torch.tensor([0.3, -0.5, 0.8])
+        pc1 = t1 * d + 0.1
+        pc2 = t2 * d + 0.1
+    _check_against_direct(rlg, pc1.contiguous(), pc2.contiguous())
