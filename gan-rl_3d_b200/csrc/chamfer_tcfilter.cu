@@ -395,6 +395,9 @@ chamfer_tcfilter_kernel(const float *__restrict__ pc1, const float *__restrict__
                         if (m < best) { best = m; bgrp = G; }
                         return;
                     }
+                    // nothing changes unless the group beats the running third; late in a large cloud that is rare for
+                    // all 32 queries of the warp at once
+                    if (!__any_sync(0xffffffffu, m < third)) return;
                     const bool p1 = m < best;
                     const float c1 = fmaxf(best, m);                    // what drops out of first place
                     const bool p2 = c1 < second;
