@@ -10,6 +10,7 @@ from typing import Optional
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "lib", "librlg_b200.so")
+EXP_LIB_PATH = os.path.join(_PKG_DIR, "lib", "librlg_b200_exp.so")
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -64,21 +65,26 @@ EXPORTS = {
 CHAMFER_WS_CLEAN = 1
 CHAMFER_ALGO_SIMPLE = 2
 CHAMFER_TILE_ONLY = 4
-CHAMFER_ALGO_DIRECT = 8
 CHAMFER_ALGO_TENSOR = 16
+CHAMFER_TRACK_TWO = 32
+CHAMFER_FILTER_ONLY = 64
+# experiments build only (librlg_b200_exp.so, tools/): kernel variants in bits 8-11, first-generation tensor sweep
+X_CHAMFER_TENSOR_V1 = 128
 CHAMFER_BWD_ACCUMULATE = 1
 
 
 def load() -> ctypes.CDLL:
-    """dlopen the in-tree library.  Raises (never falls back) if it has not been built."""
+    """dlopen the in-tree library.  Raises (never falls back) if it has not been built.
+    RLG_EXPERIMENTS_LIB=1 (tools/ only) loads the experiments build instead: same ABI plus timing variants."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = EXP_LIB_PATH if os.environ.get("RLG_EXPERIMENTS_LIB") == "1" else LIB_PATH
+    if not os.path.exists(path):
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python gan-rl_3d_b200/build.py` (or __graft_entry__.build()). "
+            f"{path} is missing: build it with `python gan-rl_3d_b200/build.py` (or __graft_entry__.build()). "
             "There is no CPU fallback for the B200 hot path.")
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     for name, (restype, argtypes) in EXPORTS.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = restype

@@ -9,7 +9,8 @@ Inputs must be CUDA fp32 (B,N,3)/(B,M,3) with N,M >= 1; there is no CPU implemen
 """
 from __future__ import annotations
 
-from typing import Dict, Optional, Tuple
+from collections import OrderedDict
+from typing import Optional, Tuple
 
 import os
 
@@ -38,23 +39,37 @@ def _require_hot_path(pc1, pc2) -> None:
 
 class _Workspace:
     """Caller-owned workspace of rlg_chamfer_fwd, cached per (device, stream, shape).  The forward leaves it
-    in the all-ones state it needs on entry, so repeat calls skip the memset (RLG_CHAMFER_WS_CLEAN)."""
-    _cache: Dict[tuple, "_Workspace"] = {}
+    in the all-ones state it needs on entry, so repeat calls skip the memset (RLG_CHAMFER_WS_CLEAN).
+
+    A call made while its stream is being captured pins the entry for the life of the process: the CUDA graph holds the
+    raw pointer, so the buffer must never go back to the allocator.  Unpinned entries are evicted one at a time, least
+    recently used first.  `clean` tracks eager execution only: a captured call that finds the workspace not yet clean
+    records the memset in the graph and leaves `clean` alone (nothing has run yet)."""
+    _cache: "OrderedDict[tuple, _Workspace]" = OrderedDict()
+    MAX_ENTRIES = 64
 
     def __init__(self, nbytes: int, device: torch.device):
         self.buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
         self.clean = False
+        self.pinned = False
 
     @classmethod
-    def get(cls, device: torch.device, stream: int, B: int, N: int, M: int) -> "_Workspace":
+    def get(cls, device: torch.device, stream: int, B: int, N: int, M: int, capturing: bool = False) -> "_Workspace":
         key = (device.index, stream, B, N, M)
         ws = cls._cache.get(key)
         if ws is None:
-            if len(cls._cache) > 64:
-                cls._cache.clear()
+            if not capturing:               # never free memory during a capture
+                for old_key in [k for k, v in cls._cache.items() if not v.pinned]:
+                    if len(cls._cache) < cls.MAX_ENTRIES:
+                        break
+                    del cls._cache[old_key]
             nbytes = _lib.load().rlg_chamfer_ws_bytes(B, N, M)
             ws = cls(nbytes, device)
             cls._cache[key] = ws
+        else:
+            cls._cache.move_to_end(key)
+        if capturing:
+            ws.pinned = True
         return ws
 
 
@@ -65,11 +80,11 @@ if _DEFAULT_SWEEP not in ("fp32", "tensor", "auto"):
 
 def set_default_sweep(kind: str) -> None:
     """Which kernel sweeps the N x M pairs when chamfer_nearest() is not told explicitly:
-    'fp32'   the FP32-pipe filter (chamfer_filter.cu),
-    'tensor' the contraction on tcgen05 with split-tf32 operands (chamfer_tcfilter.cu),
+    'fp32'   the FP32-pipe filter + refinement kernel (chamfer_filter.cu),
+    'tensor' the contraction on tcgen05 with split-tf32 operands, refinement fused in (chamfer_tcsweep.cu),
     'auto'   (default) tensor when both clouds have at least 64 points, else fp32 (a 128 x 256 tensor tile is mostly
              padding for tiny clouds).
-    Both feed the same exact refinement; the outputs are bit-identical."""
+    Both give the same bits."""
     global _DEFAULT_SWEEP
     if kind not in ("fp32", "tensor", "auto"):
         raise ValueError("kind must be 'fp32', 'tensor' or 'auto'")
@@ -87,19 +102,21 @@ def _use_tensor(tensor: Optional[bool], n: int, m: int) -> bool:
 
 
 def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = True, simple: bool = False,
-                    loss_weights: Optional[Tuple[float, float]] = None, direct: bool = False, variant: int = 0,
-                    tensor: Optional[bool] = None, zero_grads: Optional[Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]] = None):
+                    loss_weights: Optional[Tuple[float, float]] = None, tensor: Optional[bool] = None,
+                    track_two: bool = False,
+                    zero_grads: Optional[Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]] = None):
     """Nearest neighbours in both directions (no autograd).
 
     Returns (d1 (B,N) fp32, d2 (B,M) fp32, i1 (B,N) int32, i2 (B,M) int32, mean1 (B,), mean2 (B,)):
-    exactly torch.min(torch.cdist(pc1,pc2), 2) / (…, 1) of utils/losses.py:29-33 with cdist in direct mode,
-    and torch.mean(…, dim=1) of :36-37.  With loss_weights=(w1,w2) a 7th element is appended: the 0-dim
-    batch loss sum_b(w1*mean1[b] + w2*mean2[b]) reduced inside the same launch (utils/losses.py:54-59,75).
-    simple / direct select the two cross-check kernels (one thread per query; direct-form tiles) instead of the
-    filter-and-refine kernel; variant (1..15) forces an experimental tile shape; tensor=True/False selects the
+    exactly torch.min(torch.cdist(pc1,pc2), 2) / (…, 1) of utils/losses.py:29-33 with cdist in direct mode
+    (ties as torch.min sees them on the sqrt-ed distances: lowest index), and torch.mean(…, dim=1) of :36-37.
+    With loss_weights=(w1,w2) a 7th element is appended: the 0-dim batch loss sum_b(w1*mean1[b] + w2*mean2[b])
+    reduced inside the same launches (utils/losses.py:54-59,75).
+    simple selects the cross-check kernel (one thread per query, every candidate evaluated); tensor=True/False the
     pair sweep with the contraction on the tensor cores (tcgen05, split-tf32) or on the FP32 pipe (None: the module
-    default, see set_default_sweep).  All paths return the same bits.
-    zero_grads=(g1, g2): (B,N,3)/(B,M,3) buffers (each may be None) the forward zero-fills in its last launch, so
+    default, see set_default_sweep); track_two forces the tensor sweep's runner-up-group report (automatic beyond
+    4096 points).  All paths return the same bits.
+    zero_grads=(g1, g2): (B,N,3)/(B,M,3) buffers (each may be None) the forward zero-fills on the way, so
     chamfer_backward(..., out=(g1, g2), accumulate=True) is a single launch."""
     _require_hot_path(pc1, pc2)
     lib = _lib.load()
@@ -121,18 +138,21 @@ def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = Tru
     gz1, gz2 = zero_grads if zero_grads is not None else (None, None)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
-        ws = _Workspace.get(dev, stream, B, N, M)
+        capturing = torch.cuda.is_current_stream_capturing()
+        ws = _Workspace.get(dev, stream, B, N, M, capturing)
         flags = 0
         if simple:
             flags |= _lib.CHAMFER_ALGO_SIMPLE
-        elif ws.clean:
-            flags |= _lib.CHAMFER_WS_CLEAN
-        if direct:
-            flags |= _lib.CHAMFER_ALGO_DIRECT
-        elif not simple and not variant and _use_tensor(tensor, N, M):
-            flags |= _lib.CHAMFER_ALGO_TENSOR
-        flags |= (int(variant) & 15) << 8
-        ws.clean = False
+        else:
+            if ws.clean:
+                flags |= _lib.CHAMFER_WS_CLEAN
+            if _use_tensor(tensor, N, M):
+                flags |= _lib.CHAMFER_ALGO_TENSOR
+                if track_two:
+                    flags |= _lib.CHAMFER_TRACK_TWO
+        was_clean = ws.clean
+        if not capturing and not simple:
+            ws.clean = False                     # until the call has gone through
         rc = lib.rlg_chamfer_loss_fwd(pc1.data_ptr(), pc2.data_ptr(), B, N, M,
                                       d1.data_ptr(), d2.data_ptr(), i1.data_ptr(), i2.data_ptr(),
                                       m1.data_ptr() if want_means else None, m2.data_ptr() if want_means else None,
@@ -141,7 +161,10 @@ def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = Tru
                                       gz2.data_ptr() if gz2 is not None else None,
                                       ws.buf.data_ptr(), ws.buf.numel(), flags, stream)
         _lib.check("rlg_chamfer_loss_fwd", rc)
-        ws.clean = not simple
+        if not simple:
+            # eager: the forward restored the all-ones state.  Captured: nothing ran; the recorded sequence keeps the
+            # invariant on every replay, and the host-side flag stays what eager execution last established.
+            ws.clean = was_clean if capturing else True
     return (d1, d2, i1, i2, m1, m2) if loss is None else (d1, d2, i1, i2, m1, m2, loss)
 
 

@@ -348,24 +348,34 @@ int filter_pick_rows(int N) {
 
 int launch_filter(const float *pc1, const float *pc2, int B, int N, int M, int variant, const FwdWs &w, int *rows_per_lane,
                   cudaStream_t st) {
-    const int R = (variant >= 7 && variant <= 8) ? 8 : (variant == 9 ? 4 : ((variant >= 1 && variant <= 6) || variant >= 10 ? 16 : filter_pick_rows(N)));
-    *rows_per_lane = R;
-    switch (variant) {           // experimental overrides (tools/sweep_tile.py); 0 = automatic
-        case 1: return launch_filter_t<16, 2, true>(pc1, pc2, B, N, M, w, st);
-        case 2: return launch_filter_t<16, 2, false>(pc1, pc2, B, N, M, w, st);
-        case 3: return launch_filter_t<16, 3, true>(pc1, pc2, B, N, M, w, st);
-        case 4: return launch_filter_t<16, 3, false>(pc1, pc2, B, N, M, w, st);
-        case 7: return launch_filter_t<8, 3, true>(pc1, pc2, B, N, M, w, st);
-        case 8: return launch_filter_t<8, 4, false>(pc1, pc2, B, N, M, w, st);
-        case 9: return launch_filter_t<4, 4, true>(pc1, pc2, B, N, M, w, st);
-        case 10: return launch_filter_t<16, 2, false, 1>(pc1, pc2, B, N, M, w, st);
-        case 11: return launch_filter_t<16, 2, false, 2>(pc1, pc2, B, N, M, w, st);
-        case 12: return launch_filter_t<16, 2, false, 3>(pc1, pc2, B, N, M, w, st);
-        case 13: return launch_filter_t<16, 2, false, 4>(pc1, pc2, B, N, M, w, st);
-        case 14: return launch_filter_t<16, 2, false, 11>(pc1, pc2, B, N, M, w, st);
-        case 15: return launch_filter_t<16, 2, false, 15>(pc1, pc2, B, N, M, w, st);
-        default: break;
+#ifdef RLG_EXPERIMENTS
+    // experimental tile shapes and knock-out timing variants (tools/sweep_tile.py; variants >= 10 return WRONG results).
+    // They exist only in the experiments build (build.py --experiments -> librlg_b200_exp.so).
+    if (variant != 0) {
+        const int Rv = (variant >= 7 && variant <= 8) ? 8 : (variant == 9 ? 4 : 16);
+        *rows_per_lane = Rv;
+        switch (variant) {
+            case 1: return launch_filter_t<16, 2, true>(pc1, pc2, B, N, M, w, st);
+            case 2: return launch_filter_t<16, 2, false>(pc1, pc2, B, N, M, w, st);
+            case 3: return launch_filter_t<16, 3, true>(pc1, pc2, B, N, M, w, st);
+            case 4: return launch_filter_t<16, 3, false>(pc1, pc2, B, N, M, w, st);
+            case 7: return launch_filter_t<8, 3, true>(pc1, pc2, B, N, M, w, st);
+            case 8: return launch_filter_t<8, 4, false>(pc1, pc2, B, N, M, w, st);
+            case 9: return launch_filter_t<4, 4, true>(pc1, pc2, B, N, M, w, st);
+            case 10: return launch_filter_t<16, 2, false, 1>(pc1, pc2, B, N, M, w, st);
+            case 11: return launch_filter_t<16, 2, false, 2>(pc1, pc2, B, N, M, w, st);
+            case 12: return launch_filter_t<16, 2, false, 3>(pc1, pc2, B, N, M, w, st);
+            case 13: return launch_filter_t<16, 2, false, 4>(pc1, pc2, B, N, M, w, st);
+            case 14: return launch_filter_t<16, 2, false, 11>(pc1, pc2, B, N, M, w, st);
+            case 15: return launch_filter_t<16, 2, false, 15>(pc1, pc2, B, N, M, w, st);
+            default: return fail(RLG_ERR_UNSUPPORTED, "rlg_chamfer_fwd: unknown experimental variant %d", variant);
+        }
     }
+#else
+    if (variant != 0) return fail(RLG_ERR_UNSUPPORTED, "rlg_chamfer_fwd: kernel variants exist only in the experiments build");
+#endif
+    const int R = filter_pick_rows(N);
+    *rows_per_lane = R;
     if (R == 16) return launch_filter_t<16, 2, true>(pc1, pc2, B, N, M, w, st);
     if (R == 8) return launch_filter_t<8, 3, true>(pc1, pc2, B, N, M, w, st);
     return launch_filter_t<4, 4, true>(pc1, pc2, B, N, M, w, st);
@@ -392,12 +402,11 @@ size_t finalize2_ws_bytes(int B, int N, int M) {
     return fin2_counter_bytes(B) + align_up(sizeof(double) * 2 * (size_t)B * cm, 256);
 }
 
-// exact direct-form scan of candidates [first, first+step, ...) of c for query (px,py,pz): this thread's smallest t
-// and the lowest index attaining it (four independent candidates in flight)
-__device__ __forceinline__ void scan_strided(const float *__restrict__ c, int nc, int first, int step, float px, float py,
-                                             float pz, float &lt, int &lj) {
-    lt = INFINITY;
-    lj = 0x7fffffff;
+// exact direct-form scans of candidates [first, first+step, ...) of c for query (px,py,pz): this thread's smallest t
+// (four independent candidates in flight), and the lowest index with t <= h
+__device__ __forceinline__ float scan_min_strided(const float *__restrict__ c, int nc, int first, int step, float px, float py,
+                                                  float pz) {
+    float lt = INFINITY;
     int j = first;
     for (; j + 3 * step < nc; j += 4 * step) {
         const int j1 = j + step, j2 = j + 2 * step, j3 = j + 3 * step;
@@ -405,19 +414,22 @@ __device__ __forceinline__ void scan_strided(const float *__restrict__ c, int nc
         const float t1 = sqdist(px, py, pz, c[3 * j1], c[3 * j1 + 1], c[3 * j1 + 2]);
         const float t2 = sqdist(px, py, pz, c[3 * j2], c[3 * j2 + 1], c[3 * j2 + 2]);
         const float t3 = sqdist(px, py, pz, c[3 * j3], c[3 * j3 + 1], c[3 * j3 + 2]);
-        if (t0 < lt) { lt = t0; lj = j; }
-        if (t1 < lt) { lt = t1; lj = j1; }
-        if (t2 < lt) { lt = t2; lj = j2; }
-        if (t3 < lt) { lt = t3; lj = j3; }
+        lt = fminf(fminf(lt, t0), fminf(t1, fminf(t2, t3)));
     }
-    for (; j < nc; j += step) {
-        const float t = sqdist(px, py, pz, c[3 * j], c[3 * j + 1], c[3 * j + 2]);
-        if (t < lt) { lt = t; lj = j; }
-    }
+    for (; j < nc; j += step) lt = fminf(lt, sqdist(px, py, pz, c[3 * j], c[3 * j + 1], c[3 * j + 2]));
+    return lt;
+}
+__device__ __forceinline__ int scan_first_le_strided(const float *__restrict__ c, int nc, int first, int step, float px,
+                                                     float py, float pz, float h) {
+    for (int j = first; j < nc; j += step)
+        if (sqdist(px, py, pz, c[3 * j], c[3 * j + 1], c[3 * j + 2]) <= h) return j;
+    return 0x7fffffff;
 }
 
-// TWO: the sweep also reported the runner-up group and the third-smallest group minimum (tensor-core sweep on large
-// candidate clouds, rows_per_lane == 0): ambiguous points are refined on two groups when the third is out of reach
+// Tie rule (all paths): the reference's torch.min runs on the sqrt-ed distances, so candidates whose squared distances
+// share one sqrtf tie and the lowest index wins (sqrt_window_top, common.cuh; oracle ORC_TIE_FAITHFUL).
+// TWO (experiments build only): the sweep also reported the runner-up group and the third-smallest group minimum
+// (first-generation tensor-core sweep, rows_per_lane == 0): ambiguous points are refined on two groups
 template <bool SMEM, bool TWO>
 __global__ void __launch_bounds__(kFin2Threads) chamfer_finalize2_kernel(
     const float *__restrict__ pc1, const float *__restrict__ pc2, int N, int M, int rows_per_lane, FwdWs w, Fin2Ws fw,
@@ -429,7 +441,8 @@ __global__ void __launch_bounds__(kFin2Threads) chamfer_finalize2_kernel(
     __shared__ float s_q[3][kFin2Threads];            // query coordinates of the CTA's points
     __shared__ short s_list[kFin2Threads];            // ambiguous points of the CTA, in thread order
     __shared__ int s_wcount[kFin2Warps];
-    __shared__ u64 s_wbest[kFin2Warps];               // per-warp (t bits << 32 | index) of the point being scanned
+    __shared__ unsigned s_wmin[kFin2Warps];           // per-warp smallest t bits / lowest index of the point being scanned
+    __shared__ int s_wj[kFin2Warps];
     const int chunk = blockIdx.x, b = blockIdx.y, dir = blockIdx.z;
     const int B = gridDim.y;
     // dir 0: queries = pc1 rows; a candidate group = 32 consecutive columns of pc2
@@ -497,8 +510,6 @@ __global__ void __launch_bounds__(kFin2Threads) chamfer_finalize2_kernel(
     const float margin = (R > 0 ? kMarginC : kMarginT) * (norm2(qx, qy, qz) + onrm) + (strided ? kMarginQ * val : 0.0f);
     // any NaN (untouched key, non-finite input) makes the comparison false -> treated as ambiguous
     const bool amb2 = live && !(sv > val + margin);     // a second group is within the margin of the best one
-    // the tensor-core sweep also reports WHICH group that is and the third-smallest group minimum: if the third is out of
-    // reach, the exact winner lies in one of two known groups (64 candidates instead of the whole cloud)
     const bool two = TWO && amb2 && (__uint_as_float(third) > val + margin);
     const bool amb = amb2 && !two;
     // deterministic list of the CTA's ambiguous points
@@ -513,60 +524,77 @@ __global__ void __launch_bounds__(kFin2Threads) chamfer_finalize2_kernel(
     }
     if (amb) s_list[my_off + __popc(am & ((1u << lane) - 1u))] = (short)tid;
 
-    // ---- fast path: the exact winner lies in the best group; lane-serial over its <= 32 candidates.  Indices past
-    // the end are clamped to the last point: a real candidate with the highest index, so it never wins a tie it
-    // should not, and it cannot beat the group's winner unless it is the true nearest point anyway.
+    // ---- fast path: the exact winner lies in the best group (or, TWO, in one of two groups).  Pass 1 finds the smallest
+    // squared distance, pass 2 the lowest index sharing its square root.  Indices past the end are clamped to the last
+    // point: a real candidate with the highest index, so it never wins a tie it should not.
     float bt = INFINITY;
     int bj = 0x7fffffff;
     if (live && !amb) {
         const unsigned grp = (unsigned)(key & 0xffffffffu);
         const int base = strided ? (int)(grp >> 5) * (32 * R) + (int)(grp & 31u) : (int)grp * kGroup;
         const int stride = strided ? 32 : 1;
+        const int base2 = (int)sgrp * kGroup;
 #pragma unroll 4
         for (int k = 0; k < gsz; ++k) {
             const int j = min(base + ((k + lane) & (gsz - 1)) * stride, nc - 1);   // rotated per lane: conflict-free
-            const float t = sqdist(qx, qy, qz, c[3 * j], c[3 * j + 1], c[3 * j + 2]);
-            if (t < bt || (t == bt && j < bj)) { bt = t; bj = j; }
+            bt = fminf(bt, sqdist(qx, qy, qz, c[3 * j], c[3 * j + 1], c[3 * j + 2]));
         }
         if (TWO && two) {
-            const int base2 = (int)sgrp * kGroup;
             for (int k = 0; k < kGroup; ++k) {
                 const int j = min(base2 + ((k + lane) & (kGroup - 1)), nc - 1);
-                const float t = sqdist(qx, qy, qz, c[3 * j], c[3 * j + 1], c[3 * j + 2]);
-                if (t < bt || (t == bt && j < bj)) { bt = t; bj = j; }
+                bt = fminf(bt, sqdist(qx, qy, qz, c[3 * j], c[3 * j + 1], c[3 * j + 2]));
+            }
+        }
+        if (bt < INFINITY) {
+            const float h = sqrt_window_top(bt, __fsqrt_rn(bt));
+#pragma unroll 4
+            for (int k = 0; k < gsz; ++k) {
+                const int j = min(base + ((k + lane) & (gsz - 1)) * stride, nc - 1);
+                if (sqdist(qx, qy, qz, c[3 * j], c[3 * j + 1], c[3 * j + 2]) <= h) bj = min(bj, j);
+            }
+            if (TWO && two) {
+                for (int k = 0; k < kGroup; ++k) {
+                    const int j = min(base2 + ((k + lane) & (kGroup - 1)), nc - 1);
+                    if (sqdist(qx, qy, qz, c[3 * j], c[3 * j + 1], c[3 * j + 2]) <= h) bj = min(bj, j);
+                }
             }
         }
     }
     __syncthreads();                                    // s_list complete
-    // ---- ambiguous points, one after the other: all 256 threads scan the candidates exactly
+    // ---- ambiguous points, one after the other: all 256 threads scan the candidates exactly (two passes, as above)
     for (int a = 0; a < n_amb; ++a) {
         const int t_a = s_list[a];
-        float lt;
-        int lj;
-        scan_strided(c, nc, tid, kFin2Threads, s_q[0][t_a], s_q[1][t_a], s_q[2][t_a], lt, lj);
-        const unsigned tb = __float_as_uint(lt);                     // lt >= 0 or +inf: orders as unsigned
-        const unsigned mt = __reduce_min_sync(0xffffffffu, tb);
-        const int mj = __reduce_min_sync(0xffffffffu, tb == mt ? lj : 0x7fffffff);
-        if (lane == 0) s_wbest[wid] = ((u64)mt << 32) | (unsigned)mj;
+        const float ax = s_q[0][t_a], ay = s_q[1][t_a], az = s_q[2][t_a];
+        const float lt = scan_min_strided(c, nc, tid, kFin2Threads, ax, ay, az);
+        const unsigned mt = __reduce_min_sync(0xffffffffu, __float_as_uint(lt));     // lt >= 0 or +inf: orders as unsigned
+        if (lane == 0) s_wmin[wid] = mt;
+        __syncthreads();
+        unsigned mb = s_wmin[0];
+#pragma unroll
+        for (int k = 1; k < kFin2Warps; ++k) mb = min(mb, s_wmin[k]);
+        const float m = __uint_as_float(mb);
+        const float h = m < INFINITY ? sqrt_window_top(m, __fsqrt_rn(m)) : m;
+        const int lj = scan_first_le_strided(c, nc, tid, kFin2Threads, ax, ay, az, h);
+        const int mj = __reduce_min_sync(0xffffffffu, lj);
+        if (lane == 0) s_wj[wid] = mj;
         __syncthreads();
         if (tid == t_a) {
-            u64 m = s_wbest[0];
+            int jj = s_wj[0];
 #pragma unroll
-            for (int k = 1; k < kFin2Warps; ++k) m = s_wbest[k] < m ? s_wbest[k] : m;
-            bt = __uint_as_float((unsigned)(m >> 32));
-            bj = (int)(unsigned)(m & 0xffffffffu);
+            for (int k = 1; k < kFin2Warps; ++k) jj = min(jj, s_wj[k]);
+            bt = m;
+            bj = jj;
         }
         __syncthreads();
     }
     double dist_d = 0.0;
     if (live) {
-        if (!(bt < INFINITY)) {
-            // only reachable with non-finite input (outside the contract): mirror torch.min, where the first
-            // NaN wins -> candidate 0
+        if (!(bt < INFINITY) || bj == 0x7fffffff) {
+            // only reachable with non-finite input (outside the contract): candidate 0
             bj = 0;
             bt = sqdist(qx, qy, qz, cglob[0], cglob[1], cglob[2]);
         }
-        const float dist = sqrtf(bt);
+        const float dist = __fsqrt_rn(bt);
         (dir ? d2 : d1)[(size_t)b * nq + i] = dist;
         (dir ? i2 : i1)[(size_t)b * nq + i] = bj;
         dist_d = (double)dist;
@@ -634,8 +662,13 @@ int launch_finalize2(const float *pc1, const float *pc2, int B, int N, int M, in
     };
     const size_t dyn = in_smem ? align_up(cand_bytes, 16) : 0;
     int rc;
-    if (in_smem) rc = two ? launch(chamfer_finalize2_kernel<true, true>, dyn) : launch(chamfer_finalize2_kernel<true, false>, dyn);
-    else rc = two ? launch(chamfer_finalize2_kernel<false, true>, dyn) : launch(chamfer_finalize2_kernel<false, false>, dyn);
+#ifdef RLG_EXPERIMENTS
+    if (two) rc = in_smem ? launch(chamfer_finalize2_kernel<true, true>, dyn) : launch(chamfer_finalize2_kernel<false, true>, dyn);
+    else
+#else
+    if (two) return fail(RLG_ERR_UNSUPPORTED, "chamfer_finalize2_kernel: two-group refinement exists only in the experiments build");
+#endif
+    rc = in_smem ? launch(chamfer_finalize2_kernel<true, false>, dyn) : launch(chamfer_finalize2_kernel<false, false>, dyn);
     if (rc) return rc;
     return check_launch("chamfer_finalize2_kernel");
 }

@@ -50,6 +50,7 @@
 // Environment (measurement only): RLG_TF_DEBUG=1|2 prints per-role cycle counters and per-CTA time spans after a
 // synchronize; RLG_TF_TOP3=0|1 and RLG_TF_SPLIT=0|1|2 override the runner-up report and the work split; RLG_TF_KO=2
 // skips the minima (timing experiment, wrong results).
+#ifdef RLG_EXPERIMENTS      // first-generation kernel, kept for A/B timing against chamfer_tcsweep.cu
 #include "common.cuh"
 #include "tcgen05.cuh"
 #include <math.h>
@@ -555,3 +556,4 @@ int launch_tcfilter(const float *pc1, const float *pc2, int B, int N, int M, con
 }
 
 }  // namespace rlg
+#endif  // RLG_EXPERIMENTS

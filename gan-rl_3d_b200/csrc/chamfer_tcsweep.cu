@@ -1,0 +1,710 @@
+// chamfer_tcsweep.cu -- batched Chamfer distance forward in two launches: the pair sweep on the tensor cores with the
+// exact refinement fused in, and a small tail kernel (the few ambiguous points, the per-pair means, the batch loss).
+//
+// Replaces utils/losses.py:29-37 of the reference (torch.cdist -> min over both axes -> mean); the (B,N,M) matrix never
+// exists.  Filter and refine, as in chamfer_filter.cu: a cheap filter value t~(i,j) ~ |x_i - y_j|^2 for EVERY pair
+// decides which 32-candidate group can hold a query's nearest neighbour; the direct-form arithmetic
+// (t = d0*d0; t = fma(d1,d1,t); t = fma(d2,d2,t); sqrtf -- bit-identical to ATen's direct cdist) runs only there.
+//
+// The filter is a K = 16 tcgen05.mma kind::tf32 contraction with error-compensated operands:
+//       A row (query x)      x0h x0h x0l | x1h x1h x1l | x2h x2h x2l | nxh nxm nxl | 1   1   1   | 0
+//       B row (candidate y)  Y0h Y0l Y0h | Y1h Y1l Y1h | Y2h Y2l Y2h | 1   1   1   | nyh nym nyl | 0      (Y = -2y)
+//   vh = tf32(v), vl = tf32(v - vh); squared norms split three ways (exactly); only the vl x vl products are dropped.
+//   D[128 queries x 128 candidates] (fp32, TMEM) = A . B^T; a query sits on one TMEM lane, so its minimum over the
+//   candidates is a per-thread reduction of tcgen05.ld registers.  Both directions are the same problem with the clouds
+//   swapped.
+//
+// Error of the filter (u = 2^-24, a = |x_i|, b = |y_j|, S = a^2 + b^2): dropped split terms <= 12 u S, accumulation
+// inside the tensor core (modelled as fp32 truncation at each of 18 additions) <= 36 u S, computed norms <= 3 u S:
+// |t~ - t| <= 51 u S; the direct form adds <= 10 u S.  So |t~_j - D_j| <= 61 u S_j for the direct-form value D_j.
+// The refinement needs no knowledge of the candidate cloud's extent: b <= a + sqrt(t) gives S_j <= 3 a^2 + 2 t_j, and
+// from t_j <= t~_j + 51 u S_j:  S_j <= 3.001 a^2 + 2.001 t~_j.  With val = smallest group minimum (group g*) and
+// sv = smallest minimum of any other group, every candidate j outside g* has
+//       D_j >= sv (1 - 123 u) - 183.1 u a^2     and the candidate c attaining val has     D_c <= val (1 + 123 u) + 183.1 u a^2.
+// If  sv (1 - kRel) > val (1 + kRel) + kAbs a^2  with kRel = 160 u, kAbs = 420 u  (slack covers the rounding of this
+// test itself and the <= 4 u relative window in which two squared distances can share one sqrtf), the exact nearest
+// neighbour -- also under the reference's tie rule, which compares the square-rooted values -- lies in group g*:
+// 32 direct-form evaluations.  Otherwise the point is AMBIGUOUS (0.6-0.9 % of the points at N = M = 2048): with the
+// runner-up's group and the third-smallest group minimum known (TOP3, large clouds) it is refined on two groups when
+// the third is out of reach, else its index goes to a list and the tail kernel scans the whole candidate cloud.
+// Either way the outputs are independent of how the filter rounded.
+//
+// Tie rule: torch.min runs on the sqrt-ed matrix, and sqrtf maps up to three adjacent fp32 values onto one, so
+// candidates whose squared distances differ in the last bits tie there and the LOWEST INDEX wins.  The refinement finds
+// m = min t, s = sqrtf(m), the largest h with sqrtf(h) == s, and returns the lowest index with t <= h (oracle:
+// ORC_TIE_FAITHFUL).
+//
+// Roles (one CTA per SM, persistent over (direction, cloud, 128-query block) tasks; a CTA owns a contiguous task range
+// and walks it in SEGMENTS of up to 8 query blocks of one (direction, cloud) that share every converted candidate tile;
+// a "visit" = one query block x one 256-candidate tile = two 128-column halves):
+//   warps 0-15  epilogue.  Two pipeline groups of eight warps: group p takes half p of every visit and alternates between
+//               TMEM accumulators p and p+2, so the tensor cores refill one while the other is reduced.  Within a group
+//               two warps per TMEM lane quarter split the 128 columns: thread = (query row, 64 candidates).  Running
+//               (best, second, third group minimum; best / second group) per query block live in shared memory; at the
+//               end of a segment the four partial states of a query are merged and the merging thread refines it.
+//   warps 16-17 producers: convert 256 candidates per tile (and the segment's queries) to the split-tf32 rows, written
+//               straight into K-major SWIZZLE_128B operand tiles.
+//   warps 18-19 MMA issuers (one elected lane each): issuer p serves pipeline group p.  A tcgen05.mma blocks its issuer
+//               while the pipe is busy and every hand-off costs the issuer a barrier round trip (profiles/
+//               r1_umma_microbench.txt: pause + 85 cycles per hand-off); two issuers hide one another's round trips.
+#include "common.cuh"
+#include "tcgen05.cuh"
+#include <math.h>
+
+namespace rlg {
+
+constexpr int kTQ = 128;                       // queries per block (UMMA M)
+constexpr int kTC = 256;                       // candidates per tile (two UMMA N = 128 halves)
+constexpr int kQmax = 8;                       // query blocks that share one pass over the candidate tiles
+constexpr int kEpWarps = 16, kPrWarps = 2, kMmaWarps = 2;
+constexpr int kMmaWarp0 = kEpWarps + kPrWarps;
+constexpr int kThreads = (kEpWarps + kPrWarps + kMmaWarps) * 32;
+constexpr int kPrThreads = kPrWarps * 32;
+constexpr int kARows = kTQ / kPrThreads, kBRows = kTC / kPrThreads;            // rows per producer thread
+constexpr uint32_t kABytes = kTQ * 128, kBBytes = kTC * 128;
+// A rows carry K = 16 tf32 = 64 bytes, half of a SWIZZLE_128B row: two query blocks share one 16 KB tile (block q sits in
+// 16-byte chunks 4*(q&1) .. 4*(q&1)+3 of tile q>>1; the descriptor's start address selects the half)
+constexpr uint32_t kOffB = (kQmax / 2) * kABytes;                             // two candidate tiles follow the A tiles
+constexpr int kStW = 5;                                                       // state words: best, second, third, best grp, second grp
+constexpr int kSlots = 4;                                                     // partial states per query: (pipeline group, column half)
+constexpr uint32_t kOffState = kOffB + 2 * kBBytes;                           // [slot][kQmax][kStW][128]
+constexpr uint32_t kStateBytes = (uint32_t)kSlots * kQmax * kTQ * kStW * 4u;
+constexpr uint32_t kOffBar = kOffState + kStateBytes;
+constexpr uint32_t kSmem = kOffBar + 256 + 1024;                              // + barriers + alignment slack
+constexpr float kBig = 1.0e30f;
+constexpr float kU = 1.0f / 16777216.0f;                                      // 2^-24
+constexpr float kRel = 160.0f * kU, kAbs = 420.0f * kU;                       // see the header
+
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void split2(float v, float &h, float &l) {
+    h = tf32_rn(v);
+    l = tf32_rn(v - h);                                // v - h is exact
+}
+__device__ __forceinline__ void split3(float v, float &h, float &m, float &l) {
+    h = tf32_rn(v);
+    const float r = v - h;                             // exact
+    m = tf32_rn(r);
+    l = r - m;                                         // exact, at most 3 significant bits
+}
+// row `row` of a K-major SW128 tile: 16 floats as four 16-byte chunks starting at chunk `chunk0`
+__device__ __forceinline__ void store_row(unsigned char *tile, int row, const float (&e)[16], uint32_t chunk0) {
+    const uint32_t base = (uint32_t)row * 128u, x = (uint32_t)row & 7u;
+#pragma unroll
+    for (uint32_t c = 0; c < 4; ++c)
+        *reinterpret_cast<float4 *>(tile + base + (((chunk0 + c) ^ x) << 4)) = make_float4(e[4 * c], e[4 * c + 1], e[4 * c + 2], e[4 * c + 3]);
+}
+__device__ __forceinline__ float nrm2(float x, float y, float z) { return fmaf(z, z, fmaf(y, y, x * x)); }
+
+// minimum of 32 values, as a tree of 3-input minima (NaN operands are dropped)
+__device__ __forceinline__ float min32(const float (&v)[32]) {
+    float m[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) m[i] = min3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+    m[10] = fminf(v[30], v[31]);
+    const float n0 = min3(m[0], m[1], m[2]), n1 = min3(m[3], m[4], m[5]), n2 = min3(m[6], m[7], m[8]);
+    return min3(min3(n0, n1, n2), m[9], m[10]);
+}
+
+// every later use of v depends on this statement: placed after a tcgen05.wait::ld it keeps reads of v behind the wait
+__device__ __forceinline__ void pin32(float (&v)[32]) {
+    asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
+                      "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]),
+                      "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]),
+                      "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
+                 :: "memory");
+}
+
+// ---- exact arithmetic shared by the fused refinement and the tail kernel --------------------------------------------
+// direct-form squared distances of (qx,qy,qz) to candidates base .. base+31 of cloud c (indices past the end repeat the
+// last point: a real candidate with the highest index, so it can never win a tie it should not)
+__device__ __forceinline__ void eval_group(const float *__restrict__ c, int nc, int base, float qx, float qy, float qz,
+                                           float (&t)[32]) {
+    const float *p = c + 3 * (size_t)base;
+    if (base + 32 <= nc && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+        const float4 *p4 = reinterpret_cast<const float4 *>(p);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {                  // 8 candidates = 24 floats = six 16-byte loads in flight
+            float4 v[6];
+#pragma unroll
+            for (int e = 0; e < 6; ++e) v[e] = __ldg(p4 + h * 6 + e);
+            float f[24];
+#pragma unroll
+            for (int e = 0; e < 6; ++e) { f[4 * e] = v[e].x; f[4 * e + 1] = v[e].y; f[4 * e + 2] = v[e].z; f[4 * e + 3] = v[e].w; }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t[h * 8 + k] = sqdist(qx, qy, qz, f[3 * k], f[3 * k + 1], f[3 * k + 2]);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const int j = min(base + k, nc - 1);
+            t[k] = sqdist(qx, qy, qz, __ldg(c + 3 * (size_t)j), __ldg(c + 3 * (size_t)j + 1), __ldg(c + 3 * (size_t)j + 2));
+        }
+    }
+}
+// lowest k with t[k] <= h (32 if none)
+__device__ __forceinline__ int first_le(const float (&t)[32], float h) {
+    int kk = 32;
+#pragma unroll
+    for (int k = 31; k >= 0; --k) kk = (t[k] <= h) ? k : kk;
+    return kk;
+}
+
+struct SweepOut {
+    float *d1, *d2;                 // (B,N), (B,M)
+    int32_t *i1, *i2;
+    float *z1, *z2;                 // optional (B,N,3)/(B,M,3) gradient buffers to zero-fill
+    unsigned *amb_cnt;              // (2,B): ambiguous points per (direction, cloud) minus one (all-ones = none)
+    unsigned *amb_list;             // (B*N + B*M): their query indices
+    // diagnostic (RLG_CHAMFER_FILTER_ONLY): the merged filter results per query instead of the refinement
+    u64 *key1, *key2;               // (B,N), (B,M): smallest group minimum << 32 | its group
+    unsigned *sec1, *sec2;          // (B,N), (B,M): second-smallest group minimum (+inf: none)
+};
+
+struct Seg { int dir, b, qb0, Q, nq, nc, n_ct, next; };
+
+// ---- fused refinement of one query ------------------------------------------------------------------------------
+// k1 = (smallest group minimum, its group), k2 = (second smallest, its group), t3 = third smallest group minimum
+template <bool TOP3>
+__device__ __forceinline__ void refine_query(const float *__restrict__ qc, const float *__restrict__ cc, int nc, int i,
+                                             u64 k1, u64 k2, float t3, float *__restrict__ dout, int32_t *__restrict__ iout,
+                                             float *__restrict__ zero, unsigned *__restrict__ cnt, unsigned *__restrict__ list) {
+    const float qx = __ldg(qc + 3 * (size_t)i), qy = __ldg(qc + 3 * (size_t)i + 1), qz = __ldg(qc + 3 * (size_t)i + 2);
+    if (zero != nullptr) { zero[3 * (size_t)i] = 0.0f; zero[3 * (size_t)i + 1] = 0.0f; zero[3 * (size_t)i + 2] = 0.0f; }
+    const float val = __uint_as_float((unsigned)(k1 >> 32));
+    const int grp = (int)(unsigned)(k1 & 0xffffffffu);
+    const bool has2 = k2 != kKeyInit;                                   // a single candidate group: nothing to confuse
+    const float sv = has2 ? __uint_as_float((unsigned)(k2 >> 32)) : INFINITY;
+    const int sgrp = (int)(unsigned)(k2 & 0xffffffffu);
+    const float thr = fmaf(val, 1.0f + kRel, kAbs * nrm2(qx, qy, qz));
+    // any NaN (non-finite input) makes a comparison false -> ambiguous -> exact scan in the tail kernel
+    const bool clear = sv * (1.0f - kRel) > thr;
+    const bool two = TOP3 && !clear && has2 && (t3 * (1.0f - kRel) > thr);
+    bool amb = !clear && !two;
+    float m = INFINITY;
+    float t[32];
+    if (!amb) {
+        eval_group(cc, nc, grp * kGroup, qx, qy, qz, t);
+        m = min32(t);
+        if (TOP3 && two) {
+            eval_group(cc, nc, sgrp * kGroup, qx, qy, qz, t);
+            m = fminf(m, min32(t));
+        }
+        amb = !(m < INFINITY);                                          // non-finite input: the tail mirrors torch.min
+    }
+    if (amb) {
+        const unsigned pos = atomicAdd(cnt, 1u) + 1u;                   // the counter starts at all-ones
+        list[pos] = (unsigned)i;
+        return;
+    }
+    const float s = __fsqrt_rn(m);
+    const float h = sqrt_window_top(m, s);
+    int bj = 0x7fffffff;
+    if (TOP3 && two) {
+        bj = sgrp * kGroup + first_le(t, h);                            // t holds the second group (32: nothing there)
+        if (bj - sgrp * kGroup == 32) bj = 0x7fffffff;
+        eval_group(cc, nc, grp * kGroup, qx, qy, qz, t);
+    }
+    const int k = first_le(t, h);
+    if (k < 32) bj = min(bj, grp * kGroup + k);
+    dout[i] = s;
+    iout[i] = min(bj, nc - 1);
+}
+
+// TOP3: also track the runner-up's group and the third-smallest group minimum (5 more issue slots per 32 candidates;
+// pays off when ambiguous points would otherwise rescan a large candidate cloud -- see launch_tcsweep)
+template <bool TOP3>
+__global__ void __launch_bounds__(kThreads, 1)
+chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ pc2, int B, int N, int M, int n_tasks,
+                       int qb1, int qb2, SweepOut o, int refine) {
+    extern __shared__ unsigned char ts_smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t pad = (1024u - (smem_u32(ts_smem_raw) & 1023u)) & 1023u;
+    unsigned char *smem = ts_smem_raw + pad;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bars = sbase + kOffBar;
+    const uint32_t bar_afull = bars, bar_aempty = bars + 8 * kQmax;                     // [kQmax], [1]
+    const uint32_t bar_bfull = bar_aempty + 8, bar_bempty = bar_bfull + 16;             // [2] each
+    const uint32_t bar_accfull = bar_bempty + 16, bar_accempty = bar_accfull + 32;      // [4] each
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kOffBar + 8 * (kQmax + 13));
+
+    if (tid == 0) {
+        for (int q = 0; q < kQmax; ++q) mbar_init(bar_afull + 8 * q, kPrThreads);
+        mbar_init(bar_aempty, kMmaWarps);
+        for (int k = 0; k < 2; ++k) { mbar_init(bar_bfull + 8 * k, kPrThreads); mbar_init(bar_bempty + 8 * k, kMmaWarps); }
+        for (int k = 0; k < 4; ++k) { mbar_init(bar_accfull + 8 * k, 1); mbar_init(bar_accempty + 8 * k, (kEpWarps / 2) * 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kMmaWarp0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();                                   // clouds and workspace may come from the kernels right before this one
+
+    // tasks (direction, cloud, 128-query block) in direction-major order, split evenly and contiguously over the CTAs
+    const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+    const int per = n_tasks / G, rem = n_tasks - per * G;
+    const int t_begin = cta * per + min(cta, rem);
+    const int t_end = t_begin + per + (cta < rem ? 1 : 0);
+    auto seg_at = [&](int task) {
+        Seg sg;
+        const int n0 = B * qb1;
+        int qbn;
+        if (task < n0) { sg.dir = 0; sg.b = task / qb1; sg.qb0 = task - sg.b * qb1; qbn = qb1; }
+        else { const int r = task - n0; sg.dir = 1; sg.b = r / qb2; sg.qb0 = r - sg.b * qb2; qbn = qb2; }
+        sg.Q = min(kQmax, min(t_end - task, qbn - sg.qb0));
+        sg.nq = sg.dir ? M : N;
+        sg.nc = sg.dir ? N : M;
+        sg.n_ct = (sg.nc + kTC - 1) / kTC;
+        sg.next = task + sg.Q;
+        return sg;
+    };
+
+    if (warp >= kMmaWarp0) {
+        // =========================== MMA issuers ===========================
+        // half-visits in issue order: (tile k, query block q, half hf), running index gt = 2 * visit + hf; accumulator
+        // gt % 4; issuer p issues the halves hf == p (its pipeline group's accumulators p and p + 2)
+        const uint32_t me = (uint32_t)(warp - kMmaWarp0);
+        const bool leader = elect_one();
+        const uint32_t idesc = umma_idesc_tf32(kTQ, kTC / 2);
+        const uint64_t ad0 = umma_desc(sbase), bd0 = umma_desc(sbase + kOffB);
+        const uint64_t a_inc = (uint64_t)(kABytes >> 4), b_inc = (uint64_t)(kBBytes >> 4);
+        uint32_t vis = 0, bt = 0, sn = 0;
+        for (int task = t_begin; task < t_end;) {
+            const Seg sg = seg_at(task);
+            task = sg.next;
+            for (int k = 0; k < sg.n_ct; ++k, ++bt) {
+                const uint32_t sb = bt & 1u;
+                mbar_wait_spin(bar_bfull + 8 * sb, (bt >> 1) & 1u);
+                const uint64_t bh = bd0 + (uint64_t)sb * b_inc + (uint64_t)me * (b_inc >> 1);
+                for (int q = 0; q < sg.Q; ++q, ++vis) {
+                    if (k == 0) mbar_wait_spin(bar_afull + 8 * q, sn & 1u);
+                    const uint32_t gt = 2u * vis + me, ab = gt & 3u;
+                    mbar_wait_spin(bar_accempty + 8 * ab, ((gt >> 2) & 1u) ^ 1u);
+                    tc_fence_after();
+                    if (leader) {
+                        const uint64_t ad = ad0 + (uint64_t)(q >> 1) * a_inc + (uint64_t)((q & 1) * 4);
+                        const uint32_t d = tmem + ab * (uint32_t)(kTC / 2);
+                        tc_mma_tf32(d, ad, bh, idesc, 0u);                  // K columns 0..7  (32 bytes)
+                        tc_mma_tf32(d, ad + 2, bh + 2, idesc, 1u);          // K columns 8..15
+                        tc_commit(bar_accfull + 8 * ab);
+                    }
+                    __syncwarp();
+                }
+                if (leader) tc_commit(bar_bempty + 8 * sb);
+                __syncwarp();
+            }
+            if (leader) tc_commit(bar_aempty);
+            __syncwarp();
+            ++sn;
+        }
+    } else if (warp >= kEpWarps) {
+        // =========================== producers ===========================
+        const int ptid = tid - kEpWarps * 32;                           // 0..kPrThreads-1
+        unsigned char *const tileA0 = smem, *const tileB0 = smem + kOffB;
+        auto load3 = [&](const float *src, float &o0, float &o1, float &o2) {
+            // volatile: the loads stay where they are written (ahead of the barrier wait that hides their latency)
+            asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(o0) : "l"(src));
+            asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(o1) : "l"(src + 1));
+            asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(o2) : "l"(src + 2));
+        };
+        uint32_t bt = 0, sn = 0;
+        for (int task = t_begin; task < t_end;) {
+            const Seg sg = seg_at(task);
+            task = sg.next;
+            const float *qc = (sg.dir ? pc2 : pc1) + (size_t)sg.b * sg.nq * 3;
+            const float *cc = (sg.dir ? pc1 : pc2) + (size_t)sg.b * sg.nc * 3;
+            // 128 queries of block qb0+q -> A tile q (rows past the end are all-zero)
+            auto load_a = [&](int q, float (&x)[kARows][3]) {
+#pragma unroll
+                for (int h = 0; h < kARows; ++h) {
+                    const int i = (sg.qb0 + q) * kTQ + h * kPrThreads + ptid;
+                    x[h][0] = 0.f; x[h][1] = 0.f; x[h][2] = 0.f;
+                    if (i < sg.nq) load3(qc + (size_t)i * 3, x[h][0], x[h][1], x[h][2]);
+                }
+            };
+            auto store_a = [&](int q, const float (&x)[kARows][3]) {
+#pragma unroll
+                for (int h = 0; h < kARows; ++h) {
+                    const int r = h * kPrThreads + ptid;
+                    const int i = (sg.qb0 + q) * kTQ + r;
+                    float e[16];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) e[k] = 0.0f;
+                    if (i < sg.nq) {
+                        float hh, l;
+                        split2(x[h][0], hh, l); e[0] = hh; e[1] = hh; e[2] = l;
+                        split2(x[h][1], hh, l); e[3] = hh; e[4] = hh; e[5] = l;
+                        split2(x[h][2], hh, l); e[6] = hh; e[7] = hh; e[8] = l;
+                        split3(nrm2(x[h][0], x[h][1], x[h][2]), e[9], e[10], e[11]);
+                        e[12] = 1.0f; e[13] = 1.0f; e[14] = 1.0f;
+                    }
+                    store_row(tileA0 + (uint32_t)(q >> 1) * kABytes, r, e, 4u * (uint32_t)(q & 1));
+                }
+                fence_async_proxy();
+                mbar_arrive(bar_afull + 8 * q);
+            };
+            // 256 candidates of tile k -> B tile (four rows per thread); the loads are issued BEFORE the wait for the buffer
+            auto produce_b = [&](int k) {
+                const uint32_t sb = bt & 1u;
+                float y[kBRows][3];
+#pragma unroll
+                for (int h = 0; h < kBRows; ++h) {
+                    const int j = min(k * kTC + h * kPrThreads + ptid, sg.nc - 1);
+                    load3(cc + (size_t)j * 3, y[h][0], y[h][1], y[h][2]);
+                }
+                mbar_wait_spin(bar_bempty + 8 * sb, ((bt >> 1) & 1u) ^ 1u);
+#pragma unroll
+                for (int h = 0; h < kBRows; ++h) {
+                    const int r = h * kPrThreads + ptid;
+                    const bool valid = k * kTC + r < sg.nc;
+                    const float y0 = y[h][0], y1 = y[h][1], y2 = y[h][2];
+                    float e[16];
+                    float hh, l;
+                    split2(valid ? -2.0f * y0 : 0.0f, hh, l); e[0] = hh; e[1] = l; e[2] = hh;
+                    split2(valid ? -2.0f * y1 : 0.0f, hh, l); e[3] = hh; e[4] = l; e[5] = hh;
+                    split2(valid ? -2.0f * y2 : 0.0f, hh, l); e[6] = hh; e[7] = l; e[8] = hh;
+                    e[9] = 1.0f; e[10] = 1.0f; e[11] = 1.0f;
+                    split3(valid ? nrm2(y0, y1, y2) : kBig, e[12], e[13], e[14]);
+                    e[15] = 0.0f;
+                    store_row(tileB0 + sb * kBBytes, r, e, 0u);
+                }
+                fence_async_proxy();
+                mbar_arrive(bar_bfull + 8 * sb);
+                ++bt;
+            };
+            // query loads run one block ahead of their conversion; the first two are in flight under the first tile
+            float ax[2][kARows][3];
+            load_a(0, ax[0]);
+            if (sg.Q > 1) load_a(1, ax[1]);
+            produce_b(0);
+            mbar_wait_spin(bar_aempty, (sn & 1u) ^ 1u);                 // the previous segment's MMAs are done with the A tiles
+#pragma unroll
+            for (int q = 0; q < kQmax; ++q) {                           // every barrier advances once per segment
+                if (q < sg.Q) {
+                    store_a(q, ax[q & 1]);
+                    if (q + 2 < sg.Q) load_a(q + 2, ax[q & 1]);
+                } else {
+                    mbar_arrive(bar_afull + 8 * q);
+                }
+            }
+            for (int k = 1; k < sg.n_ct; ++k) produce_b(k);
+            ++sn;
+        }
+    } else {
+        // =========================== epilogue ===========================
+        const int slot = warp >> 2;                                     // partial state of a query: (pipeline group, column half)
+        const uint32_t pg = (uint32_t)slot & 1u, ch = (uint32_t)slot >> 1;
+        const int row = (warp & 3) * 32 + lane;                         // query of the block == TMEM lane
+        const uint32_t lane_base = ((uint32_t)(warp & 3) * 32u) << 16;
+        float *st = reinterpret_cast<float *>(smem + kOffState) + (slot * kQmax) * kTQ * kStW + row;
+        constexpr int kStQ = kTQ * kStW;                                // words per query block of one slot
+        uint32_t vis0 = 0;                                              // visits issued before this segment
+        for (int task = t_begin; task < t_end;) {
+            const Seg sg = seg_at(task);
+            task = sg.next;
+            for (int q = 0; q < sg.Q; ++q) {
+                float *sq = st + q * kStQ;
+                sq[0] = INFINITY; sq[kTQ] = INFINITY; sq[2 * kTQ] = INFINITY;
+                reinterpret_cast<int *>(sq)[3 * kTQ] = 0; reinterpret_cast<int *>(sq)[4 * kTQ] = 0;
+            }
+            const uint32_t n_vis = (uint32_t)sg.n_ct * (uint32_t)sg.Q;
+            int k = 0, q = 0;
+            for (uint32_t v = 0; v < n_vis; ++v) {
+                const uint32_t gt = 2u * (vis0 + v) + pg, ab = gt & 3u;
+                float *sq = st + q * kStQ;
+                float best = sq[0], second = sq[kTQ], third = TOP3 ? sq[2 * kTQ] : INFINITY;
+                int bgrp = reinterpret_cast<int *>(sq)[3 * kTQ], sgrp = TOP3 ? reinterpret_cast<int *>(sq)[4 * kTQ] : 0;
+                // running three smallest group minima (strict <: the earliest group keeps a tie) and the groups of the first two
+                auto group_done = [&](const float (&vv)[32], int Gc) {
+                    const float m = min32(vv);
+                    if (!TOP3) {
+                        second = fminf(second, fmaxf(best, m));
+                        if (m < best) { best = m; bgrp = Gc; }
+                        return;
+                    }
+                    // nothing changes unless the group beats the running third; late in a large cloud that is rare for
+                    // all 32 queries of the warp at once
+                    if (!__any_sync(0xffffffffu, m < third)) return;
+                    const bool p1 = m < best;
+                    const float c1 = fmaxf(best, m);                    // what drops out of first place
+                    const bool p2 = c1 < second;
+                    third = fminf(third, fmaxf(second, c1));
+                    second = fminf(second, c1);
+                    sgrp = p2 ? (p1 ? bgrp : Gc) : sgrp;
+                    best = fminf(best, m);
+                    bgrp = p1 ? Gc : bgrp;
+                };
+                mbar_wait_spin(bar_accfull + 8 * ab, (gt >> 2) & 1u);
+                tc_fence_after();
+                // this thread's 64 candidates of the half-visit: both loads up front, the accumulator goes back to its
+                // issuer as soon as they have landed (the group's other accumulator is being refilled meanwhile)
+                const uint32_t taddr = tmem + lane_base + ab * (uint32_t)(kTC / 2) + ch * 64u;
+                float va[32], vb[32];
+                tc_ld32_nowait(taddr, va);
+                tc_ld32_nowait(taddr + 32u, vb);
+                tc_wait_ld(va);
+                pin32(vb);
+                tc_fence_before();
+                mbar_arrive(bar_accempty + 8 * ab);
+                int G0 = k * (kTC / 32) + (int)(pg * 4u + ch * 2u);
+                asm volatile("mov.s32 %0, %0;" : "+r"(G0));             // pinned: otherwise recomputed under every predicate
+                group_done(va, G0);
+                group_done(vb, G0 + 1);
+                sq[0] = best; sq[kTQ] = second;
+                reinterpret_cast<int *>(sq)[3 * kTQ] = bgrp;
+                if (TOP3) { sq[2 * kTQ] = third; reinterpret_cast<int *>(sq)[4 * kTQ] = sgrp; }
+                if (++q == sg.Q) { q = 0; ++k; }
+            }
+            vis0 += n_vis;
+            // ---- merge the four partial states per query; the merging thread refines the query (every candidate of
+            // these queries was seen by this CTA in this segment).  Slot s merges query blocks s and s + 4.
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpWarps * 32) : "memory");
+            const float *all_st = reinterpret_cast<const float *>(smem + kOffState) + row;
+            u64 mk1[2], mk2[2];
+            float mt3[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int qq = slot + 4 * r;
+                // three smallest (value, group) keys over the four slots' top-two lists, third value also over their thirds
+                u64 k1 = kKeyInit, k2 = kKeyInit;
+                float t3 = INFINITY;
+                auto insert = [&](u64 key) {
+                    const u64 c1 = key > k1 ? key : k1;
+                    k1 = key < k1 ? key : k1;
+                    const u64 c2 = c1 > k2 ? c1 : k2;
+                    k2 = c1 < k2 ? c1 : k2;
+                    t3 = fminf(t3, __uint_as_float((unsigned)(c2 >> 32) & 0x7fffffffu));    // all-ones init -> NaN: ignored
+                };
+                if (qq < sg.Q) {
+#pragma unroll
+                    for (int g = 0; g < kSlots; ++g) {
+                        const float *sp = all_st + (g * kQmax + qq) * kStQ;
+                        const int *ip = reinterpret_cast<const int *>(sp);
+                        insert(((u64)__float_as_uint(fmaxf(sp[0], 0.0f)) << 32) | (unsigned)ip[3 * kTQ]);       // +inf if nothing seen
+                        if (TOP3) {
+                            insert(((u64)__float_as_uint(fmaxf(sp[kTQ], 0.0f)) << 32) | (unsigned)ip[4 * kTQ]);
+                            t3 = fminf(t3, fmaxf(sp[2 * kTQ], 0.0f));
+                        } else {
+                            // no runner-up group is tracked: only its value takes part (group field unused)
+                            insert(((u64)__float_as_uint(fmaxf(sp[kTQ], 0.0f)) << 32) | 0xffffffffull);
+                        }
+                    }
+                    // a slot that saw no second group reports +inf there: "no runner-up"
+                    if ((unsigned)(k2 >> 32) == 0x7f800000u) k2 = kKeyInit;
+                }
+                mk1[r] = k1; mk2[r] = k2; mt3[r] = t3;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpWarps * 32) : "memory");   // the state may be re-initialised
+            if (refine) {
+                const float *qc = (sg.dir ? pc2 : pc1) + (size_t)sg.b * sg.nq * 3;
+                const float *cc = (sg.dir ? pc1 : pc2) + (size_t)sg.b * sg.nc * 3;
+                const size_t qoff = (size_t)sg.b * sg.nq;
+                float *dout = (sg.dir ? o.d2 : o.d1) + qoff;
+                int32_t *iout = (sg.dir ? o.i2 : o.i1) + qoff;
+                float *zb = sg.dir ? o.z2 : o.z1;
+                float *zero = zb ? zb + 3 * qoff : nullptr;
+                unsigned *cnt = o.amb_cnt + (sg.dir ? B : 0) + sg.b;
+                unsigned *list = o.amb_list + (sg.dir ? (size_t)B * N : 0) + qoff;
+#pragma unroll 1
+                for (int r = 0; r < 2; ++r) {
+                    const int qq = slot + 4 * r;
+                    const int i = (sg.qb0 + qq) * kTQ + row;
+                    if (qq < sg.Q && i < sg.nq)
+                        refine_query<TOP3>(qc, cc, sg.nc, i, mk1[r], mk2[r], mt3[r], dout, iout, zero, cnt, list);
+                }
+            } else {
+                // diagnostic: publish what the filter found (tests measure its error against float64 with this)
+                u64 *keys = (sg.dir ? o.key2 : o.key1) + (size_t)sg.b * sg.nq;
+                unsigned *secs = (sg.dir ? o.sec2 : o.sec1) + (size_t)sg.b * sg.nq;
+#pragma unroll 1
+                for (int r = 0; r < 2; ++r) {
+                    const int qq = slot + 4 * r;
+                    const int i = (sg.qb0 + qq) * kTQ + row;
+                    if (qq < sg.Q && i < sg.nq) {
+                        keys[i] = mk1[r];
+                        secs[i] = mk2[r] != kKeyInit ? (unsigned)(mk2[r] >> 32) : 0x7f800000u;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
+// ---- tail kernel: the ambiguous points, the per-pair means, the batch loss ---------------------------------------
+constexpr int kTailThreads = 256, kTailWarps = kTailThreads / 32;
+
+struct TailWs {
+    unsigned *global_counter;   // 1
+    unsigned *cloud_counter;    // B
+};
+
+// grid (chunks, B, 2).  A warp scans the whole candidate cloud for one ambiguous point, mirroring torch.min on the
+// sqrt-ed row: the first NaN wins, otherwise the lowest index among the candidates that share the smallest sqrtf.
+__global__ void __launch_bounds__(kTailThreads) chamfer_tail_kernel(
+    const float *__restrict__ pc1, const float *__restrict__ pc2, int N, int M, int C1, int C2, SweepOut o, TailWs tw,
+    float *__restrict__ mean1, float *__restrict__ mean2, float *__restrict__ loss, float loss_w1, float loss_w2) {
+    __shared__ double red[kTailWarps];
+    const int chunk = blockIdx.x, b = blockIdx.y, dir = blockIdx.z, B = gridDim.y;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    pdl_launch_dependents();
+    if (chunk >= (dir ? C2 : C1)) return;
+    pdl_wait();                                         // everything below reads results of the pair sweep
+    const int nq = dir ? M : N, nc = dir ? N : M, C = dir ? C2 : C1;
+    const float *qc = (dir ? pc2 : pc1) + (size_t)b * nq * 3;
+    const float *cc = (dir ? pc1 : pc2) + (size_t)b * nc * 3;
+    float *dout = (dir ? o.d2 : o.d1) + (size_t)b * nq;
+    int32_t *iout = (dir ? o.i2 : o.i1) + (size_t)b * nq;
+    const unsigned n_amb = __ldcg(o.amb_cnt + (dir ? B : 0) + b) + 1u;
+    const unsigned *list = o.amb_list + (dir ? (size_t)B * N : 0) + (size_t)b * nq;
+    for (unsigned a = (unsigned)(chunk * kTailWarps + wid); a < n_amb; a += (unsigned)(C * kTailWarps)) {
+        const int i = (int)__ldcg(list + a);
+        const float qx = __ldg(qc + 3 * (size_t)i), qy = __ldg(qc + 3 * (size_t)i + 1), qz = __ldg(qc + 3 * (size_t)i + 2);
+        // pass 1: smallest squared distance, first NaN
+        float lm = INFINITY;
+        int nanj = 0x7fffffff;
+        for (int j = lane; j < nc; j += 32) {
+            const float t = sqdist(qx, qy, qz, __ldg(cc + 3 * (size_t)j), __ldg(cc + 3 * (size_t)j + 1), __ldg(cc + 3 * (size_t)j + 2));
+            if (t != t) nanj = min(nanj, j);
+            else lm = fminf(lm, t);
+        }
+        nanj = __reduce_min_sync(0xffffffffu, nanj);
+        const float m = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(lm)));   // t >= 0: orders as unsigned
+        float dist;
+        int bj;
+        if (nanj != 0x7fffffff) {
+            dist = __uint_as_float(0x7fc00000u);
+            bj = nanj;
+        } else {
+            dist = __fsqrt_rn(m);
+            const float h = m < INFINITY ? sqrt_window_top(m, dist) : m;
+            // pass 2: lowest index whose squared distance shares that square root
+            int fj = 0x7fffffff;
+            for (int j = lane; j < nc && fj == 0x7fffffff; j += 32) {
+                const float t = sqdist(qx, qy, qz, __ldg(cc + 3 * (size_t)j), __ldg(cc + 3 * (size_t)j + 1), __ldg(cc + 3 * (size_t)j + 2));
+                if (t <= h) fj = j;
+            }
+            bj = __reduce_min_sync(0xffffffffu, fj);
+            if (bj == 0x7fffffff) bj = 0;
+        }
+        if (lane == 0) { dout[i] = dist; iout[i] = bj; }
+    }
+    // ---- the last CTA of this cloud (both directions) reduces the means in a fixed order ----
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        // counters start at 0xffffffff (the workspace's all-ones state): the k-th arrival reads k-2
+        s_last = atomicAdd(tw.cloud_counter + b, 1u) == (unsigned)(C1 + C2 - 2);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid == 0) {
+        tw.cloud_counter[b] = 0xffffffffu;
+        o.amb_cnt[b] = 0xffffffffu;
+        o.amb_cnt[B + b] = 0xffffffffu;
+    }
+    if (mean1 == nullptr) return;
+    double sums[2];
+#pragma unroll 1
+    for (int dd = 0; dd < 2; ++dd) {
+        const int n = dd ? M : N;
+        const float *dv = (dd ? o.d2 : o.d1) + (size_t)b * n;
+        double acc = 0.0;
+        for (int e = tid; e < n; e += kTailThreads) acc += (double)__ldcg(dv + e);
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, s);
+        __syncthreads();
+        if (lane == 0) red[wid] = acc;
+        __syncthreads();
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < kTailWarps; ++w) tot += red[w];
+        sums[dd] = tot;
+    }
+    if (tid != 0) return;
+    mean1[b] = (float)(sums[0] / (double)N);
+    mean2[b] = (float)(sums[1] / (double)M);
+    if (loss == nullptr) return;
+    __threadfence();
+    if (atomicAdd(tw.global_counter, 1u) != (unsigned)(B - 2)) return;
+    __threadfence();
+    *tw.global_counter = 0xffffffffu;
+    const volatile float *m1 = mean1, *m2 = mean2;
+    double acc = 0.0;
+    for (int k = 0; k < B; ++k) acc += (double)loss_w1 * (double)m1[k] + (double)loss_w2 * (double)m2[k];
+    *loss = (float)acc;
+}
+
+static int tail_chunks(int n) {
+    const int c = (n + 1023) / 1024;
+    return c < 1 ? 1 : (c > 32 ? 32 : c);
+}
+
+size_t tcsweep_counter_bytes(int B) { return align_up(sizeof(unsigned) * (1 + (size_t)B), 256); }
+
+// The fused forward: pair sweep + refinement, then (unless sweep_only) the tail kernel.
+//   w.nrm     (2,B) unsigned, all-ones on entry and on exit: ambiguous-point counters
+//   w.rowsg   (B*N + B*M) unsigned, no invariant: ambiguous-point lists
+//   tail_ws   tcsweep_counter_bytes(B), all-ones on entry and on exit
+// sweep_only: 1 = sweep + fused refinement without the tail (measurement aid; the workspace is left dirty),
+//             2 = the filter sweep alone, its per-query results published to w.rowkey/colkey/rowsec/colsec (diagnostic)
+int launch_tcsweep(const float *pc1, const float *pc2, int B, int N, int M, const FwdWs &w, void *tail_ws,
+                   float *d1, float *d2, int32_t *i1, int32_t *i2, float *mean1, float *mean2, float *loss, float w1,
+                   float w2, float *zero1, float *zero2, int sweep_only, bool force_top3, cudaStream_t st) {
+    const int qb1 = (N + kTQ - 1) / kTQ, qb2 = (M + kTQ - 1) / kTQ;
+    const long long n_tasks = (long long)B * (qb1 + qb2);
+    if (n_tasks > 0x3fffffffLL) return fail(RLG_ERR_TOO_LARGE, "rlg_chamfer_fwd: too many query blocks");
+    if ((long long)qb1 * (long long)((M + kTC - 1) / kTC) * B > 0x3fffffffLL || (long long)qb2 * (long long)((N + kTC - 1) / kTC) * B > 0x3fffffffLL)
+        return fail(RLG_ERR_TOO_LARGE, "rlg_chamfer_fwd: too many tile visits for 32-bit counters");
+    const int sms = sm_count();
+    if (sms <= 0) return fail((int)cudaErrorNoDevice, "rlg_chamfer_fwd: no CUDA device");
+    // Ambiguous points (runner-up group within the margin) cost a scan of the whole candidate cloud in the tail kernel
+    // unless the sweep tracks three groups; their share grows with the point density.  Break-even is around 4096.
+    const bool top3 = force_top3 || N > 4096 || M > 4096;
+    // per launch (a host-side attribute write, no device work): the setting is per device and this library keeps no
+    // per-device state of its own
+    {
+        cudaError_t e = top3 ? cudaFuncSetAttribute(chamfer_tcsweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem)
+                             : cudaFuncSetAttribute(chamfer_tcsweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "chamfer_tcsweep_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
+    }
+    // the ambiguous counters live where the FP32 sweep keeps its cloud norms (all-ones invariant), the lists where the
+    // first-generation tensor sweep kept its runner-up groups (no invariant)
+    SweepOut o{d1, d2, i1, i2, zero1, zero2, w.nrm, w.rowsg, w.rowkey, w.colkey, w.rowsec, w.colsec};
+    const int grid = (int)(n_tasks < sms ? n_tasks : sms);
+    const int refine = sweep_only == 2 ? 0 : 1;
+    cudaError_t le = top3 ? launch_pdl(chamfer_tcsweep_kernel<true>, dim3((unsigned)grid), dim3(kThreads), (size_t)kSmem, st, pc1, pc2,
+                                       B, N, M, (int)n_tasks, qb1, qb2, o, refine)
+                          : launch_pdl(chamfer_tcsweep_kernel<false>, dim3((unsigned)grid), dim3(kThreads), (size_t)kSmem, st, pc1, pc2,
+                                       B, N, M, (int)n_tasks, qb1, qb2, o, refine);
+    if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "chamfer_tcsweep_kernel: %s", cudaGetErrorString(le)); }
+    if (sweep_only) return check_launch("chamfer_tcsweep_kernel");
+    TailWs tw;
+    tw.global_counter = (unsigned *)tail_ws;
+    tw.cloud_counter = tw.global_counter + 1;
+    const int C1 = tail_chunks(N), C2 = tail_chunks(M);
+    dim3 tgrid((unsigned)(C1 > C2 ? C1 : C2), (unsigned)B, 2);
+    le = launch_pdl(chamfer_tail_kernel, tgrid, dim3(kTailThreads), (size_t)0, st, pc1, pc2, N, M, C1, C2, o, tw, mean1, mean2, loss,
+                    w1, w2);
+    if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "chamfer_tail_kernel: %s", cudaGetErrorString(le)); }
+    return check_launch("chamfer_tail_kernel");
+}
+
+}  // namespace rlg

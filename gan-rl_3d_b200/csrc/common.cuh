@@ -46,13 +46,9 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
 }
 #endif
 
-// ---- Chamfer forward: shared between the tile kernel (chamfer_fwd.cu) and the finalize (chamfer_finalize.cu)
-static constexpr int kGroup = 32;           // columns per group == lanes per warp
+// ---- Chamfer forward
+static constexpr int kGroup = 32;           // candidates per group == lanes per warp
 static constexpr u64 kKeyInit = ~0ull;      // workspace state on entry and on exit of every forward
-size_t finalize_ws_bytes(int B, int N, int M);
-int launch_finalize(const float *pc1, const float *pc2, int B, int N, int M, int rows_per_group, u64 *rowkey,
-                    u64 *colkey, void *fin_ws, float *d1, float *d2, int32_t *i1, int32_t *i2, float *mean1,
-                    float *mean2, float *loss, float w1, float w2, cudaStream_t st);
 
 // ---- Chamfer forward, filter-and-refine path (chamfer_filter.cu).  Every array starts and ends all-ones.
 struct FwdWs {
@@ -67,9 +63,18 @@ struct FwdWs {
 size_t finalize2_ws_bytes(int B, int N, int M);
 int launch_filter(const float *pc1, const float *pc2, int B, int N, int M, int variant, const FwdWs &w,
                   int *rows_per_lane, cudaStream_t st);
-// tensor-core pair sweep (chamfer_tcfilter.cu): groups are 32 consecutive candidates in BOTH directions; the finalize is
-// told so by rows_per_lane <= 0 (0: the runner-up group and the third value are reported too, -1: not)
+// tensor-core pair sweep with the refinement fused in + tail kernel (chamfer_tcsweep.cu)
+size_t tcsweep_counter_bytes(int B);
+int launch_tcsweep(const float *pc1, const float *pc2, int B, int N, int M, const FwdWs &w, void *tail_ws,
+                   float *d1, float *d2, int32_t *i1, int32_t *i2, float *mean1, float *mean2, float *loss, float w1,
+                   float w2, float *zero1, float *zero2, int sweep_only, bool force_top3, cudaStream_t st);
+#ifdef RLG_EXPERIMENTS
+// experiments build only (build.py --experiments): flag bits of rlg_chamfer_fwd that select measurement variants
+#define RLG_X_CHAMFER_TENSOR_V1   128u     // first-generation tensor sweep (chamfer_tcfilter.cu) + separate finalize
+// first-generation tensor-core pair sweep (chamfer_tcfilter.cu): the finalize is told its group layout by
+// rows_per_lane <= 0 (0: the runner-up group and the third value are reported too, -1: not)
 int launch_tcfilter(const float *pc1, const float *pc2, int B, int N, int M, const FwdWs &w, int *rows_per_lane, cudaStream_t st);
+#endif
 int launch_finalize2(const float *pc1, const float *pc2, int B, int N, int M, int rows_per_lane, const FwdWs &w,
                      void *fin_ws, float *d1, float *d2, int32_t *i1, int32_t *i2, float *mean1, float *mean2,
                      float *loss, float w1, float w2, float *zero1, float *zero2, cudaStream_t st);
@@ -113,6 +118,21 @@ __device__ __forceinline__ float sqdist(float px, float py, float pz, float qx, 
     t = __fmaf_rn(d1, d1, t);
     t = __fmaf_rn(d2, d2, t);
     return t;
+}
+
+// The reference takes torch.min over the SQRT-ED distance matrix (utils/losses.py:29-33), and sqrtf maps up to three
+// adjacent fp32 values onto one: candidates whose squared distances differ only in the last bits tie there and the lowest
+// index wins.  Largest fp32 h >= m with sqrtf(h) == sqrtf(m) = s (m finite, >= 0); the exact argmin under the reference's
+// rule is the lowest index j with t_j <= h.
+__device__ __forceinline__ float sqrt_window_top(float m, float s) {
+    float h = m;
+#pragma unroll 1
+    for (int step = 0; step < 3; ++step) {
+        const float n = __uint_as_float(__float_as_uint(h) + 1u);
+        if (!(__fsqrt_rn(n) == s)) break;
+        h = n;
+    }
+    return h;
 }
 
 }  // namespace rlg

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define RLG_ABI_VERSION 3
+#define RLG_ABI_VERSION 4
 
 #define RLG_ERR_NULL_POINTER   (-1)
 #define RLG_ERR_BAD_SHAPE      (-2)   /* B < 0, N < 1, M < 1 (the reference raises IndexError for empty clouds) */
@@ -44,17 +44,30 @@ extern "C" {
 #define RLG_ERR_UNSUPPORTED    (-4)   /* layer shape / option the kernel does not cover */
 #define RLG_ERR_TOO_LARGE      (-5)   /* index would not fit the packed 32-bit fields */
 
-/* flags for rlg_chamfer_fwd */
+/* flags for rlg_chamfer_fwd / rlg_chamfer_loss_fwd.  Any other bit is rejected with RLG_ERR_UNSUPPORTED (timing
+ * variants of the kernels exist only in the separate experiments build, never in librlg_b200.so). */
 #define RLG_CHAMFER_WS_CLEAN   1u     /* workspace is known to hold the all-ones pattern the previous
                                          rlg_chamfer_fwd left behind on the same shape: skip the memset */
-#define RLG_CHAMFER_ALGO_SIMPLE 2u    /* run the simple one-thread-per-query kernel (cross-check path) */
-#define RLG_CHAMFER_TILE_ONLY  4u     /* measurement aid: enqueue only the pair-sweep kernel (no finalize,
-                                         outputs untouched, workspace left dirty) so it can be timed alone */
-#define RLG_CHAMFER_ALGO_DIRECT 8u    /* run the direct-form tile kernel (every pair evaluated exactly, 6 FP32
-                                         operations per pair) instead of the filter-and-refine kernel: cross-check */
+#define RLG_CHAMFER_ALGO_SIMPLE 2u    /* one thread per query point, every candidate in the direct form: the plain
+                                         restatement the production kernels are cross-checked against */
+#define RLG_CHAMFER_TILE_ONLY  4u     /* measurement aid: enqueue only the first launch (the pair sweep; with
+                                         RLG_CHAMFER_ALGO_TENSOR that includes the fused refinement) so it can be timed
+                                         alone: means/loss untouched, workspace left dirty */
+/* 8u is reserved (ABI <= 3: RLG_CHAMFER_ALGO_DIRECT, removed) */
 #define RLG_CHAMFER_ALGO_TENSOR 16u   /* pair sweep with the 3-term contraction on the tensor cores (tcgen05, split-tf32
-                                         operands, fp32 accumulation in TMEM) and only the minima on the CUDA cores;
-                                         same exact refinement, same outputs bit for bit (chamfer_tcfilter.cu) */
+                                         operands, fp32 accumulation in TMEM), minima and the exact refinement on the
+                                         CUDA cores of the same kernel, then a small tail kernel (chamfer_tcsweep.cu).
+                                         Without it: pair sweep on the FP32 pipe + refinement kernel (chamfer_filter.cu).
+                                         Same outputs bit for bit. */
+#define RLG_CHAMFER_TRACK_TWO  32u    /* with ALGO_TENSOR: also track the runner-up's group and the third-smallest group
+                                         minimum, so an ambiguous point is refined on two groups instead of the whole
+                                         candidate cloud.  The library switches this on by itself beyond 4096 points;
+                                         the flag forces it for smaller clouds (same outputs). */
+#define RLG_CHAMFER_FILTER_ONLY 64u   /* diagnostic, with ALGO_TENSOR: run the filter sweep alone and publish, per query,
+                                         (smallest group minimum << 32 | group) as u64 at ws[0 .. 8*B*(N+M)) (pc1's
+                                         queries first) and the second-smallest group minimum as u32 right after
+                                         (256-B aligned); d/i/means untouched, workspace left dirty.  tests/ measure the
+                                         filter's rounding error against float64 with it. */
 
 int rlg_version(void);
 const char *rlg_last_error(void);
@@ -73,12 +86,16 @@ int rlg_device_sm_count(void);
  *   ws                                            device, >= rlg_chamfer_ws_bytes(B,N,M), 256-B aligned
  *
  * Distances are computed in the direct-difference form  t=d0*d0; t=fma(d1,d1,t); t=fma(d2,d2,t);
- * sqrtf(min t)  and are bit-identical to ATen's direct-mode cdist; argmin is taken over t, lowest index on
- * ties.  The default kernel finds the candidates with a 4-operation FP32 filter (|y|^2 - 2x.y + |x|^2) and
- * re-evaluates every candidate within a rigorous rounding margin in the direct form, so the outputs do not
- * depend on the filter's rounding; clouds far from the origin relative to their extent (|p|^2 >> min
- * distance^2 * 1e5) only lose speed (more candidates are re-evaluated), not exactness.
- * Non-finite coordinates are outside the contract (NaN distances are ignored, not propagated).
+ * sqrtf(min t)  and are bit-identical to ATen's direct-mode cdist.  The argmin follows the reference's rule:
+ * torch.min runs on the SQRT-ED matrix, so candidates whose squared distances share one sqrtf (up to three
+ * adjacent fp32 values do) tie, and the lowest index among them wins.  The kernels find the candidates with a
+ * cheap filter (|x|^2 + |y|^2 - 2x.y, on the tensor cores or the FP32 pipe) and re-evaluate every candidate within
+ * a rigorous rounding margin in the direct form, so the outputs do not depend on the filter's rounding; clouds far
+ * from the origin relative to their extent (|p|^2 >> min distance^2 * 1e5) only lose speed (more candidates are
+ * re-evaluated), not exactness.
+ * Non-finite coordinates are outside the contract: a NaN/Inf QUERY point yields a NaN/Inf distance as in the
+ * reference, but a NaN CANDIDATE may be skipped where torch.min would let it win (the Python
+ * seam can check inputs with install(check_finite=True)).
  * --------------------------------------------------------------------------------------------- */
 size_t rlg_chamfer_ws_bytes(int B, int N, int M);
 

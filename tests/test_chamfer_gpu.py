@@ -11,28 +11,35 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+_TRACK_TWO = False
+
+
 @pytest.fixture(autouse=True, params=["fp32", "tensor", "tensor_top3"])
-def sweep(request, rlg, monkeypatch):
+def sweep(request, rlg):
     """Every test of this module runs once per pair-sweep kernel: the FP32-pipe filter (chamfer_filter.cu) and the
-    tensor-core filter (chamfer_tcfilter.cu), the latter with and without the runner-up-group / third-value report
-    the library otherwise enables by cloud size.  All must give the same bits."""
+    tensor-core sweep with the fused refinement (chamfer_tcsweep.cu), the latter with and without the
+    runner-up-group / third-value report the library otherwise enables by cloud size.  All must give the same bits."""
+    global _TRACK_TWO
     old = rlg.get_default_sweep()
     rlg.set_default_sweep("fp32" if request.param == "fp32" else "tensor")
-    if request.param != "fp32":
-        monkeypatch.setenv("RLG_TF_TOP3", "1" if request.param == "tensor_top3" else "0")
+    _TRACK_TWO = request.param == "tensor_top3"
     yield request.param
+    _TRACK_TWO = False
     rlg.set_default_sweep(old)
 
 
 def _run(rlg, pc1, pc2, simple=False, **kw):
+    if _TRACK_TWO and not simple:
+        kw.setdefault("track_two", True)
     d1, d2, i1, i2, m1, m2 = rlg.chamfer_nearest(pc1.to(DEV), pc2.to(DEV), simple=simple, **kw)
     torch.cuda.synchronize()
     return [t.cpu().numpy() for t in (d1, d2, i1, i2, m1, m2)]
 
 
 def _check_against_direct(rlg, pc1, pc2, simple=False, **kw):
+    """Bit-equal to the direct-form oracle under the reference's tie rule (argmin over the sqrt-ed distances)."""
     d1, d2, i1, i2, m1, m2 = _run(rlg, pc1, pc2, simple, **kw)
-    o1, o2, j1, j2 = O.chamfer_direct(pc1, pc2, O.TIE_SQUARED)
+    o1, o2, j1, j2 = O.chamfer_direct(pc1, pc2, O.TIE_FAITHFUL)
     assert np.array_equal(d1, o1) and np.array_equal(d2, o2), "distances not bit-equal to the direct oracle"
     assert np.array_equal(i1, j1) and np.array_equal(i2, j2), "argmin not equal to the direct oracle"
     w1, w2 = O.chamfer_means(o1, o2)
@@ -60,23 +67,6 @@ def test_simple_kernel_agrees_with_tile_kernel(rlg, B, N, M):
     pc1, pc2 = O.make_clouds(B, N, "sphere", 5), O.make_clouds(B, M, "sphere", 6)
     a = _check_against_direct(rlg, pc1, pc2, simple=True)
     b = _check_against_direct(rlg, pc1, pc2, simple=False)
-    for x, y in zip(a, b):
-        assert np.array_equal(x, y)
-
-
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 7, 8, 9])
-@pytest.mark.parametrize("B,N,M", [(2, 1, 1), (3, 33, 31), (2, 600, 1400), (2, 2048, 2048), (1, 1025, 70)])
-def test_every_filter_tile_shape_is_bit_exact(rlg, variant, B, N, M):
-    """Rows per lane 16 / 8 / 4, every occupancy / operand-prefetch variant: same bits as the direct oracle, ragged shapes included."""
-    pc1, pc2 = O.make_clouds(B, N, "uniform", 70 + variant), O.make_clouds(B, M, "sphere", 80 + variant)
-    _check_against_direct(rlg, pc1, pc2, variant=variant)
-
-
-@pytest.mark.parametrize("B,N,M", [(2, 31, 33), (2, 700, 2048), (2, 2048, 2048)])
-def test_direct_tile_kernel_agrees_with_filter_kernel(rlg, B, N, M):
-    pc1, pc2 = O.make_clouds(B, N, "sphere", 7), O.make_clouds(B, M, "uniform", 8)
-    a = _check_against_direct(rlg, pc1, pc2, direct=True)
-    b = _check_against_direct(rlg, pc1, pc2)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
 
@@ -172,7 +162,7 @@ def test_backward_vs_float64_truth(rlg, B, N, M):
     b = pc2.to(DEV).requires_grad_(True)
     loss = rlg.ChamferLoss()(a, b)
     loss.backward()
-    d1, d2, i1, i2 = O.chamfer_direct(pc1, pc2, O.TIE_SQUARED)
+    d1, d2, i1, i2 = O.chamfer_direct(pc1, pc2, O.TIE_FAITHFUL)
     up = np.full((B,), 0.5 / B, np.float32)
     ga, gb = O.chamfer_bwd_truth(pc1, pc2, d1, d2, i1, i2, up, up)
     # tolerance: 1e-5 relative row-wise (north_star), rows measured against max(|row|, 1e-3 * largest row)
@@ -209,7 +199,7 @@ def test_per_pair_upstream_and_unidirectional(rlg):
     cd = rlg.chamfer_distance(a, b, bidirectional=False)
     assert cd.shape == (B,)
     (cd * w.to(DEV)).sum().backward()
-    d1, d2, i1, i2 = O.chamfer_direct(pc1, pc2, O.TIE_SQUARED)
+    d1, d2, i1, i2 = O.chamfer_direct(pc1, pc2, O.TIE_FAITHFUL)
     ga, gb = O.chamfer_bwd_truth(pc1, pc2, d1, d2, i1, i2, w.numpy(), np.zeros(B, np.float32))
     assert O.rowwise_rel_err(a.grad.cpu().numpy(), ga) < 1e-5
     assert O.rowwise_rel_err(b.grad.cpu().numpy(), gb) < 1e-5
@@ -243,8 +233,10 @@ def test_full_size_properties_cfg2(rlg):
     # gathered partner really is at the reported distance
     gathered = torch.gather(b, 1, i1.long().unsqueeze(-1).expand(-1, -1, 3))
     assert torch.allclose((a - gathered).norm(dim=2), d1, rtol=1e-6, atol=1e-7)
-    # and two clouds of the oracle's budget are bit-exact
-    _check_against_direct(rlg, pc1[:2], pc2[:2])
+    # the whole batch is bit-exact against the C oracle (B=32 x 2048^2 takes it well under a second per direction)
+    o1, o2, j1, j2 = O.chamfer_direct(pc1, pc2, O.TIE_FAITHFUL)
+    assert np.array_equal(d1.cpu().numpy(), o1) and np.array_equal(d2.cpu().numpy(), o2)
+    assert np.array_equal(i1.cpu().numpy(), j1) and np.array_equal(i2.cpu().numpy(), j2)
 
 
 def test_large_cloud_16384(rlg):
@@ -284,36 +276,158 @@ def test_cuda_graph_capture(rlg):
     assert all(torch.equal(x, y) for x, y in zip(got, want))
 
 
-def test_tensor_filter_error_is_far_inside_its_margin(rlg):
-    """The tensor-core filter's value for the best candidate vs float64, in units of u (a^2 + b^2): the finalize's
-    margin (128 u) budgets 61 u for it (chamfer_tcfilter.cu); the measured error is an order of magnitude smaller."""
+def _filter_values(a, b):
+    """Per-query smallest filter value of the tensor sweep (RLG_CHAMFER_FILTER_ONLY diagnostic), both directions."""
     import importlib
     _lib = importlib.import_module("gan-rl_3d_b200._lib")
     lib = _lib.load()
+    B, N, _ = a.shape
+    M = b.shape[1]
+    d1 = torch.empty(B, N, device=DEV); d2 = torch.empty(B, M, device=DEV)
+    i1 = torch.empty(B, N, dtype=torch.int32, device=DEV); i2 = torch.empty(B, M, dtype=torch.int32, device=DEV)
+    ws = torch.empty(lib.rlg_chamfer_ws_bytes(B, N, M), dtype=torch.uint8, device=DEV).fill_(0xFF)
+    flags = _lib.CHAMFER_WS_CLEAN | _lib.CHAMFER_FILTER_ONLY | _lib.CHAMFER_ALGO_TENSOR
+    rc = lib.rlg_chamfer_fwd(a.data_ptr(), b.data_ptr(), B, N, M, d1.data_ptr(), d2.data_ptr(), i1.data_ptr(),
+                             i2.data_ptr(), None, None, ws.data_ptr(), ws.numel(), flags,
+                             torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.rlg_last_error()
+    torch.cuda.synchronize()
+    keys = ws[: 8 * B * (N + M)].view(torch.int64)
+    v1 = (keys[: B * N].view(B, N) >> 32).to(torch.int32).view(torch.float32).double()
+    v2 = (keys[B * N:].view(B, M) >> 32).to(torch.int32).view(torch.float32).double()
+    return v1, v2
+
+
+def _filter_error_in_u(a, b):
+    """Largest |filter value of the best candidate - float64 truth| in units of u (a^2 + b^2), u = 2^-24, with b^2 the
+    largest squared norm of the candidate cloud (an upper bound of the winning candidate's)."""
+    v1, v2 = _filter_values(a, b)
+    a64, b64 = a.double(), b.double()
+    D = ((a64[:, :, None, :] - b64[:, None, :, :]) ** 2).sum(-1)
+    na, nb = (a64 ** 2).sum(-1), (b64 ** 2).sum(-1)
+    u = 2.0 ** -24
+    worst = 0.0
+    for val, truth, nq, j in ((v1, D.min(2).values, na, D.argmin(2)), (v2, D.min(1).values, nb, D.argmin(1))):
+        nc = torch.gather(nb if nq is na else na, 1, j)          # squared norm of the true nearest candidate
+        worst = max(worst, float(((val - truth).abs() / (u * (nq + nc)).clamp_min(1e-300)).max()))
+    return worst
+
+
+def test_tensor_filter_error_is_far_inside_its_margin(rlg, sweep):
+    """The tensor-core filter's value for the best candidate vs float64, in units of u (a^2 + b^2): the refinement's
+    margin budgets 61 u for it (chamfer_tcsweep.cu header); the measured error is an order of magnitude smaller."""
+    if sweep != "tensor":
+        pytest.skip("one run is enough")
     B, N, M = 3, 1400, 2048
     worst = 0.0
     for kind, scale, shift in (("sphere", 1.0, 0.0), ("uniform", 1.0, 0.0), ("sphere", 0.1, 2.0), ("uniform", 50.0, 0.0)):
         a = (torch.as_tensor(O.make_clouds(B, N, kind, 11)) * scale + shift).to(DEV)
         b = (torch.as_tensor(O.make_clouds(B, M, kind, 12)) * scale + shift).to(DEV)
-        d1 = torch.empty(B, N, device=DEV); d2 = torch.empty(B, M, device=DEV)
-        i1 = torch.empty(B, N, dtype=torch.int32, device=DEV); i2 = torch.empty(B, M, dtype=torch.int32, device=DEV)
-        ws = torch.empty(lib.rlg_chamfer_ws_bytes(B, N, M), dtype=torch.uint8, device=DEV).fill_(0xFF)
-        flags = _lib.CHAMFER_WS_CLEAN | _lib.CHAMFER_TILE_ONLY | _lib.CHAMFER_ALGO_TENSOR
-        rc = lib.rlg_chamfer_fwd(a.data_ptr(), b.data_ptr(), B, N, M, d1.data_ptr(), d2.data_ptr(), i1.data_ptr(),
-                                 i2.data_ptr(), None, None, ws.data_ptr(), ws.numel(), flags,
-                                 torch.cuda.current_stream().cuda_stream)
-        assert rc == 0, lib.rlg_last_error()
-        torch.cuda.synchronize()
-        keys = ws[: 8 * B * (N + M)].view(torch.int64)
-        a64, b64 = a.double(), b.double()
-        D = ((a64[:, :, None, :] - b64[:, None, :, :]) ** 2).sum(-1)
-        na, nb = (a64 ** 2).sum(-1), (b64 ** 2).sum(-1)
-        u = 2.0 ** -24
-        for key, truth, nq, nmax in ((keys[: B * N].view(B, N), D.min(2).values, na, nb.max(1, keepdim=True).values),
-                                     (keys[B * N:].view(B, M), D.min(1).values, nb, na.max(1, keepdim=True).values)):
-            val = (key >> 32).to(torch.int32).view(torch.float32).double()
-            worst = max(worst, float(((val - truth).abs() / (u * (nq + nmax))).max()))
-    assert worst < 16.0, f"tensor filter error {worst:.1f} u(a^2+b^2): the 128 u margin assumes < 61 u"
+        worst = max(worst, _filter_error_in_u(a, b))
+    assert worst < 16.0, f"tensor filter error {worst:.1f} u(a^2+b^2): the margin assumes < 61 u"
+
+
+def test_tensor_filter_error_randomized_search(rlg, sweep):
+    """Adversarial search for the largest filter error: random draws over scale (1e-3 .. 1e4), offset from the origin
+    (0 .. 1e4, cancellation in |x|^2 + |y|^2 - 2x.y), anisotropy, clustered near-duplicates and coordinates with long
+    mantissas; then hill-climbing on the worst draw.  Every evaluation must stay below the 61 u the margin budgets."""
+    if sweep != "tensor":
+        pytest.skip("one run is enough")
+    g = torch.Generator().manual_seed(2024)
+    B, N, M = 2, 384, 512
+
+    def draw(scale, offset, aniso, cluster):
+        a = torch.randn(B, N, 3, generator=g) * scale * torch.tensor([1.0, aniso, aniso * aniso]) + offset
+        if cluster:
+            b = a[:, torch.randint(0, N, (M,), generator=g)] * (1 + 2e-7 * torch.randn(B, M, 1, generator=g))
+        else:
+            b = torch.randn(B, M, 3, generator=g) * scale + offset
+        return a.float().contiguous(), b.float().contiguous()
+
+    worst, worst_cfg = 0.0, None
+    for _ in range(60):
+        cfg = (10.0 ** float(torch.empty(1).uniform_(-3, 4, generator=g)),
+               float(torch.empty(1).uniform_(0, 1, generator=g) < 0.5) * 10.0 ** float(torch.empty(1).uniform_(-2, 4, generator=g)),
+               10.0 ** float(torch.empty(1).uniform_(-2, 0, generator=g)),
+               bool(torch.empty(1).uniform_(0, 1, generator=g) < 0.3))
+        a, b = draw(*cfg)
+        e = _filter_error_in_u(a.to(DEV), b.to(DEV))
+        if e > worst:
+            worst, worst_cfg = e, cfg
+    # hill-climb around the worst configuration
+    scale, offset, aniso, cluster = worst_cfg
+    for _ in range(30):
+        cand = (scale * 10.0 ** float(torch.empty(1).uniform_(-0.3, 0.3, generator=g)),
+                offset * 10.0 ** float(torch.empty(1).uniform_(-0.3, 0.3, generator=g)),
+                min(1.0, aniso * 10.0 ** float(torch.empty(1).uniform_(-0.3, 0.3, generator=g))), cluster)
+        a, b = draw(*cand)
+        e = _filter_error_in_u(a.to(DEV), b.to(DEV))
+        if e > worst:
+            worst, (scale, offset, aniso, cluster) = e, cand
+    assert worst < 61.0, f"tensor filter error {worst:.1f} u(a^2+b^2) at {(scale, offset, aniso, cluster)}"
+
+
+def _sqrt_collision_pair(seed=0):
+    """(r, s): from the origin (r,s,0) has a squared distance ONE ULP ABOVE that of (r,0,0) and the same sqrtf."""
+    rng = np.random.default_rng(seed)
+    for _ in range(20000):
+        r = np.float32(rng.uniform(1.42, 1.99))
+        s_ = np.float32(2.0 ** -11 * rng.uniform(0.8, 1.2))
+        tb = np.float32(r * r)
+        ta = np.float32(np.float64(s_) * np.float64(s_) + np.float64(tb))      # fmaf(s,s,t), exact in float64
+        if ta == np.nextafter(tb, np.float32(8), dtype=np.float32) and np.sqrt(ta, dtype=np.float32) == np.sqrt(tb, dtype=np.float32):
+            return float(r), float(s_)
+    raise AssertionError("no collision found")
+
+
+@pytest.mark.parametrize("lo_idx,hi_idx,n", [(3, 9, 100), (3, 70, 100), (40, 1900, 2048), (100, 101, 300)])
+def test_sqrt_ties_follow_the_reference_rule(rlg, lo_idx, hi_idx, n):
+    """two candidates with different squared distances whose square roots collide in fp32 are an exact
+    tie for torch.min on the sqrt-ed matrix, and the LOWER index wins even if it has the LARGER squared distance --
+    inside one 32-candidate group (fused refinement) and across groups (ambiguous -> tail kernel)."""
+    r, s_ = _sqrt_collision_pair()
+    c = torch.full((1, n, 3), 5.0)
+    c[0, lo_idx] = torch.tensor([r, s_, 0.0])        # larger squared distance, lower index
+    c[0, hi_idx] = torch.tensor([r, 0.0, 0.0])
+    q = torch.zeros(1, 70, 3)
+    q[0, 1:] = O.make_clouds(1, 69, "uniform", 3)[0] * 0.01 + 7.0       # other queries: far away, nearest = a (5,5,5) point
+    d1, d2, i1, i2, *_ = _check_against_direct(rlg, q, c.contiguous())
+    assert i1[0, 0] == lo_idx
+    ref_d, ref_i = torch.min(torch.cdist(q, c, compute_mode="donot_use_mm_for_euclid_dist"), dim=2)
+    assert np.array_equal(i1, ref_i.numpy().astype(np.int32)) and np.array_equal(d1, ref_d.numpy())
+
+
+def test_many_sqrt_collisions_radial_ladder(rlg):
+    """Candidates on a fine radial ladder around queries near the origin: many distinct squared distances share a sqrtf."""
+    g = torch.Generator().manual_seed(9)
+    r = 1.5 + torch.arange(600).float() * 1.2e-7
+    dirs = torch.nn.functional.normalize(torch.randn(600, 3, generator=g), dim=1)
+    c2 = (dirs * r[:, None])[torch.randperm(600, generator=g)].unsqueeze(0).contiguous()
+    q2 = torch.zeros(1, 65, 3)
+    q2[0, 1:] = torch.randn(64, 3, generator=g) * 1e-4
+    d1, d2, i1, i2, *_ = _check_against_direct(rlg, q2, c2)
+    ref_d, ref_i = torch.min(torch.cdist(q2, c2, compute_mode="donot_use_mm_for_euclid_dist"), dim=2)
+    assert np.array_equal(i1, ref_i.numpy().astype(np.int32)) and np.array_equal(d1, ref_d.numpy())
+
+
+def test_workspace_cache_evicts_lru_and_keeps_graph_workspaces(rlg):
+    """70 shapes overflow the 64-entry workspace cache; a CUDA graph captured before must still replay correctly
+    (its workspace is pinned), and a capture without an eager warm-up on that stream must record its own memset."""
+    pc1, pc2 = O.make_clouds(2, 300, "sphere", 71).to(DEV), O.make_clouds(2, 260, "sphere", 72).to(DEV)
+    want = rlg.chamfer_nearest(pc1, pc2)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):       # no warm-up on this stream: the memset must be in the graph
+            got = rlg.chamfer_nearest(pc1, pc2)
+    for n in range(70):
+        a = O.make_clouds(1, 40 + n, "uniform", n).to(DEV)
+        rlg.chamfer_nearest(a, a)
+    graph.replay()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert all(torch.equal(x, y) for x, y in zip(got, want))
 
 
 @pytest.mark.parametrize("case", ["identical", "apart", "mixed_scale", "collinear"])

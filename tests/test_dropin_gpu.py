@@ -67,7 +67,7 @@ def test_install_routes_cuda_inputs_through_the_kernels(rlg):
         v = crit_before(a, pc2)                                    # created before the patch, follows it
         assert "ChamferFnBackward" in _graph_nodes(v.grad_fn)        # the CUDA Function is in the autograd graph
         v.backward()
-        d1, d2, i1, i2 = O.chamfer_direct(pc1.cpu(), pc2.cpu(), O.TIE_SQUARED)
+        d1, d2, i1, i2 = O.chamfer_direct(pc1.cpu(), pc2.cpu(), O.TIE_FAITHFUL)
         m1, m2 = O.chamfer_means(d1, d2)
         want = float(np.mean((m1.astype(np.float64) + m2) / 2))
         assert abs(v.item() - want) <= 1e-6 * want

@@ -1,0 +1,20 @@
+#!/bin/bash
+# usage (under gpurun): bash tools/gpu_job.sh <tag> <step> [<step> ...]   -- each step writes gpurun_out/<tag>_<step>.log
+set -u
+T=$1; shift
+mkdir -p gpurun_out
+for step in "$@"; do
+  case $step in
+    chamfer)   timeout 1500 python -m pytest tests/test_chamfer_gpu.py -m gpu -q --maxfail=25 > gpurun_out/${T}_chamfer.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_chamfer.log ;;
+    pytest)    timeout 2400 python -m pytest tests -m gpu -q --maxfail=25 > gpurun_out/${T}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest.log ;;
+    breakdown) RLG_EXPERIMENTS_LIB=1 timeout 600 python tools/step_breakdown.py > gpurun_out/${T}_breakdown.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_breakdown.log ;;
+    breakdown5) RLG_EXPERIMENTS_LIB=1 timeout 600 python tools/step_breakdown.py 8 16384 16384 > gpurun_out/${T}_breakdown5.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_breakdown5.log ;;
+    smoke)     timeout 600 python __graft_entry__.py --smoke > gpurun_out/${T}_smoke.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_smoke.log ;;
+    bench)     timeout 1200 python bench.py > gpurun_out/${T}_bench.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_bench.log ;;
+    benchq)    timeout 900 python bench.py --steps 400 --warmup 20 --no-cpu-baseline > gpurun_out/${T}_benchq.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_benchq.log ;;
+    benchref)  timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/${T}_benchref.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_benchref.log ;;
+    *) echo "unknown step $step" ;;
+  esac
+done
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${T}_smi.log 2>&1
+echo done
