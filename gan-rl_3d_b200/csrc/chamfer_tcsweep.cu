@@ -17,17 +17,19 @@
 // Error of the filter (u = 2^-24, a = |x_i|, b = |y_j|, S = a^2 + b^2): dropped split terms <= 12 u S, accumulation
 // inside the tensor core (modelled as fp32 truncation at each of 18 additions) <= 36 u S, computed norms <= 3 u S:
 // |t~ - t| <= 51 u S; the direct form adds <= 10 u S.  So |t~_j - D_j| <= 61 u S_j for the direct-form value D_j.
-// The refinement needs no knowledge of the candidate cloud's extent: b <= a + sqrt(t) gives S_j <= 3 a^2 + 2 t_j, and
-// from t_j <= t~_j + 51 u S_j:  S_j <= 3.001 a^2 + 2.001 t~_j.  With val = smallest group minimum (group g*) and
-// sv = smallest minimum of any other group, every candidate j outside g* has
-//       D_j >= sv (1 - 123 u) - 183.1 u a^2     and the candidate c attaining val has     D_c <= val (1 + 123 u) + 183.1 u a^2.
-// If  sv (1 - kRel) > val (1 + kRel) + kAbs a^2  with kRel = 160 u, kAbs = 420 u  (slack covers the rounding of this
-// test itself and the <= 4 u relative window in which two squared distances can share one sqrtf), the exact nearest
-// neighbour -- also under the reference's tie rule, which compares the square-rooted values -- lies in group g*:
-// 32 direct-form evaluations.  Otherwise the point is AMBIGUOUS (0.6-0.9 % of the points at N = M = 2048): with the
-// runner-up's group and the third-smallest group minimum known (TOP3, large clouds) it is refined on two groups when
-// the third is out of reach, else its index goes to a list and the tail kernel scans the whole candidate cloud.
-// Either way the outputs are independent of how the filter rounded.
+// The refinement needs no knowledge of the candidate cloud's extent: b <= a + sqrt(t) gives
+//       S_j <= Sigma(t_j) := 2 a^2 + 2 a sqrt(t_j) + t_j      (increasing in t_j),
+// and from t_j <= t~_j + 51 u S_j <= t~_j + 51 u (3 a^2 + 2 t_j):   t_j <= t+(t~_j) := 1.0001 max(t~_j, 0) + 256 u a^2.
+// With val = smallest group minimum (group g*, attained by candidate c) and sv = smallest minimum of any other group,
+// every candidate j outside g* has D_j >= L(t~_j) := t~_j - 61 u Sigma(t+(t~_j)) with t~_j >= sv, L increasing for
+// t~ >= 1e-9 a^2, and D_c <= H(val) := val + 61 u Sigma(t+(val)).  If  sv >= 1e-9 a^2  and  L(sv) > H(val) (1 + 8 u)
+// (evaluated with 64 u instead of 61 u to cover the rounding of the test itself; the 8 u cover the <= 4 u relative window
+// in which two squared distances share one sqrtf), the exact nearest neighbour -- also under the reference's tie rule,
+// which compares the square-rooted values -- lies in group g*: 32 direct-form evaluations.  Otherwise the point is
+// AMBIGUOUS (about 0.6 % of the points at N = M = 2048 on the unit sphere): with the runner-up's group and the
+// third-smallest group minimum known (TOP3, large clouds) it is refined on two groups when the third is out of reach,
+// else its index goes to a list and the tail kernel scans the whole candidate cloud.  Either way the outputs are
+// independent of how the filter rounded.
 //
 // Tie rule: torch.min runs on the sqrt-ed matrix, and sqrtf maps up to three adjacent fp32 values onto one, so
 // candidates whose squared distances differ in the last bits tie there and the LOWEST INDEX wins.  The refinement finds
@@ -43,7 +45,10 @@
 //               (best, second, third group minimum; best / second group) per query block live in shared memory; at the
 //               end of a segment the four partial states of a query are merged and the merging thread refines it.
 //   warps 16-17 producers: convert 256 candidates per tile (and the segment's queries) to the split-tf32 rows, written
-//               straight into K-major SWIZZLE_128B operand tiles.
+//               straight into K-major SWIZZLE_128B operand tiles (rows are 64 bytes: two query blocks, and the two
+//               candidate tiles in flight, share one 128-byte-row tile; the descriptor's start address picks the half).
+//               Clouds of up to 2048 points are also kept raw in shared memory (double-buffered per segment), so the
+//               fused refinement reads its 32 candidates with LDS.128 instead of going to L2.
 //   warps 18-19 MMA issuers (one elected lane each): issuer p serves pipeline group p.  A tcgen05.mma blocks its issuer
 //               while the pipe is busy and every hand-off costs the issuer a barrier round trip (profiles/
 //               r1_umma_microbench.txt: pause + 85 cycles per hand-off); two issuers hide one another's round trips.
@@ -64,16 +69,25 @@ constexpr int kARows = kTQ / kPrThreads, kBRows = kTC / kPrThreads;            /
 constexpr uint32_t kABytes = kTQ * 128, kBBytes = kTC * 128;
 // A rows carry K = 16 tf32 = 64 bytes, half of a SWIZZLE_128B row: two query blocks share one 16 KB tile (block q sits in
 // 16-byte chunks 4*(q&1) .. 4*(q&1)+3 of tile q>>1; the descriptor's start address selects the half)
-constexpr uint32_t kOffB = (kQmax / 2) * kABytes;                             // two candidate tiles follow the A tiles
-constexpr int kStW = 5;                                                       // state words: best, second, third, best grp, second grp
+constexpr uint32_t kOffB = (kQmax / 2) * kABytes;                             // one 32 KB tile holds BOTH candidate tiles in flight
 constexpr int kSlots = 4;                                                     // partial states per query: (pipeline group, column half)
-constexpr uint32_t kOffState = kOffB + 2 * kBBytes;                           // [slot][kQmax][kStW][128]
-constexpr uint32_t kStateBytes = (uint32_t)kSlots * kQmax * kTQ * kStW * 4u;
-constexpr uint32_t kOffBar = kOffState + kStateBytes;
-constexpr uint32_t kSmem = kOffBar + 256 + 1024;                              // + barriers + alignment slack
+constexpr uint32_t kOffState = kOffB + kBBytes;                               // [slot][kQmax][kStW][128]
+// state words per (slot, query block, row): best, second, best group [, third, second group]
+constexpr int kWBest = 0, kWSecond = 1, kWBgrp = 2, kWThird = 3, kWSgrp = 4;
+template <bool TOP3> struct SweepCfg {
+    static constexpr int kStW = TOP3 ? 5 : 3;
+    static constexpr uint32_t kStateBytes = (uint32_t)kSlots * kQmax * kTQ * kStW * 4u;
+    // raw copies of the candidate cloud for the fused refinement (clouds of up to kRawMax points; two segments in flight).
+    // With TOP3 (clouds beyond 4096 points) there is nothing to stage: the refinement reads the candidates from L2.
+    static constexpr int kRawMax = TOP3 ? 0 : 2048;
+    static constexpr uint32_t kOffRaw = kOffState + kStateBytes;
+    static constexpr uint32_t kRawBytes = (uint32_t)kRawMax * 12u;
+    static constexpr uint32_t kOffBar = kOffRaw + 2 * kRawBytes;
+    static constexpr uint32_t kSmem = kOffBar + 256 + 1024;                   // + barriers + alignment slack
+};
 constexpr float kBig = 1.0e30f;
 constexpr float kU = 1.0f / 16777216.0f;                                      // 2^-24
-constexpr float kRel = 160.0f * kU, kAbs = 420.0f * kU;                       // see the header
+constexpr float kErr = 64.0f * kU;                                             // filter-vs-direct error per unit of Sigma (header)
 
 __device__ __forceinline__ float tf32_rn(float x) {
     uint32_t r;
@@ -100,22 +114,13 @@ __device__ __forceinline__ void store_row(unsigned char *tile, int row, const fl
 __device__ __forceinline__ float nrm2(float x, float y, float z) { return fmaf(z, z, fmaf(y, y, x * x)); }
 
 // minimum of 32 values, as a tree of 3-input minima (NaN operands are dropped)
-__device__ __forceinline__ float min32(const float (&v)[32]) {
+__device__ __forceinline__ float min32(const float *v) {
     float m[11];
 #pragma unroll
     for (int i = 0; i < 10; ++i) m[i] = min3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
     m[10] = fminf(v[30], v[31]);
     const float n0 = min3(m[0], m[1], m[2]), n1 = min3(m[3], m[4], m[5]), n2 = min3(m[6], m[7], m[8]);
     return min3(min3(n0, n1, n2), m[9], m[10]);
-}
-
-// every later use of v depends on this statement: placed after a tcgen05.wait::ld it keeps reads of v behind the wait
-__device__ __forceinline__ void pin32(float (&v)[32]) {
-    asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
-                      "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]),
-                      "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]),
-                      "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
-                 :: "memory");
 }
 
 // ---- exact arithmetic shared by the fused refinement and the tail kernel --------------------------------------------
@@ -145,6 +150,22 @@ __device__ __forceinline__ void eval_group(const float *__restrict__ c, int nc, 
         }
     }
 }
+// the same from the raw shared-memory copy of the candidate cloud (always 16-byte aligned, padded with copies of the
+// last point up to a multiple of 256)
+__device__ __forceinline__ void eval_group_smem(const float *raw, int base, float qx, float qy, float qz, float (&t)[32]) {
+    const float4 *p4 = reinterpret_cast<const float4 *>(raw + 3 * base);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        float4 v[6];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) v[e] = p4[h * 6 + e];
+        float f[24];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) { f[4 * e] = v[e].x; f[4 * e + 1] = v[e].y; f[4 * e + 2] = v[e].z; f[4 * e + 3] = v[e].w; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t[h * 8 + k] = sqdist(qx, qy, qz, f[3 * k], f[3 * k + 1], f[3 * k + 2]);
+    }
+}
 // lowest k with t[k] <= h (32 if none)
 __device__ __forceinline__ int first_le(const float (&t)[32], float h) {
     int kk = 32;
@@ -169,9 +190,10 @@ struct Seg { int dir, b, qb0, Q, nq, nc, n_ct, next; };
 // ---- fused refinement of one query ------------------------------------------------------------------------------
 // k1 = (smallest group minimum, its group), k2 = (second smallest, its group), t3 = third smallest group minimum
 template <bool TOP3>
-__device__ __forceinline__ void refine_query(const float *__restrict__ qc, const float *__restrict__ cc, int nc, int i,
-                                             u64 k1, u64 k2, float t3, float *__restrict__ dout, int32_t *__restrict__ iout,
-                                             float *__restrict__ zero, unsigned *__restrict__ cnt, unsigned *__restrict__ list) {
+__device__ __forceinline__ void refine_query(const float *__restrict__ qc, const float *__restrict__ cc, const float *raw,
+                                             int nc, int i, u64 k1, u64 k2, float t3, float *__restrict__ dout,
+                                             int32_t *__restrict__ iout, float *__restrict__ zero,
+                                             unsigned *__restrict__ cnt, unsigned *__restrict__ list) {
     const float qx = __ldg(qc + 3 * (size_t)i), qy = __ldg(qc + 3 * (size_t)i + 1), qz = __ldg(qc + 3 * (size_t)i + 2);
     if (zero != nullptr) { zero[3 * (size_t)i] = 0.0f; zero[3 * (size_t)i + 1] = 0.0f; zero[3 * (size_t)i + 2] = 0.0f; }
     const float val = __uint_as_float((unsigned)(k1 >> 32));
@@ -179,18 +201,31 @@ __device__ __forceinline__ void refine_query(const float *__restrict__ qc, const
     const bool has2 = k2 != kKeyInit;                                   // a single candidate group: nothing to confuse
     const float sv = has2 ? __uint_as_float((unsigned)(k2 >> 32)) : INFINITY;
     const int sgrp = (int)(unsigned)(k2 & 0xffffffffu);
-    const float thr = fmaf(val, 1.0f + kRel, kAbs * nrm2(qx, qy, qz));
-    // any NaN (non-finite input) makes a comparison false -> ambiguous -> exact scan in the tail kernel
-    const bool clear = sv * (1.0f - kRel) > thr;
-    const bool two = TOP3 && !clear && has2 && (t3 * (1.0f - kRel) > thr);
+    // the margin test of the header; any NaN (non-finite input) makes a comparison false -> ambiguous -> tail kernel
+    const float a2 = nrm2(qx, qy, qz), a = sqrtf(a2);
+    auto sigma = [&](float tt) {
+        const float tp = fmaf(fmaxf(tt, 0.0f), 1.0001f, 256.0f * kU * a2);
+        return fmaf(2.0f * a, sqrtf(tp), fmaf(2.0f, a2, tp));
+    };
+    const float hi_val = fmaf(kErr, sigma(val), val) * (1.0f + 8.0f * kU);
+    auto out_of_reach = [&](float v) {                                  // no candidate with a filter value >= v can win
+        if (v == INFINITY) return true;
+        return v >= 1.0e-9f * a2 && fmaf(-kErr, sigma(v), v) > hi_val;
+    };
+    const bool clear = out_of_reach(sv);
+    const bool two = TOP3 && !clear && has2 && out_of_reach(t3);
     bool amb = !clear && !two;
     float m = INFINITY;
     float t[32];
+    auto eval = [&](int g) {
+        if (raw != nullptr) eval_group_smem(raw, g * kGroup, qx, qy, qz, t);
+        else eval_group(cc, nc, g * kGroup, qx, qy, qz, t);
+    };
     if (!amb) {
-        eval_group(cc, nc, grp * kGroup, qx, qy, qz, t);
+        eval(grp);
         m = min32(t);
         if (TOP3 && two) {
-            eval_group(cc, nc, sgrp * kGroup, qx, qy, qz, t);
+            eval(sgrp);
             m = fminf(m, min32(t));
         }
         amb = !(m < INFINITY);                                          // non-finite input: the tail mirrors torch.min
@@ -204,9 +239,9 @@ __device__ __forceinline__ void refine_query(const float *__restrict__ qc, const
     const float h = sqrt_window_top(m, s);
     int bj = 0x7fffffff;
     if (TOP3 && two) {
-        bj = sgrp * kGroup + first_le(t, h);                            // t holds the second group (32: nothing there)
-        if (bj - sgrp * kGroup == 32) bj = 0x7fffffff;
-        eval_group(cc, nc, grp * kGroup, qx, qy, qz, t);
+        const int k2nd = first_le(t, h);                                // t holds the second group
+        if (k2nd < 32) bj = sgrp * kGroup + k2nd;
+        eval(grp);
     }
     const int k = first_le(t, h);
     if (k < 32) bj = min(bj, grp * kGroup + k);
@@ -220,21 +255,27 @@ template <bool TOP3>
 __global__ void __launch_bounds__(kThreads, 1)
 chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ pc2, int B, int N, int M, int n_tasks,
                        int qb1, int qb2, SweepOut o, int refine) {
+    using Cfg = SweepCfg<TOP3>;
+    constexpr int kStW = Cfg::kStW;
     extern __shared__ unsigned char ts_smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t pad = (1024u - (smem_u32(ts_smem_raw) & 1023u)) & 1023u;
     unsigned char *smem = ts_smem_raw + pad;
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t bars = sbase + kOffBar;
+    const uint32_t bars = sbase + Cfg::kOffBar;
     const uint32_t bar_afull = bars, bar_aempty = bars + 8 * kQmax;                     // [kQmax], [1]
     const uint32_t bar_bfull = bar_aempty + 8, bar_bempty = bar_bfull + 16;             // [2] each
     const uint32_t bar_accfull = bar_bempty + 16, bar_accempty = bar_accfull + 32;      // [4] each
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kOffBar + 8 * (kQmax + 13));
+    const uint32_t bar_rawfull = bar_accempty + 32, bar_rawempty = bar_rawfull + 16;    // [2] each
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Cfg::kOffBar + 8 * (kQmax + 17));
 
     if (tid == 0) {
         for (int q = 0; q < kQmax; ++q) mbar_init(bar_afull + 8 * q, kPrThreads);
         mbar_init(bar_aempty, kMmaWarps);
-        for (int k = 0; k < 2; ++k) { mbar_init(bar_bfull + 8 * k, kPrThreads); mbar_init(bar_bempty + 8 * k, kMmaWarps); }
+        for (int k = 0; k < 2; ++k) {
+            mbar_init(bar_bfull + 8 * k, kPrThreads); mbar_init(bar_bempty + 8 * k, kMmaWarps);
+            mbar_init(bar_rawfull + 8 * k, kPrThreads); mbar_init(bar_rawempty + 8 * k, kEpWarps * 32);
+        }
         for (int k = 0; k < 4; ++k) { mbar_init(bar_accfull + 8 * k, 1); mbar_init(bar_accempty + 8 * k, (kEpWarps / 2) * 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -247,8 +288,10 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // Wait first, THEN let the next kernel (the tail) start: its prologue reads the clouds, so it may only run once this
+    // kernel knows they are complete.  All CTAs of this grid are resident at once, so the tail is released early anyway.
+    pdl_wait();
     pdl_launch_dependents();
-    pdl_wait();                                   // clouds and workspace may come from the kernels right before this one
 
     // tasks (direction, cloud, 128-query block) in direction-major order, split evenly and contiguously over the CTAs
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
@@ -268,6 +311,8 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
         sg.next = task + sg.Q;
         return sg;
     };
+    // the raw candidate copy of a segment is kept only for clouds that fit (and only when the refinement runs)
+    auto stages_raw = [&](const Seg &sg) { return Cfg::kRawMax > 0 && refine && sg.nc <= Cfg::kRawMax; };
 
     if (warp >= kMmaWarp0) {
         // =========================== MMA issuers ===========================
@@ -277,7 +322,7 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
         const bool leader = elect_one();
         const uint32_t idesc = umma_idesc_tf32(kTQ, kTC / 2);
         const uint64_t ad0 = umma_desc(sbase), bd0 = umma_desc(sbase + kOffB);
-        const uint64_t a_inc = (uint64_t)(kABytes >> 4), b_inc = (uint64_t)(kBBytes >> 4);
+        const uint64_t a_inc = (uint64_t)(kABytes >> 4), b_half = (uint64_t)(kBBytes >> 5);   // 16-byte units
         uint32_t vis = 0, bt = 0, sn = 0;
         for (int task = t_begin; task < t_end;) {
             const Seg sg = seg_at(task);
@@ -285,7 +330,8 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
             for (int k = 0; k < sg.n_ct; ++k, ++bt) {
                 const uint32_t sb = bt & 1u;
                 mbar_wait_spin(bar_bfull + 8 * sb, (bt >> 1) & 1u);
-                const uint64_t bh = bd0 + (uint64_t)sb * b_inc + (uint64_t)me * (b_inc >> 1);
+                // candidate tile sb lives in 16-byte chunks 4*sb .. 4*sb+3 of every row; this issuer's half = rows me*128 ..
+                const uint64_t bh = bd0 + (uint64_t)(sb * 4u) + (uint64_t)me * b_half;
                 for (int q = 0; q < sg.Q; ++q, ++vis) {
                     if (k == 0) mbar_wait_spin(bar_afull + 8 * q, sn & 1u);
                     const uint32_t gt = 2u * vis + me, ab = gt & 3u;
@@ -323,6 +369,8 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
             task = sg.next;
             const float *qc = (sg.dir ? pc2 : pc1) + (size_t)sg.b * sg.nq * 3;
             const float *cc = (sg.dir ? pc1 : pc2) + (size_t)sg.b * sg.nc * 3;
+            const bool keep_raw = stages_raw(sg);
+            float *raw = reinterpret_cast<float *>(smem + Cfg::kOffRaw + (sn & 1u) * Cfg::kRawBytes);
             // 128 queries of block qb0+q -> A tile q (rows past the end are all-zero)
             auto load_a = [&](int q, float (&x)[kARows][3]) {
 #pragma unroll
@@ -368,6 +416,10 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
                     const int r = h * kPrThreads + ptid;
                     const bool valid = k * kTC + r < sg.nc;
                     const float y0 = y[h][0], y1 = y[h][1], y2 = y[h][2];
+                    if (Cfg::kRawMax > 0 && keep_raw) {         // rows past the end hold copies of the last point
+                        float *rr = raw + 3 * (k * kTC + r);
+                        rr[0] = y0; rr[1] = y1; rr[2] = y2;
+                    }
                     float e[16];
                     float hh, l;
                     split2(valid ? -2.0f * y0 : 0.0f, hh, l); e[0] = hh; e[1] = l; e[2] = hh;
@@ -376,7 +428,7 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
                     e[9] = 1.0f; e[10] = 1.0f; e[11] = 1.0f;
                     split3(valid ? nrm2(y0, y1, y2) : kBig, e[12], e[13], e[14]);
                     e[15] = 0.0f;
-                    store_row(tileB0 + sb * kBBytes, r, e, 0u);
+                    store_row(tileB0, r, e, 4u * sb);
                 }
                 fence_async_proxy();
                 mbar_arrive(bar_bfull + 8 * sb);
@@ -386,6 +438,8 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
             float ax[2][kARows][3];
             load_a(0, ax[0]);
             if (sg.Q > 1) load_a(1, ax[1]);
+            // the refinement of segment sn-2 must be done with this raw buffer
+            if (Cfg::kRawMax > 0) mbar_wait_spin(bar_rawempty + 8 * (sn & 1u), ((sn >> 1) & 1u) ^ 1u);
             produce_b(0);
             mbar_wait_spin(bar_aempty, (sn & 1u) ^ 1u);                 // the previous segment's MMAs are done with the A tiles
 #pragma unroll
@@ -398,6 +452,7 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
                 }
             }
             for (int k = 1; k < sg.n_ct; ++k) produce_b(k);
+            if (Cfg::kRawMax > 0) mbar_arrive(bar_rawfull + 8 * (sn & 1u));   // the segment's raw copy is complete
             ++sn;
         }
     } else {
@@ -408,24 +463,25 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
         const uint32_t lane_base = ((uint32_t)(warp & 3) * 32u) << 16;
         float *st = reinterpret_cast<float *>(smem + kOffState) + (slot * kQmax) * kTQ * kStW + row;
         constexpr int kStQ = kTQ * kStW;                                // words per query block of one slot
-        uint32_t vis0 = 0;                                              // visits issued before this segment
+        uint32_t vis0 = 0, sn = 0;                                      // visits issued before this segment, segment index
         for (int task = t_begin; task < t_end;) {
             const Seg sg = seg_at(task);
             task = sg.next;
             for (int q = 0; q < sg.Q; ++q) {
                 float *sq = st + q * kStQ;
-                sq[0] = INFINITY; sq[kTQ] = INFINITY; sq[2 * kTQ] = INFINITY;
-                reinterpret_cast<int *>(sq)[3 * kTQ] = 0; reinterpret_cast<int *>(sq)[4 * kTQ] = 0;
+                sq[kWBest * kTQ] = INFINITY; sq[kWSecond * kTQ] = INFINITY;
+                reinterpret_cast<int *>(sq)[kWBgrp * kTQ] = 0;
+                if (TOP3) { sq[kWThird * kTQ] = INFINITY; reinterpret_cast<int *>(sq)[kWSgrp * kTQ] = 0; }
             }
             const uint32_t n_vis = (uint32_t)sg.n_ct * (uint32_t)sg.Q;
             int k = 0, q = 0;
             for (uint32_t v = 0; v < n_vis; ++v) {
                 const uint32_t gt = 2u * (vis0 + v) + pg, ab = gt & 3u;
                 float *sq = st + q * kStQ;
-                float best = sq[0], second = sq[kTQ], third = TOP3 ? sq[2 * kTQ] : INFINITY;
-                int bgrp = reinterpret_cast<int *>(sq)[3 * kTQ], sgrp = TOP3 ? reinterpret_cast<int *>(sq)[4 * kTQ] : 0;
+                float best = sq[kWBest * kTQ], second = sq[kWSecond * kTQ], third = TOP3 ? sq[kWThird * kTQ] : INFINITY;
+                int bgrp = reinterpret_cast<int *>(sq)[kWBgrp * kTQ], sgrp = TOP3 ? reinterpret_cast<int *>(sq)[kWSgrp * kTQ] : 0;
                 // running three smallest group minima (strict <: the earliest group keeps a tie) and the groups of the first two
-                auto group_done = [&](const float (&vv)[32], int Gc) {
+                auto group_done = [&](const float *vv, int Gc) {
                     const float m = min32(vv);
                     if (!TOP3) {
                         second = fminf(second, fmaxf(best, m));
@@ -446,23 +502,20 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
                 };
                 mbar_wait_spin(bar_accfull + 8 * ab, (gt >> 2) & 1u);
                 tc_fence_after();
-                // this thread's 64 candidates of the half-visit: both loads up front, the accumulator goes back to its
-                // issuer as soon as they have landed (the group's other accumulator is being refilled meanwhile)
-                const uint32_t taddr = tmem + lane_base + ab * (uint32_t)(kTC / 2) + ch * 64u;
-                float va[32], vb[32];
-                tc_ld32_nowait(taddr, va);
-                tc_ld32_nowait(taddr + 32u, vb);
-                tc_wait_ld(va);
-                pin32(vb);
+                // this thread's 64 candidates of the half-visit in ONE tcgen05.ld (32x32b.x64: the widest shape moves
+                // 658 B/clk/SM, profiles/r1_umma_microbench.txt); the accumulator goes back to its issuer as soon as the
+                // load has landed (the group's other accumulator is being refilled meanwhile)
+                float vv[64];
+                tc_ld64(tmem + lane_base + ab * (uint32_t)(kTC / 2) + ch * 64u, vv);
                 tc_fence_before();
                 mbar_arrive(bar_accempty + 8 * ab);
                 int G0 = k * (kTC / 32) + (int)(pg * 4u + ch * 2u);
                 asm volatile("mov.s32 %0, %0;" : "+r"(G0));             // pinned: otherwise recomputed under every predicate
-                group_done(va, G0);
-                group_done(vb, G0 + 1);
-                sq[0] = best; sq[kTQ] = second;
-                reinterpret_cast<int *>(sq)[3 * kTQ] = bgrp;
-                if (TOP3) { sq[2 * kTQ] = third; reinterpret_cast<int *>(sq)[4 * kTQ] = sgrp; }
+                group_done(vv, G0);
+                group_done(vv + 32, G0 + 1);
+                sq[kWBest * kTQ] = best; sq[kWSecond * kTQ] = second;
+                reinterpret_cast<int *>(sq)[kWBgrp * kTQ] = bgrp;
+                if (TOP3) { sq[kWThird * kTQ] = third; reinterpret_cast<int *>(sq)[kWSgrp * kTQ] = sgrp; }
                 if (++q == sg.Q) { q = 0; ++k; }
             }
             vis0 += n_vis;
@@ -490,13 +543,13 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
                     for (int g = 0; g < kSlots; ++g) {
                         const float *sp = all_st + (g * kQmax + qq) * kStQ;
                         const int *ip = reinterpret_cast<const int *>(sp);
-                        insert(((u64)__float_as_uint(fmaxf(sp[0], 0.0f)) << 32) | (unsigned)ip[3 * kTQ]);       // +inf if nothing seen
+                        insert(((u64)__float_as_uint(fmaxf(sp[kWBest * kTQ], 0.0f)) << 32) | (unsigned)ip[kWBgrp * kTQ]);   // +inf if nothing seen
                         if (TOP3) {
-                            insert(((u64)__float_as_uint(fmaxf(sp[kTQ], 0.0f)) << 32) | (unsigned)ip[4 * kTQ]);
-                            t3 = fminf(t3, fmaxf(sp[2 * kTQ], 0.0f));
+                            insert(((u64)__float_as_uint(fmaxf(sp[kWSecond * kTQ], 0.0f)) << 32) | (unsigned)ip[kWSgrp * kTQ]);
+                            t3 = fminf(t3, fmaxf(sp[kWThird * kTQ], 0.0f));
                         } else {
                             // no runner-up group is tracked: only its value takes part (group field unused)
-                            insert(((u64)__float_as_uint(fmaxf(sp[kTQ], 0.0f)) << 32) | 0xffffffffull);
+                            insert(((u64)__float_as_uint(fmaxf(sp[kWSecond * kTQ], 0.0f)) << 32) | 0xffffffffull);
                         }
                     }
                     // a slot that saw no second group reports +inf there: "no runner-up"
@@ -505,6 +558,11 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
                 mk1[r] = k1; mk2[r] = k2; mt3[r] = t3;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kEpWarps * 32) : "memory");   // the state may be re-initialised
+            const float *raw = nullptr;
+            if (Cfg::kRawMax > 0) {
+                mbar_wait_spin(bar_rawfull + 8 * (sn & 1u), (sn >> 1) & 1u);   // the producers' raw copy of this segment's candidates
+                if (stages_raw(sg)) raw = reinterpret_cast<const float *>(smem + Cfg::kOffRaw + (sn & 1u) * Cfg::kRawBytes);
+            }
             if (refine) {
                 const float *qc = (sg.dir ? pc2 : pc1) + (size_t)sg.b * sg.nq * 3;
                 const float *cc = (sg.dir ? pc1 : pc2) + (size_t)sg.b * sg.nc * 3;
@@ -515,18 +573,18 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
                 float *zero = zb ? zb + 3 * qoff : nullptr;
                 unsigned *cnt = o.amb_cnt + (sg.dir ? B : 0) + sg.b;
                 unsigned *list = o.amb_list + (sg.dir ? (size_t)B * N : 0) + qoff;
-#pragma unroll 1
+#pragma unroll
                 for (int r = 0; r < 2; ++r) {
                     const int qq = slot + 4 * r;
                     const int i = (sg.qb0 + qq) * kTQ + row;
                     if (qq < sg.Q && i < sg.nq)
-                        refine_query<TOP3>(qc, cc, sg.nc, i, mk1[r], mk2[r], mt3[r], dout, iout, zero, cnt, list);
+                        refine_query<TOP3>(qc, cc, raw, sg.nc, i, mk1[r], mk2[r], mt3[r], dout, iout, zero, cnt, list);
                 }
             } else {
                 // diagnostic: publish what the filter found (tests measure its error against float64 with this)
                 u64 *keys = (sg.dir ? o.key2 : o.key1) + (size_t)sg.b * sg.nq;
                 unsigned *secs = (sg.dir ? o.sec2 : o.sec1) + (size_t)sg.b * sg.nq;
-#pragma unroll 1
+#pragma unroll
                 for (int r = 0; r < 2; ++r) {
                     const int qq = slot + 4 * r;
                     const int i = (sg.qb0 + qq) * kTQ + row;
@@ -536,6 +594,8 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
                     }
                 }
             }
+            if (Cfg::kRawMax > 0) mbar_arrive(bar_rawempty + 8 * (sn & 1u));   // done with this segment's raw copy
+            ++sn;
         }
     }
     tc_fence_before();
@@ -556,18 +616,38 @@ struct TailWs {
 
 // grid (chunks, B, 2).  A warp scans the whole candidate cloud for one ambiguous point, mirroring torch.min on the
 // sqrt-ed row: the first NaN wins, otherwise the lowest index among the candidates that share the smallest sqrtf.
+// STAGE: the candidate cloud of the CTA's (cloud, direction) is first copied to shared memory (one coalesced pass
+// instead of a latency-bound walk through L2 per point).
+template <bool STAGE>
 __global__ void __launch_bounds__(kTailThreads) chamfer_tail_kernel(
     const float *__restrict__ pc1, const float *__restrict__ pc2, int N, int M, int C1, int C2, SweepOut o, TailWs tw,
     float *__restrict__ mean1, float *__restrict__ mean2, float *__restrict__ loss, float loss_w1, float loss_w2) {
+    extern __shared__ __align__(16) float s_cand[];
     __shared__ double red[kTailWarps];
     const int chunk = blockIdx.x, b = blockIdx.y, dir = blockIdx.z, B = gridDim.y;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     pdl_launch_dependents();
     if (chunk >= (dir ? C2 : C1)) return;
-    pdl_wait();                                         // everything below reads results of the pair sweep
     const int nq = dir ? M : N, nc = dir ? N : M, C = dir ? C2 : C1;
     const float *qc = (dir ? pc2 : pc1) + (size_t)b * nq * 3;
     const float *cc = (dir ? pc1 : pc2) + (size_t)b * nc * 3;
+    const float *c = cc;
+    if (STAGE) {
+        // the clouds were complete before the pair sweep released this kernel (it waits before it triggers)
+        const int nf = nc * 3;
+        if ((reinterpret_cast<uintptr_t>(cc) & 15u) == 0) {
+            const int n4 = nf >> 2;
+            const float4 *src4 = reinterpret_cast<const float4 *>(cc);
+            float4 *dst4 = reinterpret_cast<float4 *>(s_cand);
+            for (int e = tid; e < n4; e += kTailThreads) dst4[e] = __ldg(src4 + e);
+            for (int e = (n4 << 2) + tid; e < nf; e += kTailThreads) s_cand[e] = __ldg(cc + e);
+        } else {
+            for (int e = tid; e < nf; e += kTailThreads) s_cand[e] = __ldg(cc + e);
+        }
+        c = s_cand;
+        __syncthreads();
+    }
+    pdl_wait();                                         // everything below reads results of the pair sweep
     float *dout = (dir ? o.d2 : o.d1) + (size_t)b * nq;
     int32_t *iout = (dir ? o.i2 : o.i1) + (size_t)b * nq;
     const unsigned n_amb = __ldcg(o.amb_cnt + (dir ? B : 0) + b) + 1u;
@@ -575,13 +655,22 @@ __global__ void __launch_bounds__(kTailThreads) chamfer_tail_kernel(
     for (unsigned a = (unsigned)(chunk * kTailWarps + wid); a < n_amb; a += (unsigned)(C * kTailWarps)) {
         const int i = (int)__ldcg(list + a);
         const float qx = __ldg(qc + 3 * (size_t)i), qy = __ldg(qc + 3 * (size_t)i + 1), qz = __ldg(qc + 3 * (size_t)i + 2);
-        // pass 1: smallest squared distance, first NaN
+        // pass 1: smallest squared distance, first NaN (four candidates in flight per lane)
         float lm = INFINITY;
         int nanj = 0x7fffffff;
-        for (int j = lane; j < nc; j += 32) {
-            const float t = sqdist(qx, qy, qz, __ldg(cc + 3 * (size_t)j), __ldg(cc + 3 * (size_t)j + 1), __ldg(cc + 3 * (size_t)j + 2));
+        int j = lane;
+        for (; j + 96 < nc; j += 128) {
+            float t[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) t[e] = sqdist(qx, qy, qz, c[3 * (j + 32 * e)], c[3 * (j + 32 * e) + 1], c[3 * (j + 32 * e) + 2]);
+#pragma unroll
+            for (int e = 3; e >= 0; --e) if (t[e] != t[e]) nanj = min(nanj, j + 32 * e);
+            lm = fminf(fminf(lm, t[0]), fminf(t[1], fminf(t[2], t[3])));
+        }
+        for (; j < nc; j += 32) {
+            const float t = sqdist(qx, qy, qz, c[3 * j], c[3 * j + 1], c[3 * j + 2]);
             if (t != t) nanj = min(nanj, j);
-            else lm = fminf(lm, t);
+            lm = fminf(lm, t);
         }
         nanj = __reduce_min_sync(0xffffffffu, nanj);
         const float m = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(lm)));   // t >= 0: orders as unsigned
@@ -595,10 +684,16 @@ __global__ void __launch_bounds__(kTailThreads) chamfer_tail_kernel(
             const float h = m < INFINITY ? sqrt_window_top(m, dist) : m;
             // pass 2: lowest index whose squared distance shares that square root
             int fj = 0x7fffffff;
-            for (int j = lane; j < nc && fj == 0x7fffffff; j += 32) {
-                const float t = sqdist(qx, qy, qz, __ldg(cc + 3 * (size_t)j), __ldg(cc + 3 * (size_t)j + 1), __ldg(cc + 3 * (size_t)j + 2));
-                if (t <= h) fj = j;
+            j = lane;
+            for (; j + 96 < nc; j += 128) {
+                float t[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) t[e] = sqdist(qx, qy, qz, c[3 * (j + 32 * e)], c[3 * (j + 32 * e) + 1], c[3 * (j + 32 * e) + 2]);
+#pragma unroll
+                for (int e = 3; e >= 0; --e) if (t[e] <= h) fj = min(fj, j + 32 * e);
             }
+            for (; j < nc; j += 32)
+                if (sqdist(qx, qy, qz, c[3 * j], c[3 * j + 1], c[3 * j + 2]) <= h) fj = min(fj, j);
             bj = __reduce_min_sync(0xffffffffu, fj);
             if (bj == 0x7fffffff) bj = 0;
         }
@@ -681,8 +776,8 @@ int launch_tcsweep(const float *pc1, const float *pc2, int B, int N, int M, cons
     // per launch (a host-side attribute write, no device work): the setting is per device and this library keeps no
     // per-device state of its own
     {
-        cudaError_t e = top3 ? cudaFuncSetAttribute(chamfer_tcsweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem)
-                             : cudaFuncSetAttribute(chamfer_tcsweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+        cudaError_t e = top3 ? cudaFuncSetAttribute(chamfer_tcsweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<true>::kSmem)
+                             : cudaFuncSetAttribute(chamfer_tcsweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<false>::kSmem);
         if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "chamfer_tcsweep_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
     }
     // the ambiguous counters live where the FP32 sweep keeps its cloud norms (all-ones invariant), the lists where the
@@ -690,9 +785,9 @@ int launch_tcsweep(const float *pc1, const float *pc2, int B, int N, int M, cons
     SweepOut o{d1, d2, i1, i2, zero1, zero2, w.nrm, w.rowsg, w.rowkey, w.colkey, w.rowsec, w.colsec};
     const int grid = (int)(n_tasks < sms ? n_tasks : sms);
     const int refine = sweep_only == 2 ? 0 : 1;
-    cudaError_t le = top3 ? launch_pdl(chamfer_tcsweep_kernel<true>, dim3((unsigned)grid), dim3(kThreads), (size_t)kSmem, st, pc1, pc2,
+    cudaError_t le = top3 ? launch_pdl(chamfer_tcsweep_kernel<true>, dim3((unsigned)grid), dim3(kThreads), (size_t)SweepCfg<true>::kSmem, st, pc1, pc2,
                                        B, N, M, (int)n_tasks, qb1, qb2, o, refine)
-                          : launch_pdl(chamfer_tcsweep_kernel<false>, dim3((unsigned)grid), dim3(kThreads), (size_t)kSmem, st, pc1, pc2,
+                          : launch_pdl(chamfer_tcsweep_kernel<false>, dim3((unsigned)grid), dim3(kThreads), (size_t)SweepCfg<false>::kSmem, st, pc1, pc2,
                                        B, N, M, (int)n_tasks, qb1, qb2, o, refine);
     if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "chamfer_tcsweep_kernel: %s", cudaGetErrorString(le)); }
     if (sweep_only) return check_launch("chamfer_tcsweep_kernel");
@@ -701,8 +796,19 @@ int launch_tcsweep(const float *pc1, const float *pc2, int B, int N, int M, cons
     tw.cloud_counter = tw.global_counter + 1;
     const int C1 = tail_chunks(N), C2 = tail_chunks(M);
     dim3 tgrid((unsigned)(C1 > C2 ? C1 : C2), (unsigned)B, 2);
-    le = launch_pdl(chamfer_tail_kernel, tgrid, dim3(kTailThreads), (size_t)0, st, pc1, pc2, N, M, C1, C2, o, tw, mean1, mean2, loss,
-                    w1, w2);
+    // the candidate cloud of a (cloud, direction) is staged in shared memory when it fits (<= 96 KB: 8192 points)
+    const size_t cand_bytes = align_up((size_t)(N > M ? N : M) * 12, 16);
+    if (cand_bytes <= 96u * 1024u) {
+        if (cand_bytes > 40u * 1024u) {
+            cudaError_t e = cudaFuncSetAttribute(chamfer_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96u * 1024u));
+            if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "chamfer_tail_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
+        }
+        le = launch_pdl(chamfer_tail_kernel<true>, tgrid, dim3(kTailThreads), cand_bytes, st, pc1, pc2, N, M, C1, C2, o, tw, mean1,
+                        mean2, loss, w1, w2);
+    } else {
+        le = launch_pdl(chamfer_tail_kernel<false>, tgrid, dim3(kTailThreads), (size_t)0, st, pc1, pc2, N, M, C1, C2, o, tw, mean1,
+                        mean2, loss, w1, w2);
+    }
     if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "chamfer_tail_kernel: %s", cudaGetErrorString(le)); }
     return check_launch("chamfer_tail_kernel");
 }
