@@ -39,19 +39,20 @@
 // Roles (one CTA per SM, persistent over (direction, cloud, 128-query block) tasks; a CTA owns a contiguous task range
 // and walks it in SEGMENTS of up to 8 query blocks of one (direction, cloud) that share every converted candidate tile;
 // a "visit" = one query block x one 256-candidate tile = two 128-column halves):
-//   warps 0-15  epilogue.  Two pipeline groups of eight warps: group p takes half p of every visit and alternates between
-//               TMEM accumulators p and p+2, so the tensor cores refill one while the other is reduced.  Within a group
-//               two warps per TMEM lane quarter split the 128 columns: thread = (query row, 64 candidates).  Running
+//   warps 0-15  epilogue: four groups of four warps; half-visit h (in issue order) goes to TMEM accumulator h % 4 and to
+//               group h % 4; thread = query row = TMEM lane, 128 candidates per half-visit as four tcgen05.ld of 32
+//               columns in two register sets (the load of chunk c+1 is in flight while chunk c is reduced).  Running
 //               (best, second, third group minimum; best / second group) per query block live in shared memory; at the
-//               end of a segment the four partial states of a query are merged and the merging thread refines it.
+//               end of a segment the four groups' partial states of a query are merged and the merging thread refines it.
 //   warps 16-17 producers: convert 256 candidates per tile (and the segment's queries) to the split-tf32 rows, written
 //               straight into K-major SWIZZLE_128B operand tiles (rows are 64 bytes: two query blocks, and the two
 //               candidate tiles in flight, share one 128-byte-row tile; the descriptor's start address picks the half).
 //               Clouds of up to 2048 points are also kept raw in shared memory (double-buffered per segment), so the
 //               fused refinement reads its 32 candidates with LDS.128 instead of going to L2.
-//   warps 18-19 MMA issuers (one elected lane each): issuer p serves pipeline group p.  A tcgen05.mma blocks its issuer
-//               while the pipe is busy and every hand-off costs the issuer a barrier round trip (profiles/
-//               r1_umma_microbench.txt: pause + 85 cycles per hand-off); two issuers hide one another's round trips.
+//   warps 18-19 MMA issuers (one elected lane each): issuer p issues the halves p of every visit (accumulators p, p + 2).
+//               A tcgen05.mma blocks its issuer while the pipe is busy and every hand-off costs the issuer a barrier
+//               round trip (profiles/r1_umma_microbench.txt: pause + 85 cycles per hand-off); two issuers hide one
+//               another's round trips.
 #include "common.cuh"
 #include "tcgen05.cuh"
 #include <math.h>
@@ -70,7 +71,10 @@ constexpr uint32_t kABytes = kTQ * 128, kBBytes = kTC * 128;
 // A rows carry K = 16 tf32 = 64 bytes, half of a SWIZZLE_128B row: two query blocks share one 16 KB tile (block q sits in
 // 16-byte chunks 4*(q&1) .. 4*(q&1)+3 of tile q>>1; the descriptor's start address selects the half)
 constexpr uint32_t kOffB = (kQmax / 2) * kABytes;                             // one 32 KB tile holds BOTH candidate tiles in flight
-constexpr int kSlots = 4;                                                     // partial states per query: (pipeline group, column half)
+constexpr int kSlots = 4;                                                     // partial states per query: one per epilogue group
+// raw candidate copy: a 32-candidate group takes 96 floats; a stride of 100 floats (25 x 16 bytes, odd) spreads the
+// groups over the shared-memory banks -- with 96 every thread's LDS.128 would start in the same bank quad (8-way conflict)
+constexpr int kRawStride = 100;
 constexpr uint32_t kOffState = kOffB + kBBytes;                               // [slot][kQmax][kStW][128]
 // state words per (slot, query block, row): best, second, best group [, third, second group]
 constexpr int kWBest = 0, kWSecond = 1, kWBgrp = 2, kWThird = 3, kWSgrp = 4;
@@ -81,7 +85,7 @@ template <bool TOP3> struct SweepCfg {
     // With TOP3 (clouds beyond 4096 points) there is nothing to stage: the refinement reads the candidates from L2.
     static constexpr int kRawMax = TOP3 ? 0 : 2048;
     static constexpr uint32_t kOffRaw = kOffState + kStateBytes;
-    static constexpr uint32_t kRawBytes = (uint32_t)kRawMax * 12u;
+    static constexpr uint32_t kRawBytes = (uint32_t)(kRawMax / kGroup) * kRawStride * 4u;
     static constexpr uint32_t kOffBar = kOffRaw + 2 * kRawBytes;
     static constexpr uint32_t kSmem = kOffBar + 256 + 1024;                   // + barriers + alignment slack
 };
@@ -150,10 +154,10 @@ __device__ __forceinline__ void eval_group(const float *__restrict__ c, int nc, 
         }
     }
 }
-// the same from the raw shared-memory copy of the candidate cloud (always 16-byte aligned, padded with copies of the
-// last point up to a multiple of 256)
-__device__ __forceinline__ void eval_group_smem(const float *raw, int base, float qx, float qy, float qz, float (&t)[32]) {
-    const float4 *p4 = reinterpret_cast<const float4 *>(raw + 3 * base);
+// the same from the raw shared-memory copy of the candidate cloud (group g at raw + g * kRawStride, always 16-byte
+// aligned; rows past the end of the cloud hold copies of the last point)
+__device__ __forceinline__ void eval_group_smem(const float *raw, int g, float qx, float qy, float qz, float (&t)[32]) {
+    const float4 *p4 = reinterpret_cast<const float4 *>(raw + g * kRawStride);
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
         float4 v[6];
@@ -218,7 +222,7 @@ __device__ __forceinline__ void refine_query(const float *__restrict__ qc, const
     float m = INFINITY;
     float t[32];
     auto eval = [&](int g) {
-        if (raw != nullptr) eval_group_smem(raw, g * kGroup, qx, qy, qz, t);
+        if (raw != nullptr) eval_group_smem(raw, g, qx, qy, qz, t);
         else eval_group(cc, nc, g * kGroup, qx, qy, qz, t);
     };
     if (!amb) {
@@ -276,7 +280,7 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
             mbar_init(bar_bfull + 8 * k, kPrThreads); mbar_init(bar_bempty + 8 * k, kMmaWarps);
             mbar_init(bar_rawfull + 8 * k, kPrThreads); mbar_init(bar_rawempty + 8 * k, kEpWarps * 32);
         }
-        for (int k = 0; k < 4; ++k) { mbar_init(bar_accfull + 8 * k, 1); mbar_init(bar_accempty + 8 * k, (kEpWarps / 2) * 32); }
+        for (int k = 0; k < 4; ++k) { mbar_init(bar_accfull + 8 * k, 1); mbar_init(bar_accempty + 8 * k, (kEpWarps / 4) * 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp0) {
@@ -417,7 +421,8 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
                     const bool valid = k * kTC + r < sg.nc;
                     const float y0 = y[h][0], y1 = y[h][1], y2 = y[h][2];
                     if (Cfg::kRawMax > 0 && keep_raw) {         // rows past the end hold copies of the last point
-                        float *rr = raw + 3 * (k * kTC + r);
+                        const int jj = k * kTC + r;
+                        float *rr = raw + (jj >> 5) * kRawStride + 3 * (jj & 31);
                         rr[0] = y0; rr[1] = y1; rr[2] = y2;
                     }
                     float e[16];
@@ -457,10 +462,12 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
         }
     } else {
         // =========================== epilogue ===========================
-        const int slot = warp >> 2;                                     // partial state of a query: (pipeline group, column half)
-        const uint32_t pg = (uint32_t)slot & 1u, ch = (uint32_t)slot >> 1;
+        const int slot = warp >> 2;                                     // epilogue group == accumulator == partial-state slot
         const int row = (warp & 3) * 32 + lane;                         // query of the block == TMEM lane
         const uint32_t lane_base = ((uint32_t)(warp & 3) * 32u) << 16;
+        const uint32_t taddr = tmem + lane_base + (uint32_t)slot * (uint32_t)(kTC / 2);
+        const uint32_t my_full = bar_accfull + 8 * slot, my_empty = bar_accempty + 8 * slot;
+        const int hf = slot & 1;                                        // this group's half of a visit (issued by issuer hf)
         float *st = reinterpret_cast<float *>(smem + kOffState) + (slot * kQmax) * kTQ * kStW + row;
         constexpr int kStQ = kTQ * kStW;                                // words per query block of one slot
         uint32_t vis0 = 0, sn = 0;                                      // visits issued before this segment, segment index
@@ -473,10 +480,13 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
                 reinterpret_cast<int *>(sq)[kWBgrp * kTQ] = 0;
                 if (TOP3) { sq[kWThird * kTQ] = INFINITY; reinterpret_cast<int *>(sq)[kWSgrp * kTQ] = 0; }
             }
+            // this group's half-visits of the segment: half hf of the visits v with (vis0 + v) % 2 == slot / 2
             const uint32_t n_vis = (uint32_t)sg.n_ct * (uint32_t)sg.Q;
-            int k = 0, q = 0;
-            for (uint32_t v = 0; v < n_vis; ++v) {
-                const uint32_t gt = 2u * (vis0 + v) + pg, ab = gt & 3u;
+            uint32_t v = (((uint32_t)slot >> 1) - vis0) & 1u;
+            int k = 0, q = (int)v;
+            while (q >= sg.Q) { q -= sg.Q; ++k; }
+            for (; v < n_vis; v += 2u) {
+                const uint32_t use = (2u * (vis0 + v) + (uint32_t)hf) >> 2;        // how often this accumulator was used before
                 float *sq = st + q * kStQ;
                 float best = sq[kWBest * kTQ], second = sq[kWSecond * kTQ], third = TOP3 ? sq[kWThird * kTQ] : INFINITY;
                 int bgrp = reinterpret_cast<int *>(sq)[kWBgrp * kTQ], sgrp = TOP3 ? reinterpret_cast<int *>(sq)[kWSgrp * kTQ] : 0;
@@ -500,27 +510,36 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
                     best = fminf(best, m);
                     bgrp = p1 ? Gc : bgrp;
                 };
-                mbar_wait_spin(bar_accfull + 8 * ab, (gt >> 2) & 1u);
+                mbar_wait_spin(my_full, use & 1u);
                 tc_fence_after();
-                // this thread's 64 candidates of the half-visit in ONE tcgen05.ld (32x32b.x64: the widest shape moves
-                // 658 B/clk/SM, profiles/r1_umma_microbench.txt); the accumulator goes back to its issuer as soon as the
-                // load has landed (the group's other accumulator is being refilled meanwhile)
-                float vv[64];
-                tc_ld64(tmem + lane_base + ab * (uint32_t)(kTC / 2) + ch * 64u, vv);
-                tc_fence_before();
-                mbar_arrive(bar_accempty + 8 * ab);
-                int G0 = k * (kTC / 32) + (int)(pg * 4u + ch * 2u);
+                // 4 chunks of 32 columns, two register sets: the load of chunk c+1 is in flight while c is reduced; the
+                // accumulator goes back to its issuer as soon as its last load has landed
+                float va[32], vb[32];
+                int G0 = k * (kTC / 32) + hf * 4;
                 asm volatile("mov.s32 %0, %0;" : "+r"(G0));             // pinned: otherwise recomputed under every predicate
-                group_done(vv, G0);
-                group_done(vv + 32, G0 + 1);
+                tc_ld32_nowait(taddr, va);
+                tc_wait_ld(va);
+                tc_ld32_nowait(taddr + 32u, vb);
+                group_done(va, G0);
+                tc_wait_ld(vb);
+                tc_ld32_nowait(taddr + 64u, va);
+                group_done(vb, G0 + 1);
+                tc_wait_ld(va);
+                tc_ld32_nowait(taddr + 96u, vb);
+                group_done(va, G0 + 2);
+                tc_wait_ld(vb);
+                tc_fence_before();
+                mbar_arrive(my_empty);
+                group_done(vb, G0 + 3);
                 sq[kWBest * kTQ] = best; sq[kWSecond * kTQ] = second;
                 reinterpret_cast<int *>(sq)[kWBgrp * kTQ] = bgrp;
                 if (TOP3) { sq[kWThird * kTQ] = third; reinterpret_cast<int *>(sq)[kWSgrp * kTQ] = sgrp; }
-                if (++q == sg.Q) { q = 0; ++k; }
+                q += 2;
+                while (q >= sg.Q) { q -= sg.Q; ++k; }
             }
             vis0 += n_vis;
             // ---- merge the four partial states per query; the merging thread refines the query (every candidate of
-            // these queries was seen by this CTA in this segment).  Slot s merges query blocks s and s + 4.
+            // these queries was seen by this CTA in this segment).  Group s merges query blocks s and s + 4.
             asm volatile("bar.sync 1, %0;" ::"n"(kEpWarps * 32) : "memory");
             const float *all_st = reinterpret_cast<const float *>(smem + kOffState) + row;
             u64 mk1[2], mk2[2];
@@ -733,18 +752,34 @@ __global__ void __launch_bounds__(kTailThreads) chamfer_tail_kernel(
         for (int w = 0; w < kTailWarps; ++w) tot += red[w];
         sums[dd] = tot;
     }
-    if (tid != 0) return;
-    mean1[b] = (float)(sums[0] / (double)N);
-    mean2[b] = (float)(sums[1] / (double)M);
-    if (loss == nullptr) return;
+    __shared__ int s_last_cloud;
+    if (tid == 0) {
+        mean1[b] = (float)(sums[0] / (double)N);
+        mean2[b] = (float)(sums[1] / (double)M);
+        s_last_cloud = 0;
+        if (loss != nullptr) {
+            __threadfence();
+            s_last_cloud = atomicAdd(tw.global_counter, 1u) == (unsigned)(B - 2);
+        }
+    }
+    __syncthreads();
+    if (!s_last_cloud) return;
+    // the last cloud's CTA: batch loss in a fixed order (thread-strided partial sums, lane tree, warps in order)
     __threadfence();
-    if (atomicAdd(tw.global_counter, 1u) != (unsigned)(B - 2)) return;
-    __threadfence();
-    *tw.global_counter = 0xffffffffu;
-    const volatile float *m1 = mean1, *m2 = mean2;
     double acc = 0.0;
-    for (int k = 0; k < B; ++k) acc += (double)loss_w1 * (double)m1[k] + (double)loss_w2 * (double)m2[k];
-    *loss = (float)acc;
+    for (int k = tid; k < B; k += kTailThreads)
+        acc += (double)loss_w1 * (double)__ldcg(mean1 + k) + (double)loss_w2 * (double)__ldcg(mean2 + k);
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, sft);
+    __syncthreads();
+    if (lane == 0) red[wid] = acc;
+    __syncthreads();
+    if (tid != 0) return;
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < kTailWarps; ++w) tot += red[w];
+    *tw.global_counter = 0xffffffffu;
+    *loss = (float)tot;
 }
 
 static int tail_chunks(int n) {
