@@ -80,6 +80,8 @@ def load() -> ctypes.CDLL:
     if _lib is not None:
         return _lib
     path = EXP_LIB_PATH if os.environ.get("RLG_EXPERIMENTS_LIB") == "1" else LIB_PATH
+    if os.environ.get("RLG_EXPERIMENTS_LIB", "").endswith(".so"):       # tools/: an A-B variant built by build.build_variant
+        path = os.environ["RLG_EXPERIMENTS_LIB"]
     if not os.path.exists(path):
         raise ImportError(
             f"{path} is missing: build it with `python gan-rl_3d_b200/build.py` (or __graft_entry__.build()). "

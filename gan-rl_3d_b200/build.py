@@ -51,6 +51,28 @@ def is_fresh(experiments: bool = False) -> bool:
     return os.path.exists(path) and os.path.getmtime(path) >= _newest_input()
 
 
+def build_variant(tag: str, defines) -> str:
+    """tools/ only: an experiments build with extra -D defines -> lib/librlg_b200_exp_<tag>.so (A/B timing)."""
+    nvcc = _nvcc()
+    obj_dir = OBJ_DIR + "_exp_" + tag
+    os.makedirs(obj_dir, exist_ok=True)
+    os.makedirs(LIB_DIR, exist_ok=True)
+    objs = []
+    for src in sources():
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + ["-DRLG_EXPERIMENTS"] + [f"-D{d}" for d in defines] + ["-c", src, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+        objs.append(obj)
+    out = os.path.join(LIB_DIR, f"librlg_b200_exp_{tag}.so")
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs + ["-lcuda"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return out
+
+
 def build_library(force: bool = False, verbose: bool = False, experiments: bool = False) -> str:
     """Compile every csrc/*.cu for sm_100a and link librlg_b200.so.  Returns the library path.
     experiments=True builds librlg_b200_exp.so with -DRLG_EXPERIMENTS instead: knock-out / A-B kernel variants behind

@@ -2,8 +2,8 @@
 // reference) and the independent cross-check kernel.
 //
 //   rlg_chamfer_fwd / rlg_chamfer_loss_fwd dispatch to
-//     RLG_CHAMFER_ALGO_TENSOR   chamfer_tcsweep.cu: pair sweep on the tensor cores with the exact refinement fused in,
-//                               then a small tail kernel (ambiguous points, means, loss)            -- 2 launches
+//     RLG_CHAMFER_ALGO_TENSOR   chamfer_tcsweep.cu: pair sweep on the tensor cores with the exact refinement, the
+//                               ambiguous points, the means and the loss fused in                   -- 1 launch
 //     (default)                 chamfer_filter.cu: pair sweep on the FP32 pipe, then the refinement -- 2 launches
 //     RLG_CHAMFER_ALGO_SIMPLE   one thread per query point, every candidate evaluated in the direct form: the plain
 //                               restatement the other two are cross-checked against in tests/
@@ -86,14 +86,13 @@ static size_t nrm_bytes(int B) { return align_up(sizeof(unsigned) * 2 * (size_t)
 // workspace layout (every region 256-B aligned):
 //   [0]  rowkey | colkey   u64 (B,N),(B,M)      FP32 sweep: packed (filter value, winning group)         all-ones invariant
 //   [1]  rowsec | colsec   u32                  FP32 sweep: smallest value of any other group            all-ones invariant
-//   [2]  nrm / amb_cnt     u32 (2,B)            FP32 sweep: ~max|p|^2; tensor sweep: ambiguous counters  all-ones invariant
-//   [3]  finalize / tail counters (+ FP32 finalize partial sums)                                         all-ones invariant
-//   [4]  amb_list          u32 (B*N + B*M)      tensor sweep: indices of the ambiguous points            no invariant
-//   [5]  (experiments build: third values of the first-generation tensor sweep)                          no invariant
+//   [2]  nrm               u32 (2,B)            FP32 sweep: ~max|p|^2                                    all-ones invariant
+//   [3]  counters (all-ones invariant) + partial sums of the distances (FP32 finalize / fused tensor forward)
+//   [4]  (experiments build: runner-up groups / third values of the first-generation tensor sweep)       no invariant
 size_t rlg_chamfer_ws_bytes(int B, int N, int M) {
     if (B < 0 || N < 1 || M < 1) return 0;
     size_t fin = finalize2_ws_bytes(B, N, M);
-    if (tcsweep_counter_bytes(B) > fin) fin = tcsweep_counter_bytes(B);
+    if (tcsweep_ws_bytes(B, N, M) > fin) fin = tcsweep_ws_bytes(B, N, M);
     return keys_bytes(B, N, M) + secs_bytes(B, N, M) + nrm_bytes(B) + fin + 2 * secs_bytes(B, N, M);
 }
 
@@ -163,9 +162,9 @@ int rlg_chamfer_loss_fwd(const float *pc1, const float *pc2, int B, int N, int M
     const bool tile_only = (flags & RLG_CHAMFER_TILE_ONLY) != 0;
 
     if (flags & RLG_CHAMFER_ALGO_TENSOR) {
-        const int sweep_only = (flags & RLG_CHAMFER_FILTER_ONLY) ? 2 : (tile_only ? 1 : 0);
-        return launch_tcsweep(pc1, pc2, B, N, M, w, fin, d1, d2, i1, i2, mean1, mean2, loss, w1, w2, gz1, gz2, sweep_only,
-                              (flags & RLG_CHAMFER_TRACK_TWO) != 0, st);
+        // one launch does everything: RLG_CHAMFER_TILE_ONLY changes nothing here
+        return launch_tcsweep(pc1, pc2, B, N, M, w, fin, d1, d2, i1, i2, mean1, mean2, loss, w1, w2, gz1, gz2,
+                              (flags & RLG_CHAMFER_FILTER_ONLY) != 0, (flags & RLG_CHAMFER_TRACK_TWO) != 0, st);
     }
     if (flags & (RLG_CHAMFER_TRACK_TWO | RLG_CHAMFER_FILTER_ONLY))
         return fail(RLG_ERR_UNSUPPORTED, "rlg_chamfer_fwd: RLG_CHAMFER_TRACK_TWO / FILTER_ONLY need RLG_CHAMFER_ALGO_TENSOR");

@@ -1,5 +1,5 @@
-// chamfer_tcsweep.cu -- batched Chamfer distance forward in two launches: the pair sweep on the tensor cores with the
-// exact refinement fused in, and a small tail kernel (the few ambiguous points, the per-pair means, the batch loss).
+// chamfer_tcsweep.cu -- batched Chamfer distance forward in ONE launch: the pair sweep on the tensor cores with the exact
+// refinement, the few ambiguous points, the per-pair means and the batch loss all fused in.
 //
 // Replaces utils/losses.py:29-37 of the reference (torch.cdist -> min over both axes -> mean); the (B,N,M) matrix never
 // exists.  Filter and refine, as in chamfer_filter.cu: a cheap filter value t~(i,j) ~ |x_i - y_j|^2 for EVERY pair
@@ -28,8 +28,8 @@
 // which compares the square-rooted values -- lies in group g*: 32 direct-form evaluations.  Otherwise the point is
 // AMBIGUOUS (about 0.6 % of the points at N = M = 2048 on the unit sphere): with the runner-up's group and the
 // third-smallest group minimum known (TOP3, large clouds) it is refined on two groups when the third is out of reach,
-// else its index goes to a list and the tail kernel scans the whole candidate cloud.  Either way the outputs are
-// independent of how the filter rounded.
+// else its index goes to a per-CTA list and, once the segment's queries are refined, the CTA's warps scan the whole
+// candidate cloud for it (one warp per point).  Either way the outputs are independent of how the filter rounded.
 //
 // Tie rule: torch.min runs on the sqrt-ed matrix, and sqrtf maps up to three adjacent fp32 values onto one, so
 // candidates whose squared distances differ in the last bits tie there and the LOWEST INDEX wins.  The refinement finds
@@ -45,24 +45,34 @@
 //               (best, second, third group minimum; best / second group) per query block live in shared memory; at the
 //               end of a segment the four groups' partial states of a query are merged and the merging thread refines it.
 //   warps 16-17 producers: convert 256 candidates per tile (and the segment's queries) to the split-tf32 rows, written
-//               straight into K-major SWIZZLE_128B operand tiles (rows are 64 bytes: two query blocks, and the two
-//               candidate tiles in flight, share one 128-byte-row tile; the descriptor's start address picks the half).
-//               Clouds of up to 2048 points are also kept raw in shared memory (double-buffered per segment), so the
-//               fused refinement reads its 32 candidates with LDS.128 instead of going to L2.
-//   warps 18-19 MMA issuers (one elected lane each): issuer p issues the halves p of every visit (accumulators p, p + 2).
-//               A tcgen05.mma blocks its issuer while the pipe is busy and every hand-off costs the issuer a barrier
-//               round trip (profiles/r1_umma_microbench.txt: pause + 85 cycles per hand-off); two issuers hide one
-//               another's round trips.
+//               straight into K-major SWIZZLE_128B operand tiles (rows are 64 bytes: two query blocks share one tile,
+//               the descriptor's start address picks the half).  Clouds of up to 2048 points are also kept raw in shared
+//               memory, so the fused refinement reads its 32 candidates with LDS.128 instead of going to L2.
+//   warp 18     MMA issuer (one elected lane), TMEM owner.
+// Work split: with at most as many (direction, cloud) units as CTAs every unit is cut into equal chunks, one per CTA, so
+// a CTA runs ONE segment (its fixed costs -- operand conversion, pipeline fill, merge, refinement -- are paid once);
+// otherwise the task list is split evenly and contiguously.
+// Means and loss: after a segment's queries are refined the CTA sums their distances per query block in a fixed order,
+// publishes the partial sums and counts the block as done; whoever completes a (direction, cloud) unit reduces its
+// partials to the mean, and whoever completes the last unit reduces the 2B means to the loss -- all in fixed orders, so
+// the results are bit-reproducible.  The counters start and end all-ones (the workspace invariant).
 #include "common.cuh"
 #include "tcgen05.cuh"
 #include <math.h>
 
 namespace rlg {
 
+// experiment knob (tools/ A-B builds only; the default is the product configuration): 1 or 2 MMA issuer warps.  Measured
+// at B=32, N=M=2048: no difference (28.6 vs 28.7 us for the filter sweep); packing both candidate tiles into one
+// 128-byte-row tile was measured too and costs 2-2.7 us (operand fetches and producer stores collide), so it is gone.
+#ifndef RLG_TS_ISSUERS
+#define RLG_TS_ISSUERS 1
+#endif
 constexpr int kTQ = 128;                       // queries per block (UMMA M)
 constexpr int kTC = 256;                       // candidates per tile (two UMMA N = 128 halves)
 constexpr int kQmax = 8;                       // query blocks that share one pass over the candidate tiles
-constexpr int kEpWarps = 16, kPrWarps = 2, kMmaWarps = 2;
+constexpr int kEpWarps = 16, kPrWarps = 2, kMmaWarps = RLG_TS_ISSUERS;
+constexpr int kEpThreads = kEpWarps * 32;
 constexpr int kMmaWarp0 = kEpWarps + kPrWarps;
 constexpr int kThreads = (kEpWarps + kPrWarps + kMmaWarps) * 32;
 constexpr int kPrThreads = kPrWarps * 32;
@@ -70,23 +80,25 @@ constexpr int kARows = kTQ / kPrThreads, kBRows = kTC / kPrThreads;            /
 constexpr uint32_t kABytes = kTQ * 128, kBBytes = kTC * 128;
 // A rows carry K = 16 tf32 = 64 bytes, half of a SWIZZLE_128B row: two query blocks share one 16 KB tile (block q sits in
 // 16-byte chunks 4*(q&1) .. 4*(q&1)+3 of tile q>>1; the descriptor's start address selects the half)
-constexpr uint32_t kOffB = (kQmax / 2) * kABytes;                             // one 32 KB tile holds BOTH candidate tiles in flight
+constexpr uint32_t kOffB = (kQmax / 2) * kABytes;                             // two candidate tiles follow the A tiles
 constexpr int kSlots = 4;                                                     // partial states per query: one per epilogue group
 // raw candidate copy: a 32-candidate group takes 96 floats; a stride of 100 floats (25 x 16 bytes, odd) spreads the
 // groups over the shared-memory banks -- with 96 every thread's LDS.128 would start in the same bank quad (8-way conflict)
 constexpr int kRawStride = 100;
-constexpr uint32_t kOffState = kOffB + kBBytes;                               // [slot][kQmax][kStW][128]
+constexpr uint32_t kOffState = kOffB + 2 * kBBytes;                           // [slot][kQmax][kStW][128]
 // state words per (slot, query block, row): best, second, best group [, third, second group]
 constexpr int kWBest = 0, kWSecond = 1, kWBgrp = 2, kWThird = 3, kWSgrp = 4;
 template <bool TOP3> struct SweepCfg {
     static constexpr int kStW = TOP3 ? 5 : 3;
     static constexpr uint32_t kStateBytes = (uint32_t)kSlots * kQmax * kTQ * kStW * 4u;
-    // raw copies of the candidate cloud for the fused refinement (clouds of up to kRawMax points; two segments in flight).
-    // With TOP3 (clouds beyond 4096 points) there is nothing to stage: the refinement reads the candidates from L2.
+    // raw copy of the segment's candidate cloud for the fused refinement (clouds of up to kRawMax points).  With TOP3
+    // (clouds beyond 4096 points) there is nothing to stage: the refinement reads its candidates from L2.
     static constexpr int kRawMax = TOP3 ? 0 : 2048;
     static constexpr uint32_t kOffRaw = kOffState + kStateBytes;
     static constexpr uint32_t kRawBytes = (uint32_t)(kRawMax / kGroup) * kRawStride * 4u;
-    static constexpr uint32_t kOffBar = kOffRaw + 2 * kRawBytes;
+    static constexpr uint32_t kOffDist = kOffRaw + kRawBytes;                 // float [kQmax*128]: the segment's distances
+    static constexpr uint32_t kOffAmb = kOffDist + kQmax * kTQ * 4u;          // u16 [kQmax*128]: the segment's ambiguous queries
+    static constexpr uint32_t kOffBar = kOffAmb + kQmax * kTQ * 2u;
     static constexpr uint32_t kSmem = kOffBar + 256 + 1024;                   // + barriers + alignment slack
 };
 constexpr float kBig = 1.0e30f;
@@ -182,8 +194,12 @@ struct SweepOut {
     float *d1, *d2;                 // (B,N), (B,M)
     int32_t *i1, *i2;
     float *z1, *z2;                 // optional (B,N,3)/(B,M,3) gradient buffers to zero-fill
-    unsigned *amb_cnt;              // (2,B): ambiguous points per (direction, cloud) minus one (all-ones = none)
-    unsigned *amb_list;             // (B*N + B*M): their query indices
+    float *mean1, *mean2, *loss;    // (B), (B), scalar; mean1/mean2 nullable as a pair, loss nullable
+    float w1, w2;                   // loss = sum_b w1 * mean1[b] + w2 * mean2[b]
+    double *partial;                // (2B, pq): sums of the distances per 128-query block
+    unsigned *unit_cnt;             // (2B): finished query blocks per (direction, cloud), all-ones = none
+    unsigned *global_cnt;           // (1):  finished units, all-ones = none
+    int pq;                         // query blocks per unit in `partial` (the longer direction's count)
     // diagnostic (RLG_CHAMFER_FILTER_ONLY): the merged filter results per query instead of the refinement
     u64 *key1, *key2;               // (B,N), (B,M): smallest group minimum << 32 | its group
     unsigned *sec1, *sec2;          // (B,N), (B,M): second-smallest group minimum (+inf: none)
@@ -196,8 +212,8 @@ struct Seg { int dir, b, qb0, Q, nq, nc, n_ct, next; };
 template <bool TOP3>
 __device__ __forceinline__ void refine_query(const float *__restrict__ qc, const float *__restrict__ cc, const float *raw,
                                              int nc, int i, u64 k1, u64 k2, float t3, float *__restrict__ dout,
-                                             int32_t *__restrict__ iout, float *__restrict__ zero,
-                                             unsigned *__restrict__ cnt, unsigned *__restrict__ list) {
+                                             int32_t *__restrict__ iout, float *__restrict__ zero, int local,
+                                             float *s_dist, unsigned short *s_amb, unsigned *s_namb) {
     const float qx = __ldg(qc + 3 * (size_t)i), qy = __ldg(qc + 3 * (size_t)i + 1), qz = __ldg(qc + 3 * (size_t)i + 2);
     if (zero != nullptr) { zero[3 * (size_t)i] = 0.0f; zero[3 * (size_t)i + 1] = 0.0f; zero[3 * (size_t)i + 2] = 0.0f; }
     const float val = __uint_as_float((unsigned)(k1 >> 32));
@@ -205,7 +221,7 @@ __device__ __forceinline__ void refine_query(const float *__restrict__ qc, const
     const bool has2 = k2 != kKeyInit;                                   // a single candidate group: nothing to confuse
     const float sv = has2 ? __uint_as_float((unsigned)(k2 >> 32)) : INFINITY;
     const int sgrp = (int)(unsigned)(k2 & 0xffffffffu);
-    // the margin test of the header; any NaN (non-finite input) makes a comparison false -> ambiguous -> tail kernel
+    // the margin test of the header; any NaN (non-finite input) makes a comparison false -> ambiguous -> full scan
     const float a2 = nrm2(qx, qy, qz), a = sqrtf(a2);
     auto sigma = [&](float tt) {
         const float tp = fmaf(fmaxf(tt, 0.0f), 1.0001f, 256.0f * kU * a2);
@@ -232,11 +248,10 @@ __device__ __forceinline__ void refine_query(const float *__restrict__ qc, const
             eval(sgrp);
             m = fminf(m, min32(t));
         }
-        amb = !(m < INFINITY);                                          // non-finite input: the tail mirrors torch.min
+        amb = !(m < INFINITY);                                          // non-finite input: the full scan mirrors torch.min
     }
     if (amb) {
-        const unsigned pos = atomicAdd(cnt, 1u) + 1u;                   // the counter starts at all-ones
-        list[pos] = (unsigned)i;
+        s_amb[atomicAdd(s_namb, 1u)] = (unsigned short)local;
         return;
     }
     const float s = __fsqrt_rn(m);
@@ -251,6 +266,55 @@ __device__ __forceinline__ void refine_query(const float *__restrict__ qc, const
     if (k < 32) bj = min(bj, grp * kGroup + k);
     dout[i] = s;
     iout[i] = min(bj, nc - 1);
+    s_dist[local] = s;
+}
+
+// Full exact scan of the candidate cloud for one ambiguous query by one warp, mirroring torch.min on the sqrt-ed row:
+// the first NaN wins, otherwise the lowest index among the candidates that share the smallest sqrtf.  `at(p, x, y, z)`
+// fetches candidate position p (positions past the end of the cloud repeat the last point).
+template <typename At>
+__device__ __forceinline__ void scan_query(At at, int npos, int nc, int lane, float qx, float qy, float qz, float &dist, int &bj) {
+    float lm = INFINITY;
+    int nanj = 0x7fffffff;
+    int j = lane;
+    for (; j + 96 < npos; j += 128) {                                   // four candidates in flight per lane
+        float t[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { float x, y, z; at(j + 32 * e, x, y, z); t[e] = sqdist(qx, qy, qz, x, y, z); }
+#pragma unroll
+        for (int e = 3; e >= 0; --e) if (t[e] != t[e]) nanj = min(nanj, j + 32 * e);
+        lm = fminf(fminf(lm, t[0]), fminf(t[1], fminf(t[2], t[3])));
+    }
+    for (; j < npos; j += 32) {
+        float x, y, z; at(j, x, y, z);
+        const float t = sqdist(qx, qy, qz, x, y, z);
+        if (t != t) nanj = min(nanj, j);
+        lm = fminf(lm, t);
+    }
+    nanj = __reduce_min_sync(0xffffffffu, nanj);
+    const float m = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(lm)));   // t >= 0: orders as unsigned
+    if (nanj != 0x7fffffff) {
+        dist = __uint_as_float(0x7fc00000u);
+        bj = min(nanj, nc - 1);
+        return;
+    }
+    dist = __fsqrt_rn(m);
+    const float h = m < INFINITY ? sqrt_window_top(m, dist) : m;
+    int fj = 0x7fffffff;
+    j = lane;
+    for (; j + 96 < npos; j += 128) {
+        float t[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { float x, y, z; at(j + 32 * e, x, y, z); t[e] = sqdist(qx, qy, qz, x, y, z); }
+#pragma unroll
+        for (int e = 3; e >= 0; --e) if (t[e] <= h) fj = min(fj, j + 32 * e);
+    }
+    for (; j < npos; j += 32) {
+        float x, y, z; at(j, x, y, z);
+        if (sqdist(qx, qy, qz, x, y, z) <= h) fj = min(fj, j);
+    }
+    bj = __reduce_min_sync(0xffffffffu, fj);
+    bj = bj == 0x7fffffff ? 0 : min(bj, nc - 1);
 }
 
 // TOP3: also track the runner-up's group and the third-smallest group minimum (5 more issue slots per 32 candidates;
@@ -258,10 +322,11 @@ __device__ __forceinline__ void refine_query(const float *__restrict__ qc, const
 template <bool TOP3>
 __global__ void __launch_bounds__(kThreads, 1)
 chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ pc2, int B, int N, int M, int n_tasks,
-                       int qb1, int qb2, SweepOut o, int refine) {
+                       int qb1, int qb2, int split, SweepOut o, int refine) {
     using Cfg = SweepCfg<TOP3>;
     constexpr int kStW = Cfg::kStW;
     extern __shared__ unsigned char ts_smem_raw[];
+    __shared__ unsigned s_namb;                                         // ambiguous queries of the current segment
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t pad = (1024u - (smem_u32(ts_smem_raw) & 1023u)) & 1023u;
     unsigned char *smem = ts_smem_raw + pad;
@@ -270,17 +335,16 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
     const uint32_t bar_afull = bars, bar_aempty = bars + 8 * kQmax;                     // [kQmax], [1]
     const uint32_t bar_bfull = bar_aempty + 8, bar_bempty = bar_bfull + 16;             // [2] each
     const uint32_t bar_accfull = bar_bempty + 16, bar_accempty = bar_accfull + 32;      // [4] each
-    const uint32_t bar_rawfull = bar_accempty + 32, bar_rawempty = bar_rawfull + 16;    // [2] each
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Cfg::kOffBar + 8 * (kQmax + 17));
+    const uint32_t bar_rawfull = bar_accempty + 32, bar_rawempty = bar_rawfull + 8;     // [1] each
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Cfg::kOffBar + 8 * (kQmax + 15));
 
     if (tid == 0) {
         for (int q = 0; q < kQmax; ++q) mbar_init(bar_afull + 8 * q, kPrThreads);
         mbar_init(bar_aempty, kMmaWarps);
-        for (int k = 0; k < 2; ++k) {
-            mbar_init(bar_bfull + 8 * k, kPrThreads); mbar_init(bar_bempty + 8 * k, kMmaWarps);
-            mbar_init(bar_rawfull + 8 * k, kPrThreads); mbar_init(bar_rawempty + 8 * k, kEpWarps * 32);
-        }
+        for (int k = 0; k < 2; ++k) { mbar_init(bar_bfull + 8 * k, kPrThreads); mbar_init(bar_bempty + 8 * k, kMmaWarps); }
         for (int k = 0; k < 4; ++k) { mbar_init(bar_accfull + 8 * k, 1); mbar_init(bar_accempty + 8 * k, (kEpWarps / 4) * 32); }
+        mbar_init(bar_rawfull, kPrThreads);
+        mbar_init(bar_rawempty, kEpThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp0) {
@@ -292,16 +356,28 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    // Wait first, THEN let the next kernel (the tail) start: its prologue reads the clouds, so it may only run once this
-    // kernel knows they are complete.  All CTAs of this grid are resident at once, so the tail is released early anyway.
-    pdl_wait();
     pdl_launch_dependents();
+    pdl_wait();                                   // clouds and workspace may come from the kernels right before this one
 
-    // tasks (direction, cloud, 128-query block) in direction-major order, split evenly and contiguously over the CTAs
-    const int G = (int)gridDim.x, cta = (int)blockIdx.x;
-    const int per = n_tasks / G, rem = n_tasks - per * G;
-    const int t_begin = cta * per + min(cta, rem);
-    const int t_end = t_begin + per + (cta < rem ? 1 : 0);
+    // Tasks (direction, cloud, 128-query block) in direction-major order; a CTA owns a contiguous range and walks it in
+    // SEGMENTS of up to kQmax query blocks of one (direction, cloud): they share every converted candidate tile.
+    //   split 0: even contiguous split of the task list (a CTA may straddle two clouds: two segments)
+    //   split 1: at most as many (direction, cloud) units as CTAs: every unit is cut into equal chunks, one per CTA
+    const int G = (int)gridDim.x, cta = (int)blockIdx.x, U = 2 * B;
+    int t_begin, t_end;
+    if (split == 1) {
+        const int c_lo = G / U, extra = G - c_lo * U;                // the first `extra` units get one chunk more
+        int u, ci, c;
+        if (cta < extra * (c_lo + 1)) { u = cta / (c_lo + 1); ci = cta - u * (c_lo + 1); c = c_lo + 1; }
+        else { const int r = cta - extra * (c_lo + 1); u = extra + r / c_lo; ci = r - (u - extra) * c_lo; c = c_lo; }
+        const int T = u < B ? qb1 : qb2, s0 = u < B ? u * qb1 : B * qb1 + (u - B) * qb2;
+        t_begin = s0 + (int)((long long)ci * T / c);
+        t_end = s0 + (int)((long long)(ci + 1) * T / c);
+    } else {
+        const int per = n_tasks / G, rem = n_tasks - per * G;
+        t_begin = cta * per + min(cta, rem);
+        t_end = t_begin + per + (cta < rem ? 1 : 0);
+    }
     auto seg_at = [&](int task) {
         Seg sg;
         const int n0 = B * qb1;
@@ -319,14 +395,14 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
     auto stages_raw = [&](const Seg &sg) { return Cfg::kRawMax > 0 && refine && sg.nc <= Cfg::kRawMax; };
 
     if (warp >= kMmaWarp0) {
-        // =========================== MMA issuers ===========================
+        // =========================== MMA issuer(s) ===========================
         // half-visits in issue order: (tile k, query block q, half hf), running index gt = 2 * visit + hf; accumulator
-        // gt % 4; issuer p issues the halves hf == p (its pipeline group's accumulators p and p + 2)
+        // gt % 4 == epilogue group gt % 4 (with two issuers, issuer p issues the halves hf == p)
         const uint32_t me = (uint32_t)(warp - kMmaWarp0);
         const bool leader = elect_one();
         const uint32_t idesc = umma_idesc_tf32(kTQ, kTC / 2);
         const uint64_t ad0 = umma_desc(sbase), bd0 = umma_desc(sbase + kOffB);
-        const uint64_t a_inc = (uint64_t)(kABytes >> 4), b_half = (uint64_t)(kBBytes >> 5);   // 16-byte units
+        const uint64_t a_inc = (uint64_t)(kABytes >> 4), b_inc = (uint64_t)(kBBytes >> 4);   // 16-byte units
         uint32_t vis = 0, bt = 0, sn = 0;
         for (int task = t_begin; task < t_end;) {
             const Seg sg = seg_at(task);
@@ -334,21 +410,25 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
             for (int k = 0; k < sg.n_ct; ++k, ++bt) {
                 const uint32_t sb = bt & 1u;
                 mbar_wait_spin(bar_bfull + 8 * sb, (bt >> 1) & 1u);
-                // candidate tile sb lives in 16-byte chunks 4*sb .. 4*sb+3 of every row; this issuer's half = rows me*128 ..
-                const uint64_t bh = bd0 + (uint64_t)(sb * 4u) + (uint64_t)me * b_half;
+                const uint64_t bt0 = bd0 + (uint64_t)sb * b_inc;
                 for (int q = 0; q < sg.Q; ++q, ++vis) {
                     if (k == 0) mbar_wait_spin(bar_afull + 8 * q, sn & 1u);
-                    const uint32_t gt = 2u * vis + me, ab = gt & 3u;
-                    mbar_wait_spin(bar_accempty + 8 * ab, ((gt >> 2) & 1u) ^ 1u);
-                    tc_fence_after();
-                    if (leader) {
-                        const uint64_t ad = ad0 + (uint64_t)(q >> 1) * a_inc + (uint64_t)((q & 1) * 4);
-                        const uint32_t d = tmem + ab * (uint32_t)(kTC / 2);
-                        tc_mma_tf32(d, ad, bh, idesc, 0u);                  // K columns 0..7  (32 bytes)
-                        tc_mma_tf32(d, ad + 2, bh + 2, idesc, 1u);          // K columns 8..15
-                        tc_commit(bar_accfull + 8 * ab);
+#pragma unroll
+                    for (uint32_t hf = 0; hf < 2; ++hf) {
+                        if (kMmaWarps == 2 && hf != me) continue;
+                        const uint32_t gt = 2u * vis + hf, ab = gt & 3u;
+                        mbar_wait_spin(bar_accempty + 8 * ab, ((gt >> 2) & 1u) ^ 1u);
+                        tc_fence_after();
+                        if (leader) {
+                            const uint64_t ad = ad0 + (uint64_t)(q >> 1) * a_inc + (uint64_t)((q & 1) * 4);
+                            const uint64_t bh = bt0 + (uint64_t)hf * (b_inc >> 1);
+                            const uint32_t d = tmem + ab * (uint32_t)(kTC / 2);
+                            tc_mma_tf32(d, ad, bh, idesc, 0u);                  // K columns 0..7  (32 bytes)
+                            tc_mma_tf32(d, ad + 2, bh + 2, idesc, 1u);          // K columns 8..15
+                            tc_commit(bar_accfull + 8 * ab);
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
                 if (leader) tc_commit(bar_bempty + 8 * sb);
                 __syncwarp();
@@ -361,6 +441,7 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
         // =========================== producers ===========================
         const int ptid = tid - kEpWarps * 32;                           // 0..kPrThreads-1
         unsigned char *const tileA0 = smem, *const tileB0 = smem + kOffB;
+        float *const raw = reinterpret_cast<float *>(smem + Cfg::kOffRaw);
         auto load3 = [&](const float *src, float &o0, float &o1, float &o2) {
             // volatile: the loads stay where they are written (ahead of the barrier wait that hides their latency)
             asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(o0) : "l"(src));
@@ -374,7 +455,6 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
             const float *qc = (sg.dir ? pc2 : pc1) + (size_t)sg.b * sg.nq * 3;
             const float *cc = (sg.dir ? pc1 : pc2) + (size_t)sg.b * sg.nc * 3;
             const bool keep_raw = stages_raw(sg);
-            float *raw = reinterpret_cast<float *>(smem + Cfg::kOffRaw + (sn & 1u) * Cfg::kRawBytes);
             // 128 queries of block qb0+q -> A tile q (rows past the end are all-zero)
             auto load_a = [&](int q, float (&x)[kARows][3]) {
 #pragma unroll
@@ -433,7 +513,7 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
                     e[9] = 1.0f; e[10] = 1.0f; e[11] = 1.0f;
                     split3(valid ? nrm2(y0, y1, y2) : kBig, e[12], e[13], e[14]);
                     e[15] = 0.0f;
-                    store_row(tileB0, r, e, 4u * sb);
+                    store_row(tileB0 + sb * kBBytes, r, e, 0u);
                 }
                 fence_async_proxy();
                 mbar_arrive(bar_bfull + 8 * sb);
@@ -443,8 +523,8 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
             float ax[2][kARows][3];
             load_a(0, ax[0]);
             if (sg.Q > 1) load_a(1, ax[1]);
-            // the refinement of segment sn-2 must be done with this raw buffer
-            if (Cfg::kRawMax > 0) mbar_wait_spin(bar_rawempty + 8 * (sn & 1u), ((sn >> 1) & 1u) ^ 1u);
+            // the previous segment's refinement must be done with the raw copy (one buffer: a CTA rarely has two segments)
+            if (Cfg::kRawMax > 0) mbar_wait_spin(bar_rawempty, (sn & 1u) ^ 1u);
             produce_b(0);
             mbar_wait_spin(bar_aempty, (sn & 1u) ^ 1u);                 // the previous segment's MMAs are done with the A tiles
 #pragma unroll
@@ -457,7 +537,7 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
                 }
             }
             for (int k = 1; k < sg.n_ct; ++k) produce_b(k);
-            if (Cfg::kRawMax > 0) mbar_arrive(bar_rawfull + 8 * (sn & 1u));   // the segment's raw copy is complete
+            if (Cfg::kRawMax > 0) mbar_arrive(bar_rawfull);             // the segment's raw copy is complete
             ++sn;
         }
     } else {
@@ -467,8 +547,11 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
         const uint32_t lane_base = ((uint32_t)(warp & 3) * 32u) << 16;
         const uint32_t taddr = tmem + lane_base + (uint32_t)slot * (uint32_t)(kTC / 2);
         const uint32_t my_full = bar_accfull + 8 * slot, my_empty = bar_accempty + 8 * slot;
-        const int hf = slot & 1;                                        // this group's half of a visit (issued by issuer hf)
+        const int hf = slot & 1;                                        // this group's half of a visit
         float *st = reinterpret_cast<float *>(smem + kOffState) + (slot * kQmax) * kTQ * kStW + row;
+        float *const s_dist = reinterpret_cast<float *>(smem + Cfg::kOffDist);
+        unsigned short *const s_amb = reinterpret_cast<unsigned short *>(smem + Cfg::kOffAmb);
+        const float *const raw_base = reinterpret_cast<const float *>(smem + Cfg::kOffRaw);
         constexpr int kStQ = kTQ * kStW;                                // words per query block of one slot
         uint32_t vis0 = 0, sn = 0;                                      // visits issued before this segment, segment index
         for (int task = t_begin; task < t_end;) {
@@ -513,7 +596,7 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
                 mbar_wait_spin(my_full, use & 1u);
                 tc_fence_after();
                 // 4 chunks of 32 columns, two register sets: the load of chunk c+1 is in flight while c is reduced; the
-                // accumulator goes back to its issuer as soon as its last load has landed
+                // accumulator goes back to the issuer as soon as its last load has landed
                 float va[32], vb[32];
                 int G0 = k * (kTC / 32) + hf * 4;
                 asm volatile("mov.s32 %0, %0;" : "+r"(G0));             // pinned: otherwise recomputed under every predicate
@@ -540,7 +623,7 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
             vis0 += n_vis;
             // ---- merge the four partial states per query; the merging thread refines the query (every candidate of
             // these queries was seen by this CTA in this segment).  Group s merges query blocks s and s + 4.
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpWarps * 32) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpThreads) : "memory");
             const float *all_st = reinterpret_cast<const float *>(smem + kOffState) + row;
             u64 mk1[2], mk2[2];
             float mt3[2];
@@ -576,33 +659,15 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
                 }
                 mk1[r] = k1; mk2[r] = k2; mt3[r] = t3;
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpWarps * 32) : "memory");   // the state may be re-initialised
-            const float *raw = nullptr;
-            if (Cfg::kRawMax > 0) {
-                mbar_wait_spin(bar_rawfull + 8 * (sn & 1u), (sn >> 1) & 1u);   // the producers' raw copy of this segment's candidates
-                if (stages_raw(sg)) raw = reinterpret_cast<const float *>(smem + Cfg::kOffRaw + (sn & 1u) * Cfg::kRawBytes);
-            }
-            if (refine) {
-                const float *qc = (sg.dir ? pc2 : pc1) + (size_t)sg.b * sg.nq * 3;
-                const float *cc = (sg.dir ? pc1 : pc2) + (size_t)sg.b * sg.nc * 3;
-                const size_t qoff = (size_t)sg.b * sg.nq;
-                float *dout = (sg.dir ? o.d2 : o.d1) + qoff;
-                int32_t *iout = (sg.dir ? o.i2 : o.i1) + qoff;
-                float *zb = sg.dir ? o.z2 : o.z1;
-                float *zero = zb ? zb + 3 * qoff : nullptr;
-                unsigned *cnt = o.amb_cnt + (sg.dir ? B : 0) + sg.b;
-                unsigned *list = o.amb_list + (sg.dir ? (size_t)B * N : 0) + qoff;
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const int qq = slot + 4 * r;
-                    const int i = (sg.qb0 + qq) * kTQ + row;
-                    if (qq < sg.Q && i < sg.nq)
-                        refine_query<TOP3>(qc, cc, raw, sg.nc, i, mk1[r], mk2[r], mt3[r], dout, iout, zero, cnt, list);
-                }
-            } else {
+            if (tid == 0) s_namb = 0;
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpThreads) : "memory");   // the state may be re-initialised; s_namb is zero
+            const float *qc = (sg.dir ? pc2 : pc1) + (size_t)sg.b * sg.nq * 3;
+            const float *cc = (sg.dir ? pc1 : pc2) + (size_t)sg.b * sg.nc * 3;
+            const size_t qoff = (size_t)sg.b * sg.nq;
+            if (!refine) {
                 // diagnostic: publish what the filter found (tests measure its error against float64 with this)
-                u64 *keys = (sg.dir ? o.key2 : o.key1) + (size_t)sg.b * sg.nq;
-                unsigned *secs = (sg.dir ? o.sec2 : o.sec1) + (size_t)sg.b * sg.nq;
+                u64 *keys = (sg.dir ? o.key2 : o.key1) + qoff;
+                unsigned *secs = (sg.dir ? o.sec2 : o.sec1) + qoff;
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
                     const int qq = slot + 4 * r;
@@ -612,8 +677,101 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
                         secs[i] = mk2[r] != kKeyInit ? (unsigned)(mk2[r] >> 32) : 0x7f800000u;
                     }
                 }
+                if (Cfg::kRawMax > 0) { mbar_wait_spin(bar_rawfull, sn & 1u); mbar_arrive(bar_rawempty); }
+                ++sn;
+                continue;
             }
-            if (Cfg::kRawMax > 0) mbar_arrive(bar_rawempty + 8 * (sn & 1u));   // done with this segment's raw copy
+            const float *raw = nullptr;
+            if (Cfg::kRawMax > 0) {
+                mbar_wait_spin(bar_rawfull, sn & 1u);                   // the producers' raw copy of this segment's candidates
+                if (stages_raw(sg)) raw = raw_base;
+            }
+            float *dout = (sg.dir ? o.d2 : o.d1) + qoff;
+            int32_t *iout = (sg.dir ? o.i2 : o.i1) + qoff;
+            float *zb = sg.dir ? o.z2 : o.z1;
+            float *zero = zb ? zb + 3 * qoff : nullptr;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int qq = slot + 4 * r;
+                const int i = (sg.qb0 + qq) * kTQ + row;
+                if (qq < sg.Q) {
+                    if (i < sg.nq) refine_query<TOP3>(qc, cc, raw, sg.nc, i, mk1[r], mk2[r], mt3[r], dout, iout, zero,
+                                                      qq * kTQ + row, s_dist, s_amb, &s_namb);
+                    else s_dist[qq * kTQ + row] = 0.0f;                 // rows past the end of the cloud add nothing
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpThreads) : "memory");   // the ambiguous list is complete
+            // ---- ambiguous queries: one warp per query scans the whole candidate cloud exactly
+            {
+                const int n_amb = (int)s_namb;
+                const int npos = raw != nullptr ? ((sg.nc + kGroup - 1) / kGroup) * kGroup : sg.nc;
+                for (int a = warp; a < n_amb; a += kEpWarps) {
+                    const int local = (int)s_amb[a];
+                    const int i = (sg.qb0 + (local >> 7)) * kTQ + (local & 127);
+                    const float qx = __ldg(qc + 3 * (size_t)i), qy = __ldg(qc + 3 * (size_t)i + 1), qz = __ldg(qc + 3 * (size_t)i + 2);
+                    float dist;
+                    int bj;
+                    if (raw != nullptr) {
+                        scan_query([&](int p, float &x, float &y, float &z) {
+                            const float *c = raw + (p >> 5) * kRawStride + 3 * (p & 31);
+                            x = c[0]; y = c[1]; z = c[2];
+                        }, npos, sg.nc, lane, qx, qy, qz, dist, bj);
+                    } else {
+                        scan_query([&](int p, float &x, float &y, float &z) {
+                            const float *c = cc + 3 * (size_t)p;
+                            x = __ldg(c); y = __ldg(c + 1); z = __ldg(c + 2);
+                        }, npos, sg.nc, lane, qx, qy, qz, dist, bj);
+                    }
+                    if (lane == 0) { dout[i] = dist; iout[i] = bj; s_dist[local] = dist; }
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpThreads) : "memory");   // every distance of the segment is in s_dist
+            if (Cfg::kRawMax > 0) mbar_arrive(bar_rawempty);                // done with this segment's raw copy
+            // ---- means and loss: warp w sums query block w of the segment; whoever completes the unit reduces its
+            // partial sums to the mean; whoever completes the last unit reduces the means to the loss (fixed orders)
+            if (o.mean1 != nullptr && warp < sg.Q) {
+                const float *dv = s_dist + warp * kTQ;
+                double acc = ((double)dv[lane] + (double)dv[lane + 32]) + ((double)dv[lane + 64] + (double)dv[lane + 96]);
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, sft);
+                const int unit = (sg.dir ? B : 0) + sg.b;
+                const int nblk = sg.dir ? qb2 : qb1;
+                double *parts = o.partial + (size_t)unit * o.pq;
+                unsigned last = 0;
+                if (lane == 0) {
+                    parts[sg.qb0 + warp] = acc;
+                    __threadfence();
+                    // counters start at 0xffffffff (the workspace's all-ones state): the k-th arrival reads k-2
+                    last = atomicAdd(o.unit_cnt + unit, 1u) == (unsigned)(nblk - 2);
+                }
+                last = __shfl_sync(0xffffffffu, last, 0);
+                if (last) {
+                    __threadfence();
+                    double tot = 0.0;
+                    for (int e = lane; e < nblk; e += 32) tot += __ldcg(parts + e);
+#pragma unroll
+                    for (int sft = 16; sft > 0; sft >>= 1) tot += __shfl_down_sync(0xffffffffu, tot, sft);
+                    unsigned last_unit = 0;
+                    if (lane == 0) {
+                        o.unit_cnt[unit] = 0xffffffffu;
+                        (sg.dir ? o.mean2 : o.mean1)[sg.b] = (float)(tot / (double)sg.nq);
+                        if (o.loss != nullptr) {
+                            __threadfence();
+                            last_unit = atomicAdd(o.global_cnt, 1u) == (unsigned)(2 * B - 2);
+                        }
+                    }
+                    last_unit = __shfl_sync(0xffffffffu, last_unit, 0);
+                    if (last_unit) {
+                        __threadfence();
+                        double ls = 0.0;
+                        for (int e = lane; e < B; e += 32)
+                            ls += (double)o.w1 * (double)__ldcg(o.mean1 + e) + (double)o.w2 * (double)__ldcg(o.mean2 + e);
+#pragma unroll
+                        for (int sft = 16; sft > 0; sft >>= 1) ls += __shfl_down_sync(0xffffffffu, ls, sft);
+                        if (lane == 0) { *o.global_cnt = 0xffffffffu; *o.loss = (float)ls; }
+                    }
+                }
+            }
             ++sn;
         }
     }
@@ -625,179 +783,19 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
     }
 }
 
-// ---- tail kernel: the ambiguous points, the per-pair means, the batch loss ---------------------------------------
-constexpr int kTailThreads = 256, kTailWarps = kTailThreads / 32;
-
-struct TailWs {
-    unsigned *global_counter;   // 1
-    unsigned *cloud_counter;    // B
-};
-
-// grid (chunks, B, 2).  A warp scans the whole candidate cloud for one ambiguous point, mirroring torch.min on the
-// sqrt-ed row: the first NaN wins, otherwise the lowest index among the candidates that share the smallest sqrtf.
-// STAGE: the candidate cloud of the CTA's (cloud, direction) is first copied to shared memory (one coalesced pass
-// instead of a latency-bound walk through L2 per point).
-template <bool STAGE>
-__global__ void __launch_bounds__(kTailThreads) chamfer_tail_kernel(
-    const float *__restrict__ pc1, const float *__restrict__ pc2, int N, int M, int C1, int C2, SweepOut o, TailWs tw,
-    float *__restrict__ mean1, float *__restrict__ mean2, float *__restrict__ loss, float loss_w1, float loss_w2) {
-    extern __shared__ __align__(16) float s_cand[];
-    __shared__ double red[kTailWarps];
-    const int chunk = blockIdx.x, b = blockIdx.y, dir = blockIdx.z, B = gridDim.y;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    pdl_launch_dependents();
-    if (chunk >= (dir ? C2 : C1)) return;
-    const int nq = dir ? M : N, nc = dir ? N : M, C = dir ? C2 : C1;
-    const float *qc = (dir ? pc2 : pc1) + (size_t)b * nq * 3;
-    const float *cc = (dir ? pc1 : pc2) + (size_t)b * nc * 3;
-    const float *c = cc;
-    if (STAGE) {
-        // the clouds were complete before the pair sweep released this kernel (it waits before it triggers)
-        const int nf = nc * 3;
-        if ((reinterpret_cast<uintptr_t>(cc) & 15u) == 0) {
-            const int n4 = nf >> 2;
-            const float4 *src4 = reinterpret_cast<const float4 *>(cc);
-            float4 *dst4 = reinterpret_cast<float4 *>(s_cand);
-            for (int e = tid; e < n4; e += kTailThreads) dst4[e] = __ldg(src4 + e);
-            for (int e = (n4 << 2) + tid; e < nf; e += kTailThreads) s_cand[e] = __ldg(cc + e);
-        } else {
-            for (int e = tid; e < nf; e += kTailThreads) s_cand[e] = __ldg(cc + e);
-        }
-        c = s_cand;
-        __syncthreads();
-    }
-    pdl_wait();                                         // everything below reads results of the pair sweep
-    float *dout = (dir ? o.d2 : o.d1) + (size_t)b * nq;
-    int32_t *iout = (dir ? o.i2 : o.i1) + (size_t)b * nq;
-    const unsigned n_amb = __ldcg(o.amb_cnt + (dir ? B : 0) + b) + 1u;
-    const unsigned *list = o.amb_list + (dir ? (size_t)B * N : 0) + (size_t)b * nq;
-    for (unsigned a = (unsigned)(chunk * kTailWarps + wid); a < n_amb; a += (unsigned)(C * kTailWarps)) {
-        const int i = (int)__ldcg(list + a);
-        const float qx = __ldg(qc + 3 * (size_t)i), qy = __ldg(qc + 3 * (size_t)i + 1), qz = __ldg(qc + 3 * (size_t)i + 2);
-        // pass 1: smallest squared distance, first NaN (four candidates in flight per lane)
-        float lm = INFINITY;
-        int nanj = 0x7fffffff;
-        int j = lane;
-        for (; j + 96 < nc; j += 128) {
-            float t[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) t[e] = sqdist(qx, qy, qz, c[3 * (j + 32 * e)], c[3 * (j + 32 * e) + 1], c[3 * (j + 32 * e) + 2]);
-#pragma unroll
-            for (int e = 3; e >= 0; --e) if (t[e] != t[e]) nanj = min(nanj, j + 32 * e);
-            lm = fminf(fminf(lm, t[0]), fminf(t[1], fminf(t[2], t[3])));
-        }
-        for (; j < nc; j += 32) {
-            const float t = sqdist(qx, qy, qz, c[3 * j], c[3 * j + 1], c[3 * j + 2]);
-            if (t != t) nanj = min(nanj, j);
-            lm = fminf(lm, t);
-        }
-        nanj = __reduce_min_sync(0xffffffffu, nanj);
-        const float m = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(lm)));   // t >= 0: orders as unsigned
-        float dist;
-        int bj;
-        if (nanj != 0x7fffffff) {
-            dist = __uint_as_float(0x7fc00000u);
-            bj = nanj;
-        } else {
-            dist = __fsqrt_rn(m);
-            const float h = m < INFINITY ? sqrt_window_top(m, dist) : m;
-            // pass 2: lowest index whose squared distance shares that square root
-            int fj = 0x7fffffff;
-            j = lane;
-            for (; j + 96 < nc; j += 128) {
-                float t[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) t[e] = sqdist(qx, qy, qz, c[3 * (j + 32 * e)], c[3 * (j + 32 * e) + 1], c[3 * (j + 32 * e) + 2]);
-#pragma unroll
-                for (int e = 3; e >= 0; --e) if (t[e] <= h) fj = min(fj, j + 32 * e);
-            }
-            for (; j < nc; j += 32)
-                if (sqdist(qx, qy, qz, c[3 * j], c[3 * j + 1], c[3 * j + 2]) <= h) fj = min(fj, j);
-            bj = __reduce_min_sync(0xffffffffu, fj);
-            if (bj == 0x7fffffff) bj = 0;
-        }
-        if (lane == 0) { dout[i] = dist; iout[i] = bj; }
-    }
-    // ---- the last CTA of this cloud (both directions) reduces the means in a fixed order ----
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        // counters start at 0xffffffff (the workspace's all-ones state): the k-th arrival reads k-2
-        s_last = atomicAdd(tw.cloud_counter + b, 1u) == (unsigned)(C1 + C2 - 2);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (tid == 0) {
-        tw.cloud_counter[b] = 0xffffffffu;
-        o.amb_cnt[b] = 0xffffffffu;
-        o.amb_cnt[B + b] = 0xffffffffu;
-    }
-    if (mean1 == nullptr) return;
-    double sums[2];
-#pragma unroll 1
-    for (int dd = 0; dd < 2; ++dd) {
-        const int n = dd ? M : N;
-        const float *dv = (dd ? o.d2 : o.d1) + (size_t)b * n;
-        double acc = 0.0;
-        for (int e = tid; e < n; e += kTailThreads) acc += (double)__ldcg(dv + e);
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, s);
-        __syncthreads();
-        if (lane == 0) red[wid] = acc;
-        __syncthreads();
-        double tot = 0.0;
-#pragma unroll
-        for (int w = 0; w < kTailWarps; ++w) tot += red[w];
-        sums[dd] = tot;
-    }
-    __shared__ int s_last_cloud;
-    if (tid == 0) {
-        mean1[b] = (float)(sums[0] / (double)N);
-        mean2[b] = (float)(sums[1] / (double)M);
-        s_last_cloud = 0;
-        if (loss != nullptr) {
-            __threadfence();
-            s_last_cloud = atomicAdd(tw.global_counter, 1u) == (unsigned)(B - 2);
-        }
-    }
-    __syncthreads();
-    if (!s_last_cloud) return;
-    // the last cloud's CTA: batch loss in a fixed order (thread-strided partial sums, lane tree, warps in order)
-    __threadfence();
-    double acc = 0.0;
-    for (int k = tid; k < B; k += kTailThreads)
-        acc += (double)loss_w1 * (double)__ldcg(mean1 + k) + (double)loss_w2 * (double)__ldcg(mean2 + k);
-#pragma unroll
-    for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, sft);
-    __syncthreads();
-    if (lane == 0) red[wid] = acc;
-    __syncthreads();
-    if (tid != 0) return;
-    double tot = 0.0;
-#pragma unroll
-    for (int w = 0; w < kTailWarps; ++w) tot += red[w];
-    *tw.global_counter = 0xffffffffu;
-    *loss = (float)tot;
+// workspace of the fused forward behind the shared key / second-value arrays: counters (all-ones invariant) + partial sums
+static size_t tcsweep_counter_bytes(int B) { return align_up(sizeof(unsigned) * (1 + 2 * (size_t)B), 256); }
+static int tcsweep_pq(int N, int M) { return ((N > M ? N : M) + kTQ - 1) / kTQ; }
+size_t tcsweep_ws_bytes(int B, int N, int M) {
+    return tcsweep_counter_bytes(B) + align_up(sizeof(double) * 2 * (size_t)B * tcsweep_pq(N, M), 256);
 }
 
-static int tail_chunks(int n) {
-    const int c = (n + 1023) / 1024;
-    return c < 1 ? 1 : (c > 32 ? 32 : c);
-}
-
-size_t tcsweep_counter_bytes(int B) { return align_up(sizeof(unsigned) * (1 + (size_t)B), 256); }
-
-// The fused forward: pair sweep + refinement, then (unless sweep_only) the tail kernel.
-//   w.nrm     (2,B) unsigned, all-ones on entry and on exit: ambiguous-point counters
-//   w.rowsg   (B*N + B*M) unsigned, no invariant: ambiguous-point lists
-//   tail_ws   tcsweep_counter_bytes(B), all-ones on entry and on exit
-// sweep_only: 1 = sweep + fused refinement without the tail (measurement aid; the workspace is left dirty),
-//             2 = the filter sweep alone, its per-query results published to w.rowkey/colkey/rowsec/colsec (diagnostic)
-int launch_tcsweep(const float *pc1, const float *pc2, int B, int N, int M, const FwdWs &w, void *tail_ws,
+// The fused forward (one launch).
+//   fin_ws    tcsweep_ws_bytes(B,N,M): [global counter | 2B unit counters] (all-ones on entry and on exit) | partial sums
+// filter_only: diagnostic -- the filter sweep alone, its per-query results published to w.rowkey/colkey/rowsec/colsec
+int launch_tcsweep(const float *pc1, const float *pc2, int B, int N, int M, const FwdWs &w, void *fin_ws,
                    float *d1, float *d2, int32_t *i1, int32_t *i2, float *mean1, float *mean2, float *loss, float w1,
-                   float w2, float *zero1, float *zero2, int sweep_only, bool force_top3, cudaStream_t st) {
+                   float w2, float *zero1, float *zero2, bool filter_only, bool force_top3, cudaStream_t st) {
     const int qb1 = (N + kTQ - 1) / kTQ, qb2 = (M + kTQ - 1) / kTQ;
     const long long n_tasks = (long long)B * (qb1 + qb2);
     if (n_tasks > 0x3fffffffLL) return fail(RLG_ERR_TOO_LARGE, "rlg_chamfer_fwd: too many query blocks");
@@ -805,8 +803,8 @@ int launch_tcsweep(const float *pc1, const float *pc2, int B, int N, int M, cons
         return fail(RLG_ERR_TOO_LARGE, "rlg_chamfer_fwd: too many tile visits for 32-bit counters");
     const int sms = sm_count();
     if (sms <= 0) return fail((int)cudaErrorNoDevice, "rlg_chamfer_fwd: no CUDA device");
-    // Ambiguous points (runner-up group within the margin) cost a scan of the whole candidate cloud in the tail kernel
-    // unless the sweep tracks three groups; their share grows with the point density.  Break-even is around 4096.
+    // Ambiguous points (runner-up group within the margin) cost a scan of the whole candidate cloud unless the sweep
+    // tracks three groups; their share grows with the point density.  Break-even is around 4096 candidates.
     const bool top3 = force_top3 || N > 4096 || M > 4096;
     // per launch (a host-side attribute write, no device work): the setting is per device and this library keeps no
     // per-device state of its own
@@ -815,37 +813,30 @@ int launch_tcsweep(const float *pc1, const float *pc2, int B, int N, int M, cons
                              : cudaFuncSetAttribute(chamfer_tcsweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<false>::kSmem);
         if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "chamfer_tcsweep_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
     }
-    // the ambiguous counters live where the FP32 sweep keeps its cloud norms (all-ones invariant), the lists where the
-    // first-generation tensor sweep kept its runner-up groups (no invariant)
-    SweepOut o{d1, d2, i1, i2, zero1, zero2, w.nrm, w.rowsg, w.rowkey, w.colkey, w.rowsec, w.colsec};
+    SweepOut o;
+    o.d1 = d1; o.d2 = d2; o.i1 = i1; o.i2 = i2; o.z1 = zero1; o.z2 = zero2;
+    o.mean1 = mean1; o.mean2 = mean2; o.loss = loss; o.w1 = w1; o.w2 = w2;
+    o.global_cnt = (unsigned *)fin_ws;
+    o.unit_cnt = o.global_cnt + 1;
+    o.partial = (double *)((char *)fin_ws + tcsweep_counter_bytes(B));
+    o.pq = tcsweep_pq(N, M);
+    o.key1 = w.rowkey; o.key2 = w.colkey; o.sec1 = w.rowsec; o.sec2 = w.colsec;
     const int grid = (int)(n_tasks < sms ? n_tasks : sms);
-    const int refine = sweep_only == 2 ? 0 : 1;
-    cudaError_t le = top3 ? launch_pdl(chamfer_tcsweep_kernel<true>, dim3((unsigned)grid), dim3(kThreads), (size_t)SweepCfg<true>::kSmem, st, pc1, pc2,
-                                       B, N, M, (int)n_tasks, qb1, qb2, o, refine)
-                          : launch_pdl(chamfer_tcsweep_kernel<false>, dim3((unsigned)grid), dim3(kThreads), (size_t)SweepCfg<false>::kSmem, st, pc1, pc2,
-                                       B, N, M, (int)n_tasks, qb1, qb2, o, refine);
-    if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "chamfer_tcsweep_kernel: %s", cudaGetErrorString(le)); }
-    if (sweep_only) return check_launch("chamfer_tcsweep_kernel");
-    TailWs tw;
-    tw.global_counter = (unsigned *)tail_ws;
-    tw.cloud_counter = tw.global_counter + 1;
-    const int C1 = tail_chunks(N), C2 = tail_chunks(M);
-    dim3 tgrid((unsigned)(C1 > C2 ? C1 : C2), (unsigned)B, 2);
-    // the candidate cloud of a (cloud, direction) is staged in shared memory when it fits (<= 96 KB: 8192 points)
-    const size_t cand_bytes = align_up((size_t)(N > M ? N : M) * 12, 16);
-    if (cand_bytes <= 96u * 1024u) {
-        if (cand_bytes > 40u * 1024u) {
-            cudaError_t e = cudaFuncSetAttribute(chamfer_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96u * 1024u));
-            if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "chamfer_tail_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
-        }
-        le = launch_pdl(chamfer_tail_kernel<true>, tgrid, dim3(kTailThreads), cand_bytes, st, pc1, pc2, N, M, C1, C2, o, tw, mean1,
-                        mean2, loss, w1, w2);
-    } else {
-        le = launch_pdl(chamfer_tail_kernel<false>, tgrid, dim3(kTailThreads), (size_t)0, st, pc1, pc2, N, M, C1, C2, o, tw, mean1,
-                        mean2, loss, w1, w2);
+    // unit-aligned chunks when every (direction, cloud) unit can have a CTA of its own and no chunk needs a second segment
+    const int units = 2 * B;
+    int split = 0;
+    if (units <= grid) {
+        const int c_lo = grid / units;
+        const int longest = ((qb1 > qb2 ? qb1 : qb2) + c_lo - 1) / c_lo;
+        if (longest <= kQmax) split = 1;
     }
-    if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "chamfer_tail_kernel: %s", cudaGetErrorString(le)); }
-    return check_launch("chamfer_tail_kernel");
+    const int refine = filter_only ? 0 : 1;
+    cudaError_t le = top3 ? launch_pdl(chamfer_tcsweep_kernel<true>, dim3((unsigned)grid), dim3(kThreads), (size_t)SweepCfg<true>::kSmem, st, pc1, pc2,
+                                       B, N, M, (int)n_tasks, qb1, qb2, split, o, refine)
+                          : launch_pdl(chamfer_tcsweep_kernel<false>, dim3((unsigned)grid), dim3(kThreads), (size_t)SweepCfg<false>::kSmem, st, pc1, pc2,
+                                       B, N, M, (int)n_tasks, qb1, qb2, split, o, refine);
+    if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "chamfer_tcsweep_kernel: %s", cudaGetErrorString(le)); }
+    return check_launch("chamfer_tcsweep_kernel");
 }
 
 }  // namespace rlg

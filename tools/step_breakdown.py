@@ -17,6 +17,7 @@ N = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
 M = int(sys.argv[3]) if len(sys.argv) > 3 else 2048
 KIND = sys.argv[4] if len(sys.argv) > 4 else "sphere"
 EXP = os.environ.get("RLG_EXPERIMENTS_LIB") == "1"
+ONLY = sys.argv[5] if len(sys.argv) > 5 else ""          # "tensor": only the tensor-sweep rows (A-B variant runs)
 lib = _lib.load()
 dev = torch.device("cuda:0")
 slot_bytes = (B * N + B * M) * 12
@@ -87,17 +88,20 @@ print(f"B={B} N={N} M={M} {KIND}; ring {n_ring} slots; workspace memset alone {t
 rows = [("fp32: sweep", L.CHAMFER_WS_CLEAN | L.CHAMFER_TILE_ONLY, True),
         ("fp32: forward (sweep + refinement kernel)", L.CHAMFER_WS_CLEAN, False),
         ("tensor: filter sweep only (diagnostic)", L.CHAMFER_WS_CLEAN | L.CHAMFER_ALGO_TENSOR | L.CHAMFER_FILTER_ONLY, True),
-        ("tensor: sweep + fused refinement", L.CHAMFER_WS_CLEAN | L.CHAMFER_ALGO_TENSOR | L.CHAMFER_TILE_ONLY, True),
-        ("tensor: forward (sweep + tail)", L.CHAMFER_WS_CLEAN | L.CHAMFER_ALGO_TENSOR, False),
+        ("tensor: forward (one fused launch)", L.CHAMFER_WS_CLEAN | L.CHAMFER_ALGO_TENSOR, False),
         ("tensor+track_two: forward", L.CHAMFER_WS_CLEAN | L.CHAMFER_ALGO_TENSOR | L.CHAMFER_TRACK_TWO, False)]
 if EXP:
     rows += [("tensor v1 (round 1): sweep", L.CHAMFER_WS_CLEAN | L.X_CHAMFER_TENSOR_V1 | L.CHAMFER_TILE_ONLY, True),
              ("tensor v1 (round 1): forward (sweep + finalize)", L.CHAMFER_WS_CLEAN | L.X_CHAMFER_TENSOR_V1, False)]
+if ONLY:
+    rows = [r for r in rows if r[0].startswith(ONLY)]
 for name, flags, dirty in rows:
     t = timed(lambda a, b: fwd(a, b, flags), dirty=dirty) - (t_fill if dirty else 0.0)
     print(f"{name:52s} {t:8.2f} us   {flop / t / 1e6:7.2f} TFLOP/s algorithmic")
+if ONLY:
+    sys.exit(0)
 t_bwd = timed(lambda a, b: bwd(a, b))
 print(f"{'backward (memsets + kernel)':52s} {t_bwd:8.2f} us")
 for name, algo in (("fp32", 0), ("tensor", L.CHAMFER_ALGO_TENSOR)):
     t = timed(lambda a, b: (fwd(a, b, L.CHAMFER_WS_CLEAN | algo, zero=True), bwd(a, b, L.CHAMFER_BWD_ACCUMULATE)))
-    print(f"{name + ': forward + backward (3 launches)':52s} {t:8.2f} us   {B / t * 1e6:10.0f} pairs/s")
+    print(f"{name + ': forward + backward':52s} {t:8.2f} us   {B / t * 1e6:10.0f} pairs/s")
