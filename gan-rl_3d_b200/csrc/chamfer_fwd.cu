@@ -87,13 +87,14 @@ static size_t nrm_bytes(int B) { return align_up(sizeof(unsigned) * 2 * (size_t)
 //   [0]  rowkey | colkey   u64 (B,N),(B,M)      FP32 sweep: packed (filter value, winning group)         all-ones invariant
 //   [1]  rowsec | colsec   u32                  FP32 sweep: smallest value of any other group            all-ones invariant
 //   [2]  nrm               u32 (2,B)            FP32 sweep: ~max|p|^2                                    all-ones invariant
-//   [3]  counters (all-ones invariant) + partial sums of the distances (FP32 finalize / fused tensor forward)
-//   [4]  (experiments build: runner-up groups / third values of the first-generation tensor sweep)       no invariant
+//   [3]  FP32 refinement kernel: counters (all-ones invariant) + partial sums of the distances (no invariant)
+//   [4]  fused tensor forward:   counters (all-ones invariant) + partial sums of the distances (no invariant)
+//   [5]  (experiments build: runner-up groups / third values of the first-generation tensor sweep)       no invariant
+// Regions with different invariants never overlap, so the two sweeps can alternate on one workspace with WS_CLEAN.
 size_t rlg_chamfer_ws_bytes(int B, int N, int M) {
     if (B < 0 || N < 1 || M < 1) return 0;
-    size_t fin = finalize2_ws_bytes(B, N, M);
-    if (tcsweep_ws_bytes(B, N, M) > fin) fin = tcsweep_ws_bytes(B, N, M);
-    return keys_bytes(B, N, M) + secs_bytes(B, N, M) + nrm_bytes(B) + fin + 2 * secs_bytes(B, N, M);
+    return keys_bytes(B, N, M) + secs_bytes(B, N, M) + nrm_bytes(B) + align_up(finalize2_ws_bytes(B, N, M), 256) +
+           align_up(tcsweep_ws_bytes(B, N, M), 256) + 2 * secs_bytes(B, N, M);
 }
 
 int rlg_chamfer_fwd(const float *pc1, const float *pc2, int B, int N, int M, float *d1, float *d2,
@@ -159,11 +160,12 @@ int rlg_chamfer_loss_fwd(const float *pc1, const float *pc2, int B, int N, int M
     w.rowth = (unsigned *)((char *)ws + need - secs_bytes(B, N, M));
     w.colth = w.rowth + (size_t)B * N;
     char *fin = (char *)ws + keys_bytes(B, N, M) + secs_bytes(B, N, M) + nrm_bytes(B);
+    char *fin_tc = fin + align_up(finalize2_ws_bytes(B, N, M), 256);
     const bool tile_only = (flags & RLG_CHAMFER_TILE_ONLY) != 0;
 
     if (flags & RLG_CHAMFER_ALGO_TENSOR) {
         // one launch does everything: RLG_CHAMFER_TILE_ONLY changes nothing here
-        return launch_tcsweep(pc1, pc2, B, N, M, w, fin, d1, d2, i1, i2, mean1, mean2, loss, w1, w2, gz1, gz2,
+        return launch_tcsweep(pc1, pc2, B, N, M, w, fin_tc, d1, d2, i1, i2, mean1, mean2, loss, w1, w2, gz1, gz2,
                               (flags & RLG_CHAMFER_FILTER_ONLY) != 0, (flags & RLG_CHAMFER_TRACK_TWO) != 0, st);
     }
     if (flags & (RLG_CHAMFER_TRACK_TWO | RLG_CHAMFER_FILTER_ONLY))

@@ -454,3 +454,16 @@ def test_degenerate_geometries(rlg, case):
         pc1 = t1 * d + 0.1
         pc2 = t2 * d + 0.1
     _check_against_direct(rlg, pc1.contiguous(), pc2.contiguous())
+
+
+def test_sweeps_alternate_on_one_workspace(rlg):
+    """The FP32 and the tensor forward keep different scratch data in the shared workspace; alternating them on the same
+    cached workspace (same shape, WS_CLEAN) must not disturb either -- many clouds, so that the regions are long."""
+    pc1, pc2 = O.make_clouds(300, 130, "sphere", 81), O.make_clouds(300, 70, "sphere", 82)
+    want = O.chamfer_direct(pc1, pc2, O.TIE_FAITHFUL)
+    w1, w2 = O.chamfer_means(want[0], want[1])
+    for tensor in (False, True, False, True, True):
+        d1, d2, i1, i2, m1, m2 = _run(rlg, pc1, pc2, tensor=tensor)
+        assert np.array_equal(d1, want[0]) and np.array_equal(i2, want[3])
+        np.testing.assert_allclose(m1, w1, rtol=2e-7)
+        np.testing.assert_allclose(m2, w2, rtol=2e-7)
