@@ -98,7 +98,7 @@ template <bool TOP3> struct SweepCfg {
     static constexpr uint32_t kRawBytes = (uint32_t)(kRawMax / kGroup) * kRawStride * 4u;
     static constexpr uint32_t kOffDist = kOffRaw + kRawBytes;                 // float [kQmax*128]: the segment's distances
     static constexpr uint32_t kOffAmb = kOffDist + kQmax * kTQ * 4u;          // u16 [kQmax*128]: the segment's ambiguous queries
-    static constexpr uint32_t kOffBar = kOffAmb + kQmax * kTQ * 2u;
+    static constexpr uint32_t kOffBar = kOffAmb + kQmax * kTQ * 2u + 2u * kEpWarps * 4u;   // + scratch of scan_query_cta
     static constexpr uint32_t kSmem = kOffBar + 256 + 1024;                   // + barriers + alignment slack
 };
 constexpr float kBig = 1.0e30f;
@@ -222,15 +222,23 @@ __device__ __forceinline__ void refine_query(const float *__restrict__ qc, const
     const float sv = has2 ? __uint_as_float((unsigned)(k2 >> 32)) : INFINITY;
     const int sgrp = (int)(unsigned)(k2 & 0xffffffffu);
     // the margin test of the header; any NaN (non-finite input) makes a comparison false -> ambiguous -> full scan
-    const float a2 = nrm2(qx, qy, qz), a = sqrtf(a2);
+    const float a2 = nrm2(qx, qy, qz);
     auto sigma = [&](float tt) {
+        const float a = sqrtf(a2);
         const float tp = fmaf(fmaxf(tt, 0.0f), 1.0001f, 256.0f * kU * a2);
         return fmaf(2.0f * a, sqrtf(tp), fmaf(2.0f, a2, tp));
     };
-    const float hi_val = fmaf(kErr, sigma(val), val) * (1.0f + 8.0f * kU);
+    // cheap sufficient test first (2 a sqrt(t) <= a^2 + t, so Sigma <= 3 a^2 + 2 t: no square roots); the sharper bound
+    // only for the few queries that fail it
+    const float hi_cheap = fmaf(kErr, fmaf(2.02f, fmaxf(val, 0.0f), 3.01f * a2), val) * (1.0f + 8.0f * kU);
+    float hi_val = 0.0f;
+    bool have_hi = false;
     auto out_of_reach = [&](float v) {                                  // no candidate with a filter value >= v can win
         if (v == INFINITY) return true;
-        return v >= 1.0e-9f * a2 && fmaf(-kErr, sigma(v), v) > hi_val;
+        if (!(v >= 1.0e-9f * a2)) return false;
+        if (fmaf(-kErr, fmaf(2.02f, v, 3.01f * a2), v) > hi_cheap) return true;
+        if (!have_hi) { hi_val = fmaf(kErr, sigma(val), val) * (1.0f + 8.0f * kU); have_hi = true; }
+        return fmaf(-kErr, sigma(v), v) > hi_val;
     };
     const bool clear = out_of_reach(sv);
     const bool two = TOP3 && !clear && has2 && out_of_reach(t3);
@@ -315,6 +323,67 @@ __device__ __forceinline__ void scan_query(At at, int npos, int nc, int lane, fl
     }
     bj = __reduce_min_sync(0xffffffffu, fj);
     bj = bj == 0x7fffffff ? 0 : min(bj, nc - 1);
+}
+
+// The same scan by ALL epilogue threads for one query, candidates read from global memory (clouds too large to stage):
+// a single warp walking a 16384-point cloud through L2 is latency-bound for ~40 us; 512 threads with eight loads in
+// flight each take ~3 us.  s_red: 2 x kEpWarps words of scratch.  Every epilogue thread must call it (named barrier 1).
+__device__ __forceinline__ void scan_query_cta(const float *__restrict__ cc, int nc, int etid, float qx, float qy, float qz,
+                                               unsigned *s_red, float &dist, int &bj) {
+    const int lane = etid & 31, w = etid >> 5;
+    auto block_min = [&](unsigned v0, unsigned v1, unsigned &r0, unsigned &r1) {
+        v0 = __reduce_min_sync(0xffffffffu, v0);
+        v1 = __reduce_min_sync(0xffffffffu, v1);
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpThreads) : "memory");   // previous readers of s_red are done
+        if (lane == 0) { s_red[w] = v0; s_red[kEpWarps + w] = v1; }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpThreads) : "memory");
+        r0 = s_red[0]; r1 = s_red[kEpWarps];
+#pragma unroll
+        for (int k = 1; k < kEpWarps; ++k) { r0 = min(r0, s_red[k]); r1 = min(r1, s_red[kEpWarps + k]); }
+    };
+    auto dist2 = [&](int j) {
+        const float *c = cc + 3 * (size_t)j;
+        return sqdist(qx, qy, qz, __ldg(c), __ldg(c + 1), __ldg(c + 2));
+    };
+    float lm = INFINITY;
+    int nanj = 0x7fffffff;
+    int j = etid;
+    for (; j + 7 * kEpThreads < nc; j += 8 * kEpThreads) {
+        float t[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t[e] = dist2(j + e * kEpThreads);
+#pragma unroll
+        for (int e = 7; e >= 0; --e) { if (t[e] != t[e]) nanj = min(nanj, j + e * kEpThreads); lm = fminf(lm, t[e]); }
+    }
+    for (; j < nc; j += kEpThreads) {
+        const float t = dist2(j);
+        if (t != t) nanj = min(nanj, j);
+        lm = fminf(lm, t);
+    }
+    unsigned mb, nb;
+    block_min(__float_as_uint(lm), (unsigned)nanj, mb, nb);             // t >= 0: orders as unsigned
+    if (nb != 0x7fffffffu) {
+        dist = __uint_as_float(0x7fc00000u);
+        bj = (int)nb;
+        return;
+    }
+    const float m = __uint_as_float(mb);
+    dist = __fsqrt_rn(m);
+    const float h = m < INFINITY ? sqrt_window_top(m, dist) : m;
+    int fj = 0x7fffffff;
+    j = etid;
+    for (; j + 7 * kEpThreads < nc; j += 8 * kEpThreads) {
+        float t[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t[e] = dist2(j + e * kEpThreads);
+#pragma unroll
+        for (int e = 7; e >= 0; --e) if (t[e] <= h) fj = min(fj, j + e * kEpThreads);
+    }
+    for (; j < nc; j += kEpThreads)
+        if (dist2(j) <= h) fj = min(fj, j);
+    unsigned fb, dummy;
+    block_min((unsigned)fj, 0u, fb, dummy);
+    bj = fb == 0x7fffffffu ? 0 : (int)fb;
 }
 
 // TOP3: also track the runner-up's group and the third-smallest group minimum (5 more issue slots per 32 candidates;
@@ -701,28 +770,35 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
                 }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kEpThreads) : "memory");   // the ambiguous list is complete
-            // ---- ambiguous queries: one warp per query scans the whole candidate cloud exactly
+            // ---- ambiguous queries: the whole candidate cloud is scanned exactly -- one warp per query from the staged
+            // copy, all epilogue threads per query when the cloud is read from global memory
             {
                 const int n_amb = (int)s_namb;
-                const int npos = raw != nullptr ? ((sg.nc + kGroup - 1) / kGroup) * kGroup : sg.nc;
-                for (int a = warp; a < n_amb; a += kEpWarps) {
-                    const int local = (int)s_amb[a];
-                    const int i = (sg.qb0 + (local >> 7)) * kTQ + (local & 127);
-                    const float qx = __ldg(qc + 3 * (size_t)i), qy = __ldg(qc + 3 * (size_t)i + 1), qz = __ldg(qc + 3 * (size_t)i + 2);
-                    float dist;
-                    int bj;
-                    if (raw != nullptr) {
+                if (raw != nullptr) {
+                    const int npos = ((sg.nc + kGroup - 1) / kGroup) * kGroup;
+                    for (int a = warp; a < n_amb; a += kEpWarps) {
+                        const int local = (int)s_amb[a];
+                        const int i = (sg.qb0 + (local >> 7)) * kTQ + (local & 127);
+                        const float qx = __ldg(qc + 3 * (size_t)i), qy = __ldg(qc + 3 * (size_t)i + 1), qz = __ldg(qc + 3 * (size_t)i + 2);
+                        float dist;
+                        int bj;
                         scan_query([&](int p, float &x, float &y, float &z) {
                             const float *c = raw + (p >> 5) * kRawStride + 3 * (p & 31);
                             x = c[0]; y = c[1]; z = c[2];
                         }, npos, sg.nc, lane, qx, qy, qz, dist, bj);
-                    } else {
-                        scan_query([&](int p, float &x, float &y, float &z) {
-                            const float *c = cc + 3 * (size_t)p;
-                            x = __ldg(c); y = __ldg(c + 1); z = __ldg(c + 2);
-                        }, npos, sg.nc, lane, qx, qy, qz, dist, bj);
+                        if (lane == 0) { dout[i] = dist; iout[i] = bj; s_dist[local] = dist; }
                     }
-                    if (lane == 0) { dout[i] = dist; iout[i] = bj; s_dist[local] = dist; }
+                } else {
+                    unsigned *s_red = reinterpret_cast<unsigned *>(smem + Cfg::kOffAmb) + (kQmax * kTQ) / 2;   // behind the list
+                    for (int a = 0; a < n_amb; ++a) {
+                        const int local = (int)s_amb[a];
+                        const int i = (sg.qb0 + (local >> 7)) * kTQ + (local & 127);
+                        const float qx = __ldg(qc + 3 * (size_t)i), qy = __ldg(qc + 3 * (size_t)i + 1), qz = __ldg(qc + 3 * (size_t)i + 2);
+                        float dist;
+                        int bj;
+                        scan_query_cta(cc, sg.nc, tid, qx, qy, qz, s_red, dist, bj);
+                        if (tid == 0) { dout[i] = dist; iout[i] = bj; s_dist[local] = dist; }
+                    }
                 }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kEpThreads) : "memory");   // every distance of the segment is in s_dist
