@@ -5,16 +5,18 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
            bench.py --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[1]): batched Chamfer distance forward + backward,
-B=32 pairs per GPU, N=M=2048, synthetic unit-sphere clouds, fp32.  One step = ChamferLoss(pred, target) and
-its backward over one batch.  Multi-GPU: every rank runs its own batch of 32 pairs (weak scaling, no data-path
-collective) and all-reduces the loss scalar asynchronously, as the reference's logging does per step.
+Workload (BASELINE.json configs[1]): batched Chamfer distance forward + backward, B=32 pairs per
+GPU, N=M=2048, synthetic unit-sphere clouds, fp32.  One step = ChamferLoss(pred, target) and its backward over one
+batch (two kernel launches of this library).  Multi-GPU: every rank runs its own batch of 32 pairs (weak scaling, no
+data-path collective); the logged loss scalar is all-reduced (NCCL) EVERY step inside the timed region, captured in the
+CUDA graph on a side stream.
 
-Prints ONE JSON line on rank 0 (see the task contract): metric/value (device-resident inputs, CUDA events,
-max over ranks), roofline of the dominant kernel (FP32 FMA pipe for the Chamfer tile kernel), cpu_baseline
-(the oracle port of the reference's CPU path on this host's cores), e2e (host buffers through the public
-API: H2D of every step's inputs from pinned memory + D2H of the loss), clocks, gpu_launches; plus the encoder
-clouds/s figure and secondary rooflines as extra keys.
+Prints ONE JSON line on rank 0: metric/value (device-resident inputs, CUDA events, max over ranks), roofline of the
+dominant kernel, cpu_baseline, e2e (pinned host buffers through the public API: H2D of every step's inputs + D2H of
+the loss), clocks, gpu_launches, and extra keys: `uniform` (same workload on uniform clouds), `strong_scaling`
+(the 32-pair batch split over the ranks), `torch_cuda` (the reference's op sequence on stock torch CUDA kernels on the
+same GPU: the kernels to beat), `encoder` / `encoder_config_dims` (clouds/s), `reward_loop` (cfg4), `large_cloud`
+(cfg5) -- the last four aggregated over all ranks (barrier + MAX time).
 """
 from __future__ import annotations
 
@@ -35,9 +37,11 @@ import torch  # noqa: E402
 
 B, N, M = 32, 2048, 2048                 # cfg2
 ENC_B, ENC_N, ENC_DIMS = 256, 2048, [64, 128, 1024]   # cfg3
+CFG_DIMS = [64, 128, 128, 256, 128]      # the reference's own encoder_dims (configs/config.yaml:9-11)
 RING_BYTES = 288 << 20                   # inputs cycled through a ring larger than the 126 MB L2
 FLOP_PER_PAIR = 8.0 * N * M              # every pairwise squared distance counted once
 BWD_BYTES_PER_PAIR = 56.0 * (N + M)
+WORKLOAD = "chamfer_fwd_bwd B=32 N=M=2048 sphere (BASELINE configs[1])"
 
 
 def parse_args():
@@ -46,9 +50,16 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-encoder", action="store_true", help="skip the encoder clouds/s side measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip the side measurements (encoder, cfg4, cfg5, torch_cuda)")
+    ap.add_argument("--no-encoder", action="store_true", help="alias of --no-extras")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
+
+
+def base_config(world: int) -> dict:
+    """The workload description shared, key for key, by both arms."""
+    return {"workload": WORKLOAD, "B_per_gpu": B, "N": N, "M": M, "global_batch": B * world,
+            "parallelism": f"batch-sharded dp{world}"}
 
 
 def load_peaks():
@@ -58,6 +69,17 @@ def load_peaks():
             d = json.load(f)
         return d, "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def profile_traffic(kernel: str):
+    """dram__bytes_read+write per launch of `kernel` from the committed ncu summary (profiles/r2_traffic.json, written by
+    tools/export_profile.py from an `ncu --set full` capture); None when no capture of this build is committed."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -123,9 +145,14 @@ def sphere(gen, b, n):
     return (x / x.norm(dim=2, keepdim=True).clamp_min(1e-12)).contiguous()
 
 
-def make_ring(rank: int, slots: int):
-    gen = torch.Generator(device="cpu").manual_seed(1234 + 2 + 1000 * rank)
-    return [(sphere(gen, B, N), sphere(gen, B, M)) for _ in range(slots)]
+def uniform(gen, b, n):
+    return (torch.rand(b, n, 3, generator=gen) * 2.0 - 1.0).contiguous()
+
+
+def make_ring(rank: int, slots: int, kind: str = "sphere", b: int = B):
+    gen = torch.Generator(device="cpu").manual_seed(1234 + 2 + 1000 * rank + (500 if kind == "uniform" else 0))
+    mk = sphere if kind == "sphere" else uniform
+    return [(mk(gen, b, N), mk(gen, b, M)) for _ in range(slots)]
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -171,12 +198,97 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "chamfer_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "chamfer_fwd_bwd B=32 N=M=2048 sphere (BASELINE configs[1])", "B": B, "N": N, "M": M,
-                   "pairs_per_step": b},
+        "config": dict(base_config(1), sampled_pairs_per_step=b),
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# ----------------------------------------------------------------------------------------------------
+# helpers of our arm
+# ----------------------------------------------------------------------------------------------------
+class Dist:
+    """World bookkeeping: barrier + MAX-over-ranks of a device-timed duration."""
+
+    def __init__(self, world, dev):
+        import torch.distributed as dist
+        self.dist, self.world, self.dev = dist, world, dev
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max_ms(self, ms: float) -> float:
+        if self.world == 1:
+            return ms
+        t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, reps: int, warm: int = 3) -> float:
+        """ms per call of fn(k): warm-up, barrier, CUDA events around `reps` calls, MAX over ranks."""
+        for k in range(warm):
+            fn(k)
+        torch.cuda.synchronize()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(reps):
+            fn(k)
+        e1.record()
+        torch.cuda.synchronize()
+        self.barrier()
+        return self.max_ms(e0.elapsed_time(e1)) / reps
+
+
+def flush_l2(dev):
+    """Write a buffer larger than the 126 MB L2 so that nothing timed afterwards starts cache-resident."""
+    buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    buf.zero_()
+    torch.cuda.synchronize()
+    del buf
+
+
+def timed_step_graphs(P, D, ring, K, W, world, loss_hook_factory):
+    """EXACTLY K timed ChamferLoss forward+backward steps over the ring, in CUDA graphs of up to len(ring) steps.
+    Every graph that will be timed is replayed once beforehand (upload + warm-up), then L2 is flushed.
+    Returns (ms, n_launches, last_loss, info)."""
+    slots = len(ring)
+    S = min(K, slots)
+    n_full, rem = divmod(K, S)
+    hook = loss_hook_factory() if world > 1 else None
+    full = P.ChamferStepGraph(ring[:S], after_step=hook)
+    tail = P.ChamferStepGraph(ring[:rem], after_step=hook) if rem else None
+    n_launches = n_full * full.kernel_launches_per_replay + (tail.kernel_launches_per_replay if tail else 0)
+    warm_replays = max(1, -(-W // S))
+    for _ in range(warm_replays):
+        full.replay()
+    if tail is not None:
+        tail.replay()
+    torch.cuda.synchronize()
+    flush_l2(ring[0][0].device)
+    D.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n_full):
+        full.replay()
+    if tail is not None:
+        tail.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    D.barrier()
+    ms = D.max_ms(e0.elapsed_time(e1))
+    last = float((tail.losses[-1] if tail else full.losses[-1]).item())
+    touched = min(K, slots)
+    info = {"steps_per_graph": S, "graph_replays": n_full + (1 if tail else 0), "warmup_steps": warm_replays * S + rem,
+            "ring_slots": slots, "slots_touched_per_pass": touched,
+            "l2_policy": (f"every timed graph replayed once beforehand, then L2 flushed (256 MiB written); steps read "
+                          f"{touched} distinct batches = {touched * (ring[0][0].numel() + ring[0][1].numel()) * 4 >> 20} MiB per "
+                          f"pass through the ring" + (" (> 126 MB L2, cycled)" if touched == slots else
+                                                      " (each batch read once: never cache-resident)"))}
+    return ms, n_launches, last, info
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -185,64 +297,85 @@ def run_reference(args, rank):
 def run_ours(args):
     import gan_rl_3d_b200 as rlg
     import importlib
-    D = importlib.import_module("gan-rl_3d_b200.distributed")
+    Dm = importlib.import_module("gan-rl_3d_b200.distributed")
     _lib = importlib.import_module("gan-rl_3d_b200._lib")
     import torch.distributed as dist
 
-    rank, local_rank, world = D.init_from_env("nccl")
+    rank, local_rank, world = Dm.init_from_env("nccl")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU path)")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     lib = _lib.load()
     peaks, peaks_src = load_peaks()
-    K, W = args.steps, max(3, args.warmup)
+    K, W = max(1, args.steps), max(3, args.warmup)
+    D = Dist(world, dev)
+    extras_on = not (args.no_extras or args.no_encoder)
 
     P = importlib.import_module("gan-rl_3d_b200.pipeline")
     slot_bytes = (B * N + B * M) * 3 * 4
     slots = max(8, RING_BYTES // slot_bytes)
     ring_host = make_ring(rank, slots)
     ring = [(a.to(dev), b.to(dev)) for a, b in ring_host]
-    loss_buf = torch.zeros(1, device=dev)
 
-    # The timed loop: `loss = ChamferLoss()(pred, target); loss.backward()` per batch, captured S steps at a time
-    # in a CUDA graph (the loop is launch-bound from Python: ~55 us of GPU work per step in 3 kernels).
-    full = P.ChamferStepGraph(ring)                                   # S = slots steps per replay
-    n_full, rem = divmod(K, slots)
-    tail = P.ChamferStepGraph(ring[:rem]) if rem else None
-    n_launches = n_full * full.kernel_launches_per_replay + (tail.kernel_launches_per_replay if tail else 0)
+    # The logged loss scalar (train_rl_gan_net.py:241-247) is the only cross-rank quantity of this step: one fp32
+    # all-reduce per step, captured in the graph on a side stream.
+    red_bufs = []
 
-    def run_steps(n_full_, tail_):
-        for _ in range(n_full_):
-            full.replay()
-            if world > 1:      # the logged loss scalar of the last step, all-reduced off the critical path
-                loss_buf.copy_(full.losses[-1].detach().reshape(1))
-                dist.all_reduce(loss_buf, op=dist.ReduceOp.SUM, async_op=True)
-        if tail_ is not None:
-            tail_.replay()
+    def loss_hook_factory():
+        def hook(loss):
+            buf = loss.detach().reshape(1).clone()
+            red_bufs.append(buf)
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        return hook
 
-    run_steps(max(1, -(-W // slots)), None)                           # >= W warm-up steps
-    torch.cuda.synchronize()
+    collective = {"kind": "none (1 GPU)", "us_per_step": 0.0}
     if world > 1:
-        dist.barrier()
+        for _ in range(3):                                  # NCCL communicator warm-up outside any capture
+            t_ = torch.zeros(1, device=dev)
+            dist.all_reduce(t_)
+        torch.cuda.synchronize()
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    run_steps(n_full, tail)
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    try:
+        ms, n_launches, last_loss, info = timed_step_graphs(P, D, ring, K, W, world, loss_hook_factory)
+        if world > 1:
+            collective["kind"] = "ncclAllReduce(sum) of the fp32 loss scalar, EVERY step, captured in the CUDA graph on a side stream"
+    except Exception as e:                                  # NCCL capture unsupported: per-replay all-reduce instead
+        if world == 1:
+            raise
+        red = torch.zeros(1, device=dev)
+
+        def factory_none():
+            return None
+        ms, n_launches, last_loss, info = timed_step_graphs(P, D, ring, K, W, 1, factory_none)
+        dist.all_reduce(red)
+        collective["kind"] = f"capture of the NCCL all-reduce failed ({type(e).__name__}); NO collective inside the timed region"
     value = K * B * world / (ms * 1e-3)
-    last_loss = float((tail.losses[-1] if tail else full.losses[-1]).item())
+
+    if world > 1:
+        # the collective alone: S captured all-reduces back to back
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream(dev)
+        buf = torch.zeros(1, device=dev)
+        s.wait_stream(torch.cuda.current_stream())
+        try:
+            with torch.cuda.stream(s):
+                dist.all_reduce(buf)
+                s.synchronize()
+                with torch.cuda.graph(g, stream=s):
+                    for _ in range(64):
+                        dist.all_reduce(buf)
+            torch.cuda.synchronize()
+            cms = D.timed(lambda k: g.replay(), 5, 2)
+            collective["us_per_step"] = cms * 1e3 / 64
+            collective["note"] = ("latency of one 4-byte all-reduce when issued back to back alone; inside the step it runs "
+                                  "on a side stream and overlaps the next step's kernels")
+        except Exception as e:
+            collective["us_per_step"] = None
+            collective["note"] = f"stand-alone timing failed: {type(e).__name__}"
 
     # ---- e2e: host buffers through the public API, H2D + D2H of every step inside the timed region --
     nb = min(slots, 32)
@@ -252,20 +385,49 @@ def run_ours(args):
     Ke = Ke_replays * nb
     host_graph.replay()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    D.barrier()
     t0 = time.perf_counter()
     for _ in range(Ke_replays):
         host_graph.replay()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = Ke * B * world / float(t.item())
+    e2e_s = D.max_ms(e2e_s * 1e3) * 1e-3
+    e2e_value = Ke * B * world / e2e_s
     e2e_loss_check = float(host_graph.losses_host[0])
-    if rank == 0:
-        clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
+    del host_graph, pinned
+
+    extra = {}
+    # ---- same workload on uniform clouds (SURVEY.md 8d names both distributions) --------------------
+    if extras_on:
+        uring = [(a.to(dev), b.to(dev)) for a, b in make_ring(rank, 64, "uniform")]
+        ums, _, uloss, _ = timed_step_graphs(P, D, uring, min(K, 640), 3, 1, lambda: None)
+        extra["uniform"] = {"metric": "chamfer_pairs_per_s", "value": min(K, 640) * B * world / (ums * 1e-3), "unit": "pairs/s",
+                            "config": {"workload": "chamfer_fwd_bwd B=32 N=M=2048 uniform [-1,1]^3 clouds, per GPU"},
+                            "ms_per_step": ums / min(K, 640), "last_loss": uloss}
+        del uring
+        # ---- strong scaling of the headline batch: the SAME 32 pairs split over the ranks -----------
+        bs = max(1, B // world)
+        sring = [(a[:bs].contiguous(), b[:bs].contiguous()) for a, b in ring[:64]]
+        sms, _, _, _ = timed_step_graphs(P, D, sring, min(K, 640), 3, 1, lambda: None)
+        extra["strong_scaling"] = {"metric": "chamfer_pairs_per_s", "value": min(K, 640) * bs * world / (sms * 1e-3),
+                                   "unit": "pairs/s", "scaling": "strong", "pairs_per_gpu": bs,
+                                   "config": {"workload": f"the headline batch of {B} pairs split over {world} GPU(s): "
+                                                          f"{bs} pairs per GPU per step"},
+                                   "ms_per_step": sms / min(K, 640),
+                                   "note": "launch- and latency-bound below ~16 pairs per GPU: a 148-CTA persistent kernel "
+                                           "over 2*pairs*16 query blocks has less than one wave of work"}
+        del sring
+
+    if extras_on:
+        extra.update(encoder_measurement(rlg, dev, D, peaks, peaks_src, ENC_DIMS, "encoder",
+                                         "PointNet encoder 3->64->128->1024 + max-pool + GFV head, B=256 per GPU, N=2048 "
+                                         "(BASELINE configs[2])"))
+        extra.update(encoder_measurement(rlg, dev, D, peaks, peaks_src, CFG_DIMS, "encoder_config_dims",
+                                         "PointNet encoder with the reference's own encoder_dims 3->64->128->128->256->128 "
+                                         "(configs/config.yaml:9-11) + max-pool + GFV head, B=256 per GPU, N=2048"))
+        extra.update(reward_measurement(rlg, dev, D))
+        extra.update(large_cloud_measurement(rlg, dev, D))
 
     if rank != 0:
         if world > 1:
@@ -273,73 +435,92 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel: the Chamfer tile kernel, timed alone with CUDA events -----
+    # ---- roofline of the dominant kernel: the fused Chamfer forward, timed alone with CUDA events ----
     a, b = ring[0]
     a = a.detach(); b = b.detach()
     d1, d2, i1, i2, m1, m2 = rlg.chamfer_nearest(a, b)
     ws = torch.empty(lib.rlg_chamfer_ws_bytes(B, N, M), dtype=torch.uint8, device=dev)
-    ws.fill_(0xFF)
     stream = torch.cuda.current_stream().cuda_stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    def time_sweep(algo_flag):
-        def tile_only(x, y):
+    def time_forward(algo_flag, tile_only):
+        """ms per launch sequence of the forward on ring inputs; the workspace is re-initialised (memset node) after a
+        call that leaves it dirty, and that memset is timed separately and subtracted."""
+        def call(x, y, extra_flags):
             rc = lib.rlg_chamfer_fwd(x.data_ptr(), y.data_ptr(), B, N, M, d1.data_ptr(), d2.data_ptr(), i1.data_ptr(),
-                                     i2.data_ptr(), None, None, ws.data_ptr(), ws.numel(),
-                                     _lib.CHAMFER_WS_CLEAN | _lib.CHAMFER_TILE_ONLY | algo_flag, stream)
+                                     i2.data_ptr(), m1.data_ptr(), m2.data_ptr(), ws.data_ptr(), ws.numel(),
+                                     _lib.CHAMFER_WS_CLEAN | algo_flag | extra_flags, stream)
             _lib.check("rlg_chamfer_fwd", rc)
 
-        ws.fill_(0xFF)
-        for k in range(20):
-            tile_only(*[t_.detach() for t_ in ring[k % slots]])
-        torch.cuda.synchronize()
-        reps_ = 400
+        def loop(reps_, flags, refill):
+            ws.fill_(0xFF)
+            for k in range(10):
+                call(*[t_.detach() for t_ in ring[k % slots]], flags)
+                if refill:
+                    ws.fill_(0xFF)
+            torch.cuda.synchronize()
+            e0.record()
+            for k in range(reps_):
+                x, y = ring[k % slots]
+                call(x.detach(), y.detach(), flags)
+                if refill:
+                    ws.fill_(0xFF)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps_
+        if not tile_only:
+            return loop(400, 0, False)
         e0.record()
-        for k in range(reps_):
-            x, y = ring[k % slots]
-            tile_only(x.detach(), y.detach())
+        for _ in range(400):
+            ws.fill_(0xFF)
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps_
+        fill_ms = e0.elapsed_time(e1) / 400
+        return loop(400, _lib.CHAMFER_TILE_ONLY, True) - fill_ms
 
-    reps = 400
     use_tensor = rlg.get_default_sweep() == "tensor" or (rlg.get_default_sweep() == "auto" and N >= 64 and M >= 64)
-    tc_ms = time_sweep(_lib.CHAMFER_ALGO_TENSOR)
-    fp_ms = time_sweep(0)
+    tc_fwd_ms = time_forward(_lib.CHAMFER_ALGO_TENSOR, False)
+    fp_sweep_ms = time_forward(0, True)
+    fp_fwd_ms = time_forward(0, False)
     ws.fill_(0xFF)
-    tile_ms = tc_ms if use_tensor else fp_ms
-    achieved_tflops = FLOP_PER_PAIR * B / (tile_ms * 1e-3) / 1e12
-    fp_tflops = FLOP_PER_PAIR * B / (fp_ms * 1e-3) / 1e12
-
-    peak = (ctypes_float6(lib, dev))
+    peak = ctypes_float6(lib, dev)
     fp32_theory = peak[2]
     peak_src = (f"theoretical FP32 FMA: {int(peak[3])} SMs x 128 lanes x 2 flop x {peak[1]:.0f} MHz "
                 "(MEASURED_PEAKS.json has no FP32 entry; north_star names the FFMA peak)")
-    fp32_sweep = {"bound": "fp32", "kernel": "chamfer_filter_kernel<16>", "achieved": fp_tflops, "peak": fp32_theory,
-                  "unit": "TFLOP/s", "frac": fp_tflops / fp32_theory,
-                  "traffic": 3174656,   # dram__bytes_read+write per launch, profiles/r1_chamfer_kernels_ncu.txt (ncu --set full)
-                  "peak_source": peak_src, "fp32_pipe_ops_per_pair": 4, "launch_us": fp_ms * 1e3,
-                  "note": "the FP32-pipe sweep (RLG_CHAMFER_SWEEP=fp32): 3 FFMA + 1 FADD + 2 min slots per pair through one "
-                          "dispatch port per SM sub-partition caps the FFMA pipe near 60 % (tools/ubench2.cu, DESIGN.md 3.1)"}
+    flops = FLOP_PER_PAIR * B
+    # what the fused tensor kernel can at best reach: its minima cost one dispatch slot per (query, candidate, direction)
+    # value and lane -- 4 sub-partitions x 32 lanes per SM and clock -- i.e. 64 pairs per SM and clock
+    issue_bound_tflops = int(peak[3]) * 64 * peak[1] * 1e6 * 8.0 / 1e12
+    fp32_sweep = {"bound": "fp32", "kernel": "chamfer_filter_kernel<16> (pair sweep of the FP32 path, alone)",
+                  "achieved": flops / (fp_sweep_ms * 1e-3) / 1e12, "peak": fp32_theory, "unit": "TFLOP/s",
+                  "frac": flops / (fp_sweep_ms * 1e-3) / 1e12 / fp32_theory, "traffic": profile_traffic("chamfer_filter_kernel"),
+                  "launch_us": fp_sweep_ms * 1e3, "forward_us": fp_fwd_ms * 1e3,
+                  "note": "RLG_CHAMFER_SWEEP=fp32: 3 FFMA + 1 FADD + 2 min slots per pair through one dispatch port per SM "
+                          "sub-partition cap the FFMA pipe near 60 % (DESIGN.md 3.1)"}
     if use_tensor:
-        roofline = {"bound": "fp32", "kernel": "chamfer_tcfilter_kernel", "achieved": achieved_tflops, "peak": fp32_theory,
-                    "unit": "TFLOP/s", "frac": achieved_tflops / fp32_theory,
-                    "traffic": 1634048,   # dram__bytes_read+write per launch, profiles/r1b_chamfer_kernels_ncu.txt (inputs: 1.57 MB)
-                    "peak_source": peak_src, "peak_measured_ffma": peak[0], "peak_measured_ffma2": peak[4],
-                    "note": "algorithmic 8 flop per point pair against the FP32 FFMA peak north_star names.  This kernel "
-                            "runs the 3-term contraction on the tensor pipe (tcgen05 kind::tf32, split-tf32 operands, "
-                            "2 x 128x128x8 MMAs per 128x128 pairs: 2*16 flop per pair on a pipe with ~1.1 PFLOP/s) and "
-                            "only the minima on the CUDA cores (~1.4 issue slots per pair and direction); its bound is "
-                            "the SM issue rate of the min reduction, not the FFMA pipe",
-                    "frac_of_measured_ffma": achieved_tflops / peak[0] if peak[0] else None,
-                    "launch_us": tile_ms * 1e3, "algorithmic_flop_per_launch": FLOP_PER_PAIR * B,
+        tf = flops / (tc_fwd_ms * 1e-3) / 1e12
+        roofline = {"bound": "fp32", "kernel": "chamfer_tcsweep_kernel (the whole forward: pair sweep + exact refinement + means + loss, ONE launch)",
+                    "achieved": tf, "peak": fp32_theory, "unit": "TFLOP/s", "frac": tf / fp32_theory,
+                    "traffic": profile_traffic("chamfer_tcsweep_kernel"), "peak_source": peak_src,
+                    "peak_measured_ffma": peak[0], "frac_of_measured_ffma": tf / peak[0] if peak[0] else None,
+                    "launch_us": tc_fwd_ms * 1e3, "algorithmic_flop_per_launch": flops,
+                    "issue_bound_tflops": issue_bound_tflops, "frac_of_issue_bound": tf / issue_bound_tflops,
+                    "note": "algorithmic 8 flop per point pair against the FP32 FFMA peak north_star names.  The kernel runs the "
+                            "3-term contraction on the tensor pipe (tcgen05 kind::tf32, split-tf32 operands) and only the "
+                            "minima and the exact refinement on the CUDA cores; the bound it can reach is the dispatch rate of "
+                            "the min reduction (issue_bound_tflops: one slot per value and lane), not the FFMA pipe",
                     "fp32_sweep": fp32_sweep}
+        roofline_fwd = dict(roofline, kernel="chamfer_distance_l2 forward (one launch)")
     else:
-        roofline = dict(fp32_sweep, peak_measured_ffma=peak[0], peak_measured_ffma2=peak[4],
-                        frac_of_measured_ffma=fp_tflops / peak[0] if peak[0] else None,
-                        algorithmic_flop_per_launch=FLOP_PER_PAIR * B)
+        tf = flops / (fp_fwd_ms * 1e-3) / 1e12
+        roofline = dict(fp32_sweep, peak_source=peak_src, peak_measured_ffma=peak[0], algorithmic_flop_per_launch=flops)
+        roofline_fwd = {"bound": "fp32", "kernel": "chamfer_distance_l2 forward (pair sweep + refinement kernel)", "achieved": tf,
+                        "peak": fp32_theory, "unit": "TFLOP/s", "frac": tf / fp32_theory, "traffic": None,
+                        "launch_us": fp_fwd_ms * 1e3}
 
     # backward: HBM-bound by bytes, launch-bound at this size
     g = torch.full((B,), 0.5 / B, device=dev)
+    reps = 400
     for _ in range(10):
         rlg.chamfer_backward(a, b, d1, d2, i1, i2, g, g)
     torch.cuda.synchronize()
@@ -352,15 +533,13 @@ def run_ours(args):
     bwd_gbs = BWD_BYTES_PER_PAIR * B / (bwd_ms * 1e-3) / 1e9
     roofline_bwd = {"bound": "hbm", "kernel": "memset x2 + chamfer_bwd_kernel (stand-alone call; inside a training step the "
                     "forward zero-fills and the backward is the single kernel)", "achieved": bwd_gbs,
-                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": bwd_gbs / peaks["hbm_gbs"], "traffic": None,
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": bwd_gbs / peaks["hbm_gbs"],
+                    "traffic": profile_traffic("chamfer_bwd_kernel"),
                     "peak_source": f"{peaks_src} MEASURED_PEAKS.json hbm_gbs", "launch_us": bwd_ms * 1e3,
                     "note": "7.3 MB per call: launch-latency bound at this shape; timed through Python (ctypes) calls"}
 
-    extra = {}
-    if not args.no_encoder:
-        extra.update(encoder_side_measurement(rlg, dev, peaks, peaks_src))
-        extra.update(reward_side_measurement(rlg, dev, fp32_theory))
-        extra.update(large_cloud_measurement(rlg, dev, fp32_theory))
+    if extras_on:
+        extra.update(torch_cuda_measurement(dev, ring))
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
@@ -377,22 +556,23 @@ def run_ours(args):
                         "sample": f"{n} steps of ChamferLoss fwd+bwd, B={B}, N=M={N}, torch CPU ops as the reference "
                                   f"runs them (oracle port), {dt:.1f} s"}
 
+    cfg = base_config(world)
+    cfg.update(info)
+    cfg.update({"step": "ChamferLoss forward + backward (autograd), S steps per CUDA graph; at n_gpus > 1 the loss scalar is "
+                        "all-reduced every step inside the graph (side stream)", "last_loss": last_loss,
+                "collective": collective,
+                "pair_sweep": "tensor (tcgen05 kind::tf32 contraction + CUDA-core minima, refinement fused)" if use_tensor
+                else "fp32 (FFMA pipe)"})
     out = {
         "metric": "chamfer_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": "chamfer_fwd_bwd B=32 N=M=2048 sphere (BASELINE configs[1])", "B_per_gpu": B, "N": N,
-                   "M": M, "global_batch": B * world, "parallelism": f"batch-sharded dp{world}",
-                   "l2_policy": f"inputs cycle through a ring of {slots} batches = {slots * slot_bytes >> 20} MiB > 126 MB L2",
-                   "step": "ChamferLoss forward + backward (autograd), captured S steps per CUDA graph; loss all-reduce async "
-                           "per replay when n_gpus > 1", "steps_per_graph": slots, "last_loss": last_loss,
-                   "pair_sweep": "tensor (tcgen05 kind::tf32 contraction + CUDA-core minima)" if use_tensor else "fp32 (FFMA pipe)"},
-        "roofline": roofline, "roofline_bwd": roofline_bwd, "cpu_baseline": cpu_baseline,
+        "data": "synthetic", "config": cfg,
+        "roofline": roofline, "roofline_fwd": roofline_fwd, "roofline_bwd": roofline_bwd, "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": slot_bytes, "d2h_bytes_per_step": 4,
                 "steps": Ke, "loss_step0": e2e_loss_check,
                 "how": "HostChamferStepGraph: per step ONE H2D transfer of the pinned (pred,target) buffer -> ChamferLoss -> "
                        "backward -> D2H of the loss (own stream), 32 steps per CUDA-graph replay, copies double-buffered "
-                       "against the previous step's kernels; wall clock around replays + synchronize"},
+                       "against the previous step's kernels; wall clock around replays + synchronize, max over ranks"},
         "gpu_launches": n_launches, "clocks": clocks,
     }
     out.update(extra)
@@ -412,37 +592,49 @@ def ctypes_float6(lib, dev):
     return [float(v) for v in out]
 
 
-def encoder_side_measurement(rlg, dev, peaks, peaks_src):
-    """Encoder clouds/s at cfg3 (B=256, N=2048, dims 3->64->128->1024 + max-pool + global MLP -> GFV), the second
-    half of the BASELINE metric, through the public module call `enc(x)` in eval mode.  Reported as extra keys of
-    the same JSON line: the tcgen05 bf16 path (headline), its e2e figure from pinned host clouds, and the fp32
-    CUDA-core path for comparison."""
-    from oracle import oracle as O
+def randomize_bn(module, seed=0):
+    """Non-trivial BatchNorm statistics/affine -- a fresh BN is identity-like."""
+    g = torch.Generator().manual_seed(seed)
+    for m in module.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            with torch.no_grad():
+                m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.5)
+                m.running_var.copy_(torch.rand(m.num_features, generator=g) * 1.7 + 0.3)
+                m.weight.copy_(1.0 + torch.randn(m.num_features, generator=g) * 0.5)
+                m.bias.copy_(torch.randn(m.num_features, generator=g) * 0.3)
+
+
+def encoder_measurement(rlg, dev, D, peaks, peaks_src, dims, key, workload):
+    """Encoder clouds/s through the public module call `enc(x)` in eval mode, every rank on its own 256 clouds (weak
+    scaling), aggregated over ranks: the fastest available path (tensor cores where the widths allow) as the headline
+    of the key, the fp32 path beside it, and an e2e figure from pinned host clouds."""
     torch.manual_seed(0)
-    enc = rlg.PointNetEncoder(3, 128, ENC_DIMS)
-    O.randomize_bn(enc, 0)
+    enc = rlg.PointNetEncoder(3, 128, dims)
+    randomize_bn(enc, 0)
     enc = enc.eval().to(dev)
-    gen = torch.Generator(device="cpu").manual_seed(1234 + 3)
+    gen = torch.Generator(device="cpu").manual_seed(1234 + 3 + 1000 * D.dist.get_rank() if D.world > 1 else 1234 + 3)
     xs_host = [sphere(gen, ENC_B, ENC_N).pin_memory() for _ in range(24)]      # 24 x 6.3 MB = 151 MB > L2
     xs = [x.to(dev) for x in xs_host]
-    flop = 2.0 * ENC_N * (3 * 64 + 64 * 128 + 128 * 1024) * ENC_B
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    out = {}
-    for precision, reps in (("bf16", 240), ("fp32", 12)):
+    widths = [3] + list(dims)
+    flop = 2.0 * ENC_N * sum(widths[i] * widths[i + 1] for i in range(len(dims))) * ENC_B
+    res = {}
+    for precision, reps in (("bf16", 120), ("fp32", 12)):
         enc.rlg_precision = precision
-        with torch.no_grad():
-            for k in range(3):
-                enc(xs[k])
-            torch.cuda.synchronize()
-            e0.record()
-            for k in range(reps):
-                enc(xs[k % len(xs)])
-            e1.record()
-            torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
-        out[precision] = (ms, flop / (ms * 1e-3) / 1e12)
+
+        def call(k):
+            with torch.no_grad():
+                return enc(xs[k % len(xs)])
+        try:
+            call(0)
+            path = rlg.encoder_path_of(enc) if hasattr(rlg, "encoder_path_of") else precision
+        except Exception as e:
+            res[precision] = {"error": f"{type(e).__name__}: {e}"[:200]}
+            continue
+        ms = D.timed(call, reps)
+        res[precision] = {"ms": ms, "tflops": flop / (ms * 1e-3) / 1e12, "path": path}
+    best = "bf16" if "ms" in res.get("bf16", {}) else "fp32"
+    enc.rlg_precision = best
     # e2e: pinned host clouds -> H2D -> enc(x) -> GFV D2H, every step, double-buffered on two streams
-    enc.rlg_precision = "bf16"
     gfv_host = torch.empty(len(xs_host), ENC_B, 128).pin_memory()
     copy_s, comp_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     stage = [torch.empty_like(xs[0]) for _ in range(2)]
@@ -466,91 +658,152 @@ def encoder_side_measurement(rlg, dev, peaks, peaks_src):
         comp_s.synchronize()
 
     e2e_pass(4)
-    n = 96
+    D.barrier()
+    n = 48 if best == "bf16" else 8
     t0 = time.perf_counter()
     e2e_pass(n)
-    e2e_s = time.perf_counter() - t0
-    ms, tf = out["bf16"]
-    return {"encoder": {"metric": "encoder_clouds_per_s", "value": ENC_B / (ms * 1e-3), "unit": "clouds/s",
-                        "config": {"workload": "PointNet encoder 3->64->128->1024 + max-pool + GFV head, B=256, N=2048 "
-                                               "(BASELINE configs[2])", "l2_policy": "24 input batches = 151 MB cycled"},
-                        "dtype": "bf16", "path": "tcgen05/TMEM bf16 fused trunk (rlg_encoder_fwd_bf16) + stock global_mlp",
-                        "ms_per_step": ms,
-                        "roofline": {"bound": "tensor", "kernel": "encoder_tc_kernel", "achieved": tf,
-                                     "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                                     "frac": tf / peaks["bf16_tflops_sustained"], "traffic": None,
-                                     "peak_source": f"{peaks_src} MEASURED_PEAKS.json bf16_tflops_sustained",
-                                     "algorithmic_flop_per_launch": flop},
-                        "e2e": {"value": n * ENC_B / e2e_s, "unit": "clouds/s", "h2d_bytes_per_step": ENC_B * ENC_N * 12,
-                                "d2h_bytes_per_step": ENC_B * 128 * 4, "steps": n},
-                        "fp32_path": {"value": ENC_B / (out["fp32"][0] * 1e-3), "unit": "clouds/s",
-                                      "ms_per_step": out["fp32"][0], "tflops": out["fp32"][1],
-                                      "path": "fp32 CUDA-core fused trunk (rlg_encoder_fwd)"}}}
+    e2e_s = D.max_ms((time.perf_counter() - t0) * 1e3) * 1e-3
+    ms, tf = res[best]["ms"], res[best]["tflops"]
+    tensor = best == "bf16"
+    peak = peaks["bf16_tflops_sustained"] if tensor else None
+    out = {"metric": "encoder_clouds_per_s", "value": ENC_B * D.world / (ms * 1e-3), "unit": "clouds/s", "n_gpus": D.world,
+           "scaling": "weak", "config": {"workload": workload, "l2_policy": "24 input batches = 151 MB cycled"},
+           "dtype": best, "path": res[best]["path"], "ms_per_step": ms,
+           "roofline": {"bound": "tensor", "kernel": res[best]["path"], "achieved": tf, "peak": peak, "unit": "TFLOP/s",
+                        "frac": tf / peak if peak else None, "traffic": profile_traffic("encoder_tc_kernel"),
+                        "peak_source": f"{peaks_src} MEASURED_PEAKS.json bf16_tflops_sustained" if peak else
+                        "fp32 CUDA-core path: no tensor roofline applies", "algorithmic_flop_per_launch": flop},
+           "e2e": {"value": n * ENC_B * D.world / e2e_s, "unit": "clouds/s", "h2d_bytes_per_step": ENC_B * ENC_N * 12,
+                   "d2h_bytes_per_step": ENC_B * 128 * 4, "steps": n},
+           "paths": res}
+    del xs, xs_host
+    return {key: out}
 
 
-def reward_side_measurement(rlg, dev, fp32_peak):
+def reward_measurement(rlg, dev, D):
     """BASELINE configs[3]: reward evaluation for E=1024 episodes (decoder output vs complete cloud, N=M=2048) in one
-    batched forward-only pass (rlg.batched_rewards; the reference loops B=1 with a host sync per episode)."""
-    E, n = 1024, 2048
-    gen = torch.Generator(device="cpu").manual_seed(1234 + 4)
+    batched forward-only pass, the 1024 episodes sharded over the ranks (strong scaling: 1024/n_gpus per GPU)."""
+    E_total, n = 1024, 2048
+    E = max(1, E_total // D.world)
+    rank = D.dist.get_rank() if D.world > 1 else 0
+    gen = torch.Generator(device="cpu").manual_seed(1234 + 4 + 1000 * rank)
     batches = []
-    for _ in range(3):                                   # 3 x 50 MB of clouds > L2
+    for _ in range(max(3, (140 << 20) // (E * n * 24) + 1)):        # > L2 in total
         batches.append((sphere(gen, E, n).to(dev), sphere(gen, E, n).to(dev), torch.rand(E, 128, generator=gen).to(dev),
                         torch.rand(E, 128, generator=gen).to(dev), torch.randn(E, 1, generator=gen).to(dev)))
-    for k in range(3):
-        rlg.batched_rewards(*batches[k])
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 12
-    e0.record()
-    for k in range(reps):
-        r = rlg.batched_rewards(*batches[k % 3])
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    tf = 8.0 * n * n * E / (ms * 1e-3) / 1e12
-    return {"reward_loop": {"metric": "reward_evals_per_s", "value": E / (ms * 1e-3), "unit": "episodes/s", "ms_per_step": ms,
-                            "config": {"workload": "RewardFunction for E=1024 episodes, Chamfer N=M=2048 forward only + GFV MSE + "
-                                                   "discriminator term (BASELINE configs[3])"},
-                            "chamfer_tflops": tf, "frac_of_fp32_peak": tf / fp32_peak, "last_reward_mean": float(r.mean().item())}}
+    out = {}
+
+    def call(k):
+        out["r"] = rlg.batched_rewards(*batches[k % len(batches)])
+    ms = D.timed(call, 12)
+    tf = 8.0 * n * n * E * D.world / (ms * 1e-3) / 1e12
+    return {"reward_loop": {"metric": "reward_evals_per_s", "value": E * D.world / (ms * 1e-3), "unit": "episodes/s",
+                            "n_gpus": D.world, "scaling": "strong", "episodes_per_gpu": E, "ms_per_step": ms,
+                            "config": {"workload": "RewardFunction for E=1024 episodes sharded over the GPUs, Chamfer N=M=2048 forward "
+                                                   "only + GFV MSE + discriminator term (BASELINE configs[3])"},
+                            "chamfer_tflops_algorithmic": tf, "last_reward_mean": float(out["r"].mean().item())}}
 
 
-def large_cloud_measurement(rlg, dev, fp32_peak):
-    """BASELINE configs[4] as it lands on ONE GPU of the 8-GPU box: 8 of the 64 pairs, N=M=16384, ChamferLoss forward +
-    backward.  Reported as an extra key (parity at this size is tests/test_chamfer_gpu.py::test_large_cloud_16384)."""
-    B, N, M = 8, 16384, 16384
-    g = torch.Generator().manual_seed(1238)
-
-    def sphere(b, n):
-        x = torch.randn(b, n, 3, generator=g)
-        return (x / x.norm(dim=2, keepdim=True)).to(dev)
-
-    ring = [(sphere(B, N).requires_grad_(True), sphere(B, M)) for _ in range(4)]
+def large_cloud_measurement(rlg, dev, D):
+    """BASELINE configs[4]: ChamferLoss forward + backward, B=64 pairs of N=M=16384 sharded over the ranks (64/n_gpus per
+    GPU), the loss scalar all-reduced every step (NCCL)."""
+    Bt, n = 64, 16384
+    Bl = max(1, Bt // D.world)
+    rank = D.dist.get_rank() if D.world > 1 else 0
+    g = torch.Generator().manual_seed(1238 + 1000 * rank)
+    ring = [(sphere(g, Bl, n).to(dev).requires_grad_(True), sphere(g, Bl, n).to(dev)) for _ in range(max(2, 160 // Bl))]
     crit = rlg.ChamferLoss()
     one = torch.ones((), device=dev)
+    out = {}
 
     def step(k):
         a, b = ring[k % len(ring)]
         a.grad = None
         loss = crit(a, b)
         loss.backward(gradient=one)
+        if D.world > 1:
+            red = loss.detach().reshape(1).clone()
+            D.dist.all_reduce(red)
+        out["loss"] = loss
+
+    ms = D.timed(step, 10)
+    tf = 8.0 * n * n * Bl * D.world / (ms * 1e-3) / 1e12
+    return {"large_cloud": {"metric": "chamfer_pairs_per_s", "value": Bl * D.world / (ms * 1e-3), "unit": "pairs/s",
+                            "n_gpus": D.world, "scaling": "strong", "pairs_per_gpu": Bl, "ms_per_step": ms,
+                            "config": {"workload": "ChamferLoss fwd+bwd, B=64 pairs of N=M=16384 sharded over the GPUs, loss "
+                                                   "all-reduce per step (BASELINE configs[4])"},
+                            "algorithmic_tflops": tf, "last_loss": float(out["loss"].item())}}
+
+
+def torch_cuda_measurement(dev, ring):
+    """The kernels to beat: the reference's own op sequence on stock torch CUDA kernels on this GPU.
+    Chamfer: torch.cdist -> min x2 -> mean, autograd backward (utils/losses.py:29-37,54-59,75), fp32 (TF32 off, as torch
+    defaults).  Encoder: the stock Conv1d/BatchNorm1d/ReLU stack + max + Linear head in eval mode
+    (models/autoencoder.py:13-76), fp32 and under bf16 autocast.  Plain torch calls written out here; rank 0 only."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def chamfer_step(a, b):
+        a = a.detach().requires_grad_(True)
+        dm = torch.cdist(a, b, p=2)
+        loss = torch.mean((torch.mean(torch.min(dm, dim=2)[0], dim=1) + torch.mean(torch.min(dm, dim=1)[0], dim=1)) / 2.0)
+        loss.backward()
         return loss
 
-    for k in range(3):
-        step(k)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 20
-    e0.record()
-    for k in range(reps):
-        loss = step(k)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    tf = 8.0 * N * M * B / (ms * 1e-3) / 1e12
-    return {"large_cloud": {"metric": "chamfer_pairs_per_s", "value": B / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
-                            "config": {"workload": "ChamferLoss fwd+bwd, 8 pairs per GPU of B=64, N=M=16384 (BASELINE configs[4])"},
-                            "algorithmic_tflops": tf, "frac_of_fp32_peak": tf / fp32_peak, "last_loss": float(loss.item())}}
+    out = {}
+    try:
+        for k in range(3):
+            chamfer_step(*ring[k])
+        torch.cuda.synchronize()
+        reps = 20
+        e0.record()
+        for k in range(reps):
+            chamfer_step(*ring[k % len(ring)])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out["chamfer_fwd_bwd"] = {"value": B / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
+                                  "what": "torch.cdist -> min x2 -> mean + autograd backward, B=32 N=M=2048, fp32, eager"}
+    except Exception as e:
+        out["chamfer_fwd_bwd"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    torch.cuda.empty_cache()
+
+    def stock_encoder(dims):
+        seq, c_in = [], 3
+        for c in dims:
+            seq += [torch.nn.Conv1d(c_in, c, 1), torch.nn.BatchNorm1d(c), torch.nn.ReLU(inplace=True)]
+            c_in = c
+        trunk = torch.nn.Sequential(*seq)
+        head = torch.nn.Sequential(torch.nn.Linear(c_in, 128), torch.nn.BatchNorm1d(128), torch.nn.ReLU(inplace=True))
+        return trunk.eval().to(dev), head.eval().to(dev)
+
+    gen = torch.Generator(device="cpu").manual_seed(77)
+    xs = [sphere(gen, ENC_B, ENC_N).to(dev) for _ in range(4)]
+    for name, dims in (("encoder", ENC_DIMS), ("encoder_config_dims", CFG_DIMS)):
+        torch.manual_seed(0)
+        trunk, head = stock_encoder(dims)
+        for mode in ("fp32", "bf16_autocast"):
+            try:
+                def fwd(x):
+                    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode != "fp32")):
+                        return head(torch.max(trunk(x.transpose(2, 1)), dim=2)[0])
+                for k in range(2):
+                    fwd(xs[k])
+                torch.cuda.synchronize()
+                reps = 8
+                e0.record()
+                for k in range(reps):
+                    fwd(xs[k % len(xs)])
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / reps
+                out[f"{name}_{mode}"] = {"value": ENC_B / (ms * 1e-3), "unit": "clouds/s", "ms_per_step": ms,
+                                         "what": f"stock Conv1d/BatchNorm1d/ReLU x{len(dims)} + max + Linear head, eval, "
+                                                 f"B=256 N=2048, dims {dims}, {mode}"}
+            except Exception as e:
+                out[f"{name}_{mode}"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        del trunk, head
+        torch.cuda.empty_cache()
+    return {"torch_cuda": out}
 
 
 def main():

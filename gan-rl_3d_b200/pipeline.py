@@ -1,6 +1,6 @@
 """CUDA-graph step runners for the Chamfer hot path.
 
-At the headline shape (B=32, N=M=2048) one ChamferLoss forward+backward is ~60 us of GPU work in four kernel
+At the headline shape (B=32, N=M=2048) one ChamferLoss forward+backward is ~50 us of GPU work in two kernel
 launches, less than the Python/ctypes cost of enqueuing it.  These helpers capture S steps -- exactly the calls a
 user makes, `loss = ChamferLoss()(pred, target); loss.backward()` -- into one CUDA graph so the launch-bound
 loop is replayed by the driver instead of re-issued from Python (train_rl_gan_net.py:220-249 is such a loop).
@@ -12,11 +12,17 @@ loop is replayed by the driver instead of re-issued from Python (train_rl_gan_ne
 """
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
 
-from .chamfer import ChamferLoss
+from .chamfer import ChamferLoss, _use_tensor
+
+
+def launches_per_step(n: int, m: int) -> int:
+    """Kernels of this library in one ChamferLoss forward + backward: the fused tensor forward is ONE launch, the FP32
+    path two (pair sweep + refinement); the backward is one (the forward zero-fills the gradient buffers)."""
+    return 2 if _use_tensor(None, n, m) else 3
 
 
 class ChamferStepGraph:
@@ -24,14 +30,20 @@ class ChamferStepGraph:
     After replay(): self.losses[k] (0-dim tensors) and self.grads[k] (d loss / d pred) hold step k's results."""
 
     def __init__(self, batches: Sequence[Tuple[torch.Tensor, torch.Tensor]], bidirectional: bool = True,
-                 grad_target: bool = False):
+                 grad_target: bool = False, after_step: Optional[Callable[[torch.Tensor], None]] = None):
+        """after_step(loss): optional hook captured after every step ON A SIDE STREAM (forked after the step's kernels,
+        joined at the end of the graph) -- e.g. the data-parallel all-reduce of the logged loss scalar, which then
+        overlaps the next step's kernels instead of serialising with them."""
         assert len(batches) > 0 and batches[0][0].is_cuda
         self.crit = ChamferLoss(bidirectional)
         self.batches = [(a.detach().requires_grad_(True), b.detach().requires_grad_(grad_target)) for a, b in batches]
         self.device = self.batches[0][0].device
         self.losses: List[torch.Tensor] = []
         self.grads: List[torch.Tensor] = []
-        self.kernel_launches_per_replay = 3 * len(self.batches)    # pair sweep + finalize + backward
+        self.after_step = after_step
+        self.side = torch.cuda.Stream(self.device) if after_step is not None else None
+        a0, b0 = self.batches[0]
+        self.kernel_launches_per_replay = launches_per_step(a0.shape[1], b0.shape[1]) * len(self.batches)
         self._one = torch.ones((), dtype=torch.float32, device=self.device)   # d loss / d loss, made once (no fill per step)
         self.stream = torch.cuda.Stream(self.device)
         self.graph = torch.cuda.CUDAGraph()
@@ -55,6 +67,12 @@ class ChamferStepGraph:
             for k in range(len(self.batches)):
                 self.losses.append(self._one_step(k))
                 self.grads.append(self.batches[k][0].grad)
+                if self.after_step is not None:
+                    self.side.wait_stream(self.stream)
+                    with torch.cuda.stream(self.side):
+                        self.after_step(self.losses[-1])
+            if self.after_step is not None:
+                self.stream.wait_stream(self.side)
         torch.cuda.current_stream(self.device).wait_stream(self.stream)
 
     def replay(self) -> None:
@@ -97,7 +115,7 @@ class HostChamferStepGraph:
         self.losses_host = torch.zeros(self.S, dtype=torch.float32).pin_memory()
         self.h2d_bytes_per_step = (a0.numel() + b0.numel()) * 4
         self.d2h_bytes_per_step = 4
-        self.kernel_launches_per_replay = 3 * self.S
+        self.kernel_launches_per_replay = launches_per_step(a0.shape[1], b0.shape[1]) * self.S
         self._one = torch.ones((), dtype=torch.float32, device=device)
         self.compute = torch.cuda.Stream(device)
         self.copy = torch.cuda.Stream(device)
