@@ -59,6 +59,14 @@ EXPORTS = {
     "rlg_encoder_fwd_bf16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(RlgLayer),
                                             ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
                                             ctypes.c_void_p]),
+    "rlg_encoder_gemm_pack_bytes": (ctypes.c_size_t, [ctypes.POINTER(RlgLayer), ctypes.c_int, ctypes.c_int]),
+    "rlg_encoder_gemm_pack": (ctypes.c_int, [ctypes.POINTER(RlgLayer), ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_void_p,
+                                             ctypes.c_size_t, ctypes.c_void_p]),
+    "rlg_encoder_gemm_ws_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(RlgLayer), ctypes.c_int,
+                                                    ctypes.c_int]),
+    "rlg_encoder_gemm_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(RlgLayer), ctypes.c_int,
+                                            ctypes.c_int, c_float_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "rlg_fp32_peak": (ctypes.c_int, [c_float_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
 }
 
@@ -71,6 +79,8 @@ CHAMFER_FILTER_ONLY = 64
 # experiments build only (librlg_b200_exp.so, tools/): kernel variants in bits 8-11, first-generation tensor sweep
 X_CHAMFER_TENSOR_V1 = 128
 CHAMFER_BWD_ACCUMULATE = 1
+ENC_BF16 = 1
+ENC_FP32X = 2
 
 
 def load() -> ctypes.CDLL:

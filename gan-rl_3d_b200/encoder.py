@@ -5,9 +5,10 @@ Mirrors models/autoencoder.py:13-76 of phanich004/GAN-RL_3D.  `fused_forward` ha
 layout (`point_mlp` = [Conv1d(k=1), BatchNorm1d, ReLU] x L, `global_mlp` = [Linear, BatchNorm1d, ReLU]), so
 rebinding the class attribute keeps parameters, buffers and state_dict keys untouched.
 
-Eval mode only: BatchNorm with running statistics is an affine map and is folded into the conv weights
-(cached; invalidated when any parameter/buffer changes).  In train mode BatchNorm needs batch statistics over
-B*N points and updates its buffers, so the stock submodules run instead.
+Eval mode: BatchNorm with running statistics is an affine map and is folded into the conv weights (cached;
+invalidated when any parameter/buffer changes); the trunk then runs on the tensor cores at fp32 accuracy by default
+(layer-wise tcgen05 GEMMs on fp16 hi+lo operand pairs), see set_encoder_precision.  In train mode BatchNorm needs
+batch statistics over B*N points and updates its buffers: see train.py.
 """
 from __future__ import annotations
 
@@ -75,14 +76,17 @@ def folded_trunk_cached(module: nn.Module) -> List[Tuple[torch.Tensor, torch.Ten
     return cache[1]
 
 
+def _packed_cache(module: nn.Module) -> dict:
+    folded_trunk_cached(module)                      # invalidates the packed images together with the folded weights
+    return module.__dict__.setdefault("_rlg_packed", {})
+
+
 def packed_trunk_cached(module: nn.Module) -> torch.Tensor:
-    """bf16 images of the folded weights, cached next to (and invalidated with) the folded fp32 weights."""
-    layers = folded_trunk_cached(module)
-    packed = module.__dict__.get("_rlg_packed")
-    if packed is None:
-        packed = pack_bf16(layers)
-        module.__dict__["_rlg_packed"] = packed
-    return packed
+    """bf16 image of the folded weights for the single fused tcgen05 kernel, cached next to the folded fp32 weights."""
+    cache = _packed_cache(module)
+    if "fused" not in cache:
+        cache["fused"] = pack_bf16(folded_trunk_cached(module))
+    return cache["fused"]
 
 
 # ---- the CUDA trunk ---------------------------------------------------------------------------------
@@ -91,16 +95,22 @@ def is_hot_path_input(x) -> bool:
             and x.shape[2] == 3 and x.shape[1] >= 1)
 
 
-_PRECISION = "fp32"
+PRECISIONS = ("auto", "fp32", "fp32x", "bf16")
+_PRECISION = "auto"
 
 
 def set_encoder_precision(precision: str) -> None:
-    """Default arithmetic of the fused trunk: "fp32" (CUDA cores, GFVs within 1e-5 of the reference) or "bf16"
-    (tcgen05/TMEM tensor-core GEMMs with fp32 accumulation, GFVs within 2e-2; widths must fit the tensor path).
-    A module can override it with an attribute `rlg_precision`."""
+    """Arithmetic of the fused trunk (a module can override it with an attribute `rlg_precision`):
+      "fp32x"  tensor cores at fp32 accuracy: layer-wise tcgen05 GEMMs on fp16 hi+lo operand pairs (22 bits), GFVs within
+               1e-5 of the reference.  Widths must be multiples of 64 with hidden widths <= 256.
+      "fp32"   the CUDA-core kernel (any widths, reports argmax indices), GFVs within 1e-5.
+      "bf16"   bf16 tensor-core GEMMs with fp32 accumulation, GFVs within 2e-2: the single fused tcgen05 kernel when the
+               widths fit it (hidden <= 128, last a multiple of 128), else the layer-wise bf16 GEMMs.
+      "auto"   (default) "fp32x" where the widths allow, else "fp32".
+    A precision whose kernels do not cover the module's widths falls back to "fp32" (never raises)."""
     global _PRECISION
-    if precision not in ("fp32", "bf16"):
-        raise ValueError("precision must be 'fp32' or 'bf16'")
+    if precision not in PRECISIONS:
+        raise ValueError(f"precision must be one of {PRECISIONS}")
     _PRECISION = precision
 
 
@@ -124,8 +134,8 @@ def _layer_array(layers):
 
 
 def pack_bf16(layers: List[Tuple[torch.Tensor, torch.Tensor]]) -> torch.Tensor:
-    """bf16 weight images of layers >= 1 in the swizzled shared-memory layout the tcgen05 kernel loads with TMA
-    bulk copies.  Raises RlgError (RLG_ERR_UNSUPPORTED) if the widths do not fit the tensor path."""
+    """bf16 weight images of layers >= 1 in the swizzled shared-memory layout the fused tcgen05 kernel loads with TMA
+    bulk copies.  Raises RlgError (RLG_ERR_UNSUPPORTED) if the widths do not fit that kernel."""
     lib = _lib.load()
     arr, keep = _layer_array(layers)
     dev = layers[0][0].device
@@ -140,13 +150,93 @@ def pack_bf16(layers: List[Tuple[torch.Tensor, torch.Tensor]]) -> torch.Tensor:
     return packed
 
 
+def fused_tc_supported(layers) -> bool:
+    """Widths the single fused tcgen05 kernel (encoder_tc.cu) covers."""
+    dims = [w.shape[0] for w, _ in layers]
+    return (len(dims) >= 2 and all(d in (64, 128) for d in dims[:-1]) and dims[-1] % 128 == 0)
+
+
+def gemm_supported(layers) -> bool:
+    """Widths the layer-wise tcgen05 GEMM path (encoder_layers.cu) covers."""
+    dims = [w.shape[0] for w, _ in layers]
+    return (2 <= len(dims) <= 8 and all(d % 64 == 0 and d >= 64 for d in dims) and all(d <= 256 for d in dims[:-1])
+            and layers[0][0].shape[1] == 3)
+
+
+def pack_gemm(layers, mode: int):
+    """Operand image of the folded weights for the layer-wise GEMM path + the per-layer power-of-two weight scales
+    (largest power of two with max|w| * scale <= 2^14; a host synchronisation, paid when the weights change)."""
+    lib = _lib.load()
+    arr, keep = _layer_array(layers)
+    dev = layers[0][0].device
+    L = len(layers)
+    scales = (ctypes.c_float * L)()
+    scales[0] = 1.0
+    for l in range(1, L):
+        m = float(layers[l][0].abs().max().item()) if mode == _lib.ENC_FP32X else 1.0
+        e = 0 if mode != _lib.ENC_FP32X or not (m > 0.0) or m != m else max(-20, min(20, int(torch.floor(torch.log2(torch.tensor(16384.0 / m))).item())))
+        scales[l] = float(2.0 ** e)
+    with torch.cuda.device(dev):
+        nbytes = lib.rlg_encoder_gemm_pack_bytes(arr, L, mode)
+        if nbytes == 0:
+            _lib.check("rlg_encoder_gemm_pack_bytes", -4)
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        rc = lib.rlg_encoder_gemm_pack(arr, L, mode, scales, packed.data_ptr(), packed.numel(),
+                                       torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check("rlg_encoder_gemm_pack", rc)
+    return packed, scales
+
+
+_gemm_ws = {}
+
+
+def _gemm_workspace(dev, stream, nbytes):
+    key = (dev.index, stream)
+    ws = _gemm_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        if torch.cuda.is_current_stream_capturing() and ws is not None:
+            raise RuntimeError("the encoder workspace cannot grow while its stream is being captured: run the shape once eagerly first")
+        ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+        _gemm_ws[key] = ws
+    return ws
+
+
+def encoder_pool_gemm(x: torch.Tensor, layers, mode: int, packed=None) -> torch.Tensor:
+    """pooled (B, C_last) through the layer-wise tcgen05 GEMM path (mode = _lib.ENC_BF16 or _lib.ENC_FP32X)."""
+    if not is_hot_path_input(x):
+        raise ValueError("gan-rl_3d_b200 encoder needs a CUDA float32 tensor (B,N,3) with N >= 1; there is no CPU path")
+    lib = _lib.load()
+    x = x.contiguous()
+    B, N, _ = x.shape
+    L = len(layers)
+    arr, keep = _layer_array(layers)
+    if packed is None:
+        packed = pack_gemm(layers, mode)
+    image, scales = packed
+    pooled = torch.empty((B, layers[-1][0].shape[0]), dtype=torch.float32, device=x.device)
+    if B == 0:
+        return pooled
+    with torch.cuda.device(x.device):
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        ws = _gemm_workspace(x.device, stream, lib.rlg_encoder_gemm_ws_bytes(B, N, arr, L, mode))
+        rc = lib.rlg_encoder_gemm_fwd(x.data_ptr(), B, N, arr, L, mode, scales, image.data_ptr(), image.numel(),
+                                      pooled.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+        _lib.check("rlg_encoder_gemm_fwd", rc)
+    return pooled
+
+
 def encoder_pool(x: torch.Tensor, layers: List[Tuple[torch.Tensor, torch.Tensor]], want_argmax: bool = False,
                  precision: str = "fp32", packed: Optional[torch.Tensor] = None):
     """pooled (B, C_last) = max over points of the folded per-point MLP (ReLU after every layer), i.e.
     torch.max(point_mlp(x.transpose(2,1)), dim=2)[0] of models/autoencoder.py:65-71 in eval mode.
-    Returns (pooled fp32, argmax int32 or None).  precision="bf16" runs layers >= 1 on the tensor cores."""
+    Returns (pooled fp32, argmax int32 or None).  precision: "fp32" (CUDA cores, optional argmax), "bf16" (the single
+    fused tcgen05 kernel), "fp32x" / "bf16_layers" (layer-wise tcgen05 GEMMs, see set_encoder_precision)."""
     if not is_hot_path_input(x):
         raise ValueError("gan-rl_3d_b200 encoder needs a CUDA float32 tensor (B,N,3) with N >= 1; there is no CPU path")
+    if precision in ("fp32x", "bf16_layers"):
+        if want_argmax:
+            raise ValueError("the tensor-core paths do not report argmax indices")
+        return encoder_pool_gemm(x, layers, _lib.ENC_FP32X if precision == "fp32x" else _lib.ENC_BF16, packed), None
     lib = _lib.load()
     x = x.contiguous()
     B, N, _ = x.shape
@@ -181,15 +271,54 @@ def encoder_pool(x: torch.Tensor, layers: List[Tuple[torch.Tensor, torch.Tensor]
     return pooled, argmax
 
 
+def resolve_path(layers, precision: str) -> str:
+    """Which kernel family runs a layer list under a requested precision: "fp32", "fp32x", "bf16" (fused) or
+    "bf16_layers".  Unsupported widths fall back to "fp32"."""
+    if precision in ("auto", "fp32x"):
+        return "fp32x" if gemm_supported(layers) else "fp32"
+    if precision == "bf16":
+        if fused_tc_supported(layers):
+            return "bf16"
+        return "bf16_layers" if gemm_supported(layers) else "fp32"
+    return "fp32"
+
+
+_PATH_NAMES = {"fp32": "fp32 CUDA-core fused trunk (encoder_fp32_kernel)",
+               "fp32x": "layer-wise tcgen05 GEMMs, fp16 hi+lo operands = fp32-grade (encoder_layer_kernel<2>)",
+               "bf16": "single fused tcgen05/TMEM bf16 kernel (encoder_tc_kernel)",
+               "bf16_layers": "layer-wise tcgen05 GEMMs, bf16 operands (encoder_layer_kernel<1>)"}
+
+
+def encoder_path_of(module: nn.Module) -> str:
+    """Human-readable name of the kernel family `module` runs in eval mode under its current precision setting."""
+    return _PATH_NAMES[resolve_path(folded_trunk_cached(module), getattr(module, "rlg_precision", _PRECISION))]
+
+
+class _bn_eval:
+    """Run a trunk with its BatchNorm layers in eval semantics regardless of module.training (restored on exit)."""
+
+    def __init__(self, seq: nn.Sequential):
+        self.bns = [m for m in seq if isinstance(m, nn.BatchNorm1d) and m.training]
+
+    def __enter__(self):
+        for m in self.bns:
+            m.training = False
+
+    def __exit__(self, *exc):
+        for m in self.bns:
+            m.training = True
+
+
 class EncoderTrunkFn(torch.autograd.Function):
     """x (B,N,3) -> pooled (B,C_last) through the fused kernel.  The backward (rare: eval mode with autograd
-    on) recomputes the trunk with the module's own stock layers and differentiates that, so gradients reach
-    the input and the original parameters exactly as in the reference graph."""
+    on) recomputes the trunk with the module's own stock layers -- BatchNorm forced to the eval semantics of the forward,
+    whatever mode the module is in by then -- and differentiates that, so gradients reach the input and the original
+    parameters exactly as in the reference graph."""
 
     @staticmethod
     def forward(ctx, x, module, *params):
         pooled = _trunk_pool(module, x)
-        ctx.module = module
+        ctx.point_mlp = module.point_mlp
         ctx.n_params = len(params)
         ctx.save_for_backward(x)
         return pooled
@@ -197,11 +326,11 @@ class EncoderTrunkFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (x,) = ctx.saved_tensors
-        module = ctx.module
-        params = list(module.point_mlp.parameters())
-        with torch.enable_grad():
+        point_mlp = ctx.point_mlp
+        params = list(point_mlp.parameters())
+        with torch.enable_grad(), _bn_eval(point_mlp):
             xin = x.detach().requires_grad_(True)
-            feat = torch.max(module.point_mlp(xin.transpose(2, 1)), dim=2)[0]
+            feat = torch.max(point_mlp(xin.transpose(2, 1)), dim=2)[0]
             wanted = [xin] + params
             grads = torch.autograd.grad(feat, wanted, g, allow_unused=True)
         gx = grads[0] if ctx.needs_input_grad[0] else None
@@ -210,16 +339,32 @@ class EncoderTrunkFn(torch.autograd.Function):
 
 
 def _trunk_pool(module: nn.Module, x: torch.Tensor) -> torch.Tensor:
-    precision = getattr(module, "rlg_precision", _PRECISION)
     layers = folded_trunk_cached(module)
-    if precision == "bf16":
+    path = resolve_path(layers, getattr(module, "rlg_precision", _PRECISION))
+    if path == "fp32":
+        return encoder_pool(x, layers)[0]
+    cache = _packed_cache(module)
+    if path == "bf16":
         return encoder_pool(x, layers, precision="bf16", packed=packed_trunk_cached(module))[0]
-    return encoder_pool(x, layers)[0]
+    mode = _lib.ENC_FP32X if path == "fp32x" else _lib.ENC_BF16
+    if path not in cache:
+        cache[path] = pack_gemm(layers, mode)
+    return encoder_pool_gemm(x, layers, mode, cache[path])
+
+
+def _module_is_hot(self: nn.Module, x) -> bool:
+    """The module has the reference's trunk layout and lives on the device of x."""
+    try:
+        _trunk_layers(self.point_mlp)
+    except (ValueError, AttributeError):
+        return False
+    p = next(self.point_mlp.parameters(), None)
+    return p is not None and p.device == x.device and p.dtype == torch.float32
 
 
 def fused_forward(self: nn.Module, x: torch.Tensor, _original=None) -> torch.Tensor:
     """Drop-in for PointNetEncoder.forward (models/autoencoder.py:56-76)."""
-    if self.training or not is_hot_path_input(x) or x.shape[0] == 0:
+    if self.training or not is_hot_path_input(x) or x.shape[0] == 0 or not _module_is_hot(self, x):
         if _original is not None:
             return _original(self, x)
         # stock path with the module's own layers (train-mode BatchNorm needs batch statistics)

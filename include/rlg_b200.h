@@ -181,6 +181,27 @@ int rlg_encoder_pack_bf16(const rlg_layer *layers, int L, void *packed, size_t p
 int rlg_encoder_fwd_bf16(const float *x, int B, int N, const rlg_layer *layers, int L,
                          const void *packed, size_t packed_bytes, float *pooled, void *stream);
 
+/* Layer-by-layer tensor-core path (encoder_layers.cu): TMA-fed tcgen05 GEMMs with the layer's weights resident in shared
+ * memory and the activations in HBM between layers.  Any layer list with widths that are multiples of 64, hidden widths
+ * <= 256 (the reference's own 3->64->128->128->256->128 included; anything else: RLG_ERR_UNSUPPORTED -> rlg_encoder_fwd).
+ *   mode RLG_ENC_BF16   bf16 operands, fp32 accumulation (2e-2 class)
+ *        RLG_ENC_FP32X  fp32-grade: operands carried as fp16 hi + lo pairs (22 bits), three MMAs per K step
+ *   weight_scales       host array of L floats (entry 0 unused): per-layer power-of-two scale applied to the weights
+ *                       when packing and undone in the epilogue; choose the largest power of two with
+ *                       max|w| * scale <= 2^14 (RLG_ENC_FP32X; ignored for RLG_ENC_BF16).  Same values for pack and fwd.
+ *   rlg_encoder_gemm_pack_bytes / rlg_encoder_gemm_pack   packed operand image of the weights (repack when they change)
+ *   rlg_encoder_gemm_ws_bytes                             two ping-pong activation buffers (caller-owned)
+ *   rlg_encoder_gemm_fwd                                  pooled (B, C_last) fp32, fully overwritten */
+#define RLG_ENC_BF16  1
+#define RLG_ENC_FP32X 2
+size_t rlg_encoder_gemm_pack_bytes(const rlg_layer *layers, int L, int mode);
+int rlg_encoder_gemm_pack(const rlg_layer *layers, int L, int mode, const float *weight_scales,
+                          void *packed, size_t packed_bytes, void *stream);
+size_t rlg_encoder_gemm_ws_bytes(int B, int N, const rlg_layer *layers, int L, int mode);
+int rlg_encoder_gemm_fwd(const float *x, int B, int N, const rlg_layer *layers, int L, int mode,
+                         const float *weight_scales, const void *packed, size_t packed_bytes,
+                         float *pooled, void *ws, size_t ws_bytes, void *stream);
+
 /* FP32 CUDA-core peak microbenchmark (measurement helper, not on the hot path; it synchronises).
  * Fills host array out[0..5]:
  *   [0] measured scalar FFMA TFLOP/s     [1] max SM clock (MHz)      [2] theoretical SMs*128*2*clock TFLOP/s

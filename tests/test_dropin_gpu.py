@@ -101,14 +101,22 @@ def test_autoencoder_training_step_with_chamfer_loss(rlg):
     model = AE().to(DEV).train()
     x = O.make_clouds(8, 180, "sphere", 7).to(DEV)
     target = O.make_clouds(8, 256, "sphere", 8).to(DEV)
-    # gradient parity with the stock loss on the same graph
-    model.zero_grad()
-    rlg.ChamferLoss()(model(x), target).backward()
+    # gradient of the loss w.r.t. the decoder output against the float64 closed form
+    pred = model(x)
+    pred.retain_grad()
+    rlg.ChamferLoss()(pred, target).backward()
     ours = [p.grad.clone() for p in model.parameters()]
+    pc, tc = pred.detach().cpu(), target.cpu()
+    d1, d2, i1, i2 = O.chamfer_direct(pc, tc, O.TIE_FAITHFUL)
+    up = np.full((8,), 0.5 / 8, np.float32)
+    g_pred, _ = O.chamfer_bwd_truth(pc, tc, d1, d2, i1, i2, up, up)      # float64 closed form for the oracle's indices
+    assert O.rowwise_rel_err(pred.grad.cpu().numpy(), g_pred) < 1e-5
+    # parameter gradients against the stock loss on the same graph: the stock path is the noisy matmul-expansion cdist and
+    # may route near-ties differently (an untrained decoder emits a tight blob of points), so norm-wise only
     model.zero_grad()
     O.ref_port_chamfer_loss(model(x), target).backward()
     for g, p in zip(ours, model.parameters()):
-        assert torch.allclose(g, p.grad, rtol=2e-2, atol=1e-5)      # stock path: matmul-expansion cdist noise
+        assert (g - p.grad).norm() <= 5e-2 * p.grad.norm() + 1e-6
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5)
     crit = rlg.ChamferLoss()
     first = last = None

@@ -176,3 +176,91 @@ def test_bf16_unsupported_widths_fail_loudly(rlg):
     layers = rlg.fold_trunk(enc.point_mlp)
     with pytest.raises(RuntimeError, match="hidden width"):
         rlg.encoder_pool(torch.zeros(1, 64, 3, device=DEV), layers, precision="bf16")
+
+
+# ---- layer-wise tcgen05 GEMM path (encoder_layers.cu): TMA-fed, weights resident, any widths that are multiples of 64 ----
+GEMM_DIMS = [[64, 128, 128, 256, 128], [64, 128, 1024], [64, 64], [128, 256, 64], [64, 256, 256, 192]]
+
+
+@pytest.mark.parametrize("dims", GEMM_DIMS)
+@pytest.mark.parametrize("B,N", [(2, 200), (1, 1), (3, 128), (2, 2048), (5, 1300), (9, 127)])
+def test_fp32x_tensor_path_holds_the_fp32_tolerance(rlg, dims, B, N):
+    """fp16 hi+lo operand pairs, three MMAs per K step: GFV trunk outputs within the FP32 tolerance of the float64 stack."""
+    enc = _port(dims, 32, len(dims) + 5)
+    x = O.make_clouds(B, N, "sphere", 1200 + N)
+    with torch.no_grad():
+        want = enc.double().pooled(x.double()).float().numpy()
+    enc = enc.float().to(DEV)
+    layers = rlg.fold_trunk(enc.point_mlp)
+    assert rlg.resolve_path(layers, "auto") == "fp32x"
+    pooled, _ = rlg.encoder_pool(x.to(DEV), layers, precision="fp32x")
+    torch.cuda.synchronize()
+    ok, err = O.gfv_close(pooled.cpu().numpy(), want, FP32_TOL)
+    assert ok, err
+    # clouds far from the origin and large activations (scale 30): the same tolerance
+    x2 = (x * 30.0 + 3.0).contiguous()
+    with torch.no_grad():
+        want2 = enc.double().cpu().pooled(x2.double()).float().numpy()
+    enc = enc.float().to(DEV)
+    pooled2, _ = rlg.encoder_pool(x2.to(DEV), layers, precision="fp32x")
+    ok, err = O.gfv_close(pooled2.cpu().numpy(), want2, FP32_TOL)
+    assert ok, err
+
+
+@pytest.mark.parametrize("dims", GEMM_DIMS)
+@pytest.mark.parametrize("B,N", [(2, 200), (1, 1), (2, 2048), (5, 1300)])
+def test_bf16_layerwise_path_vs_float64_stack(rlg, dims, B, N):
+    enc = _port(dims, 32, len(dims) + 6)
+    x = O.make_clouds(B, N, "sphere", 1300 + N)
+    with torch.no_grad():
+        want = enc.double().pooled(x.double()).float().numpy()
+    enc = enc.float().to(DEV)
+    layers = rlg.fold_trunk(enc.point_mlp)
+    pooled, _ = rlg.encoder_pool(x.to(DEV), layers, precision="bf16_layers")
+    torch.cuda.synchronize()
+    got = pooled.cpu().numpy()
+    ok, err = O.gfv_close(got, want, BF16_TOL, BF16_FLOOR)
+    assert ok, err
+    assert np.linalg.norm(got - want) <= 2 * BF16_NORM * np.linalg.norm(want)      # two to four bf16 layers deep
+
+
+def test_reference_config_runs_on_tensor_cores_by_default_and_under_bf16(rlg):
+    """The reference's own encoder_dims (configs/config.yaml:9-11): default precision -> fp32-grade tensor path within
+    1e-5; rlg_precision = "bf16" -> the layer-wise bf16 GEMMs (the single fused kernel cannot hold a 256-wide layer),
+    never an exception."""
+    enc = _port([64, 128, 128, 256, 128], 128, 21)
+    x = O.make_clouds(6, 1400, "sphere", 22)
+    with torch.no_grad():
+        want = enc.double()(x.double()).float().numpy()
+    enc = enc.float().to(DEV)
+    assert "fp16 hi+lo" in rlg.encoder_path_of(enc)
+    with torch.no_grad():
+        gfv = rlg.fused_forward(enc, x.to(DEV))
+    ok, err = O.gfv_close(gfv.cpu().numpy(), want, FP32_TOL)
+    assert ok, err
+    enc.rlg_precision = "bf16"
+    assert "bf16 operands" in rlg.encoder_path_of(enc)
+    with torch.no_grad():
+        gfv16 = rlg.fused_forward(enc, x.to(DEV))
+    assert O.gfv_close(gfv16.cpu().numpy(), want, BF16_TOL, BF16_FLOOR)[0]
+    # widths no tensor path covers fall back to the CUDA-core kernel, whatever precision is asked for
+    odd = _port([10, 70, 33], 12, 23).to(DEV)
+    odd.rlg_precision = "bf16"
+    assert "CUDA-core" in rlg.encoder_path_of(odd)
+    with torch.no_grad():
+        rlg.fused_forward(odd, x.to(DEV))
+
+
+def test_module_on_another_device_or_layout_delegates(rlg):
+    """A trunk that is not [Conv1d, BatchNorm1d, ReLU] x L, or a module whose weights are not on x's device, is not the
+    hot path: the original forward runs (and raises what the reference would raise)."""
+    import torch.nn as nn
+    enc = _port([16, 32], 8, 3)                      # weights on the CPU, input on the GPU
+    x = O.make_clouds(2, 50, "sphere", 4).to(DEV)
+    with pytest.raises(RuntimeError):
+        rlg.fused_forward(enc, x)
+    enc = enc.to(DEV)
+    enc.point_mlp = nn.Sequential(nn.Conv1d(3, 16, 1), nn.ReLU(), nn.Conv1d(16, 32, 1)).to(DEV)   # no BatchNorm
+    with torch.no_grad():
+        out = rlg.fused_forward(enc, x)
+    assert out.shape == (2, 8)
