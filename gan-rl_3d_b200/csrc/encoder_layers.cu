@@ -25,10 +25,12 @@
 //                  (hi = fp16(v), lo = fp16(v - hi): 22 significant bits, like split-tf32 but at the full f16 MMA rate and
 //                  half the bytes); three MMAs per K step (hi.hi + hi.lo + lo.hi, fp32 accumulation in TMEM), the lo.lo
 //                  term (2^-22 relative) is dropped.  The tensor core's fp32 accumulation truncates, so its error is biased
-//                  and grows with the number of additions into one accumulator: the two cross terms (2^-11 of the result)
-//                  therefore go to a SECOND accumulator and the main one only takes the K/16 hi.hi steps; the epilogue
-//                  adds the two in round-to-nearest (measured: 1-3.5e-5 -> see tests/test_encoder_gpu.py).  Weights are scaled by a power of two per layer so that max|w| lands
-//                  near 2^14 (the lo parts stay normal fp16 numbers); the epilogue undoes the scale exactly.  Activations
+//                  and grows with the number of additions into one accumulator (measured on the reference's dims: 3.6e-5 with
+//                  one accumulator).  So the two cross terms (2^-11 of the result) go to an accumulator of their own and the
+//                  hi.hi steps rotate over THREE main accumulators (at most six additions each at K = 256); the epilogue
+//                  adds the four in round-to-nearest.  That takes all 512 TMEM columns, so this mode is single-buffered
+//                  (MMA and epilogue of consecutive tiles alternate) -- the path is HBM-bound either way.
+//                  Weights are scaled by a power of two per layer so that max|w| lands near 2^14 (the lo parts stay normal fp16 numbers); the epilogue undoes the scale exactly.  Activations
 //                  are stored unscaled: values in [2^-3, 65504] keep all 22 bits, smaller ones an absolute error <= 2^-25,
 //                  larger ones saturate (post-ReLU activations of a BatchNorm-folded network are nowhere near 6.5e4).
 // Between layers the activations live in HBM in exactly the format the next TMA load wants (row-major [points x C],
@@ -152,12 +154,14 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
         mbar_wait_wd(bar_w, 0);
         uint32_t it = 0, ti = 0;
         for (int t = first; t < n_tiles; t += step, ++ti) {
-            const uint32_t acc = ti & 1u;
-            mbar_wait_wd(bar_accempty + 8 * acc, ((ti >> 1) & 1u) ^ 1u);
+            // bf16: two 128-column accumulators alternate between tiles.  fp16 hi+lo: ONE set of four -- three main
+            // accumulators (hi.hi steps rotate over them) at columns 0/128/256 and the cross terms at 384.
+            const uint32_t acc = PIECES == 1 ? (ti & 1u) : 0u;
+            const uint32_t par = PIECES == 1 ? ((ti >> 1) & 1u) : (ti & 1u);
+            mbar_wait_wd(bar_accempty + 8 * acc, par ^ 1u);
             tc_fence_after();
-            // accumulator buffer `acc`: main (hi.hi) at columns acc*256, cross terms (hi.lo + lo.hi) at acc*256 + 128
-            const uint32_t d = tmem + acc * 2u * (uint32_t)kLN, dx = d + (uint32_t)kLN;
-            uint32_t accum = 0;
+            const uint32_t d = tmem + acc * (uint32_t)kLN, dx = tmem + 3u * (uint32_t)kLN;
+            uint32_t accum = 0, used = 0, ks = 0;
             for (int kb = 0; kb < kblocks; ++kb, ++it) {
                 const uint32_t s = it % (uint32_t)a.stages, use = it / (uint32_t)a.stages;
                 mbar_wait_wd(bar_full + 8 * s, use & 1u);
@@ -167,17 +171,18 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
                     const uint64_t w0 = umma_desc(sbase + w_off + (uint32_t)kb * kLBlk);
                     const uint64_t xp = (uint64_t)(kLBlk >> 4), wp = (uint64_t)(((uint32_t)kblocks * kLBlk) >> 4);   // piece strides
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {          // 16 elements = 32 bytes per MMA along K
+                    for (int k4 = 0; k4 < 4; ++k4, ++ks) {    // 16 elements = 32 bytes per MMA along K
                         const uint64_t ko = (uint64_t)(k4 * 2);
                         if (PIECES == 1) {
                             tc_mma_bf16(d, x0 + ko, w0 + ko, idesc, accum);
-                            accum = 1;
                         } else {
-                            tc_mma_bf16(dx, x0 + xp + ko, w0 + ko, idesc, accum);         // lo . hi  -> cross accumulator
-                            tc_mma_bf16(dx, x0 + ko, w0 + wp + ko, idesc, 1u);            // hi . lo  -> cross accumulator
-                            tc_mma_bf16(d, x0 + ko, w0 + ko, idesc, accum);               // hi . hi  -> main accumulator
-                            accum = 1;
+                            const uint32_t m = ks % 3u;
+                            tc_mma_bf16(dx, x0 + xp + ko, w0 + ko, idesc, accum);                         // lo . hi  -> cross
+                            tc_mma_bf16(dx, x0 + ko, w0 + wp + ko, idesc, 1u);                            // hi . lo  -> cross
+                            tc_mma_bf16(tmem + m * (uint32_t)kLN, x0 + ko, w0 + ko, idesc, (used >> m) & 1u);   // hi . hi  -> main m
+                            used |= 1u << m;
                         }
+                        accum = 1;
                     }
                     tc_commit(bar_empty + 8 * s);
                 }
@@ -193,22 +198,31 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
         const uint32_t lane_base = ((uint32_t)q * 32u) << 16;
         const int c_base = slice * kLN;
         uint32_t ti = 0;
+        const int n_main = PIECES == 1 ? 1 : min(3, a.K / 16);        // main accumulators in use (K >= 64: all three)
         for (int t = first; t < n_tiles; t += step, ++ti) {
-            const uint32_t acc = ti & 1u;
+            const uint32_t acc = PIECES == 1 ? (ti & 1u) : 0u;
+            const uint32_t par = PIECES == 1 ? ((ti >> 1) & 1u) : (ti & 1u);
             const int b = t / a.tiles_per_cloud, n0 = (t - b * a.tiles_per_cloud) * kLT;
             const bool valid = n0 + row < a.N;
             const size_t grow = (size_t)b * a.N + n0 + row;
-            mbar_wait_wd(bar_accfull + 8 * acc, (ti >> 1) & 1u);
+            mbar_wait_wd(bar_accfull + 8 * acc, par);
             tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < kLN / 32; ++c) {
                 const int col0 = c_base + c * 32;
                 if (col0 >= a.C_out) break;                            // warp-uniform
                 float v[32];
-                tc_ld32(tmem + lane_base + acc * 2u * (uint32_t)kLN + (uint32_t)(c * 32), v);
+                tc_ld32(tmem + lane_base + acc * (uint32_t)kLN + (uint32_t)(c * 32), v);
                 if (PIECES == 2) {
+                    // (main0 + main1 + main2) + cross, every addition in round-to-nearest
                     float vx[32];
-                    tc_ld32(tmem + lane_base + acc * 2u * (uint32_t)kLN + (uint32_t)kLN + (uint32_t)(c * 32), vx);
+#pragma unroll 1
+                    for (int m = 1; m < n_main; ++m) {
+                        tc_ld32(tmem + lane_base + (uint32_t)m * (uint32_t)kLN + (uint32_t)(c * 32), vx);
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) v[e] += vx[e];
+                    }
+                    tc_ld32(tmem + lane_base + 3u * (uint32_t)kLN + (uint32_t)(c * 32), vx);
 #pragma unroll
                     for (int e = 0; e < 32; ++e) v[e] += vx[e];
                 }
