@@ -26,9 +26,10 @@
 //                  half the bytes); three MMAs per K step (hi.hi + hi.lo + lo.hi, fp32 accumulation in TMEM), the lo.lo
 //                  term (2^-22 relative) is dropped.  The tensor core's fp32 accumulation truncates, so its error is biased
 //                  and grows with the number of additions into one accumulator (measured on the reference's dims: 3.6e-5 with
-//                  one accumulator).  So the two cross terms (2^-11 of the result) go to an accumulator of their own and the
-//                  hi.hi steps rotate over THREE main accumulators (at most six additions each at K = 256); the epilogue
-//                  adds the four in round-to-nearest.  That takes all 512 TMEM columns, so this mode is single-buffered
+//                  one accumulator).  So the K steps are dealt out over FOUR accumulators (a quarter of the hi.hi steps each,
+//                  at most four additions at K = 256); the cross terms (2^-11 of the result, so their own truncation is
+//                  harmless) all go to the fourth one BEFORE its hi.hi steps; the epilogue adds the four in
+//                  round-to-nearest.  That takes all 512 TMEM columns, so this mode is single-buffered
 //                  (MMA and epilogue of consecutive tiles alternate) -- the path is HBM-bound either way.
 //                  Weights are scaled by a power of two per layer so that max|w| lands near 2^14 (the lo parts stay normal fp16 numbers); the epilogue undoes the scale exactly.  Activations
 //                  are stored unscaled: values in [2^-3, 65504] keep all 22 bits, smaller ones an absolute error <= 2^-25,
@@ -161,6 +162,7 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
             mbar_wait_wd(bar_accempty + 8 * acc, par ^ 1u);
             tc_fence_after();
             const uint32_t d = tmem + acc * (uint32_t)kLN, dx = tmem + 3u * (uint32_t)kLN;
+            const uint32_t n_steps = (uint32_t)a.K / 16u, q_steps = (n_steps + 3u) / 4u;   // hi.hi steps per accumulator
             uint32_t accum = 0, used = 0, ks = 0;
             for (int kb = 0; kb < kblocks; ++kb, ++it) {
                 const uint32_t s = it % (uint32_t)a.stages, use = it / (uint32_t)a.stages;
@@ -170,19 +172,28 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
                     const uint64_t x0 = umma_desc(sbase + x_off + (s * PIECES) * kLBlk);
                     const uint64_t w0 = umma_desc(sbase + w_off + (uint32_t)kb * kLBlk);
                     const uint64_t xp = (uint64_t)(kLBlk >> 4), wp = (uint64_t)(((uint32_t)kblocks * kLBlk) >> 4);   // piece strides
+                    if (PIECES == 2) {
+                        // this block's cross terms first: accumulator 3 must have all of them before its own hi.hi steps
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const uint64_t ko = (uint64_t)(k4 * 2);
+                            tc_mma_bf16(dx, x0 + xp + ko, w0 + ko, idesc, accum);             // lo . hi
+                            tc_mma_bf16(dx, x0 + ko, w0 + wp + ko, idesc, 1u);                // hi . lo
+                            accum = 1;
+                        }
+                        used |= 8u;
+                    }
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4, ++ks) {    // 16 elements = 32 bytes per MMA along K
                         const uint64_t ko = (uint64_t)(k4 * 2);
                         if (PIECES == 1) {
                             tc_mma_bf16(d, x0 + ko, w0 + ko, idesc, accum);
+                            accum = 1;
                         } else {
-                            const uint32_t m = ks % 3u;
-                            tc_mma_bf16(dx, x0 + xp + ko, w0 + ko, idesc, accum);                         // lo . hi  -> cross
-                            tc_mma_bf16(dx, x0 + ko, w0 + wp + ko, idesc, 1u);                            // hi . lo  -> cross
-                            tc_mma_bf16(tmem + m * (uint32_t)kLN, x0 + ko, w0 + ko, idesc, (used >> m) & 1u);   // hi . hi  -> main m
+                            const uint32_t m = min(3u, ks / q_steps);
+                            tc_mma_bf16(tmem + m * (uint32_t)kLN, x0 + ko, w0 + ko, idesc, (used >> m) & 1u);   // hi . hi
                             used |= 1u << m;
                         }
-                        accum = 1;
                     }
                     tc_commit(bar_empty + 8 * s);
                 }
@@ -198,7 +209,7 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
         const uint32_t lane_base = ((uint32_t)q * 32u) << 16;
         const int c_base = slice * kLN;
         uint32_t ti = 0;
-        const int n_main = PIECES == 1 ? 1 : min(3, a.K / 16);        // main accumulators in use (K >= 64: all three)
+        const int n_acc = PIECES == 1 ? 1 : 4;                         // accumulators to add up (K >= 64: all four are in use)
         for (int t = first; t < n_tiles; t += step, ++ti) {
             const uint32_t acc = PIECES == 1 ? (ti & 1u) : 0u;
             const uint32_t par = PIECES == 1 ? ((ti >> 1) & 1u) : (ti & 1u);
@@ -214,17 +225,14 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
                 float v[32];
                 tc_ld32(tmem + lane_base + acc * (uint32_t)kLN + (uint32_t)(c * 32), v);
                 if (PIECES == 2) {
-                    // (main0 + main1 + main2) + cross, every addition in round-to-nearest
+                    // the four partial accumulators, every addition in round-to-nearest
                     float vx[32];
 #pragma unroll 1
-                    for (int m = 1; m < n_main; ++m) {
+                    for (int m = 1; m < n_acc; ++m) {
                         tc_ld32(tmem + lane_base + (uint32_t)m * (uint32_t)kLN + (uint32_t)(c * 32), vx);
 #pragma unroll
                         for (int e = 0; e < 32; ++e) v[e] += vx[e];
                     }
-                    tc_ld32(tmem + lane_base + 3u * (uint32_t)kLN + (uint32_t)(c * 32), vx);
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] += vx[e];
                 }
                 const float4 *bp = reinterpret_cast<const float4 *>(a.bias + col0);
 #pragma unroll
