@@ -618,7 +618,7 @@ def encoder_measurement(rlg, dev, D, peaks, peaks_src, dims, key, workload):
     widths = [3] + list(dims)
     flop = 2.0 * ENC_N * sum(widths[i] * widths[i + 1] for i in range(len(dims))) * ENC_B
     res = {}
-    for precision, reps in (("bf16", 120), ("fp32", 12)):
+    for precision, reps in (("bf16", 120), ("auto", 60), ("fp32", 12)):
         enc.rlg_precision = precision
 
         def call(k):
@@ -675,7 +675,9 @@ def encoder_measurement(rlg, dev, D, peaks, peaks_src, dims, key, workload):
                         "fp32 CUDA-core path: no tensor roofline applies", "algorithmic_flop_per_launch": flop},
            "e2e": {"value": n * ENC_B * D.world / e2e_s, "unit": "clouds/s", "h2d_bytes_per_step": ENC_B * ENC_N * 12,
                    "d2h_bytes_per_step": ENC_B * 128 * 4, "steps": n},
-           "paths": res}
+           "paths": res,
+           "note": "paths: bf16 = bf16 tensor-core GEMMs (2e-2 class); auto = the default precision of the drop-in (fp32-grade "
+                   "tensor-core GEMMs on fp16 hi+lo operand pairs where the widths allow); fp32 = the CUDA-core kernel"}
     del xs, xs_host
     return {key: out}
 

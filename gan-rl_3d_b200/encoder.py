@@ -58,10 +58,9 @@ def fold_trunk(point_mlp: nn.Sequential) -> List[Tuple[torch.Tensor, torch.Tenso
 
 
 def _trunk_state_version(point_mlp: nn.Sequential) -> tuple:
-    sig = []
-    for t in list(point_mlp.parameters()) + list(point_mlp.buffers()):
-        sig.append((t.data_ptr(), t._version, t.device.index))
-    return tuple(sig)
+    """Changes whenever a parameter or buffer of the trunk is modified in place, moved or replaced."""
+    return tuple((id(t), t.data_ptr(), t._version) for m in point_mlp for t in (*m._parameters.values(), *m._buffers.values())
+                 if t is not None)
 
 
 def folded_trunk_cached(module: nn.Module) -> List[Tuple[torch.Tensor, torch.Tensor]]:
@@ -338,28 +337,84 @@ class EncoderTrunkFn(torch.autograd.Function):
         return (gx, None) + gps
 
 
+class _Plan:
+    """Everything derived from a trunk's weights that a forward needs, built once per state version: folded layers, the
+    ctypes layer array, the resolved kernel family and its packed operand image."""
+    __slots__ = ("layers", "arr", "keep", "path", "packed", "c_last", "device")
+
+    def __init__(self, module: nn.Module, precision: str):
+        self.layers = folded_trunk_cached(module)
+        self.arr, self.keep = _layer_array(self.layers)
+        self.path = resolve_path(self.layers, precision)
+        self.c_last = self.layers[-1][0].shape[0]
+        self.device = self.layers[0][0].device
+        cache = _packed_cache(module)
+        if self.path == "fp32":
+            self.packed = None
+        elif self.path == "bf16":
+            self.packed = packed_trunk_cached(module)
+        else:
+            if self.path not in cache:
+                cache[self.path] = pack_gemm(self.layers, _lib.ENC_FP32X if self.path == "fp32x" else _lib.ENC_BF16)
+            self.packed = cache[self.path]
+
+
+def _plan_of(module: nn.Module) -> Optional["_Plan"]:
+    """The cached plan of `module`, or None when its trunk does not have the reference's layout."""
+    precision = getattr(module, "rlg_precision", _PRECISION)
+    try:
+        ver = (_trunk_state_version(module.point_mlp), precision)
+    except AttributeError:
+        return None
+    hit = module.__dict__.get("_rlg_plan")
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    try:
+        _trunk_layers(module.point_mlp)
+    except (ValueError, AttributeError):
+        return None
+    plan = _Plan(module, precision)
+    module.__dict__["_rlg_plan"] = (ver, plan)
+    return plan
+
+
+def _run_plan(plan: "_Plan", x: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    x = x.contiguous()
+    B, N, _ = x.shape
+    L = len(plan.layers)
+    pooled = torch.empty((B, plan.c_last), dtype=torch.float32, device=x.device)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    with torch.cuda.device(x.device):
+        if plan.path == "fp32":
+            ws = torch.empty(max(lib.rlg_encoder_ws_bytes(B, N, plan.arr, L), 256), dtype=torch.uint8, device=x.device)
+            rc = lib.rlg_encoder_fwd(x.data_ptr(), B, N, plan.arr, L, pooled.data_ptr(), None, ws.data_ptr(), ws.numel(), stream)
+            _lib.check("rlg_encoder_fwd", rc)
+        elif plan.path == "bf16":
+            rc = lib.rlg_encoder_fwd_bf16(x.data_ptr(), B, N, plan.arr, L, plan.packed.data_ptr(), plan.packed.numel(),
+                                          pooled.data_ptr(), stream)
+            _lib.check("rlg_encoder_fwd_bf16", rc)
+        else:
+            mode = _lib.ENC_FP32X if plan.path == "fp32x" else _lib.ENC_BF16
+            image, scales = plan.packed
+            ws = _gemm_workspace(x.device, stream, lib.rlg_encoder_gemm_ws_bytes(B, N, plan.arr, L, mode))
+            rc = lib.rlg_encoder_gemm_fwd(x.data_ptr(), B, N, plan.arr, L, mode, scales, image.data_ptr(), image.numel(),
+                                          pooled.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+            _lib.check("rlg_encoder_gemm_fwd", rc)
+    return pooled
+
+
 def _trunk_pool(module: nn.Module, x: torch.Tensor) -> torch.Tensor:
-    layers = folded_trunk_cached(module)
-    path = resolve_path(layers, getattr(module, "rlg_precision", _PRECISION))
-    if path == "fp32":
-        return encoder_pool(x, layers)[0]
-    cache = _packed_cache(module)
-    if path == "bf16":
-        return encoder_pool(x, layers, precision="bf16", packed=packed_trunk_cached(module))[0]
-    mode = _lib.ENC_FP32X if path == "fp32x" else _lib.ENC_BF16
-    if path not in cache:
-        cache[path] = pack_gemm(layers, mode)
-    return encoder_pool_gemm(x, layers, mode, cache[path])
+    plan = _plan_of(module)
+    if plan is None:
+        raise ValueError("point_mlp is not [Conv1d(k=1), BatchNorm1d, ReLU] x L")
+    return _run_plan(plan, x)
 
 
 def _module_is_hot(self: nn.Module, x) -> bool:
-    """The module has the reference's trunk layout and lives on the device of x."""
-    try:
-        _trunk_layers(self.point_mlp)
-    except (ValueError, AttributeError):
-        return False
-    p = next(self.point_mlp.parameters(), None)
-    return p is not None and p.device == x.device and p.dtype == torch.float32
+    """The module has the reference's trunk layout and its (float32) weights live on the device of x."""
+    plan = _plan_of(self)
+    return plan is not None and plan.device == x.device
 
 
 def fused_forward(self: nn.Module, x: torch.Tensor, _original=None) -> torch.Tensor:
