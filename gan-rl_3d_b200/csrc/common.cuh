@@ -79,6 +79,19 @@ int launch_finalize2(const float *pc1, const float *pc2, int B, int N, int M, in
                      void *fin_ws, float *d1, float *d2, int32_t *i1, int32_t *i2, float *mean1, float *mean2,
                      float *loss, float w1, float w2, float *zero1, float *zero2, cudaStream_t st);
 
+// ---- one tcgen05 layer GEMM of the encoder (encoder_layers.cu), shared with the train-mode path (encoder_train.cu)
+struct GemmCall {
+    int B, N, K, C_out, pieces;       // X is (B, N, K), W is (C_out, K); pieces: 1 = bf16, 2 = fp16 hi + lo
+    const void *x0, *x1, *w0, *w1;    // operand piece arrays (2-byte elements, row-major, K contiguous)
+    const float *bias;                // fp32 (C_out), nullable with epi 2
+    float out_scale;                  // multiplies the accumulator (undoes power-of-two operand scales)
+    const float *dscale0, *dscale1;   // optional DEVICE scalars multiplied into out_scale
+    int epi;                          // 0: ReLU -> next operand pieces y0/y1; 1: ReLU + max over points -> pooled; 2: raw fp32 -> y0
+    void *y0, *y1;
+    float *pooled;
+};
+int launch_layer_gemm(const GemmCall &g, int sms, cudaStream_t st);
+
 // ---- packed fp32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2) ------------------------------
 // One instruction issues two IEEE fp32 operations, halving the issue-slot cost of the distance math.
 __device__ __forceinline__ u64 pack2(float lo, float hi) {

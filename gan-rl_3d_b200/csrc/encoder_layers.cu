@@ -56,11 +56,15 @@ static constexpr int kLMaxStages = 8;
 struct LayerArgs {
     int B, N, K, C_out;
     int tiles_per_cloud, n_slices, stages;
-    const float *bias;             // fp32 [C_out] (folded)
+    const float *bias;             // fp32 [C_out] (folded); nullable in the RAW epilogue
     float out_scale;               // 1 / weight scale (a power of two); 1 for bf16
-    void *y0, *y1;                 // next layer's operand pieces [B*N x C_out] (2-byte elements); null with POOL
-    float *pooled;                 // POOL: (B, C_out) fp32, zero-filled before the launch
+    const float *dscale0, *dscale1;  // optional device scalars multiplied into out_scale (train mode: the operand scales are
+                                     // found on the device -- no host synchronisation -- and undone here)
+    void *y0, *y1;                 // EPI_ACT: next layer's operand pieces [B*N x C_out] (2-byte elements)
+                                   // EPI_RAW: y0 = fp32 [B*N x C_out] (scale + bias only, no ReLU)
+    float *pooled;                 // EPI_POOL: (B, C_out) fp32, zero-filled before the launch
 };
+enum { EPI_ACT = 0, EPI_POOL = 1, EPI_RAW = 2 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -88,8 +92,10 @@ __device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
     return __half22float2(*reinterpret_cast<const __half2 *>(&v));
 }
 
-// PIECES: 1 = bf16, 2 = fp16 hi/lo.  POOL: last layer (max over the points instead of storing the activation).
-template <int PIECES, bool POOL>
+// PIECES: 1 = bf16, 2 = fp16 hi/lo.  EPI: what the epilogue does with scale * acc + bias:
+//   EPI_ACT ReLU and store as the next layer's operand rows; EPI_POOL ReLU and max over the points (last layer, eval);
+//   EPI_RAW store as fp32 (train mode: pre-BatchNorm outputs and gradient GEMMs)
+template <int PIECES, int EPI>
 __global__ void __launch_bounds__(kLThreads, 1)
 encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CUtensorMap tmx1,
                      const __grid_constant__ CUtensorMap tmw0, const __grid_constant__ CUtensorMap tmw1, LayerArgs a) {
@@ -210,6 +216,8 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
         const int c_base = slice * kLN;
         uint32_t ti = 0;
         const int n_acc = PIECES == 1 ? 1 : 4;                         // accumulators to add up (K >= 64: all four are in use)
+        constexpr bool POOL = EPI == EPI_POOL;
+        const float sc = a.out_scale * (a.dscale0 ? __ldg(a.dscale0) : 1.0f) * (a.dscale1 ? __ldg(a.dscale1) : 1.0f);
         for (int t = first; t < n_tiles; t += step, ++ti) {
             const uint32_t acc = PIECES == 1 ? (ti & 1u) : 0u;
             const uint32_t par = PIECES == 1 ? ((ti >> 1) & 1u) : (ti & 1u);
@@ -234,14 +242,34 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
                         for (int e = 0; e < 32; ++e) v[e] += vx[e];
                     }
                 }
+                if (EPI == EPI_RAW) {
+                    if (a.bias != nullptr) {
+                        const float4 *bp = reinterpret_cast<const float4 *>(a.bias + col0);
+#pragma unroll
+                        for (int e4 = 0; e4 < 8; ++e4) {
+                            const float4 bb = __ldg(bp + e4);
+                            v[4 * e4] = fmaf(v[4 * e4], sc, bb.x); v[4 * e4 + 1] = fmaf(v[4 * e4 + 1], sc, bb.y);
+                            v[4 * e4 + 2] = fmaf(v[4 * e4 + 2], sc, bb.z); v[4 * e4 + 3] = fmaf(v[4 * e4 + 3], sc, bb.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) v[e] *= sc;
+                    }
+                    if (valid) {
+                        float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(a.y0) + grow * a.C_out + col0);
+#pragma unroll
+                        for (int e4 = 0; e4 < 8; ++e4) dst[e4] = make_float4(v[4 * e4], v[4 * e4 + 1], v[4 * e4 + 2], v[4 * e4 + 3]);
+                    }
+                    continue;
+                }
                 const float4 *bp = reinterpret_cast<const float4 *>(a.bias + col0);
 #pragma unroll
                 for (int e4 = 0; e4 < 8; ++e4) {
                     const float4 bb = __ldg(bp + e4);
-                    v[4 * e4] = fmaxf(fmaf(v[4 * e4], a.out_scale, bb.x), 0.0f);
-                    v[4 * e4 + 1] = fmaxf(fmaf(v[4 * e4 + 1], a.out_scale, bb.y), 0.0f);
-                    v[4 * e4 + 2] = fmaxf(fmaf(v[4 * e4 + 2], a.out_scale, bb.z), 0.0f);
-                    v[4 * e4 + 3] = fmaxf(fmaf(v[4 * e4 + 3], a.out_scale, bb.w), 0.0f);
+                    v[4 * e4] = fmaxf(fmaf(v[4 * e4], sc, bb.x), 0.0f);
+                    v[4 * e4 + 1] = fmaxf(fmaf(v[4 * e4 + 1], sc, bb.y), 0.0f);
+                    v[4 * e4 + 2] = fmaxf(fmaf(v[4 * e4 + 2], sc, bb.z), 0.0f);
+                    v[4 * e4 + 3] = fmaxf(fmaf(v[4 * e4 + 3], sc, bb.w), 0.0f);
                 }
                 if (POOL) {
                     // max over the 32 points of this warp per channel; lane e keeps channel e's result
@@ -377,6 +405,63 @@ static int make_map(CUtensorMap *tm, int pieces_fmt, void *base, int rank, const
     return 0;
 }
 
+// one layer GEMM: Y = epi(X[B*N x K] . W[C_out x K]^T), operands as 2-byte piece arrays (see the file header)
+int launch_layer_gemm(const GemmCall &g, int sms, cudaStream_t st) {
+    const int pieces = g.pieces;
+    if (g.K % kLKB != 0 || g.K < kLKB || g.K > 256 || g.C_out % 64 != 0 || g.C_out < 64)
+        return fail(RLG_ERR_UNSUPPORTED, "encoder_layer_kernel: K=%d / C_out=%d not covered (multiples of 64, K <= 256)", g.K, g.C_out);
+    LayerArgs a;
+    a.B = g.B; a.N = g.N; a.K = g.K; a.C_out = g.C_out;
+    a.tiles_per_cloud = (g.N + kLT - 1) / kLT;
+    a.n_slices = (g.C_out + kLN - 1) / kLN;
+    a.bias = g.bias;
+    a.out_scale = g.out_scale;
+    a.dscale0 = g.dscale0; a.dscale1 = g.dscale1;
+    a.y0 = g.y0; a.y1 = g.y1; a.pooled = g.pooled;
+    const int kblocks = g.K / kLKB;
+    const size_t w_bytes = (size_t)pieces * kblocks * kLBlk, stage_bytes = (size_t)pieces * kLBlk;
+    const size_t budget = 226u * 1024u - 256u;             // 227 KB per CTA minus the alignment slack and the barriers
+    long long stages = ((long long)budget - (long long)w_bytes) / (long long)stage_bytes;
+    if (stages < 2) return fail(RLG_ERR_UNSUPPORTED, "encoder_layer_kernel: K=%d does not fit in shared memory", g.K);
+    if (stages > kLMaxStages) stages = kLMaxStages;
+    a.stages = (int)stages;
+    const size_t smem_bytes = w_bytes + (size_t)stages * stage_bytes + 256 + 1024;
+    CUtensorMap tmx[2], tmw[2];
+    for (int p = 0; p < 2; ++p) {
+        const bool second = p == 1 && pieces == 2;
+        const cuuint64_t xd[3] = {(cuuint64_t)g.K, (cuuint64_t)g.N, (cuuint64_t)g.B};
+        const cuuint64_t xs[2] = {(cuuint64_t)g.K * 2, (cuuint64_t)g.N * g.K * 2};
+        const cuuint32_t xb[3] = {(cuuint32_t)kLKB, (cuuint32_t)kLT, 1};
+        int rc = make_map(&tmx[p], pieces, const_cast<void *>(second ? g.x1 : g.x0), 3, xd, xs, xb);
+        if (rc) return rc;
+        const cuuint64_t wd[2] = {(cuuint64_t)g.K, (cuuint64_t)g.C_out};
+        const cuuint64_t wst[1] = {(cuuint64_t)g.K * 2};
+        const cuuint32_t wb[2] = {(cuuint32_t)kLKB, (cuuint32_t)kLN};
+        rc = make_map(&tmw[p], pieces, const_cast<void *>(second ? g.w1 : g.w0), 2, wd, wst, wb);
+        if (rc) return rc;
+    }
+    const long long tiles = (long long)g.B * a.tiles_per_cloud;
+    long long per_slice = sms / a.n_slices;
+    if (per_slice < 1) per_slice = 1;
+    if (per_slice > tiles) per_slice = tiles;
+    const unsigned grid = (unsigned)(per_slice * a.n_slices);
+    auto launch = [&](auto kernel) -> int {
+        cudaError_t ae = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (ae != cudaSuccess) { cudaGetLastError(); return fail((int)ae, "encoder_layer_kernel: cudaFuncSetAttribute(%zu): %s", smem_bytes, cudaGetErrorString(ae)); }
+        cudaError_t le = launch_pdl(kernel, dim3(grid), dim3(kLThreads), smem_bytes, st, tmx[0], tmx[1], tmw[0], tmw[1], a);
+        if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "encoder_layer_kernel: %s", cudaGetErrorString(le)); }
+        return 0;
+    };
+    if (pieces == 1) {
+        if (g.epi == EPI_POOL) return launch(encoder_layer_kernel<1, EPI_POOL>);
+        if (g.epi == EPI_ACT) return launch(encoder_layer_kernel<1, EPI_ACT>);
+        return fail(RLG_ERR_UNSUPPORTED, "encoder_layer_kernel: the raw epilogue exists for the fp16 hi+lo operands only");
+    }
+    if (g.epi == EPI_POOL) return launch(encoder_layer_kernel<2, EPI_POOL>);
+    if (g.epi == EPI_ACT) return launch(encoder_layer_kernel<2, EPI_ACT>);
+    return launch(encoder_layer_kernel<2, EPI_RAW>);
+}
+
 static int gemm_check(const rlg_layer *layers, int L, int mode) {
     if (mode != RLG_ENC_BF16 && mode != RLG_ENC_FP32X) return fail(RLG_ERR_UNSUPPORTED, "rlg_encoder_gemm: unknown mode %d", mode);
     if (!layers || L < 2 || L > kLMaxLayers) return fail(RLG_ERR_UNSUPPORTED, "rlg_encoder_gemm: need 2..%d layers, got %d", kLMaxLayers, L);
@@ -479,52 +564,19 @@ int rlg_encoder_gemm_fwd(const float *x, int B, int N, const rlg_layer *layers, 
     for (int l = 1; l < L; ++l) {
         const bool last = l == L - 1;
         const int K = layers[l].c_in, C = layers[l].c_out;
-        LayerArgs a;
-        a.B = B; a.N = N; a.K = K; a.C_out = C;
-        a.tiles_per_cloud = (N + kLT - 1) / kLT;
-        a.n_slices = (C + kLN - 1) / kLN;
-        a.bias = layers[l].b;
-        a.out_scale = pieces == 1 ? 1.0f : 1.0f / weight_scales[l];
-        a.y0 = last ? nullptr : act(cur ^ 1, 0);
-        a.y1 = last || pieces == 1 ? nullptr : act(cur ^ 1, 1);
-        a.pooled = last ? pooled : nullptr;
-        const int kblocks = K / kLKB;
-        const size_t w_bytes = (size_t)pieces * kblocks * kLBlk, stage_bytes = (size_t)pieces * kLBlk;
-        const size_t budget = 226u * 1024u - 256u;             // 227 KB per CTA minus the alignment slack and the barriers
-        long long stages = ((long long)budget - (long long)w_bytes) / (long long)stage_bytes;
-        if (stages < 2) return fail(RLG_ERR_UNSUPPORTED, "rlg_encoder_gemm_fwd: layer %d (K=%d) does not fit in shared memory", l, K);
-        if (stages > kLMaxStages) stages = kLMaxStages;
-        a.stages = (int)stages;
-        const size_t smem_bytes = w_bytes + (size_t)stages * stage_bytes + 256 + 1024;
-        CUtensorMap tmx[2], tmw[2];
-        for (int p = 0; p < 2; ++p) {
-            const int pp = p < pieces ? p : 0;
-            const cuuint64_t xd[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)B};
-            const cuuint64_t xs[2] = {(cuuint64_t)K * 2, (cuuint64_t)N * K * 2};
-            const cuuint32_t xb[3] = {(cuuint32_t)kLKB, (cuuint32_t)kLT, 1};
-            rc = make_map(&tmx[p], pieces, act(cur, pp), 3, xd, xs, xb);
-            if (rc) return rc;
-            char *wbase = (char *)packed + pack_layer_off(layers, l, pieces) + (size_t)pp * align_up((size_t)C * K * 2, 256);
-            const cuuint64_t wd[2] = {(cuuint64_t)K, (cuuint64_t)C};
-            const cuuint64_t wst[1] = {(cuuint64_t)K * 2};
-            const cuuint32_t wb[2] = {(cuuint32_t)kLKB, (cuuint32_t)kLN};
-            rc = make_map(&tmw[p], pieces, wbase, 2, wd, wst, wb);
-            if (rc) return rc;
-        }
-        const long long tiles = (long long)B * a.tiles_per_cloud;
-        long long per_slice = sms / a.n_slices;
-        if (per_slice < 1) per_slice = 1;
-        if (per_slice > tiles) per_slice = tiles;
-        const unsigned grid = (unsigned)(per_slice * a.n_slices);
-        auto launch = [&](auto kernel) -> int {
-            cudaError_t ae = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-            if (ae != cudaSuccess) { cudaGetLastError(); return fail((int)ae, "rlg_encoder_gemm_fwd: cudaFuncSetAttribute(%zu): %s", smem_bytes, cudaGetErrorString(ae)); }
-            cudaError_t le = launch_pdl(kernel, dim3(grid), dim3(kLThreads), smem_bytes, st, tmx[0], tmx[1], tmw[0], tmw[1], a);
-            if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "encoder_layer_kernel: %s", cudaGetErrorString(le)); }
-            return 0;
-        };
-        if (pieces == 1) rc = last ? launch(encoder_layer_kernel<1, true>) : launch(encoder_layer_kernel<1, false>);
-        else rc = last ? launch(encoder_layer_kernel<2, true>) : launch(encoder_layer_kernel<2, false>);
+        GemmCall g;
+        g.B = B; g.N = N; g.K = K; g.C_out = C; g.pieces = pieces;
+        g.x0 = act(cur, 0); g.x1 = pieces == 2 ? act(cur, 1) : nullptr;
+        g.w0 = (char *)packed + pack_layer_off(layers, l, pieces);
+        g.w1 = pieces == 2 ? (char *)g.w0 + align_up((size_t)C * K * 2, 256) : nullptr;
+        g.bias = layers[l].b;
+        g.out_scale = pieces == 1 ? 1.0f : 1.0f / weight_scales[l];
+        g.dscale0 = g.dscale1 = nullptr;
+        g.epi = last ? EPI_POOL : EPI_ACT;
+        g.y0 = last ? nullptr : act(cur ^ 1, 0);
+        g.y1 = last || pieces == 1 ? nullptr : act(cur ^ 1, 1);
+        g.pooled = last ? pooled : nullptr;
+        rc = launch_layer_gemm(g, sms, st);
         if (rc) return rc;
         cur ^= 1;
     }

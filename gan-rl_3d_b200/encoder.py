@@ -370,8 +370,11 @@ def _plan_of(module: nn.Module) -> Optional["_Plan"]:
     if hit is not None and hit[0] == ver:
         return hit[1]
     try:
-        _trunk_layers(module.point_mlp)
+        pairs = _trunk_layers(module.point_mlp)
     except (ValueError, AttributeError):
+        return None
+    w0 = pairs[0][0].weight
+    if not w0.is_cuda or w0.dtype != torch.float32:          # CPU / fp64 / half modules are not the hot path
         return None
     plan = _Plan(module, precision)
     module.__dict__["_rlg_plan"] = (ver, plan)
