@@ -24,6 +24,18 @@ class RlgLayer(ctypes.Structure):
                 ("c_in", ctypes.c_int32), ("c_out", ctypes.c_int32)]
 
 
+class RlgBnLayer(ctypes.Structure):
+    """struct rlg_bn_layer (include/rlg_b200.h)."""
+    _fields_ = [("w", ctypes.c_void_p), ("b", ctypes.c_void_p), ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p),
+                ("running_mean", ctypes.c_void_p), ("running_var", ctypes.c_void_p),
+                ("eps", ctypes.c_float), ("momentum", ctypes.c_float), ("c_in", ctypes.c_int32), ("c_out", ctypes.c_int32)]
+
+
+class RlgBnGrads(ctypes.Structure):
+    """struct rlg_bn_grads (include/rlg_b200.h)."""
+    _fields_ = [("dw", ctypes.c_void_p), ("db", ctypes.c_void_p), ("dgamma", ctypes.c_void_p), ("dbeta", ctypes.c_void_p)]
+
+
 class RlgError(RuntimeError):
     def __init__(self, fn: str, code: int, msg: str):
         super().__init__(f"{fn} failed with code {code}: {msg}")
@@ -67,6 +79,16 @@ EXPORTS = {
     "rlg_encoder_gemm_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(RlgLayer), ctypes.c_int,
                                             ctypes.c_int, c_float_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
                                             ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "rlg_encoder_train_saved_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(RlgBnLayer), ctypes.c_int]),
+    "rlg_encoder_train_ws_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(RlgBnLayer), ctypes.c_int]),
+    "rlg_encoder_train_saved_layout": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(RlgBnLayer), ctypes.c_int,
+                                                      ctypes.POINTER(ctypes.c_size_t), ctypes.c_int]),
+    "rlg_encoder_train_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(RlgBnLayer), ctypes.c_int,
+                                             ctypes.c_uint, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                             ctypes.c_size_t, ctypes.c_void_p]),
+    "rlg_encoder_train_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(RlgBnLayer), ctypes.c_int,
+                                             ctypes.c_uint, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                             ctypes.POINTER(RlgBnGrads), ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "rlg_fp32_peak": (ctypes.c_int, [c_float_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
 }
 
@@ -81,6 +103,7 @@ X_CHAMFER_TENSOR_V1 = 128
 CHAMFER_BWD_ACCUMULATE = 1
 ENC_BF16 = 1
 ENC_FP32X = 2
+ENC_BATCH_STATS = 1
 
 
 def load() -> ctypes.CDLL:

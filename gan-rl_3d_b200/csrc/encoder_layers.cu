@@ -66,14 +66,6 @@ struct LayerArgs {
 };
 enum { EPI_ACT = 0, EPI_POOL = 1, EPI_RAW = 2 };
 
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
 // cute::UMMA::InstrDescriptor: D fp32, A/B both bf16 (fmt 1) or both f16 (fmt 0), K-major
 __device__ __forceinline__ uint32_t umma_idesc_16(int M, int Nn, uint32_t fmt) {
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(Nn >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -83,15 +75,6 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
-__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
-    uint32_t r;
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
-__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
-    return __half22float2(*reinterpret_cast<const __half2 *>(&v));
-}
-
 // PIECES: 1 = bf16, 2 = fp16 hi/lo.  EPI: what the epilogue does with scale * acc + bias:
 //   EPI_ACT ReLU and store as the next layer's operand rows; EPI_POOL ReLU and max over the points (last layer, eval);
 //   EPI_RAW store as fp32 (train mode: pre-BatchNorm outputs and gradient GEMMs)
@@ -158,6 +141,10 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
         // =========================== MMA issuer ===========================
         const bool leader = elect_one();
         const uint32_t idesc = umma_idesc_16(kLT, kLN, PIECES == 1 ? 1u : 0u);
+        // fp16 hi+lo: the accumulators 1 and 3 collect NEGATED products (a_negate, bit 13) and are subtracted in the
+        // epilogue.  The tensor core's fp32 accumulation rounds toward minus infinity, a bias that adds up coherently over
+        // the points in the column sums of the training backward; with half of every sum carried negated it cancels.
+        const uint32_t idesc_neg = idesc | (1u << 13);
         mbar_wait_wd(bar_w, 0);
         uint32_t it = 0, ti = 0;
         for (int t = first; t < n_tiles; t += step, ++ti) {
@@ -183,8 +170,8 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) {
                             const uint64_t ko = (uint64_t)(k4 * 2);
-                            tc_mma_bf16(dx, x0 + xp + ko, w0 + ko, idesc, accum);             // lo . hi
-                            tc_mma_bf16(dx, x0 + ko, w0 + wp + ko, idesc, 1u);                // hi . lo
+                            tc_mma_bf16(dx, x0 + xp + ko, w0 + ko, idesc_neg, accum);         // -(lo . hi)
+                            tc_mma_bf16(dx, x0 + ko, w0 + wp + ko, idesc_neg, 1u);            // -(hi . lo)
                             accum = 1;
                         }
                         used |= 8u;
@@ -197,7 +184,7 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
                             accum = 1;
                         } else {
                             const uint32_t m = min(3u, ks / q_steps);
-                            tc_mma_bf16(tmem + m * (uint32_t)kLN, x0 + ko, w0 + ko, idesc, (used >> m) & 1u);   // hi . hi
+                            tc_mma_bf16(tmem + m * (uint32_t)kLN, x0 + ko, w0 + ko, (m & 1u) ? idesc_neg : idesc, (used >> m) & 1u);   // +-(hi . hi)
                             used |= 1u << m;
                         }
                     }
@@ -239,7 +226,7 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
                     for (int m = 1; m < n_acc; ++m) {
                         tc_ld32(tmem + lane_base + (uint32_t)m * (uint32_t)kLN + (uint32_t)(c * 32), vx);
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) v[e] += vx[e];
+                        for (int e = 0; e < 32; ++e) v[e] = (m & 1) ? v[e] - vx[e] : v[e] + vx[e];
                     }
                 }
                 if (EPI == EPI_RAW) {
@@ -393,7 +380,7 @@ static EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-static int make_map(CUtensorMap *tm, int pieces_fmt, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
+int make_map(CUtensorMap *tm, int pieces_fmt, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
                     const cuuint32_t *box) {
     EncodeTiledFn f = encode_tiled();
     if (!f) return fail(RLG_ERR_UNSUPPORTED, "rlg_encoder_gemm: cuTensorMapEncodeTiled is not available from this driver");

@@ -1,0 +1,936 @@
+// encoder_train.cu -- the PointNet encoder trunk WITH its BatchNorm layers, forward and backward: what the autoencoder
+// training step runs (train_rl_gan_net.py:220-249 -> models/autoencoder.py:32-47,65-71 with model.train()).
+//
+// Per block  z = Conv1d_k1(a_prev) ; y = BatchNorm1d(z) ; a = ReLU(y) ; the last block is followed by max over the points.
+//
+//   forward   layer 0 (3 -> C0)  CUDA cores, fp32
+//             layer l >= 1       tcgen05 GEMM of encoder_layers.cu (fp16 hi+lo operands = fp32 grade, raw fp32 epilogue)
+//             BatchNorm          one pass of shifted sums per channel (float64 accumulators) -> mean / biased variance ->
+//                                running-stat update -> one pass that normalises, applies ReLU and writes the next GEMM's
+//                                operand pieces (or, for the last layer, reduces max + arg-max over the points)
+//   backward  BatchNorm          dz = gamma*invstd * (dy - mean(dy) - zhat * mean(dy*zhat)),  dy = da * [y > 0]
+//                                (one pass for the two sums, one pass that writes dz as scaled operand pieces)
+//             input gradient     da_prev = dz . W          the same GEMM kernel with the transposed weight image
+//             weight gradient    dW = dz^T . a_prev        encoder_wgrad_kernel below: both operands are read straight from
+//                                the point-major piece arrays as MN-MAJOR tcgen05 operands (TMA boxes of 64 channels x 64
+//                                points), split over the points across the SMs, partial tiles reduced in a fixed order
+//             layer 0            dW0 = dz0^T . x on the CUDA cores (K = 3)
+//
+// Operand scaling: fp16 pieces need |v| <= 65504 and lose their low part below 2^-14, so weights and gradients are scaled
+// by a power of two found ON THE DEVICE (no host synchronisation: training changes the weights every step) -- weights by
+// their max, dz by a bound computed from the sums of its own formula -- and the GEMM epilogues undo the scale exactly.
+// The tensor core's fp32 accumulation truncates; long sums are cut into short chains (the forward GEMM's four
+// accumulators; the weight-gradient kernel drains its accumulators into registers every 192 points and adds there in
+// round-to-nearest).
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace rlg {
+
+static constexpr int kTMaxLayers = 8;
+static constexpr int kTMaxC = 256;
+enum { EPI_RAW_ = 2 };
+
+// ---- buffer layouts ---------------------------------------------------------------------------------------------------
+struct SavedLayout {
+    size_t z[kTMaxLayers];        // fp32 [P x C_l]   pre-BatchNorm outputs
+    size_t ahi[kTMaxLayers];      // fp16 [P x C_l]   activation pieces (l < L-1)
+    size_t alo[kTMaxLayers];
+    size_t bnp[kTMaxLayers];      // fp32 [4 x C_l]   scale = gamma*invstd, shift = beta - mean*scale, mean*invstd, invstd
+    size_t zmax[kTMaxLayers];     // u32  [C_l]       bit pattern of max |zhat| per channel
+    size_t keys;                  // u64  [B x C_last] (value bits << 32 | ~point index) of the max-pool
+    size_t total;
+};
+static SavedLayout saved_layout(long long P, int B, const rlg_bn_layer *layers, int L) {
+    SavedLayout s;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+    for (int l = 0; l < L; ++l) {
+        const size_t C = (size_t)layers[l].c_out;
+        s.z[l] = take((size_t)P * C * 4);
+        s.ahi[l] = l < L - 1 ? take((size_t)P * C * 2) : 0;
+        s.alo[l] = l < L - 1 ? take((size_t)P * C * 2) : 0;
+        s.bnp[l] = take(4 * C * 4);
+        s.zmax[l] = take(C * 4);
+    }
+    s.keys = take((size_t)B * layers[L - 1].c_out * 8);
+    s.total = off;
+    return s;
+}
+
+struct WsLayout {
+    // zero-filled at the start of every call: [0, zero_bytes)
+    size_t stat;                  // f64 [L][2][256]   forward: shifted sum, shifted sum of squares; backward: sum dy, sum dy*zhat
+    size_t mxdy;                  // u32 [L][256]      backward: bit pattern of max |dy| per channel
+    size_t w0acc;                 // f64 [256 x 3]     layer-0 weight gradient accumulators
+    size_t zero_bytes;
+    size_t wscale;                // f32 [L][2]        weight scale and its inverse (device scalars)
+    size_t dscale;                // f32 [L][2]        dz scale and its inverse
+    size_t m12;                   // f32 [L][2][256]   mean(dy), mean(dy*zhat)
+    size_t wp[kTMaxLayers][4];    // fp16 pieces of W_l: hi, lo (c_out x c_in) and of W_l^T: hi, lo (c_in x c_out)
+    size_t da;                    // fp32 [P x Cmax]   gradient w.r.t. a layer's activations
+    size_t dzhi, dzlo;            // fp16 [P x Cmax]
+    size_t partial;               // fp32 [sms][128 x 128] weight-gradient partial tiles
+    size_t total;
+};
+static WsLayout ws_layout(long long P, const rlg_bn_layer *layers, int L, int sms) {
+    WsLayout w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+    w.stat = take((size_t)L * 2 * kTMaxC * 8);
+    w.mxdy = take((size_t)L * kTMaxC * 4);
+    w.w0acc = take((size_t)kTMaxC * 3 * 8);
+    w.zero_bytes = off;
+    w.wscale = take((size_t)L * 2 * 4);
+    w.dscale = take((size_t)L * 2 * 4);
+    w.m12 = take((size_t)L * 2 * kTMaxC * 4);
+    int cmax = 0;
+    for (int l = 0; l < L; ++l) {
+        cmax = layers[l].c_out > cmax ? layers[l].c_out : cmax;
+        for (int k = 0; k < 4; ++k) w.wp[l][k] = l >= 1 ? take((size_t)layers[l].c_out * layers[l].c_in * 2) : 0;
+    }
+    w.da = take((size_t)P * cmax * 4);
+    w.dzhi = take((size_t)P * cmax * 2);
+    w.dzlo = take((size_t)P * cmax * 2);
+    w.partial = take((size_t)(sms > 0 ? sms : 1) * 128 * 128 * 4);
+    w.total = off;
+    return w;
+}
+
+// ---- per-channel reductions over the points: 256 threads, a thread owns 4 consecutive channels of every RPI-th row ------
+struct ColGeom {
+    int tpr, rpi, tx, ty;
+    bool active;
+    __device__ __forceinline__ ColGeom(int C) {
+        tpr = C >> 2;
+        rpi = 256 / tpr;
+        tx = threadIdx.x % tpr;
+        ty = threadIdx.x / tpr;
+        active = ty < rpi;
+    }
+};
+// red: shared [Q][rpi][C]; after the call threads c < C hold the column totals of quantity q in out[q] (as double)
+template <int Q>
+__device__ __forceinline__ void col_reduce_sum(const float (&v)[Q][4], const ColGeom &g, int C, float *red, double (&out)[Q]) {
+    if (g.active) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) red[(q * g.rpi + g.ty) * C + 4 * g.tx + k] = v[q][k];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < C) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            double s = 0.0;
+            for (int r = 0; r < g.rpi; ++r) s += (double)red[(q * g.rpi + r) * C + threadIdx.x];
+            out[q] = s;
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void col_reduce_max(const float (&v)[4], const ColGeom &g, int C, float *red, float &out) {
+    if (g.active) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) red[g.ty * C + 4 * g.tx + k] = v[k];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < C) {
+        float m = 0.0f;
+        for (int r = 0; r < g.rpi; ++r) m = fmaxf(m, red[r * C + threadIdx.x]);
+        out = m;
+    }
+    __syncthreads();
+}
+
+// ---- forward kernels --------------------------------------------------------------------------------------------------
+// layer 0: z0[p][c] = b[c] + x[p] . w[c]   (one thread per point and 8 channels)
+__global__ void __launch_bounds__(256) train_layer0_kernel(const float *__restrict__ x, long long P, int C, const float *__restrict__ w,
+                                                          const float *__restrict__ bias, float *__restrict__ z) {
+    const int chunks = C / 8;
+    const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (e >= P * chunks) return;
+    const long long p = e / chunks;
+    const int c0 = (int)(e - p * chunks) * 8;
+    const float px = __ldg(x + 3 * p), py = __ldg(x + 3 * p + 1), pz = __ldg(x + 3 * p + 2);
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float *wr = w + 3 * (c0 + k);
+        v[k] = fmaf(pz, __ldg(wr + 2), fmaf(py, __ldg(wr + 1), fmaf(px, __ldg(wr), bias ? __ldg(bias + c0 + k) : 0.0f)));
+    }
+    float4 *dst = reinterpret_cast<float4 *>(z + p * C + c0);
+    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// shifted sums per channel: acc[c] += sum_p (z - K_c), acc[256 + c] += sum_p (z - K_c)^2 with K_c = z[0][c] (any sample of
+// the channel keeps the subtraction in the variance formula harmless)
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float *__restrict__ z, long long P, int C, double *__restrict__ acc) {
+    __shared__ float red[2 * 1024];
+    const ColGeom g(C);
+    float v[2][4] = {};
+    if (g.active) {
+        const float4 k4 = __ldg(reinterpret_cast<const float4 *>(z) + g.tx);
+        for (long long row = (long long)blockIdx.x * g.rpi + g.ty; row < P; row += (long long)gridDim.x * g.rpi) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(z + row * C) + g.tx);
+            const float d0 = t.x - k4.x, d1 = t.y - k4.y, d2 = t.z - k4.z, d3 = t.w - k4.w;
+            v[0][0] += d0; v[0][1] += d1; v[0][2] += d2; v[0][3] += d3;
+            v[1][0] = fmaf(d0, d0, v[1][0]); v[1][1] = fmaf(d1, d1, v[1][1]);
+            v[1][2] = fmaf(d2, d2, v[1][2]); v[1][3] = fmaf(d3, d3, v[1][3]);
+        }
+    }
+    double out[2];
+    col_reduce_sum<2>(v, g, C, red, out);
+    if ((int)threadIdx.x < C) {
+        atomicAdd(acc + threadIdx.x, out[0]);
+        atomicAdd(acc + kTMaxC + threadIdx.x, out[1]);
+    }
+}
+
+// one CTA: batch (or running) statistics -> the affine map of the layer; running-stat update in train mode
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float *__restrict__ z, long long P, int C, const double *__restrict__ acc,
+                                                         const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                         float *__restrict__ rmean, float *__restrict__ rvar, float eps, float momentum,
+                                                         int batch_stats, float *__restrict__ bnp) {
+    const int c = threadIdx.x;
+    if (c >= C) return;
+    double mean, var;
+    if (batch_stats) {
+        const double n = (double)P, s1 = acc[c], s2 = acc[kTMaxC + c];
+        const double dm = s1 / n;
+        mean = (double)z[c] + dm;
+        var = s2 / n - dm * dm;
+        if (var < 0.0) var = 0.0;
+        if (rmean) rmean[c] = (float)((1.0 - (double)momentum) * (double)rmean[c] + (double)momentum * mean);
+        if (rvar) rvar[c] = (float)((1.0 - (double)momentum) * (double)rvar[c] + (double)momentum * var * (n / (n - 1.0)));
+    } else {
+        mean = (double)rmean[c];
+        var = (double)rvar[c];
+    }
+    const double invstd = 1.0 / sqrt(var + (double)eps);
+    const double ga = gamma ? (double)gamma[c] : 1.0, be = beta ? (double)beta[c] : 0.0;
+    bnp[c] = (float)(ga * invstd);
+    bnp[C + c] = (float)(be - mean * ga * invstd);
+    bnp[2 * C + c] = (float)(mean * invstd);
+    bnp[3 * C + c] = (float)invstd;
+}
+
+// a = ReLU(z * scale + shift) -> fp16 hi+lo operand rows of the next GEMM; max |zhat| per channel for the backward's scale
+__global__ void __launch_bounds__(256) bn_act_kernel(const float *__restrict__ z, long long P, int C, const float *__restrict__ bnp,
+                                                    unsigned short *__restrict__ ahi, unsigned short *__restrict__ alo,
+                                                    unsigned *__restrict__ zmax) {
+    __shared__ float red[1024];
+    const ColGeom g(C);
+    float zm[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (g.active) {
+        const float4 sc = __ldg(reinterpret_cast<const float4 *>(bnp) + g.tx), sh = __ldg(reinterpret_cast<const float4 *>(bnp + C) + g.tx);
+        const float4 mi = __ldg(reinterpret_cast<const float4 *>(bnp + 2 * C) + g.tx), is = __ldg(reinterpret_cast<const float4 *>(bnp + 3 * C) + g.tx);
+        for (long long row = (long long)blockIdx.x * g.rpi + g.ty; row < P; row += (long long)gridDim.x * g.rpi) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(z + row * C) + g.tx);
+            const float a0 = fmaxf(fmaf(t.x, sc.x, sh.x), 0.0f), a1 = fmaxf(fmaf(t.y, sc.y, sh.y), 0.0f);
+            const float a2 = fmaxf(fmaf(t.z, sc.z, sh.z), 0.0f), a3 = fmaxf(fmaf(t.w, sc.w, sh.w), 0.0f);
+            zm[0] = fmaxf(zm[0], fabsf(fmaf(t.x, is.x, -mi.x))); zm[1] = fmaxf(zm[1], fabsf(fmaf(t.y, is.y, -mi.y)));
+            zm[2] = fmaxf(zm[2], fabsf(fmaf(t.z, is.z, -mi.z))); zm[3] = fmaxf(zm[3], fabsf(fmaf(t.w, is.w, -mi.w)));
+            uint32_t h0, l0, h1, l1;
+            split_f16x2(a0, a1, h0, l0);
+            split_f16x2(a2, a3, h1, l1);
+            const size_t o = ((size_t)row * C + 4 * g.tx);
+            *reinterpret_cast<uint2 *>(ahi + o) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2 *>(alo + o) = make_uint2(l0, l1);
+        }
+    }
+    float m;
+    col_reduce_max(zm, g, C, red, m);
+    if ((int)threadIdx.x < C && m > 0.0f) atomicMax(zmax + threadIdx.x, __float_as_uint(m));
+}
+
+// last layer: a = ReLU(BatchNorm(z)), max and arg-max over the points of a cloud.  grid (chunks of points, B)
+__global__ void __launch_bounds__(256) bn_pool_kernel(const float *__restrict__ z, int N, int C, int rows_per_cta, const float *__restrict__ bnp,
+                                                     u64 *__restrict__ keys, unsigned *__restrict__ zmax) {
+    __shared__ u64 kred[1024];
+    __shared__ float red[1024];
+    const ColGeom g(C);
+    const int b = blockIdx.y;
+    const int n_begin = blockIdx.x * rows_per_cta, n_end = min(N, n_begin + rows_per_cta);
+    float zm[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    u64 best[4] = {0, 0, 0, 0};
+    if (g.active) {
+        const float4 sc = __ldg(reinterpret_cast<const float4 *>(bnp) + g.tx), sh = __ldg(reinterpret_cast<const float4 *>(bnp + C) + g.tx);
+        const float4 mi = __ldg(reinterpret_cast<const float4 *>(bnp + 2 * C) + g.tx), is = __ldg(reinterpret_cast<const float4 *>(bnp + 3 * C) + g.tx);
+        for (int n = n_begin + g.ty; n < n_end; n += g.rpi) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(z + ((size_t)b * N + n) * C) + g.tx);
+            const float a[4] = {fmaxf(fmaf(t.x, sc.x, sh.x), 0.0f), fmaxf(fmaf(t.y, sc.y, sh.y), 0.0f),
+                                fmaxf(fmaf(t.z, sc.z, sh.z), 0.0f), fmaxf(fmaf(t.w, sc.w, sh.w), 0.0f)};
+            zm[0] = fmaxf(zm[0], fabsf(fmaf(t.x, is.x, -mi.x))); zm[1] = fmaxf(zm[1], fabsf(fmaf(t.y, is.y, -mi.y)));
+            zm[2] = fmaxf(zm[2], fabsf(fmaf(t.z, is.z, -mi.z))); zm[3] = fmaxf(zm[3], fabsf(fmaf(t.w, is.w, -mi.w)));
+            const u64 low = (u64)(0xFFFFFFFFu - (unsigned)n);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const u64 key = ((u64)__float_as_uint(a[k]) << 32) | low;    // a >= 0: the bit pattern orders like the value
+                best[k] = key > best[k] ? key : best[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) kred[g.ty * C + 4 * g.tx + k] = best[k];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < C) {
+        u64 m = 0;
+        for (int r = 0; r < g.rpi; ++r) m = kred[r * C + threadIdx.x] > m ? kred[r * C + threadIdx.x] : m;
+        if (n_begin < n_end) atomicMax(keys + (size_t)b * C + threadIdx.x, m);
+    }
+    __syncthreads();
+    float m;
+    col_reduce_max(zm, g, C, red, m);
+    if ((int)threadIdx.x < C && m > 0.0f) atomicMax(zmax + threadIdx.x, __float_as_uint(m));
+}
+
+__global__ void __launch_bounds__(256) pool_decode_kernel(const u64 *__restrict__ keys, int n, float *__restrict__ pooled) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) pooled[i] = __uint_as_float((unsigned)(keys[i] >> 32));
+}
+
+// weights of the layers >= 1 -> fp16 hi+lo pieces scaled by a power of two (max |w| * scale in (2^13, 2^14]), in both
+// orientations: (c_out x c_in) for the forward GEMM and (c_in x c_out) for the input-gradient GEMM.  One CTA per layer.
+struct PackArgs {
+    const float *w[kTMaxLayers];
+    unsigned short *p[kTMaxLayers][4];
+    int c_out[kTMaxLayers], c_in[kTMaxLayers];
+    float *wscale;
+};
+__global__ void __launch_bounds__(1024) train_pack_kernel(PackArgs a) {
+    __shared__ float red[32];
+    __shared__ float s_scale;
+    const int l = blockIdx.x + 1;
+    const int co = a.c_out[l], ci = a.c_in[l], n = co * ci;
+    const float *w = a.w[l];
+    float m = 0.0f;
+    for (int e = threadIdx.x; e < n; e += 1024) m = fmaxf(m, fabsf(w[e]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float mm = 0.0f;
+        for (int k = 0; k < 32; ++k) mm = fmaxf(mm, red[k]);
+        int e = 0;
+        if (mm > 0.0f && mm < 3.0e38f) e = 14 - (ilogbf(mm) + 1);        // mm * 2^e in [2^13, 2^14)
+        e = max(-100, min(100, e));
+        s_scale = ldexpf(1.0f, e);
+        a.wscale[2 * l] = s_scale;
+        a.wscale[2 * l + 1] = ldexpf(1.0f, -e);
+    }
+    __syncthreads();
+    const float sc = s_scale;
+    for (int e = threadIdx.x; e < n; e += 1024) {
+        const float v = w[e] * sc;
+        const __half h = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(h));
+        const unsigned short hb = *reinterpret_cast<const unsigned short *>(&h), lb = *reinterpret_cast<const unsigned short *>(&lo);
+        const int r = e / ci, c = e - r * ci;
+        a.p[l][0][e] = hb;
+        a.p[l][1][e] = lb;
+        a.p[l][2][c * co + r] = hb;
+        a.p[l][3][c * co + r] = lb;
+    }
+}
+
+// ---- backward kernels -------------------------------------------------------------------------------------------------
+// last layer: dy is non-zero only at the arg-max point of each (cloud, channel) with a positive maximum
+__global__ void __launch_bounds__(256) pool_bwd_stats_kernel(const float *__restrict__ z, const float *__restrict__ gp, const u64 *__restrict__ keys,
+                                                            int B, int N, int C, const float *__restrict__ bnp, double *__restrict__ acc,
+                                                            unsigned *__restrict__ mxdy) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= B * C) return;
+    const int b = i / C, c = i - b * C;
+    const u64 key = keys[i];
+    if (__uint_as_float((unsigned)(key >> 32)) > 0.0f) {
+        const int n = (int)(0xFFFFFFFFu - (unsigned)key);
+        const float g = gp[i];
+        const float zh = fmaf(z[((size_t)b * N + n) * C + c], bnp[3 * C + c], -bnp[2 * C + c]);
+        atomicAdd(acc + c, (double)g);
+        atomicAdd(acc + kTMaxC + c, (double)g * (double)zh);
+        atomicMax(mxdy + c, __float_as_uint(fabsf(g)));
+    }
+}
+
+// hidden layers: dy = da * [y > 0];  acc[c] += sum dy, acc[256 + c] += sum dy * zhat, mxdy[c] = max |dy|
+__global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const float *__restrict__ z, const float *__restrict__ da, long long P, int C,
+                                                          const float *__restrict__ bnp, double *__restrict__ acc, unsigned *__restrict__ mxdy) {
+    __shared__ float red[2 * 1024];
+    const ColGeom g(C);
+    float v[2][4] = {};
+    float mx[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (g.active) {
+        const float4 sc = __ldg(reinterpret_cast<const float4 *>(bnp) + g.tx), sh = __ldg(reinterpret_cast<const float4 *>(bnp + C) + g.tx);
+        const float4 mi = __ldg(reinterpret_cast<const float4 *>(bnp + 2 * C) + g.tx), is = __ldg(reinterpret_cast<const float4 *>(bnp + 3 * C) + g.tx);
+        for (long long row = (long long)blockIdx.x * g.rpi + g.ty; row < P; row += (long long)gridDim.x * g.rpi) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(z + row * C) + g.tx);
+            const float4 d = __ldg(reinterpret_cast<const float4 *>(da + row * C) + g.tx);
+            const float dy0 = fmaf(t.x, sc.x, sh.x) > 0.0f ? d.x : 0.0f, dy1 = fmaf(t.y, sc.y, sh.y) > 0.0f ? d.y : 0.0f;
+            const float dy2 = fmaf(t.z, sc.z, sh.z) > 0.0f ? d.z : 0.0f, dy3 = fmaf(t.w, sc.w, sh.w) > 0.0f ? d.w : 0.0f;
+            v[0][0] += dy0; v[0][1] += dy1; v[0][2] += dy2; v[0][3] += dy3;
+            v[1][0] = fmaf(dy0, fmaf(t.x, is.x, -mi.x), v[1][0]); v[1][1] = fmaf(dy1, fmaf(t.y, is.y, -mi.y), v[1][1]);
+            v[1][2] = fmaf(dy2, fmaf(t.z, is.z, -mi.z), v[1][2]); v[1][3] = fmaf(dy3, fmaf(t.w, is.w, -mi.w), v[1][3]);
+            mx[0] = fmaxf(mx[0], fabsf(dy0)); mx[1] = fmaxf(mx[1], fabsf(dy1));
+            mx[2] = fmaxf(mx[2], fabsf(dy2)); mx[3] = fmaxf(mx[3], fabsf(dy3));
+        }
+    }
+    double out[2];
+    col_reduce_sum<2>(v, g, C, red, out);
+    if ((int)threadIdx.x < C) {
+        atomicAdd(acc + threadIdx.x, out[0]);
+        atomicAdd(acc + kTMaxC + threadIdx.x, out[1]);
+    }
+    float m;
+    col_reduce_max(mx, g, C, red, m);
+    if ((int)threadIdx.x < C && m > 0.0f) atomicMax(mxdy + threadIdx.x, __float_as_uint(m));
+}
+
+// one CTA: the two means of the BatchNorm backward, the parameter gradients they are, and the power-of-two scale of dz
+__global__ void __launch_bounds__(256) bn_bwd_scale_kernel(long long P, int C, int batch_stats, const double *__restrict__ acc,
+                                                          const unsigned *__restrict__ mxdy, const unsigned *__restrict__ zmax,
+                                                          const float *__restrict__ bnp, float *__restrict__ m12, float *__restrict__ dscale,
+                                                          float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ dbias) {
+    __shared__ float red[8];
+    const int c = threadIdx.x;
+    float bound = 0.0f;
+    if (c < C) {
+        const double s1 = acc[c], s2 = acc[kTMaxC + c];
+        const float m1 = batch_stats ? (float)(s1 / (double)P) : 0.0f, m2 = batch_stats ? (float)(s2 / (double)P) : 0.0f;
+        m12[c] = m1;
+        m12[kTMaxC + c] = m2;
+        if (dgamma) dgamma[c] = (float)s2;
+        if (dbeta) dbeta[c] = (float)s1;
+        if (dbias) dbias[c] = batch_stats ? 0.0f : (float)((double)bnp[c] * s1);      // sum_p dz (zero through batch statistics)
+        bound = fabsf(bnp[c]) * (__uint_as_float(mxdy[c]) + fabsf(m1) + __uint_as_float(zmax[c]) * fabsf(m2));
+    }
+    for (int o = 16; o > 0; o >>= 1) bound = fmaxf(bound, __shfl_xor_sync(0xffffffffu, bound, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = bound;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float mm = 0.0f;
+        for (int k = 0; k < 8; ++k) mm = fmaxf(mm, red[k]);
+        int e = 0;
+        if (mm > 0.0f && mm < 3.0e38f) e = 14 - (ilogbf(mm) + 1);
+        e = max(-100, min(100, e));
+        dscale[0] = ldexpf(1.0f, e);
+        dscale[1] = ldexpf(1.0f, -e);
+    }
+}
+
+// dz = scale * (dy - m1 - zhat * m2), written as fp16 hi+lo operand rows multiplied by the device scale s.
+// LAST: dy comes from the arg-max keys and the pooled upstream gradient; else dy = da * [y > 0].
+template <bool LAST>
+__global__ void __launch_bounds__(256) bn_bwd_dz_kernel(const float *__restrict__ z, const float *__restrict__ da, long long P, int N, int C,
+                                                       const float *__restrict__ bnp, const float *__restrict__ m12,
+                                                       const float *__restrict__ dscale, const u64 *__restrict__ keys,
+                                                       const float *__restrict__ gp, unsigned short *__restrict__ dzhi,
+                                                       unsigned short *__restrict__ dzlo) {
+    const int chunks = C / 8;
+    const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (e >= P * chunks) return;
+    const long long p = e / chunks;
+    const int c0 = (int)(e - p * chunks) * 8;
+    const float s = __ldg(dscale);
+    float zz[8], dy[8];
+    {
+        const float4 *zp = reinterpret_cast<const float4 *>(z + p * C + c0);
+        const float4 t0 = __ldg(zp), t1 = __ldg(zp + 1);
+        zz[0] = t0.x; zz[1] = t0.y; zz[2] = t0.z; zz[3] = t0.w; zz[4] = t1.x; zz[5] = t1.y; zz[6] = t1.z; zz[7] = t1.w;
+    }
+    if (LAST) {
+        const long long b = p / N;
+        const unsigned n = (unsigned)(p - b * N);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const u64 key = __ldg(keys + b * C + c0 + k);
+            const bool hit = (0xFFFFFFFFu - (unsigned)key) == n && __uint_as_float((unsigned)(key >> 32)) > 0.0f;
+            dy[k] = hit ? __ldg(gp + b * C + c0 + k) : 0.0f;
+        }
+    } else {
+        const float4 *dp = reinterpret_cast<const float4 *>(da + p * C + c0);
+        const float4 d0 = __ldg(dp), d1 = __ldg(dp + 1);
+        const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dy[k] = fmaf(zz[k], __ldg(bnp + c0 + k), __ldg(bnp + C + c0 + k)) > 0.0f ? dd[k] : 0.0f;
+    }
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = c0 + k;
+        const float zh = fmaf(zz[k], __ldg(bnp + 3 * C + c), -__ldg(bnp + 2 * C + c));
+        v[k] = (__ldg(bnp + c) * s) * (dy[k] - __ldg(m12 + c) - zh * __ldg(m12 + kTMaxC + c));
+    }
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) split_f16x2(v[2 * k], v[2 * k + 1], h[k], l[k]);
+    const size_t off = (size_t)p * C + c0;
+    *reinterpret_cast<uint4 *>(dzhi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4 *>(dzlo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// layer 0: dW0[c][k] = sum_p dz0[p][c] * x[p][k] on the CUDA cores (K = 3), dz0 formed on the fly
+__global__ void __launch_bounds__(256) layer0_wgrad_kernel(const float *__restrict__ z, const float *__restrict__ da, const float *__restrict__ x,
+                                                          long long P, int C, const float *__restrict__ bnp, const float *__restrict__ m12,
+                                                          double *__restrict__ w0acc) {
+    __shared__ float red[3 * 1024];
+    const ColGeom g(C);
+    float v[3][4] = {};
+    if (g.active) {
+        const float4 sc = __ldg(reinterpret_cast<const float4 *>(bnp) + g.tx), sh = __ldg(reinterpret_cast<const float4 *>(bnp + C) + g.tx);
+        const float4 mi = __ldg(reinterpret_cast<const float4 *>(bnp + 2 * C) + g.tx), is = __ldg(reinterpret_cast<const float4 *>(bnp + 3 * C) + g.tx);
+        const float4 m1 = __ldg(reinterpret_cast<const float4 *>(m12) + g.tx), m2 = __ldg(reinterpret_cast<const float4 *>(m12 + kTMaxC) + g.tx);
+        for (long long row = (long long)blockIdx.x * g.rpi + g.ty; row < P; row += (long long)gridDim.x * g.rpi) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(z + row * C) + g.tx);
+            const float4 d = __ldg(reinterpret_cast<const float4 *>(da + row * C) + g.tx);
+            const float px = __ldg(x + 3 * row), py = __ldg(x + 3 * row + 1), pz = __ldg(x + 3 * row + 2);
+            const float tz[4] = {t.x, t.y, t.z, t.w}, dd[4] = {d.x, d.y, d.z, d.w};
+            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w}, miv[4] = {mi.x, mi.y, mi.z, mi.w};
+            const float isv[4] = {is.x, is.y, is.z, is.w}, m1v[4] = {m1.x, m1.y, m1.z, m1.w}, m2v[4] = {m2.x, m2.y, m2.z, m2.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float dy = fmaf(tz[k], scv[k], shv[k]) > 0.0f ? dd[k] : 0.0f;
+                const float dz = scv[k] * (dy - m1v[k] - fmaf(tz[k], isv[k], -miv[k]) * m2v[k]);
+                v[0][k] = fmaf(dz, px, v[0][k]);
+                v[1][k] = fmaf(dz, py, v[1][k]);
+                v[2][k] = fmaf(dz, pz, v[2][k]);
+            }
+        }
+    }
+    double out[3];
+    col_reduce_sum<3>(v, g, C, red, out);
+    if ((int)threadIdx.x < C) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) atomicAdd(w0acc + 3 * threadIdx.x + k, out[k]);
+    }
+}
+__global__ void __launch_bounds__(256) layer0_wgrad_finish_kernel(const double *__restrict__ w0acc, int n, float *__restrict__ dw) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) dw[i] = (float)w0acc[i];
+}
+
+// ---- weight gradient on the tensor cores: dW[co][ci] = sum_p dz[p][co] * a[p][ci] ------------------------------------------
+// Both operands are point-major rows (the K dimension of this GEMM is the slow axis), i.e. MN-major tcgen05 operands: a TMA
+// box of 64 channels x 64 points with the 128-byte swizzle IS the canonical MN-major SWIZZLE_128B tile (8-point groups 1024 B
+// apart = SBO, the two 64-channel halves of a 128-wide operand one box apart = LBO).  A CTA owns one 128 x 128 tile of dW and
+// a contiguous range of 64-point chunks; warp 0 feeds a three-stage TMA ring, warp 1 issues the MMAs (dealt over four TMEM
+// accumulators, two of them carrying negated products), warps 2-5 drain the accumulators into registers every three
+// chunks (192 points: at most four truncating additions per accumulator) and finally store the partial tile.
+static constexpr int kWgThreads = 192;
+static constexpr int kWgStages = 3;
+static constexpr int kWgFlush = 3;                     // chunks per accumulator drain
+static constexpr uint32_t kWgBox = 64 * 128;           // bytes of one box: 64 points x 64 channels x 2 B
+static constexpr uint32_t kWgStage = 8 * kWgBox;       // A: 2 pieces x 2 boxes, B: 2 pieces x 2 boxes
+
+struct WgradArgs {
+    int chunks, tiles_n, n_tiles, n_split;
+    float *partial;                                    // [n_split][n_tiles][128][128]
+};
+
+// MN-major SWIZZLE_128B shared-memory matrix descriptor: LBO = one box (between 64-wide MN halves), SBO = 1024 B (8 K rows)
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(kWgBox >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+encoder_wgrad_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant__ CUtensorMap tma1,
+                     const __grid_constant__ CUtensorMap tmb0, const __grid_constant__ CUtensorMap tmb1, WgradArgs a) {
+    extern __shared__ unsigned char wg_smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t pad = (1024u - (smem_u32(wg_smem_raw) & 1023u)) & 1023u;
+    unsigned char *smem = wg_smem_raw + pad;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bars = sbase + kWgStages * kWgStage;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * kWgStages, bar_accfull = bar_empty + 8 * kWgStages, bar_accempty = bar_accfull + 8;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kWgStages * kWgStage + 8 * (2 * kWgStages + 2));
+
+    if (tid == 0) {
+        for (int s = 0; s < kWgStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_accfull, 1);
+        mbar_init(bar_accempty, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
+
+    const int tile = (int)blockIdx.x % a.n_tiles, split = (int)blockIdx.x / a.n_tiles;
+    const int tm = tile / a.tiles_n, tn = tile - tm * a.tiles_n;
+    const int c_begin = (int)((long long)split * a.chunks / a.n_split), c_end = (int)((long long)(split + 1) * a.chunks / a.n_split);
+    const int n_chunks = c_end - c_begin, n_groups = (n_chunks + kWgFlush - 1) / kWgFlush;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            for (int i = 0; i < n_chunks; ++i) {
+                const uint32_t s = (uint32_t)i % kWgStages, use = (uint32_t)i / kWgStages;
+                mbar_wait_wd(bar_empty + 8 * s, (use & 1u) ^ 1u);
+                mbar_arrive_expect_tx(bar_full + 8 * s, kWgStage);
+                const uint32_t dst = sbase + s * kWgStage;
+                const int p0 = (c_begin + i) * 64;
+                for (int h = 0; h < 2; ++h) {                       // the two 64-channel halves of the 128-wide tile
+                    tma_load_2d(dst + (0 + h) * kWgBox, &tma0, tm * 128 + h * 64, p0, bar_full + 8 * s);
+                    tma_load_2d(dst + (2 + h) * kWgBox, &tma1, tm * 128 + h * 64, p0, bar_full + 8 * s);
+                    tma_load_2d(dst + (4 + h) * kWgBox, &tmb0, tn * 128 + h * 64, p0, bar_full + 8 * s);
+                    tma_load_2d(dst + (6 + h) * kWgBox, &tmb1, tn * 128 + h * 64, p0, bar_full + 8 * s);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const bool leader = elect_one();
+        // D fp32, A/B fp16, both MN-major, M = N = 128
+        const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_neg = idesc | (1u << 13);                // a_negate
+        int i = 0;
+        for (int grp = 0; grp < n_groups; ++grp) {
+            mbar_wait_wd(bar_accempty, ((uint32_t)grp & 1u) ^ 1u);
+            tc_fence_after();
+            uint32_t used = 0, ks = 0;
+            const int i_end = min(n_chunks, i + kWgFlush);
+            for (; i < i_end; ++i) {
+                const uint32_t s = (uint32_t)i % kWgStages, use = (uint32_t)i / kWgStages;
+                mbar_wait_wd(bar_full + 8 * s, use & 1u);
+                tc_fence_after();
+                if (leader) {
+                    const uint32_t st = sbase + s * kWgStage;
+                    const uint64_t ah = umma_desc_mn(st), al = umma_desc_mn(st + 2 * kWgBox);
+                    const uint64_t bh = umma_desc_mn(st + 4 * kWgBox), bl = umma_desc_mn(st + 6 * kWgBox);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4, ++ks) {          // 16 points per MMA = two 8-point groups = 2048 bytes
+                        const uint64_t ko = (uint64_t)(k4 * (2048 >> 4));
+                        // accumulators 1 and 3 take negated products and are subtracted when drained: the fp32 accumulation of
+                        // the tensor core rounds toward minus infinity, and carrying half of the sum negated cancels that bias.
+                        // Per step: hi.hi -> accumulator ks % 4, the two cross terms -> its neighbours of the other sign.
+                        const uint32_t m = ks & 3u, m1 = (ks + 1u) & 3u, m3 = (ks + 3u) & 3u;
+                        tc_mma_bf16(tmem + m * 128u, ah + ko, bh + ko, (m & 1u) ? idesc_neg : idesc, (used >> m) & 1u);     // hi . hi
+                        used |= 1u << m;
+                        tc_mma_bf16(tmem + m1 * 128u, al + ko, bh + ko, (m1 & 1u) ? idesc_neg : idesc, (used >> m1) & 1u);  // lo . hi
+                        used |= 1u << m1;
+                        tc_mma_bf16(tmem + m3 * 128u, ah + ko, bl + ko, (m3 & 1u) ? idesc_neg : idesc, (used >> m3) & 1u);  // hi . lo
+                        used |= 1u << m3;
+                    }
+                    tc_commit(bar_empty + 8 * s);
+                }
+                __syncwarp();
+            }
+            if (leader) tc_commit(bar_accfull);
+            __syncwarp();
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                              // output channel of the tile = TMEM lane
+        const uint32_t lane_base = ((uint32_t)q * 32u) << 16;
+        float r[128];
+#pragma unroll
+        for (int e = 0; e < 128; ++e) r[e] = 0.0f;
+        for (int grp = 0; grp < n_groups; ++grp) {
+            mbar_wait_wd(bar_accfull, (uint32_t)grp & 1u);
+            tc_fence_after();
+            // a group of fewer than three 16-point steps cannot happen (a chunk is four steps): all four accumulators are live
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float v[32], vx[32];
+                tc_ld32(tmem + lane_base + (uint32_t)(c * 32), v);
+#pragma unroll 1
+                for (int m = 1; m < 4; ++m) {
+                    tc_ld32(tmem + lane_base + (uint32_t)m * 128u + (uint32_t)(c * 32), vx);
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = (m & 1) ? v[e] - vx[e] : v[e] + vx[e];
+                }
+#pragma unroll
+                for (int e = 0; e < 32; ++e) r[c * 32 + e] += v[e];
+            }
+            tc_fence_before();
+            mbar_arrive(bar_accempty);
+        }
+        float4 *dst = reinterpret_cast<float4 *>(a.partial + (((size_t)split * a.n_tiles + tile) * 128 + row) * 128);
+#pragma unroll
+        for (int e4 = 0; e4 < 32; ++e4) dst[e4] = make_float4(r[4 * e4], r[4 * e4 + 1], r[4 * e4 + 2], r[4 * e4 + 3]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
+// dW = inv_scale * sum over the splits of the partial tiles, in a fixed order (deterministic)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restrict__ partial, int n_split, int n_tiles, int tiles_n, int C_out,
+                                                          int C_in, const float *__restrict__ dscale, float *__restrict__ dw) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= C_out * C_in) return;
+    const int co = i / C_in, ci = i - co * C_in;
+    const int tile = (co >> 7) * tiles_n + (ci >> 7);
+    const float *src = partial + ((size_t)tile * 128 + (co & 127)) * 128 + (ci & 127);
+    float s = 0.0f;
+    for (int k = 0; k < n_split; ++k) s += src[(size_t)k * n_tiles * 128 * 128];
+    dw[i] = s * __ldg(dscale + 1);
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------------
+static int train_check(const char *fn, const rlg_bn_layer *layers, int L, unsigned flags) {
+    if (flags & ~RLG_ENC_BATCH_STATS) return fail(RLG_ERR_UNSUPPORTED, "%s: unknown flag bits 0x%x", fn, flags);
+    if (!layers || L < 2 || L > kTMaxLayers) return fail(RLG_ERR_UNSUPPORTED, "%s: need 2..%d layers, got %d", fn, kTMaxLayers, L);
+    if (layers[0].c_in != 3) return fail(RLG_ERR_UNSUPPORTED, "%s: layer 0 must have c_in == 3", fn);
+    for (int l = 0; l < L; ++l) {
+        const rlg_bn_layer &y = layers[l];
+        if (!y.w) return fail(RLG_ERR_NULL_POINTER, "%s: layer %d has no weights", fn, l);
+        if (l > 0 && y.c_in != layers[l - 1].c_out) return fail(RLG_ERR_BAD_SHAPE, "%s: layer %d c_in %d != previous c_out %d", fn, l, y.c_in, layers[l - 1].c_out);
+        if (y.c_out % 64 != 0 || y.c_out < 64 || y.c_out > kTMaxC)
+            return fail(RLG_ERR_UNSUPPORTED, "%s: width %d is not a multiple of 64 in [64, %d]", fn, y.c_out, kTMaxC);
+        if (!(flags & RLG_ENC_BATCH_STATS) && (!y.running_mean || !y.running_var))
+            return fail(RLG_ERR_NULL_POINTER, "%s: layer %d needs running statistics in eval mode", fn, l);
+        if (((uintptr_t)y.w | (uintptr_t)y.b | (uintptr_t)y.gamma | (uintptr_t)y.beta) & 15u)
+            return fail(RLG_ERR_UNSUPPORTED, "%s: layer %d parameters must be 16-byte aligned", fn, l);
+    }
+    return 0;
+}
+
+static inline unsigned row_grid(long long P, int C, int sms) {
+    const int rpi = 256 / (C / 4);
+    long long want = (P + (long long)rpi * 8 - 1) / ((long long)rpi * 8);      // ~8 rows per thread
+    const long long cap = (long long)sms * 8;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    return (unsigned)want;
+}
+
+static int launch_wgrad(const void *dzhi, const void *dzlo, const void *ahi, const void *alo, long long P, int C_out, int C_in,
+                        const float *dscale, float *partial, float *dw, int sms, cudaStream_t st) {
+    WgradArgs a;
+    a.chunks = (int)((P + 63) / 64);
+    const int tiles_m = (C_out + 127) / 128;
+    a.tiles_n = (C_in + 127) / 128;
+    a.n_tiles = tiles_m * a.tiles_n;
+    a.n_split = sms / a.n_tiles;
+    if (a.n_split < 1) a.n_split = 1;
+    if (a.n_split > a.chunks) a.n_split = a.chunks;
+    a.partial = partial;
+    CUtensorMap tm[4];
+    const void *base[4] = {dzhi, dzlo, ahi, alo};
+    for (int k = 0; k < 4; ++k) {
+        const int C = k < 2 ? C_out : C_in;
+        const cuuint64_t d[2] = {(cuuint64_t)C, (cuuint64_t)P};
+        const cuuint64_t s[1] = {(cuuint64_t)C * 2};
+        const cuuint32_t b[2] = {64, 64};
+        int rc = make_map(&tm[k], 2, const_cast<void *>(base[k]), 2, d, s, b);
+        if (rc) return rc;
+    }
+    const size_t smem_bytes = (size_t)kWgStages * kWgStage + 256 + 1024;
+    cudaError_t ae = cudaFuncSetAttribute(encoder_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (ae != cudaSuccess) { cudaGetLastError(); return fail((int)ae, "encoder_wgrad_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(ae)); }
+    cudaError_t le = launch_pdl(encoder_wgrad_kernel, dim3((unsigned)(a.n_split * a.n_tiles)), dim3(kWgThreads), smem_bytes, st,
+                                tm[0], tm[1], tm[2], tm[3], a);
+    if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "encoder_wgrad_kernel: %s", cudaGetErrorString(le)); }
+    const int n = C_out * C_in;
+    wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(partial, a.n_split, a.n_tiles, a.tiles_n, C_out, C_in, dscale, dw);
+    return 0;
+}
+
+static int launch_pack(const rlg_bn_layer *layers, int L, char *ws, const WsLayout &w, cudaStream_t st) {
+    PackArgs pa = {};
+    for (int l = 1; l < L; ++l) {
+        pa.w[l] = layers[l].w;
+        pa.c_out[l] = layers[l].c_out;
+        pa.c_in[l] = layers[l].c_in;
+        for (int k = 0; k < 4; ++k) pa.p[l][k] = reinterpret_cast<unsigned short *>(ws + w.wp[l][k]);
+    }
+    pa.wscale = reinterpret_cast<float *>(ws + w.wscale);
+    train_pack_kernel<<<L - 1, 1024, 0, st>>>(pa);
+    return 0;
+}
+
+}  // namespace rlg
+
+using namespace rlg;
+
+extern "C" {
+
+size_t rlg_encoder_train_saved_bytes(int B, int N, const rlg_bn_layer *layers, int L) {
+    if (B < 1 || N < 1 || train_check("rlg_encoder_train_saved_bytes", layers, L, RLG_ENC_BATCH_STATS) != 0) return 0;
+    return saved_layout((long long)B * N, B, layers, L).total;
+}
+
+int rlg_encoder_train_saved_layout(int B, int N, const rlg_bn_layer *layers, int L, size_t *offsets, int n_offsets) {
+    const char *fn = "rlg_encoder_train_saved_layout";
+    if (B < 1 || N < 1) return fail(RLG_ERR_BAD_SHAPE, "%s: bad shape B=%d N=%d", fn, B, N);
+    int rc = train_check(fn, layers, L, RLG_ENC_BATCH_STATS);
+    if (rc) return rc;
+    if (!offsets || n_offsets < 5 * L + 1) return fail(RLG_ERR_NULL_POINTER, "%s: need room for %d offsets", fn, 5 * L + 1);
+    const SavedLayout sl = saved_layout((long long)B * N, B, layers, L);
+    for (int l = 0; l < L; ++l) {
+        offsets[5 * l] = sl.z[l];
+        offsets[5 * l + 1] = sl.ahi[l];
+        offsets[5 * l + 2] = sl.alo[l];
+        offsets[5 * l + 3] = sl.bnp[l];
+        offsets[5 * l + 4] = sl.zmax[l];
+    }
+    offsets[5 * L] = sl.keys;
+    return 0;
+}
+
+size_t rlg_encoder_train_ws_bytes(int B, int N, const rlg_bn_layer *layers, int L) {
+    if (B < 1 || N < 1 || train_check("rlg_encoder_train_ws_bytes", layers, L, RLG_ENC_BATCH_STATS) != 0) return 0;
+    return ws_layout((long long)B * N, layers, L, sm_count()).total;
+}
+
+int rlg_encoder_train_fwd(const float *x, int B, int N, const rlg_bn_layer *layers, int L, unsigned flags, float *pooled, void *saved,
+                          size_t saved_bytes, void *ws, size_t ws_bytes, void *stream) {
+    const char *fn = "rlg_encoder_train_fwd";
+    if (B < 1 || N < 1) return fail(RLG_ERR_BAD_SHAPE, "%s: bad shape B=%d N=%d", fn, B, N);
+    int rc = train_check(fn, layers, L, flags);
+    if (rc) return rc;
+    const bool batch = (flags & RLG_ENC_BATCH_STATS) != 0;
+    const long long P = (long long)B * N;
+    if (batch && P < 2) return fail(RLG_ERR_BAD_SHAPE, "%s: batch statistics need more than one point per channel", fn);
+    if (P > 0x7fffffffLL / 256) return fail(RLG_ERR_TOO_LARGE, "%s: B*N too large", fn);
+    if (!x || !pooled) return fail(RLG_ERR_NULL_POINTER, "%s: null pointer", fn);
+    const int sms = sm_count();
+    if (sms <= 0) return fail((int)cudaErrorNoDevice, "%s: no CUDA device", fn);
+    const SavedLayout sl = saved_layout(P, B, layers, L);
+    const WsLayout wl = ws_layout(P, layers, L, sms);
+    if (!saved || saved_bytes < sl.total || ((uintptr_t)saved & 255u))
+        return fail(RLG_ERR_WORKSPACE, "%s: saved buffer %p/%zu bytes, need %zu bytes 256-B aligned", fn, saved, saved_bytes, sl.total);
+    if (!ws || ws_bytes < wl.total || ((uintptr_t)ws & 255u))
+        return fail(RLG_ERR_WORKSPACE, "%s: workspace %p/%zu bytes, need %zu bytes 256-B aligned", fn, ws, ws_bytes, wl.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    char *sv = (char *)saved, *w = (char *)ws;
+    const int CL = layers[L - 1].c_out;
+
+    cudaError_t e = cudaMemsetAsync(w, 0, wl.zero_bytes, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(sv + sl.keys, 0, (size_t)B * CL * 8, st);
+    for (int l = 0; l < L && e == cudaSuccess; ++l) e = cudaMemsetAsync(sv + sl.zmax[l], 0, (size_t)layers[l].c_out * 4, st);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "%s: cudaMemsetAsync: %s", fn, cudaGetErrorString(e)); }
+    rc = launch_pack(layers, L, w, wl, st);
+    if (rc) return rc;
+
+    for (int l = 0; l < L; ++l) {
+        const rlg_bn_layer &y = layers[l];
+        const int C = y.c_out;
+        float *z = reinterpret_cast<float *>(sv + sl.z[l]);
+        float *bnp = reinterpret_cast<float *>(sv + sl.bnp[l]);
+        unsigned *zmax = reinterpret_cast<unsigned *>(sv + sl.zmax[l]);
+        double *acc = reinterpret_cast<double *>(w + wl.stat) + (size_t)l * 2 * kTMaxC;
+        if (l == 0) {
+            const long long n = P * (C / 8);
+            train_layer0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, P, C, y.w, y.b, z);
+        } else {
+            GemmCall g;
+            g.B = B; g.N = N; g.K = y.c_in; g.C_out = C; g.pieces = 2;
+            g.x0 = sv + sl.ahi[l - 1]; g.x1 = sv + sl.alo[l - 1];
+            g.w0 = w + wl.wp[l][0]; g.w1 = w + wl.wp[l][1];
+            g.bias = y.b;
+            g.out_scale = 1.0f;
+            g.dscale0 = reinterpret_cast<const float *>(w + wl.wscale) + 2 * l + 1;
+            g.dscale1 = nullptr;
+            g.epi = EPI_RAW_;
+            g.y0 = z; g.y1 = nullptr; g.pooled = nullptr;
+            rc = launch_layer_gemm(g, sms, st);
+            if (rc) return rc;
+        }
+        if (batch) bn_stats_kernel<<<row_grid(P, C, sms), 256, 0, st>>>(z, P, C, acc);
+        bn_finalize_kernel<<<1, 256, 0, st>>>(z, P, C, acc, y.gamma, y.beta, y.running_mean, y.running_var, y.eps, y.momentum, batch ? 1 : 0, bnp);
+        if (l < L - 1) {
+            bn_act_kernel<<<row_grid(P, C, sms), 256, 0, st>>>(z, P, C, bnp, reinterpret_cast<unsigned short *>(sv + sl.ahi[l]),
+                                                                reinterpret_cast<unsigned short *>(sv + sl.alo[l]), zmax);
+        } else {
+            const int rpi = 256 / (C / 4);
+            int per = (N + 7) / 8;                                   // up to 8 CTAs per cloud
+            per = (per + rpi - 1) / rpi * rpi;
+            if (per < rpi) per = rpi;
+            const unsigned gx = (unsigned)((N + per - 1) / per);
+            u64 *keys = reinterpret_cast<u64 *>(sv + sl.keys);
+            bn_pool_kernel<<<dim3(gx, (unsigned)B), 256, 0, st>>>(z, N, C, per, bnp, keys, zmax);
+            pool_decode_kernel<<<(B * C + 255) / 256, 256, 0, st>>>(keys, B * C, pooled);
+        }
+    }
+    return check_launch(fn);
+}
+
+int rlg_encoder_train_bwd(const float *x, int B, int N, const rlg_bn_layer *layers, int L, unsigned flags, const float *g_pooled,
+                          const void *saved, size_t saved_bytes, const rlg_bn_grads *grads, void *ws, size_t ws_bytes, void *stream) {
+    const char *fn = "rlg_encoder_train_bwd";
+    if (B < 1 || N < 1) return fail(RLG_ERR_BAD_SHAPE, "%s: bad shape B=%d N=%d", fn, B, N);
+    int rc = train_check(fn, layers, L, flags);
+    if (rc) return rc;
+    const bool batch = (flags & RLG_ENC_BATCH_STATS) != 0;
+    const long long P = (long long)B * N;
+    if (P > 0x7fffffffLL / 256) return fail(RLG_ERR_TOO_LARGE, "%s: B*N too large", fn);
+    if (!x || !g_pooled || !grads) return fail(RLG_ERR_NULL_POINTER, "%s: null pointer", fn);
+    const int sms = sm_count();
+    if (sms <= 0) return fail((int)cudaErrorNoDevice, "%s: no CUDA device", fn);
+    const SavedLayout sl = saved_layout(P, B, layers, L);
+    const WsLayout wl = ws_layout(P, layers, L, sms);
+    if (!saved || saved_bytes < sl.total || ((uintptr_t)saved & 255u))
+        return fail(RLG_ERR_WORKSPACE, "%s: saved buffer %p/%zu bytes, need %zu bytes 256-B aligned", fn, saved, saved_bytes, sl.total);
+    if (!ws || ws_bytes < wl.total || ((uintptr_t)ws & 255u))
+        return fail(RLG_ERR_WORKSPACE, "%s: workspace %p/%zu bytes, need %zu bytes 256-B aligned", fn, ws, ws_bytes, wl.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    const char *sv = (const char *)saved;
+    char *w = (char *)ws;
+
+    cudaError_t e = cudaMemsetAsync(w, 0, wl.zero_bytes, st);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "%s: cudaMemsetAsync: %s", fn, cudaGetErrorString(e)); }
+    rc = launch_pack(layers, L, w, wl, st);
+    if (rc) return rc;
+    float *da = reinterpret_cast<float *>(w + wl.da);
+    unsigned short *dzhi = reinterpret_cast<unsigned short *>(w + wl.dzhi), *dzlo = reinterpret_cast<unsigned short *>(w + wl.dzlo);
+    const u64 *keys = reinterpret_cast<const u64 *>(sv + sl.keys);
+
+    for (int l = L - 1; l >= 0; --l) {
+        const rlg_bn_layer &y = layers[l];
+        const int C = y.c_out;
+        const float *z = reinterpret_cast<const float *>(sv + sl.z[l]);
+        const float *bnp = reinterpret_cast<const float *>(sv + sl.bnp[l]);
+        const unsigned *zmax = reinterpret_cast<const unsigned *>(sv + sl.zmax[l]);
+        double *acc = reinterpret_cast<double *>(w + wl.stat) + (size_t)l * 2 * kTMaxC;
+        unsigned *mxdy = reinterpret_cast<unsigned *>(w + wl.mxdy) + (size_t)l * kTMaxC;
+        float *m12 = reinterpret_cast<float *>(w + wl.m12) + (size_t)l * 2 * kTMaxC;
+        float *dscale = reinterpret_cast<float *>(w + wl.dscale) + 2 * l;
+        const bool last = l == L - 1;
+        if (last) pool_bwd_stats_kernel<<<(B * C + 255) / 256, 256, 0, st>>>(z, g_pooled, keys, B, N, C, bnp, acc, mxdy);
+        else bn_bwd_stats_kernel<<<row_grid(P, C, sms), 256, 0, st>>>(z, da, P, C, bnp, acc, mxdy);
+        bn_bwd_scale_kernel<<<1, 256, 0, st>>>(P, C, batch ? 1 : 0, acc, mxdy, zmax, bnp, m12, dscale, grads[l].dgamma, grads[l].dbeta, grads[l].db);
+        if (l == 0) {
+            if (grads[0].dw) {
+                double *w0acc = reinterpret_cast<double *>(w + wl.w0acc);
+                layer0_wgrad_kernel<<<row_grid(P, C, sms), 256, 0, st>>>(z, da, x, P, C, bnp, m12, w0acc);
+                layer0_wgrad_finish_kernel<<<(3 * C + 255) / 256, 256, 0, st>>>(w0acc, 3 * C, grads[0].dw);
+            }
+            break;
+        }
+        const long long n = P * (C / 8);
+        if (last) bn_bwd_dz_kernel<true><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(z, nullptr, P, N, C, bnp, m12, dscale, keys, g_pooled, dzhi, dzlo);
+        else bn_bwd_dz_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(z, da, P, N, C, bnp, m12, dscale, nullptr, nullptr, dzhi, dzlo);
+        if (grads[l].dw) {
+            rc = launch_wgrad(dzhi, dzlo, sv + sl.ahi[l - 1], sv + sl.alo[l - 1], P, C, y.c_in, dscale, reinterpret_cast<float *>(w + wl.partial),
+                              grads[l].dw, sms, st);
+            if (rc) return rc;
+        }
+        // da_{l-1} = dz_l . W_l   (the dead da_l buffer is overwritten)
+        GemmCall g;
+        g.B = B; g.N = N; g.K = C; g.C_out = y.c_in; g.pieces = 2;
+        g.x0 = dzhi; g.x1 = dzlo;
+        g.w0 = w + wl.wp[l][2]; g.w1 = w + wl.wp[l][3];
+        g.bias = nullptr;
+        g.out_scale = 1.0f;
+        g.dscale0 = dscale + 1;
+        g.dscale1 = reinterpret_cast<const float *>(w + wl.wscale) + 2 * l + 1;
+        g.epi = EPI_RAW_;
+        g.y0 = da; g.y1 = nullptr; g.pooled = nullptr;
+        rc = launch_layer_gemm(g, sms, st);
+        if (rc) return rc;
+    }
+    return check_launch(fn);
+}
+
+}  // extern "C"

@@ -2,6 +2,8 @@
 // the encoder trunk (encoder_tc.cu) and the tensor-core Chamfer filter (chamfer_tcfilter.cu).  sm_100a only.
 #pragma once
 #include "common.cuh"
+#include <cuda.h>
+#include <cuda_fp16.h>
 
 namespace rlg {
 
@@ -154,5 +156,34 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
 __device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+
+// ---- TMA tensor-map loads (cp.async.bulk.tensor) and the fp16 hi+lo operand split, shared by the layer GEMMs
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
+    return __half22float2(*reinterpret_cast<const __half2 *>(&v));
+}
+
+// hi = fp16(v), lo = fp16(v - hi): 22 significant bits in two fp16 numbers (the residual is exact in fp32)
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t &h, uint32_t &l) {
+    h = pack_f16x2_sat(x0, x1);
+    const float2 hf = unpack_f16x2(h);
+    l = pack_f16x2_sat(x0 - hf.x, x1 - hf.y);
+}
+
+// host: a SWIZZLE_128B tensor map over 2-byte elements (pieces_fmt 1 = bf16, 2 = fp16); defined in encoder_layers.cu
+int make_map(CUtensorMap *tm, int pieces_fmt, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
+             const cuuint32_t *box);
 
 }  // namespace rlg

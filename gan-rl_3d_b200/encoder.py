@@ -420,17 +420,54 @@ def _module_is_hot(self: nn.Module, x) -> bool:
     return plan is not None and plan.device == x.device
 
 
+_TRAIN_PATH = True
+
+
+def set_train_path(enabled: bool) -> None:
+    """Whether train-mode forwards (BatchNorm batch statistics) and eval-mode forwards under autograd run the B200
+    train kernels (train.py) where the widths allow; off = the module's own stock layers."""
+    global _TRAIN_PATH
+    _TRAIN_PATH = bool(enabled)
+
+
+def _train_plan_ok(self: nn.Module, x: torch.Tensor) -> bool:
+    """The B200 train kernels cover this module and input (cached per parameter-storage layout)."""
+    if not _TRAIN_PATH or x.requires_grad or x.shape[0] * x.shape[1] < 2:
+        return False
+    from .train import train_supported
+    try:
+        key = tuple((id(t), t.data_ptr()) for m in self.point_mlp for t in (*m._parameters.values(), *m._buffers.values())
+                    if t is not None)
+    except AttributeError:
+        return False
+    hit = self.__dict__.get("_rlg_train_ok")
+    if hit is None or hit[0] != key:
+        hit = (key, train_supported(self.point_mlp))
+        self.__dict__["_rlg_train_ok"] = hit
+    if not hit[1]:
+        return False
+    return self.point_mlp[0].weight.device == x.device
+
+
 def fused_forward(self: nn.Module, x: torch.Tensor, _original=None) -> torch.Tensor:
     """Drop-in for PointNetEncoder.forward (models/autoencoder.py:56-76)."""
-    if self.training or not is_hot_path_input(x) or x.shape[0] == 0 or not _module_is_hot(self, x):
+    hot = is_hot_path_input(x) and x.shape[0] > 0
+    if hot and self.training and _train_plan_ok(self, x):
+        from .train import trunk_pool_autograd
+        return self.global_mlp(trunk_pool_autograd(self, x, batch_stats=True))
+    if self.training or not hot or not _module_is_hot(self, x):
         if _original is not None:
             return _original(self, x)
-        # stock path with the module's own layers (train-mode BatchNorm needs batch statistics)
+        # stock path with the module's own layers
         feat = torch.max(self.point_mlp(x.transpose(2, 1)), dim=2)[0]
         return self.global_mlp(feat)
     params = list(self.point_mlp.parameters())
     if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
-        pooled = EncoderTrunkFn.apply(x, self, *params)
+        if _train_plan_ok(self, x):
+            from .train import trunk_pool_autograd
+            pooled = trunk_pool_autograd(self, x, batch_stats=False)
+        else:
+            pooled = EncoderTrunkFn.apply(x, self, *params)
     else:
         pooled = _trunk_pool(self, x)
     return self.global_mlp(pooled)

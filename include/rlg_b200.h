@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define RLG_ABI_VERSION 4
+#define RLG_ABI_VERSION 5
 
 #define RLG_ERR_NULL_POINTER   (-1)
 #define RLG_ERR_BAD_SHAPE      (-2)   /* B < 0, N < 1, M < 1 (the reference raises IndexError for empty clouds) */
@@ -201,6 +201,63 @@ size_t rlg_encoder_gemm_ws_bytes(int B, int N, const rlg_layer *layers, int L, i
 int rlg_encoder_gemm_fwd(const float *x, int B, int N, const rlg_layer *layers, int L, int mode,
                          const float *weight_scales, const void *packed, size_t packed_bytes,
                          float *pooled, void *ws, size_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * PointNet encoder trunk WITH its BatchNorm layers: forward and backward  (models/autoencoder.py:32-47,65-71 as
+ * driven by the autoencoder training step, train_rl_gan_net.py:220-249: model.train(), loss.backward()).
+ *
+ * Each block is Conv1d(k=1) -> BatchNorm1d -> ReLU; the last block is followed by the max over the points.
+ *   flags & RLG_ENC_BATCH_STATS   train mode: BatchNorm normalises with the statistics of this batch (biased variance
+ *                                 over the B*N points) and updates running_mean / running_var in place
+ *                                 (running = (1-momentum)*running + momentum*batch, unbiased variance), as
+ *                                 torch.nn.BatchNorm1d does.  The caller increments num_batches_tracked.
+ *   without it                    eval mode: BatchNorm uses running_mean / running_var (read only); the backward is that
+ *                                 of the affine map (this is the encoder backward of SURVEY 8(b), rlg_encoder_bwd).
+ * GEMMs (layers >= 1, forward, input-gradient and weight-gradient) run on the tensor cores at fp32 grade (tcgen05,
+ * fp16 hi+lo operand pairs, fp32 accumulation in TMEM); statistics are accumulated in float64.
+ * Widths: c_in of layer 0 is 3, every c_out a multiple of 64 and <= 256, 2 <= L <= 8 (else RLG_ERR_UNSUPPORTED: the
+ * caller keeps the stock layers).  B*N >= 2 in train mode.
+ *
+ *   rlg_encoder_train_fwd   pooled (B, C_last) fp32 = max over points of the trunk's output; `saved` (caller-owned,
+ *                           >= rlg_encoder_train_saved_bytes) receives what the backward needs (pre-BatchNorm outputs,
+ *                           operand pieces of the activations, batch statistics, arg-max keys); `ws` is scratch.
+ *   rlg_encoder_train_bwd   g_pooled (B, C_last) fp32 upstream gradient; grads[l] receives dL/d(conv weight) (c_out,c_in),
+ *                           dL/d(conv bias), dL/d(gamma), dL/d(beta) (each nullable).  No gradient for x (the clouds
+ *                           are data).  Must see the same layers (weights unchanged) and the `saved` of its forward.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct rlg_bn_layer {
+    const float *w;          /* device, (c_out, c_in) row-major: Conv1d weight with the kernel axis squeezed */
+    const float *b;          /* device, (c_out) Conv1d bias, nullable */
+    const float *gamma;      /* device, (c_out) BatchNorm weight, nullable (= 1) */
+    const float *beta;       /* device, (c_out) BatchNorm bias, nullable (= 0) */
+    float *running_mean;     /* device, (c_out); updated in train mode, read in eval mode */
+    float *running_var;      /* device, (c_out) */
+    float eps;
+    float momentum;
+    int32_t c_in;
+    int32_t c_out;
+} rlg_bn_layer;
+
+typedef struct rlg_bn_grads {
+    float *dw;               /* device, (c_out, c_in), nullable */
+    float *db;               /* device, (c_out), nullable (exactly 0 in train mode: BatchNorm removes the bias) */
+    float *dgamma;           /* device, (c_out), nullable */
+    float *dbeta;            /* device, (c_out), nullable */
+} rlg_bn_grads;
+
+#define RLG_ENC_BATCH_STATS 1u
+size_t rlg_encoder_train_saved_bytes(int B, int N, const rlg_bn_layer *layers, int L);
+size_t rlg_encoder_train_ws_bytes(int B, int N, const rlg_bn_layer *layers, int L);
+/* Where things live inside `saved` (inspection / tests): offsets[5*l + k] for layer l with k = 0: z, fp32 (B*N, c_out)
+ * pre-BatchNorm outputs; 1, 2: hi and lo fp16 pieces (B*N, c_out) of the post-ReLU activations (absent = 0 for the
+ * last layer); 3: fp32 (4, c_out) = gamma*invstd, beta - mean*gamma*invstd, mean*invstd, invstd; 4: u32 (c_out) bit
+ * pattern of max |zhat|;  offsets[5*L]: u64 (B, C_last) max-pool keys = (value bits << 32) | (0xFFFFFFFF - point). */
+int rlg_encoder_train_saved_layout(int B, int N, const rlg_bn_layer *layers, int L, size_t *offsets, int n_offsets);
+int rlg_encoder_train_fwd(const float *x, int B, int N, const rlg_bn_layer *layers, int L, unsigned flags,
+                          float *pooled, void *saved, size_t saved_bytes, void *ws, size_t ws_bytes, void *stream);
+int rlg_encoder_train_bwd(const float *x, int B, int N, const rlg_bn_layer *layers, int L, unsigned flags,
+                          const float *g_pooled, const void *saved, size_t saved_bytes,
+                          const rlg_bn_grads *grads, void *ws, size_t ws_bytes, void *stream);
 
 /* FP32 CUDA-core peak microbenchmark (measurement helper, not on the hot path; it synchronises).
  * Fills host array out[0..5]:

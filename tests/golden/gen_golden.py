@@ -117,6 +117,54 @@ def main():
     enc_out["enc_count"] = np.int32(len(cfgs))
     np.savez_compressed(os.path.join(HERE, "encoder_ref.npz"), **enc_out)
 
+    # --- Encoder, TRAIN mode (train_rl_gan_net.py:220-249): the reference module itself, run in float64, one training
+    #     forward + backward: GFV, every parameter gradient, the BatchNorm buffers after the step.  The seed is searched so
+    #     that no pre-activation is within 3e-6 (relative) of zero: there the gradient is continuous and an fp32 run must
+    #     reproduce it.
+    tr_out = {}
+    dims, latent, B, N = [64, 128, 64], 32, 4, 96
+    for seed in range(500):
+        torch.manual_seed(5000 + seed)
+        enc = ae.PointNetEncoder(3, latent, dims).double()
+        O.randomize_bn(enc, seed=40 + seed)
+        enc.train()
+        sd0 = {k: v.clone() for k, v in enc.state_dict().items()}
+        x = O.make_clouds(B, N, "sphere", seed=650 + seed)
+        margins = []
+        hooks = [m.register_forward_hook(lambda mod, i, o: margins.append(float(o.abs().min() / o.abs().max())))
+                 for m in enc.modules() if isinstance(m, torch.nn.BatchNorm1d)]
+        gfv = enc(x.double())                                                    # autoencoder.py:56-76, train mode
+        for h in hooks:
+            h.remove()
+        if min(margins) > 3e-6:
+            break
+    coef = torch.randn(B, latent, generator=torch.Generator().manual_seed(77)).double()
+    (gfv * coef).sum().backward()
+    # the trunk alone (autoencoder.py:65-71) from the same initial state: pooled features and their gradients
+    import copy
+    trunk = copy.deepcopy(enc)
+    trunk.load_state_dict(sd0)
+    trunk.train()
+    trunk.zero_grad()
+    pooled = torch.max(trunk.point_mlp(x.double().transpose(2, 1)), dim=2)[0]
+    pcoef = torch.randn(B, dims[-1], generator=torch.Generator().manual_seed(78)).double()
+    (pooled * pcoef).sum().backward()
+    tr_out["pooled"], tr_out["pcoef"] = pooled.detach().numpy(), pcoef.numpy()
+    for name, q in trunk.point_mlp.named_parameters():
+        tr_out[f"pgrad_{name}"] = q.grad.numpy()
+    tr_out["dims"], tr_out["latent"] = np.array(dims, np.int32), np.int32(latent)
+    tr_out["x"], tr_out["coef"], tr_out["gfv"] = x.numpy(), coef.numpy(), gfv.detach().numpy()
+    tr_out["margin"] = np.float64(min(margins))
+    tr_out["keys"] = np.array(list(sd0.keys()))
+    for name, v in sd0.items():
+        tr_out[f"sd_{name}"] = v.numpy().astype(np.float32) if v.is_floating_point() else v.numpy()
+    for name, v in enc.state_dict().items():
+        if "running" in name or "num_batches" in name:
+            tr_out[f"after_{name}"] = v.numpy()
+    for name, q in enc.named_parameters():
+        tr_out[f"grad_{name}"] = q.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "encoder_train_ref.npz"), **tr_out)
+
     # --- Reward: the reference's RewardFunction (utils/losses.py:209-246) called episode by episode
     #     with B=1 tensors, exactly as RLGANNetEnvironment.step does (models/rl_gan_net.py:316-324)
     rw_out = {}

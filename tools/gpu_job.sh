@@ -17,6 +17,8 @@ for step in "$@"; do
     encoder)   timeout 1500 python -m pytest tests/test_encoder_gpu.py -m gpu -q --maxfail=60 > gpurun_out/${T}_encoder.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_encoder.log ;;
     encprobe)  timeout 900 python tools/encoder_probe.py > gpurun_out/${T}_encprobe.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_encprobe.log ;;
     aeprobe)   for b in 8 16 32; do timeout 300 python tools/ae_probe.py $b >> gpurun_out/${T}_aeprobe.log 2>&1; done ;;
+    train)     timeout 900 python -m pytest tests/test_encoder_train_gpu.py -m gpu -q -s --maxfail=60 > gpurun_out/${T}_train.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_train.log ;;
+    trainprobe) timeout 600 python tools/train_probe.py > gpurun_out/${T}_trainprobe.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_trainprobe.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
