@@ -428,6 +428,7 @@ def run_ours(args):
                                          "(configs/config.yaml:9-11) + max-pool + GFV head, B=256 per GPU, N=2048"))
         extra.update(reward_measurement(rlg, dev, D))
         extra.update(large_cloud_measurement(rlg, dev, D))
+        extra.update(ae_step_measurement(rlg, dev, D, rank))
 
     if rank != 0:
         if world > 1:
@@ -735,6 +736,111 @@ def large_cloud_measurement(rlg, dev, D):
                             "config": {"workload": "ChamferLoss fwd+bwd, B=64 pairs of N=M=16384 sharded over the GPUs, loss "
                                                    "all-reduce per step (BASELINE configs[4])"},
                             "algorithmic_tflops": tf, "last_loss": float(out["loss"].item())}}
+
+
+def ae_step_measurement(rlg, dev, D, rank):
+    """BASELINE configs[0]: the autoencoder training step (train_rl_gan_net.py:220-249) at the reference's own dims
+    (configs/config.yaml: encoder [64,128,128,256,128], latent 128, decoder [256,256,6144], Adam lr 1e-3 wd 1e-5), incomplete
+    clouds of 1400 points in, 2048-point reconstruction against the complete cloud.  Per GPU batch 16 (config_quick.yaml) and
+    32 (config.yaml), weak scaling; at n_gpus > 1 the flat gradient all-reduce runs every step inside the captured graph.
+    Rank 0 also times the same step on stock torch CUDA kernels (reference-shaped modules, cdist Chamfer, eager)."""
+    import importlib
+    import torch.distributed as dist
+    AE = importlib.import_module("gan-rl_3d_b200.ae_step")
+    world = D.world
+    out = {}
+    S = 8
+    for bsz in (16, 32):
+        torch.manual_seed(0)                                   # same initial weights on every rank
+        model = AE.PointCloudAutoencoder().to(dev).train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5, capturable=True)
+        gen = torch.Generator(device="cpu").manual_seed(4242 + rank)
+        batches = [(sphere(gen, bsz, 1400).to(dev), sphere(gen, bsz, 2048).to(dev)) for _ in range(S)]
+        g = AE.AEStepGraph(model, opt, batches, world=world)
+        reps = 6
+        for _ in range(2):
+            g.replay()
+        torch.cuda.synchronize()
+        D.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        D.barrier()
+        ms = D.max_ms(e0.elapsed_time(e1)) / (reps * S)
+        coll_us = 0.0
+        if world > 1:                                          # the same all-reduce alone, for the collective's share
+            flat = torch.zeros(g.grad_bytes // 4, device=dev)
+            coll_us = D.timed(lambda k: dist.all_reduce(flat), 20) * 1e3
+        entry = {"metric": "ae_train_clouds_per_s", "value": bsz * world / (ms * 1e-3), "unit": "clouds/s", "n_gpus": world,
+                 "scaling": "weak", "ms_per_step": ms, "batch_per_gpu": bsz, "steps_per_graph": S,
+                 "last_loss": float(g.losses[-1].item()),
+                 "collective": {"kind": "none (1 GPU)" if world == 1 else "NCCL all-reduce of the flat fp32 gradient bucket, every step, "
+                                "captured in the graph between backward and optimizer.step()",
+                                "bytes": g.grad_bytes if world > 1 else 0, "us_alone": coll_us},
+                 "config": {"workload": "AE train step (BASELINE configs[0] at the reference's dims): encoder trunk fwd+bwd with "
+                                        "BatchNorm batch statistics and Chamfer fwd+bwd on this library's kernels; global MLP, decoder "
+                                        "MLP and Adam on stock torch; incomplete N=1400 -> reconstruction 2048 vs complete 2048"}}
+        del g, model, opt
+        torch.cuda.empty_cache()
+        if rank == 0:
+            try:
+                torch.manual_seed(0)
+                stock = StockAutoencoder().to(dev).train()
+                sopt = torch.optim.Adam(stock.parameters(), lr=1e-3, weight_decay=1e-5)
+
+                def stock_step(k):
+                    x, y = batches[k % S]
+                    sopt.zero_grad()
+                    dm = torch.cdist(stock(x), y, p=2)
+                    loss = torch.mean((torch.mean(torch.min(dm, dim=2)[0], dim=1) + torch.mean(torch.min(dm, dim=1)[0], dim=1)) / 2.0)
+                    loss.backward()
+                    sopt.step()
+                for k in range(3):
+                    stock_step(k)
+                torch.cuda.synchronize()
+                e0.record()
+                for k in range(10):
+                    stock_step(k)
+                e1.record()
+                torch.cuda.synchronize()
+                sms = e0.elapsed_time(e1) / 10
+                entry["torch_cuda"] = {"value": bsz / (sms * 1e-3), "unit": "clouds/s", "ms_per_step": sms,
+                                       "what": "the same step on stock torch CUDA kernels (Conv1d/BatchNorm1d/ReLU encoder, cdist->min->mean "
+                                               "Chamfer, autograd, Adam), eager, one GPU"}
+                del stock, sopt
+            except Exception as e:
+                entry["torch_cuda"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+            torch.cuda.empty_cache()
+        D.barrier()
+        out[f"ae_step_b{bsz}"] = entry
+    return out
+
+
+class StockAutoencoder(torch.nn.Module):
+    """The reference's autoencoder restated with stock torch layers (models/autoencoder.py:13-171), for the torch_cuda arm."""
+
+    def __init__(self, dims=(64, 128, 128, 256, 128), latent=128, dec=(256, 256, 6144)):
+        super().__init__()
+        nn = torch.nn
+        seq, c_in = [], 3
+        for c in dims:
+            seq += [nn.Conv1d(c_in, c, 1), nn.BatchNorm1d(c), nn.ReLU(inplace=True)]
+            c_in = c
+        self.point_mlp = nn.Sequential(*seq)
+        self.global_mlp = nn.Sequential(nn.Linear(c_in, latent), nn.BatchNorm1d(latent), nn.ReLU(inplace=True))
+        seq, c_in = [], latent
+        for c in dec[:-1]:
+            seq += [nn.Linear(c_in, c), nn.BatchNorm1d(c), nn.ReLU(inplace=True)]
+            c_in = c
+        seq.append(nn.Linear(c_in, dec[-1]))
+        self.mlp = nn.Sequential(*seq)
+
+    def forward(self, x):
+        g = self.global_mlp(torch.max(self.point_mlp(x.transpose(2, 1)), dim=2)[0])
+        return self.mlp(g).view(x.shape[0], -1, 3)
 
 
 def torch_cuda_measurement(dev, ring):

@@ -19,6 +19,7 @@ for step in "$@"; do
     aeprobe)   for b in 8 16 32; do timeout 300 python tools/ae_probe.py $b >> gpurun_out/${T}_aeprobe.log 2>&1; done ;;
     train)     timeout 900 python -m pytest tests/test_encoder_train_gpu.py -m gpu -q -s --maxfail=60 > gpurun_out/${T}_train.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_train.log ;;
     trainprobe) timeout 600 python tools/train_probe.py > gpurun_out/${T}_trainprobe.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_trainprobe.log ;;
+    aestep)    timeout 900 python -m pytest tests/test_ae_step_gpu.py -m gpu -q -s > gpurun_out/${T}_aestep.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_aestep.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
