@@ -44,6 +44,14 @@ BWD_BYTES_PER_PAIR = 56.0 * (N + M)
 WORKLOAD = "chamfer_fwd_bwd B=32 N=M=2048 sphere (BASELINE configs[1])"
 
 
+_T0 = time.perf_counter()
+
+
+def log(msg: str) -> None:
+    """Progress on stderr (stdout carries the one JSON line): shows where a multi-GPU run is when it is cut off."""
+    print(f"[bench r{os.environ.get('RANK', '0')} +{time.perf_counter() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -339,6 +347,7 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    log("timed step graphs")
     try:
         ms, n_launches, last_loss, info = timed_step_graphs(P, D, ring, K, W, world, loss_hook_factory)
         if world > 1:
@@ -355,6 +364,7 @@ def run_ours(args):
         collective["kind"] = f"capture of the NCCL all-reduce failed ({type(e).__name__}); NO collective inside the timed region"
     value = K * B * world / (ms * 1e-3)
 
+    log(f"headline done: {value:.0f} pairs/s")
     if world > 1:
         # the collective alone: S captured all-reduces back to back
         g = torch.cuda.CUDAGraph()
@@ -377,6 +387,7 @@ def run_ours(args):
             collective["us_per_step"] = None
             collective["note"] = f"stand-alone timing failed: {type(e).__name__}"
 
+    log("e2e")
     # ---- e2e: host buffers through the public API, H2D + D2H of every step inside the timed region --
     nb = min(slots, 32)
     pinned = [P.pin_pair(a, b) for a, b in ring_host[:nb]]      # (pred, target) of a step: one pinned buffer, one transfer
@@ -398,6 +409,7 @@ def run_ours(args):
     del host_graph, pinned
 
     extra = {}
+    log("extras")
     # ---- same workload on uniform clouds (SURVEY.md 8d names both distributions) --------------------
     if extras_on:
         uring = [(a.to(dev), b.to(dev)) for a, b in make_ring(rank, 64, "uniform")]
@@ -420,21 +432,33 @@ def run_ours(args):
         del sring
 
     if extras_on:
+        log("encoder_measurement")
         extra.update(encoder_measurement(rlg, dev, D, peaks, peaks_src, ENC_DIMS, "encoder",
                                          "PointNet encoder 3->64->128->1024 + max-pool + GFV head, B=256 per GPU, N=2048 "
                                          "(BASELINE configs[2])"))
+        log("encoder_measurement")
         extra.update(encoder_measurement(rlg, dev, D, peaks, peaks_src, CFG_DIMS, "encoder_config_dims",
                                          "PointNet encoder with the reference's own encoder_dims 3->64->128->128->256->128 "
                                          "(configs/config.yaml:9-11) + max-pool + GFV head, B=256 per GPU, N=2048"))
+        log("reward_measurement")
         extra.update(reward_measurement(rlg, dev, D))
+        log("env_step_measurement")
+        extra.update(env_step_measurement(rlg, dev, D))
+        log("large_cloud_measurement")
         extra.update(large_cloud_measurement(rlg, dev, D))
+        log("ae_step_measurement")
         extra.update(ae_step_measurement(rlg, dev, D, rank))
 
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
+        # the other ranks have nothing left to measure: meet rank 0 at its final barrier and leave WITHOUT tearing the
+        # communicator down (graphs holding captured NCCL collectives are still alive; destroy_process_group hangs under them)
+        log("done, waiting for rank 0")
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
     # ---- roofline of the dominant kernel: the fused Chamfer forward, timed alone with CUDA events ----
     a, b = ring[0]
@@ -577,10 +601,19 @@ def run_ours(args):
         "gpu_launches": n_launches, "clocks": clocks,
     }
     out.update(extra)
-    print(json.dumps(out))
+    if rank == 0:
+        print(json.dumps(out), flush=True)
     if world > 1:
+        # CUDA graphs that captured NCCL collectives are still alive here; tearing the communicator down under them hangs
+        # (ProcessGroupNCCL watchdog, observed on 2 GPUs).  Everything has been measured and printed: meet once more and
+        # leave without the teardown.
+        log("done, leaving")
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def ctypes_float6(lib, dev):
@@ -705,6 +738,51 @@ def reward_measurement(rlg, dev, D):
                             "config": {"workload": "RewardFunction for E=1024 episodes sharded over the GPUs, Chamfer N=M=2048 forward "
                                                    "only + GFV MSE + discriminator term (BASELINE configs[3])"},
                             "chamfer_tflops_algorithmic": tf, "last_reward_mean": float(out["r"].mean().item())}}
+
+
+def env_step_measurement(rlg, dev, D):
+    """SURVEY 8(f)-1 / BASELINE configs[3]: the WHOLE environment step for E=1024 episodes (sharded over the GPUs): action z ->
+    latent-GAN generator -> decoder -> 2048-point completion; discriminator logit; Chamfer against the complete cloud; GFV MSE
+    against the complete cloud's GFV (encoder, once per reset) -> (E,) rewards, device-resident, one CUDA-graph replay per step.
+    Reference-shaped modules at the reference's dims (models/latent_gan.py, models/autoencoder.py), random weights, eval."""
+    import importlib
+    Env = importlib.import_module("gan-rl_3d_b200.environment").BatchedRLEnvironment
+    AE = importlib.import_module("gan-rl_3d_b200.ae_step")
+    nn = torch.nn
+    E_total, n = 1024, 2048
+    E = max(1, E_total // D.world)
+    rank = D.dist.get_rank() if D.world > 1 else 0
+    torch.manual_seed(0)
+    ae = AE.PointCloudAutoencoder().to(dev).eval()
+    gen_dims, disc_dims = [256, 512, 512, 256, 128], [128, 256, 512, 256, 1]
+    seq, c_in = [], 1
+    for c in gen_dims[:-1]:
+        seq += [nn.Linear(c_in, c), nn.BatchNorm1d(c), nn.ReLU(inplace=True)]
+        c_in = c
+    generator = nn.Sequential(*seq, nn.Linear(c_in, gen_dims[-1]), nn.Tanh()).to(dev).eval()
+    seq, c_in = [], 128
+    for c in disc_dims[:-1]:
+        seq += [nn.utils.spectral_norm(nn.Linear(c_in, c)), nn.LayerNorm(c), nn.LeakyReLU(0.2, inplace=True), nn.Dropout(0.3)]
+        c_in = c
+    discriminator = nn.Sequential(*seq, nn.utils.spectral_norm(nn.Linear(c_in, disc_dims[-1]))).to(dev).eval()
+    env = Env(ae.encode, generator, ae.decode, discriminator, dev, capture=True)
+    g = torch.Generator(device="cpu").manual_seed(99 + rank)
+    t0 = time.perf_counter()
+    states = env.reset({"incomplete": sphere(g, E, 1400), "complete": sphere(g, E, n)})
+    torch.cuda.synchronize()
+    reset_ms = (time.perf_counter() - t0) * 1e3
+    actions = [torch.randn(E, 1, generator=g).to(dev) for _ in range(4)]
+    out = {}
+
+    def call(k):
+        out["r"] = env.step(actions[k % 4])[1]
+    ms = D.timed(call, 12)
+    return {"env_step": {"metric": "env_steps_per_s", "value": E * D.world / (ms * 1e-3), "unit": "episodes/s", "n_gpus": D.world,
+                         "scaling": "strong", "episodes_per_gpu": E, "ms_per_step": ms, "reset_ms_first_call": reset_ms,
+                         "config": {"workload": "batched RLGANNetEnvironment.step, E=1024 episodes sharded over the GPUs: generator + "
+                                                "decoder + discriminator (stock torch MLPs) + Chamfer 2048x2048 forward + reward, one graph "
+                                                "replay per step, no host synchronisation (models/rl_gan_net.py:299-339)"},
+                         "last_reward_mean": float(out["r"].mean().item()), "state_shape": list(states.shape)}}
 
 
 def large_cloud_measurement(rlg, dev, D):

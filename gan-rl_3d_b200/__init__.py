@@ -27,13 +27,14 @@ from .encoder import (EncoderTrunkFn, PointNetEncoder, encoder_path_of, encoder_
 from .train import EncoderTrainFn, train_supported, trunk_pool_autograd
 from .ae_step import AEStepGraph, PointCloudAutoencoder, PointNetDecoder
 from . import train
+from .environment import BatchedRLEnvironment
 
 __all__ = ["install", "uninstall", "is_installed", "chamfer_distance_l2", "chamfer_distance", "ChamferLoss",
            "ChamferFn", "ChamferLossFn", "chamfer_nearest", "chamfer_backward", "set_default_sweep", "get_default_sweep", "PointNetEncoder", "EncoderTrunkFn", "encoder_pool",
            "fold_trunk", "folded_trunk_cached", "fused_forward", "set_encoder_precision", "get_encoder_precision",
            "pack_bf16", "pack_gemm", "packed_trunk_cached", "encoder_pool_gemm", "encoder_path_of", "resolve_path", "RewardFunction", "batched_rewards", "library_path", "abi_version",
            "EncoderTrainFn", "train_supported", "trunk_pool_autograd", "set_train_path",
-           "AEStepGraph", "PointCloudAutoencoder", "PointNetDecoder"]
+           "AEStepGraph", "PointCloudAutoencoder", "PointNetDecoder", "BatchedRLEnvironment"]
 
 _installed = {}
 

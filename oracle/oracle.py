@@ -203,6 +203,60 @@ class RefEncoderPort(nn.Module):
         return self.global_mlp(self.pooled(x))
 
 
+class RefDecoderPort(nn.Module):
+    """models/autoencoder.py:79-129 restated: Linear+BatchNorm1d+ReLU blocks, a final Linear, view (B, num_points, 3)."""
+
+    def __init__(self, latent_dim: int = 128, num_points: int = 2048, hidden_dims=(256, 256, 6144)):
+        super().__init__()
+        seq, c_in = [], latent_dim
+        for c in hidden_dims[:-1]:
+            seq += [nn.Linear(c_in, c), nn.BatchNorm1d(c), nn.ReLU(inplace=True)]
+            c_in = c
+        seq.append(nn.Linear(c_in, hidden_dims[-1]))
+        self.mlp = nn.Sequential(*seq)
+        self.num_points = num_points
+
+    def forward(self, gfv):
+        return self.mlp(gfv).view(-1, self.num_points, 3)
+
+
+class _Seq(nn.Module):
+    def __init__(self, name: str, seq: nn.Sequential):
+        super().__init__()
+        setattr(self, name, seq)
+        self._name = name
+
+    def forward(self, x):
+        return getattr(self, self._name)(x)
+
+
+class RefLatentGANPort(nn.Module):
+    """models/latent_gan.py restated with the same module tree (state_dict keys generator.generator.N.*,
+    discriminator.discriminator.N.*): generator = Linear+BatchNorm1d+ReLU blocks, Linear, Tanh (:14-62); improved
+    discriminator = spectral-norm Linear + LayerNorm + LeakyReLU(0.2) + Dropout(0.3) blocks, spectral-norm Linear (:143-203)."""
+
+    def __init__(self, z_dim=1, latent_dim=128, generator_dims=(256, 512, 512, 256, 128), discriminator_dims=(128, 256, 512, 256, 1)):
+        super().__init__()
+        seq, c_in = [], z_dim
+        for c in generator_dims[:-1]:
+            seq += [nn.Linear(c_in, c), nn.BatchNorm1d(c), nn.ReLU(inplace=True)]
+            c_in = c
+        seq += [nn.Linear(c_in, generator_dims[-1]), nn.Tanh()]
+        self.generator = _Seq("generator", nn.Sequential(*seq))
+        seq, c_in = [], latent_dim
+        for c in discriminator_dims[:-1]:
+            seq += [nn.utils.spectral_norm(nn.Linear(c_in, c)), nn.LayerNorm(c), nn.LeakyReLU(0.2, inplace=True), nn.Dropout(0.3)]
+            c_in = c
+        seq.append(nn.utils.spectral_norm(nn.Linear(c_in, discriminator_dims[-1])))
+        self.discriminator = _Seq("discriminator", nn.Sequential(*seq))
+
+    def generate(self, z):
+        return self.generator(z)
+
+    def discriminate(self, gfv):
+        return self.discriminator(gfv)
+
+
 def randomize_bn(module: nn.Module, seed: int = 0) -> None:
     """Non-trivial BatchNorm statistics/affine (a fresh BN is identity-like and hides folding bugs).
     SURVEY.md 8d: running_mean~N(0,.5), running_var~U(.3,2), gamma~N(1,.5), beta~N(0,.3)."""

@@ -187,6 +187,62 @@ def main():
         rw_out[f"rw{k}_rewards"] = rewards.numpy()
     rw_out["rw_count"] = np.int32(len(shapes))
     np.savez_compressed(os.path.join(HERE, "reward_ref.npz"), **rw_out)
+
+    # --- Environment step: the reference's own RLGANNet + RLGANNetEnvironment (models/rl_gan_net.py:33-339)
+    #     on a reduced configuration (so the fixture stays small), eval mode, one episode per reset/step pair exactly as
+    #     train_rl_agent drives it (train_rl_gan_net.py:406-429): env-style batch keys 'incomplete' / 'complete'.
+    import types
+    import yaml
+    sys.modules.setdefault("h5py", types.ModuleType("h5py"))       # utils/__init__ imports it; nothing here uses it
+    sys.path.insert(0, REF)
+    import importlib
+    rlmod = importlib.import_module("models.rl_gan_net")
+    with open(os.path.join(REF, "configs", "config_quick.yaml")) as f:
+        cfg = yaml.safe_load(f)
+
+    def numeric(o):        # PyYAML reads 1e-4 as a string; the reference's trainer patches that (train_rl_gan_net.py:72-101)
+        if isinstance(o, dict):
+            return {k: numeric(v) for k, v in o.items()}
+        if isinstance(o, list):
+            return [numeric(v) for v in o]
+        if isinstance(o, str):
+            try:
+                return float(o)
+            except ValueError:
+                return o
+        return o
+    cfg = numeric(cfg)
+    cfg["training"]["device"] = "cpu"
+    cfg["model"]["autoencoder"].update(latent_dim=32, num_points=256, encoder_dims=[64, 128, 64], decoder_dims=[64, 768])
+    cfg["model"]["lgan"].update(z_dim=2, latent_dim=32, generator_dims=[48, 32], discriminator_dims=[32, 16, 1])
+    cfg["model"]["rl_agent"].update(state_dim=32, action_dim=2, hidden_dims=[16, 16, 16, 16])
+    torch.manual_seed(123)
+    net = rlmod.RLGANNet(cfg)
+    O.randomize_bn(net, seed=55)
+    net.eval()
+    env = rlmod.RLGANNetEnvironment(net, None)
+    E = 6
+    incomplete = O.make_clouds(E, 180, "sphere", seed=1100)
+    complete = O.make_clouds(E, 256, "sphere", seed=1101)
+    actions = torch.randn(E, 2, generator=torch.Generator().manual_seed(1102)).numpy().astype(np.float32)
+    states, next_states, rewards = [], [], []
+    for e in range(E):
+        batch = {"incomplete": incomplete[e:e + 1], "complete": complete[e:e + 1]}
+        states.append(env.reset(batch))                                        # rl_gan_net.py:279-297
+        ns, r, done, info = env.step(actions[e])                               # :299-339
+        assert done
+        next_states.append(ns)
+        rewards.append(r)
+    ev_out = {"E": np.int32(E), "incomplete": incomplete.numpy(), "complete": complete.numpy(), "actions": actions,
+              "states": np.stack(states), "next_states": np.stack(next_states), "rewards": np.array(rewards, np.float64),
+              "weights": np.array([net.reward_function.w_chamfer, net.reward_function.w_gfv, net.reward_function.w_discriminator]),
+              "ae_dims": np.array([32, 256], np.int32)}
+    for prefix, mod in (("ae", net.autoencoder), ("lgan", net.latent_gan)):
+        sd = mod.state_dict()
+        ev_out[f"{prefix}_keys"] = np.array(list(sd.keys()))
+        for name, v in sd.items():
+            ev_out[f"{prefix}_sd_{name}"] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, "environment_ref.npz"), **ev_out)
     print("wrote", os.listdir(HERE))
 
 

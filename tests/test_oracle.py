@@ -179,3 +179,30 @@ def test_reward_golden_is_the_reference_formula(golden_reward):
         gfv = ((g[f"rw{k}_pred_gfv"].astype(np.float64) - g[f"rw{k}_target_gfv"]) ** 2).mean(1)
         truth = -(100.0 * cd + 10.0 * gfv + 0.01 * (-g[f"rw{k}_disc"].astype(np.float64).reshape(E)))
         assert O.rel_err(g[f"rw{k}_rewards"], truth) < 5e-5
+
+
+def test_environment_ports_reproduce_the_reference_episodes():
+    """oracle.RefEncoderPort / RefDecoderPort / RefLatentGANPort loaded with the reference's weights replay the golden
+    environment episodes (tests/golden/environment_ref.npz, generated by the reference's RLGANNetEnvironment) on the CPU."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "environment_ref.npz"))
+    latent, points = (int(v) for v in g["ae_dims"])
+    enc = O.RefEncoderPort(3, latent, [64, 128, 64])
+    dec = O.RefDecoderPort(latent, points, [64, points * 3])
+    ae_sd = {str(n): torch.from_numpy(g[f"ae_sd_{n}"]) for n in g["ae_keys"]}
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in ae_sd.items() if k.startswith("encoder.")})
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in ae_sd.items() if k.startswith("decoder.")})
+    gan = O.RefLatentGANPort(2, latent, [48, 32], [32, 16, 1])
+    gan.load_state_dict({str(n): torch.from_numpy(g[f"lgan_sd_{n}"]) for n in g["lgan_keys"]})
+    enc.eval(), dec.eval(), gan.eval()
+    w = g["weights"]
+    with torch.no_grad():
+        for e in range(int(g["E"])):
+            inc, comp = torch.from_numpy(g["incomplete"][e:e + 1]), torch.from_numpy(g["complete"][e:e + 1])
+            assert np.allclose(enc(inc)[0].numpy(), g["states"][e], rtol=0, atol=1e-6)
+            clean = gan.generate(torch.from_numpy(g["actions"][e]).unsqueeze(0))
+            assert np.allclose(clean[0].numpy(), g["next_states"][e], rtol=0, atol=1e-6)
+            cd = O.ref_port_chamfer_loss(dec(clean), comp)
+            mse = torch.nn.functional.mse_loss(clean, enc(comp))
+            reward = -(w[0] * cd + w[1] * mse + w[2] * (-gan.discriminate(clean).mean()))
+            assert abs(float(reward) - float(g["rewards"][e])) <= 1e-5 * abs(float(g["rewards"][e]))

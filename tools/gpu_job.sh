@@ -20,6 +20,8 @@ for step in "$@"; do
     train)     timeout 900 python -m pytest tests/test_encoder_train_gpu.py -m gpu -q -s --maxfail=60 > gpurun_out/${T}_train.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_train.log ;;
     trainprobe) timeout 600 python tools/train_probe.py > gpurun_out/${T}_trainprobe.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_trainprobe.log ;;
     aestep)    timeout 900 python -m pytest tests/test_ae_step_gpu.py -m gpu -q -s > gpurun_out/${T}_aestep.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_aestep.log ;;
+    envtest)   timeout 900 python -m pytest tests/test_environment_gpu.py -m gpu -q -s > gpurun_out/${T}_envtest.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_envtest.log ;;
+    property)  timeout 900 python -m pytest tests/test_chamfer_property_gpu.py -m gpu -q > gpurun_out/${T}_property.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_property.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
