@@ -831,7 +831,7 @@ def ae_step_measurement(rlg, dev, D, rank):
     for bsz in (16, 32):
         torch.manual_seed(0)                                   # same initial weights on every rank
         model = AE.PointCloudAutoencoder().to(dev).train()
-        opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5, capturable=True)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5, capturable=True, fused=True)
         gen = torch.Generator(device="cpu").manual_seed(4242 + rank)
         batches = [(sphere(gen, bsz, 1400).to(dev), sphere(gen, bsz, 2048).to(dev)) for _ in range(S)]
         g = AE.AEStepGraph(model, opt, batches, world=world)
@@ -867,7 +867,7 @@ def ae_step_measurement(rlg, dev, D, rank):
             try:
                 torch.manual_seed(0)
                 stock = StockAutoencoder().to(dev).train()
-                sopt = torch.optim.Adam(stock.parameters(), lr=1e-3, weight_decay=1e-5)
+                sopt = torch.optim.Adam(stock.parameters(), lr=1e-3, weight_decay=1e-5, fused=True)
 
                 def stock_step(k):
                     x, y = batches[k % S]

@@ -39,6 +39,8 @@ struct SavedLayout {
     size_t bnp[kTMaxLayers];      // fp32 [4 x C_l]   scale = gamma*invstd, shift = beta - mean*scale, mean*invstd, invstd
     size_t zmax[kTMaxLayers];     // u32  [C_l]       bit pattern of max |zhat| per channel
     size_t keys;                  // u64  [B x C_last] (value bits << 32 | ~point index) of the max-pool
+    size_t wscale;                // f32  [L][2]      weight scale and its inverse (device scalars)
+    size_t wp[kTMaxLayers][4];    // fp16 pieces of W_l: hi, lo (c_out x c_in) and of W_l^T: hi, lo (c_in x c_out); l >= 1
     size_t total;
 };
 static SavedLayout saved_layout(long long P, int B, const rlg_bn_layer *layers, int L) {
@@ -54,6 +56,9 @@ static SavedLayout saved_layout(long long P, int B, const rlg_bn_layer *layers, 
         s.zmax[l] = take(C * 4);
     }
     s.keys = take((size_t)B * layers[L - 1].c_out * 8);
+    s.wscale = take((size_t)L * 2 * 4);
+    for (int l = 0; l < L; ++l)
+        for (int k = 0; k < 4; ++k) s.wp[l][k] = l >= 1 ? take((size_t)layers[l].c_out * layers[l].c_in * 2) : 0;
     s.total = off;
     return s;
 }
@@ -63,11 +68,10 @@ struct WsLayout {
     size_t stat;                  // f64 [L][2][256]   forward: shifted sum, shifted sum of squares; backward: sum dy, sum dy*zhat
     size_t mxdy;                  // u32 [L][256]      backward: bit pattern of max |dy| per channel
     size_t w0acc;                 // f64 [256 x 3]     layer-0 weight gradient accumulators
+    size_t wamax;                 // u32 [L]           forward: bit pattern of max |w| per layer
     size_t zero_bytes;
-    size_t wscale;                // f32 [L][2]        weight scale and its inverse (device scalars)
     size_t dscale;                // f32 [L][2]        dz scale and its inverse
     size_t m12;                   // f32 [L][2][256]   mean(dy), mean(dy*zhat)
-    size_t wp[kTMaxLayers][4];    // fp16 pieces of W_l: hi, lo (c_out x c_in) and of W_l^T: hi, lo (c_in x c_out)
     size_t da;                    // fp32 [P x Cmax]   gradient w.r.t. a layer's activations
     size_t dzhi, dzlo;            // fp16 [P x Cmax]
     size_t partial;               // fp32 [sms][128 x 128] weight-gradient partial tiles
@@ -80,15 +84,12 @@ static WsLayout ws_layout(long long P, const rlg_bn_layer *layers, int L, int sm
     w.stat = take((size_t)L * 2 * kTMaxC * 8);
     w.mxdy = take((size_t)L * kTMaxC * 4);
     w.w0acc = take((size_t)kTMaxC * 3 * 8);
+    w.wamax = take((size_t)kTMaxLayers * 4);
     w.zero_bytes = off;
-    w.wscale = take((size_t)L * 2 * 4);
     w.dscale = take((size_t)L * 2 * 4);
     w.m12 = take((size_t)L * 2 * kTMaxC * 4);
     int cmax = 0;
-    for (int l = 0; l < L; ++l) {
-        cmax = layers[l].c_out > cmax ? layers[l].c_out : cmax;
-        for (int k = 0; k < 4; ++k) w.wp[l][k] = l >= 1 ? take((size_t)layers[l].c_out * layers[l].c_in * 2) : 0;
-    }
+    for (int l = 0; l < L; ++l) cmax = layers[l].c_out > cmax ? layers[l].c_out : cmax;
     w.da = take((size_t)P * cmax * 4);
     w.dzhi = take((size_t)P * cmax * 2);
     w.dzlo = take((size_t)P * cmax * 2);
@@ -291,39 +292,48 @@ __global__ void __launch_bounds__(256) pool_decode_kernel(const u64 *__restrict_
     if (i < n) pooled[i] = __uint_as_float((unsigned)(keys[i] >> 32));
 }
 
-// weights of the layers >= 1 -> fp16 hi+lo pieces scaled by a power of two (max |w| * scale in (2^13, 2^14]), in both
-// orientations: (c_out x c_in) for the forward GEMM and (c_in x c_out) for the input-gradient GEMM.  One CTA per layer.
+// weights of the layers >= 1 -> fp16 hi+lo pieces scaled by a power of two (max |w| * scale in [2^13, 2^14)), in both
+// orientations: (c_out x c_in) for the forward GEMM and (c_in x c_out) for the input-gradient GEMM.  Two launches over
+// (chunk, layer): the per-layer max, then the split; the backward reuses the forward's pieces (they live in `saved`).
+static constexpr int kPackChunks = 16;
 struct PackArgs {
     const float *w[kTMaxLayers];
     unsigned short *p[kTMaxLayers][4];
     int c_out[kTMaxLayers], c_in[kTMaxLayers];
+    unsigned *wamax;
     float *wscale;
 };
-__global__ void __launch_bounds__(1024) train_pack_kernel(PackArgs a) {
-    __shared__ float red[32];
-    __shared__ float s_scale;
-    const int l = blockIdx.x + 1;
-    const int co = a.c_out[l], ci = a.c_in[l], n = co * ci;
+__global__ void __launch_bounds__(256) train_wamax_kernel(PackArgs a) {
+    __shared__ float red[8];
+    const int l = blockIdx.y + 1;
+    const int n = a.c_out[l] * a.c_in[l];
     const float *w = a.w[l];
     float m = 0.0f;
-    for (int e = threadIdx.x; e < n; e += 1024) m = fmaxf(m, fabsf(w[e]));
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < n; e += kPackChunks * 256) m = fmaxf(m, fabsf(__ldg(w + e)));
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
     __syncthreads();
     if (threadIdx.x == 0) {
         float mm = 0.0f;
-        for (int k = 0; k < 32; ++k) mm = fmaxf(mm, red[k]);
-        int e = 0;
-        if (mm > 0.0f && mm < 3.0e38f) e = 14 - (ilogbf(mm) + 1);        // mm * 2^e in [2^13, 2^14)
-        e = max(-100, min(100, e));
-        s_scale = ldexpf(1.0f, e);
-        a.wscale[2 * l] = s_scale;
-        a.wscale[2 * l + 1] = ldexpf(1.0f, -e);
+        for (int k = 0; k < 8; ++k) mm = fmaxf(mm, red[k]);
+        if (mm > 0.0f) atomicMax(a.wamax + l, __float_as_uint(mm));
     }
-    __syncthreads();
-    const float sc = s_scale;
-    for (int e = threadIdx.x; e < n; e += 1024) {
-        const float v = w[e] * sc;
+}
+__global__ void __launch_bounds__(256) train_pack_kernel(PackArgs a) {
+    const int l = blockIdx.y + 1;
+    const int co = a.c_out[l], ci = a.c_in[l], n = co * ci;
+    const float *w = a.w[l];
+    const float mm = __uint_as_float(a.wamax[l]);
+    int ex = 0;
+    if (mm > 0.0f && mm < 3.0e38f) ex = 14 - (ilogbf(mm) + 1);           // mm * 2^ex in [2^13, 2^14)
+    ex = max(-100, min(100, ex));
+    const float sc = ldexpf(1.0f, ex);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.wscale[2 * l] = sc;
+        a.wscale[2 * l + 1] = ldexpf(1.0f, -ex);
+    }
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < n; e += kPackChunks * 256) {
+        const float v = __ldg(w + e) * sc;
         const __half h = __float2half_rn(v);
         const __half lo = __float2half_rn(v - __half2float(h));
         const unsigned short hb = *reinterpret_cast<const unsigned short *>(&h), lb = *reinterpret_cast<const unsigned short *>(&lo);
@@ -524,7 +534,7 @@ static constexpr uint32_t kWgBox = 64 * 128;           // bytes of one box: 64 p
 static constexpr uint32_t kWgStage = 8 * kWgBox;       // A: 2 pieces x 2 boxes, B: 2 pieces x 2 boxes
 
 struct WgradArgs {
-    int chunks, tiles_n, n_tiles, n_split;
+    int chunks, tiles_n, n_tiles, n_split, C_out, C_in;
     float *partial;                                    // [n_split][n_tiles][128][128]
 };
 
@@ -651,9 +661,14 @@ encoder_wgrad_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_cons
             tc_fence_before();
             mbar_arrive(bar_accempty);
         }
-        float4 *dst = reinterpret_cast<float4 *>(a.partial + (((size_t)split * a.n_tiles + tile) * 128 + row) * 128);
+        // only the part of the tile inside dW is stored (and read back by the reduction)
+        if (tm * 128 + row < a.C_out) {
+            float4 *dst = reinterpret_cast<float4 *>(a.partial + (((size_t)split * a.n_tiles + tile) * 128 + row) * 128);
+            const int n4 = min(32, (a.C_in - tn * 128) >> 2);
 #pragma unroll
-        for (int e4 = 0; e4 < 32; ++e4) dst[e4] = make_float4(r[4 * e4], r[4 * e4 + 1], r[4 * e4 + 2], r[4 * e4 + 3]);
+            for (int e4 = 0; e4 < 32; ++e4)
+                if (e4 < n4) dst[e4] = make_float4(r[4 * e4], r[4 * e4 + 1], r[4 * e4 + 2], r[4 * e4 + 3]);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -663,17 +678,23 @@ encoder_wgrad_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_cons
     }
 }
 
-// dW = inv_scale * sum over the splits of the partial tiles, in a fixed order (deterministic)
+// dW = inv_scale * sum over the splits of the partial tiles, in a fixed order (deterministic): 64 outputs per CTA, four
+// threads per output each summing every fourth split, combined in shared memory
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restrict__ partial, int n_split, int n_tiles, int tiles_n, int C_out,
                                                           int C_in, const float *__restrict__ dscale, float *__restrict__ dw) {
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= C_out * C_in) return;
-    const int co = i / C_in, ci = i - co * C_in;
-    const int tile = (co >> 7) * tiles_n + (ci >> 7);
-    const float *src = partial + ((size_t)tile * 128 + (co & 127)) * 128 + (ci & 127);
+    __shared__ float red[4][64];
+    const int e = threadIdx.x & 63, j = threadIdx.x >> 6;
+    const int i = blockIdx.x * 64 + e;
     float s = 0.0f;
-    for (int k = 0; k < n_split; ++k) s += src[(size_t)k * n_tiles * 128 * 128];
-    dw[i] = s * __ldg(dscale + 1);
+    if (i < C_out * C_in) {
+        const int co = i / C_in, ci = i - co * C_in;
+        const int tile = (co >> 7) * tiles_n + (ci >> 7);
+        const float *src = partial + ((size_t)tile * 128 + (co & 127)) * 128 + (ci & 127);
+        for (int k = j; k < n_split; k += 4) s += __ldg(src + (size_t)k * n_tiles * 128 * 128);
+    }
+    red[j][e] = s;
+    __syncthreads();
+    if (j == 0 && i < C_out * C_in) dw[i] = ((red[0][e] + red[1][e]) + (red[2][e] + red[3][e])) * __ldg(dscale + 1);
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------------
@@ -707,13 +728,15 @@ static inline unsigned row_grid(long long P, int C, int sms) {
 static int launch_wgrad(const void *dzhi, const void *dzlo, const void *ahi, const void *alo, long long P, int C_out, int C_in,
                         const float *dscale, float *partial, float *dw, int sms, cudaStream_t st) {
     WgradArgs a;
+    a.C_out = C_out; a.C_in = C_in;
     a.chunks = (int)((P + 63) / 64);
     const int tiles_m = (C_out + 127) / 128;
     a.tiles_n = (C_in + 127) / 128;
     a.n_tiles = tiles_m * a.tiles_n;
+    // every CTA writes (and the reduction re-reads) a 64 KB partial tile: give a CTA at least four chunks (256 points)
     a.n_split = sms / a.n_tiles;
+    if (a.n_split > a.chunks / 4) a.n_split = a.chunks / 4;
     if (a.n_split < 1) a.n_split = 1;
-    if (a.n_split > a.chunks) a.n_split = a.chunks;
     a.partial = partial;
     CUtensorMap tm[4];
     const void *base[4] = {dzhi, dzlo, ahi, alo};
@@ -732,20 +755,22 @@ static int launch_wgrad(const void *dzhi, const void *dzlo, const void *ahi, con
                                 tm[0], tm[1], tm[2], tm[3], a);
     if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "encoder_wgrad_kernel: %s", cudaGetErrorString(le)); }
     const int n = C_out * C_in;
-    wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(partial, a.n_split, a.n_tiles, a.tiles_n, C_out, C_in, dscale, dw);
+    wgrad_reduce_kernel<<<(n + 63) / 64, 256, 0, st>>>(partial, a.n_split, a.n_tiles, a.tiles_n, C_out, C_in, dscale, dw);
     return 0;
 }
 
-static int launch_pack(const rlg_bn_layer *layers, int L, char *ws, const WsLayout &w, cudaStream_t st) {
+static int launch_pack(const rlg_bn_layer *layers, int L, char *sv, const SavedLayout &sl, char *ws, const WsLayout &w, cudaStream_t st) {
     PackArgs pa = {};
     for (int l = 1; l < L; ++l) {
         pa.w[l] = layers[l].w;
         pa.c_out[l] = layers[l].c_out;
         pa.c_in[l] = layers[l].c_in;
-        for (int k = 0; k < 4; ++k) pa.p[l][k] = reinterpret_cast<unsigned short *>(ws + w.wp[l][k]);
+        for (int k = 0; k < 4; ++k) pa.p[l][k] = reinterpret_cast<unsigned short *>(sv + sl.wp[l][k]);
     }
-    pa.wscale = reinterpret_cast<float *>(ws + w.wscale);
-    train_pack_kernel<<<L - 1, 1024, 0, st>>>(pa);
+    pa.wamax = reinterpret_cast<unsigned *>(ws + w.wamax);
+    pa.wscale = reinterpret_cast<float *>(sv + sl.wscale);
+    train_wamax_kernel<<<dim3(kPackChunks, L - 1), 256, 0, st>>>(pa);
+    train_pack_kernel<<<dim3(kPackChunks, L - 1), 256, 0, st>>>(pa);
     return 0;
 }
 
@@ -810,7 +835,7 @@ int rlg_encoder_train_fwd(const float *x, int B, int N, const rlg_bn_layer *laye
     if (e == cudaSuccess) e = cudaMemsetAsync(sv + sl.keys, 0, (size_t)B * CL * 8, st);
     for (int l = 0; l < L && e == cudaSuccess; ++l) e = cudaMemsetAsync(sv + sl.zmax[l], 0, (size_t)layers[l].c_out * 4, st);
     if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "%s: cudaMemsetAsync: %s", fn, cudaGetErrorString(e)); }
-    rc = launch_pack(layers, L, w, wl, st);
+    rc = launch_pack(layers, L, sv, sl, w, wl, st);
     if (rc) return rc;
 
     for (int l = 0; l < L; ++l) {
@@ -827,10 +852,10 @@ int rlg_encoder_train_fwd(const float *x, int B, int N, const rlg_bn_layer *laye
             GemmCall g;
             g.B = B; g.N = N; g.K = y.c_in; g.C_out = C; g.pieces = 2;
             g.x0 = sv + sl.ahi[l - 1]; g.x1 = sv + sl.alo[l - 1];
-            g.w0 = w + wl.wp[l][0]; g.w1 = w + wl.wp[l][1];
+            g.w0 = sv + sl.wp[l][0]; g.w1 = sv + sl.wp[l][1];
             g.bias = y.b;
             g.out_scale = 1.0f;
-            g.dscale0 = reinterpret_cast<const float *>(w + wl.wscale) + 2 * l + 1;
+            g.dscale0 = reinterpret_cast<const float *>(sv + sl.wscale) + 2 * l + 1;
             g.dscale1 = nullptr;
             g.epi = EPI_RAW_;
             g.y0 = z; g.y1 = nullptr; g.pooled = nullptr;
@@ -880,8 +905,6 @@ int rlg_encoder_train_bwd(const float *x, int B, int N, const rlg_bn_layer *laye
 
     cudaError_t e = cudaMemsetAsync(w, 0, wl.zero_bytes, st);
     if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "%s: cudaMemsetAsync: %s", fn, cudaGetErrorString(e)); }
-    rc = launch_pack(layers, L, w, wl, st);
-    if (rc) return rc;
     float *da = reinterpret_cast<float *>(w + wl.da);
     unsigned short *dzhi = reinterpret_cast<unsigned short *>(w + wl.dzhi), *dzlo = reinterpret_cast<unsigned short *>(w + wl.dzlo);
     const u64 *keys = reinterpret_cast<const u64 *>(sv + sl.keys);
@@ -920,11 +943,11 @@ int rlg_encoder_train_bwd(const float *x, int B, int N, const rlg_bn_layer *laye
         GemmCall g;
         g.B = B; g.N = N; g.K = C; g.C_out = y.c_in; g.pieces = 2;
         g.x0 = dzhi; g.x1 = dzlo;
-        g.w0 = w + wl.wp[l][2]; g.w1 = w + wl.wp[l][3];
+        g.w0 = sv + sl.wp[l][2]; g.w1 = sv + sl.wp[l][3];           // the forward's transposed weight pieces
         g.bias = nullptr;
         g.out_scale = 1.0f;
         g.dscale0 = dscale + 1;
-        g.dscale1 = reinterpret_cast<const float *>(w + wl.wscale) + 2 * l + 1;
+        g.dscale1 = reinterpret_cast<const float *>(sv + sl.wscale) + 2 * l + 1;
         g.epi = EPI_RAW_;
         g.y0 = da; g.y1 = nullptr; g.pooled = nullptr;
         rc = launch_layer_gemm(g, sms, st);

@@ -113,9 +113,9 @@ class EncoderTrainFn(torch.autograd.Function):
             _lib.check("rlg_encoder_train_fwd", rc)
         if batch_stats:
             with torch.no_grad():
-                for _, bn in pairs:
-                    if bn.num_batches_tracked is not None:
-                        bn.num_batches_tracked += 1
+                counters = [bn.num_batches_tracked for _, bn in pairs if bn.num_batches_tracked is not None]
+                if counters:
+                    torch._foreach_add_(counters, 1)            # one launch for all blocks
         ctx.pairs, ctx.flags, ctx.shape = pairs, flags, (B, N)
         ctx.save_for_backward(x, saved, *[p for p in params if p is not None])
         ctx.present = [p is not None for p in params]
