@@ -165,6 +165,24 @@ __global__ void __launch_bounds__(256) train_layer0_kernel(const float *__restri
     dst[1] = make_float4(v[4], v[5], v[6], v[7]);
 }
 
+// Row loops of the per-channel kernels: a thread visits the rows  first, first + stride, ...  four at a time, so four
+// independent loads are in flight per thread (one per iteration left these kernels latency-bound at a sixth of HBM speed)
+template <typename Load, typename Use>
+__device__ __forceinline__ void rows4(long long first, long long stride, long long P, Load load, Use use) {
+    for (long long row0 = first; row0 < P; row0 += 4 * stride) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long row = row0 + (long long)u * stride;
+            load(u, row, row < P);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long row = row0 + (long long)u * stride;
+            if (row < P) use(u, row);
+        }
+    }
+}
+
 // shifted sums per channel: acc[c] += sum_p (z - K_c), acc[256 + c] += sum_p (z - K_c)^2 with K_c = z[0][c] (any sample of
 // the channel keeps the subtraction in the variance formula harmless)
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float *__restrict__ z, long long P, int C, double *__restrict__ acc) {
@@ -173,13 +191,15 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float *__restrict__
     float v[2][4] = {};
     if (g.active) {
         const float4 k4 = __ldg(reinterpret_cast<const float4 *>(z) + g.tx);
-        for (long long row = (long long)blockIdx.x * g.rpi + g.ty; row < P; row += (long long)gridDim.x * g.rpi) {
-            const float4 t = __ldg(reinterpret_cast<const float4 *>(z + row * C) + g.tx);
-            const float d0 = t.x - k4.x, d1 = t.y - k4.y, d2 = t.z - k4.z, d3 = t.w - k4.w;
-            v[0][0] += d0; v[0][1] += d1; v[0][2] += d2; v[0][3] += d3;
-            v[1][0] = fmaf(d0, d0, v[1][0]); v[1][1] = fmaf(d1, d1, v[1][1]);
-            v[1][2] = fmaf(d2, d2, v[1][2]); v[1][3] = fmaf(d3, d3, v[1][3]);
-        }
+        float4 t[4];
+        rows4((long long)blockIdx.x * g.rpi + g.ty, (long long)gridDim.x * g.rpi, P,
+                  [&](int u, long long row, bool ok) { t[u] = ok ? __ldg(reinterpret_cast<const float4 *>(z + row * C) + g.tx) : k4; },
+                  [&](int u, long long row) {
+                      const float d0 = t[u].x - k4.x, d1 = t[u].y - k4.y, d2 = t[u].z - k4.z, d3 = t[u].w - k4.w;
+                      v[0][0] += d0; v[0][1] += d1; v[0][2] += d2; v[0][3] += d3;
+                      v[1][0] = fmaf(d0, d0, v[1][0]); v[1][1] = fmaf(d1, d1, v[1][1]);
+                      v[1][2] = fmaf(d2, d2, v[1][2]); v[1][3] = fmaf(d3, d3, v[1][3]);
+                  });
     }
     double out[2];
     col_reduce_sum<2>(v, g, C, red, out);
@@ -189,57 +209,72 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float *__restrict__
     }
 }
 
-// one CTA: batch (or running) statistics -> the affine map of the layer; running-stat update in train mode
-__global__ void __launch_bounds__(256) bn_finalize_kernel(const float *__restrict__ z, long long P, int C, const double *__restrict__ acc,
-                                                         const float *__restrict__ gamma, const float *__restrict__ beta,
-                                                         float *__restrict__ rmean, float *__restrict__ rvar, float eps, float momentum,
-                                                         int batch_stats, float *__restrict__ bnp) {
+// What BatchNorm makes of a layer's statistics, computed by EVERY CTA of the consuming kernel into shared memory (C <= 256
+// channels: cheaper than a launch of its own); `writer` (one CTA) also stores it for the backward and updates the running
+// statistics in train mode.  s_bnp[0..C) = gamma*invstd, [C..2C) = beta - mean*gamma*invstd, [2C..3C) = mean*invstd, [3C..4C) = invstd.
+struct BnArgs {
+    const double *acc;            // shifted sums of bn_stats_kernel (train mode)
+    const float *gamma, *beta;
+    float *rmean, *rvar;
+    float eps, momentum;
+    int batch_stats;
+    float *bnp;                   // out (saved): [4][C]
+};
+__device__ __forceinline__ void bn_prologue(const float *__restrict__ z, long long P, int C, const BnArgs &a, bool writer, float *s_bnp) {
     const int c = threadIdx.x;
-    if (c >= C) return;
-    double mean, var;
-    if (batch_stats) {
-        const double n = (double)P, s1 = acc[c], s2 = acc[kTMaxC + c];
-        const double dm = s1 / n;
-        mean = (double)z[c] + dm;
-        var = s2 / n - dm * dm;
-        if (var < 0.0) var = 0.0;
-        if (rmean) rmean[c] = (float)((1.0 - (double)momentum) * (double)rmean[c] + (double)momentum * mean);
-        if (rvar) rvar[c] = (float)((1.0 - (double)momentum) * (double)rvar[c] + (double)momentum * var * (n / (n - 1.0)));
-    } else {
-        mean = (double)rmean[c];
-        var = (double)rvar[c];
+    if (c < C) {
+        double mean, var;
+        if (a.batch_stats) {
+            const double n = (double)P, s1 = a.acc[c], s2 = a.acc[kTMaxC + c];
+            const double dm = s1 / n;
+            mean = (double)z[c] + dm;
+            var = s2 / n - dm * dm;
+            if (var < 0.0) var = 0.0;
+            if (writer) {
+                if (a.rmean) a.rmean[c] = (float)((1.0 - (double)a.momentum) * (double)a.rmean[c] + (double)a.momentum * mean);
+                if (a.rvar) a.rvar[c] = (float)((1.0 - (double)a.momentum) * (double)a.rvar[c] + (double)a.momentum * var * (n / (n - 1.0)));
+            }
+        } else {
+            mean = (double)a.rmean[c];
+            var = (double)a.rvar[c];
+        }
+        const double invstd = 1.0 / sqrt(var + (double)a.eps);
+        const double ga = a.gamma ? (double)a.gamma[c] : 1.0, be = a.beta ? (double)a.beta[c] : 0.0;
+        const float f0 = (float)(ga * invstd), f1 = (float)(be - mean * ga * invstd), f2 = (float)(mean * invstd), f3 = (float)invstd;
+        s_bnp[c] = f0; s_bnp[C + c] = f1; s_bnp[2 * C + c] = f2; s_bnp[3 * C + c] = f3;
+        if (writer) { a.bnp[c] = f0; a.bnp[C + c] = f1; a.bnp[2 * C + c] = f2; a.bnp[3 * C + c] = f3; }
     }
-    const double invstd = 1.0 / sqrt(var + (double)eps);
-    const double ga = gamma ? (double)gamma[c] : 1.0, be = beta ? (double)beta[c] : 0.0;
-    bnp[c] = (float)(ga * invstd);
-    bnp[C + c] = (float)(be - mean * ga * invstd);
-    bnp[2 * C + c] = (float)(mean * invstd);
-    bnp[3 * C + c] = (float)invstd;
+    __syncthreads();
 }
 
 // a = ReLU(z * scale + shift) -> fp16 hi+lo operand rows of the next GEMM; max |zhat| per channel for the backward's scale
-__global__ void __launch_bounds__(256) bn_act_kernel(const float *__restrict__ z, long long P, int C, const float *__restrict__ bnp,
+__global__ void __launch_bounds__(256) bn_act_kernel(const float *__restrict__ z, long long P, int C, BnArgs bn,
                                                     unsigned short *__restrict__ ahi, unsigned short *__restrict__ alo,
                                                     unsigned *__restrict__ zmax) {
     __shared__ float red[1024];
+    __shared__ __align__(16) float s_bnp[4 * kTMaxC];
+    bn_prologue(z, P, C, bn, blockIdx.x == 0, s_bnp);
     const ColGeom g(C);
     float zm[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     if (g.active) {
-        const float4 sc = __ldg(reinterpret_cast<const float4 *>(bnp) + g.tx), sh = __ldg(reinterpret_cast<const float4 *>(bnp + C) + g.tx);
-        const float4 mi = __ldg(reinterpret_cast<const float4 *>(bnp + 2 * C) + g.tx), is = __ldg(reinterpret_cast<const float4 *>(bnp + 3 * C) + g.tx);
-        for (long long row = (long long)blockIdx.x * g.rpi + g.ty; row < P; row += (long long)gridDim.x * g.rpi) {
-            const float4 t = __ldg(reinterpret_cast<const float4 *>(z + row * C) + g.tx);
-            const float a0 = fmaxf(fmaf(t.x, sc.x, sh.x), 0.0f), a1 = fmaxf(fmaf(t.y, sc.y, sh.y), 0.0f);
-            const float a2 = fmaxf(fmaf(t.z, sc.z, sh.z), 0.0f), a3 = fmaxf(fmaf(t.w, sc.w, sh.w), 0.0f);
-            zm[0] = fmaxf(zm[0], fabsf(fmaf(t.x, is.x, -mi.x))); zm[1] = fmaxf(zm[1], fabsf(fmaf(t.y, is.y, -mi.y)));
-            zm[2] = fmaxf(zm[2], fabsf(fmaf(t.z, is.z, -mi.z))); zm[3] = fmaxf(zm[3], fabsf(fmaf(t.w, is.w, -mi.w)));
-            uint32_t h0, l0, h1, l1;
-            split_f16x2(a0, a1, h0, l0);
-            split_f16x2(a2, a3, h1, l1);
-            const size_t o = ((size_t)row * C + 4 * g.tx);
-            *reinterpret_cast<uint2 *>(ahi + o) = make_uint2(h0, h1);
-            *reinterpret_cast<uint2 *>(alo + o) = make_uint2(l0, l1);
-        }
+        const float4 sc = reinterpret_cast<const float4 *>(s_bnp)[g.tx], sh = reinterpret_cast<const float4 *>(s_bnp + C)[g.tx];
+        const float4 mi = reinterpret_cast<const float4 *>(s_bnp + 2 * C)[g.tx], is = reinterpret_cast<const float4 *>(s_bnp + 3 * C)[g.tx];
+        float4 t[4];
+        rows4((long long)blockIdx.x * g.rpi + g.ty, (long long)gridDim.x * g.rpi, P,
+                  [&](int u, long long row, bool ok) { t[u] = ok ? __ldg(reinterpret_cast<const float4 *>(z + row * C) + g.tx) : make_float4(0.f, 0.f, 0.f, 0.f); },
+                  [&](int u, long long row) {
+                      const float4 tt = t[u];
+                      const float a0 = fmaxf(fmaf(tt.x, sc.x, sh.x), 0.0f), a1 = fmaxf(fmaf(tt.y, sc.y, sh.y), 0.0f);
+                      const float a2 = fmaxf(fmaf(tt.z, sc.z, sh.z), 0.0f), a3 = fmaxf(fmaf(tt.w, sc.w, sh.w), 0.0f);
+                      zm[0] = fmaxf(zm[0], fabsf(fmaf(tt.x, is.x, -mi.x))); zm[1] = fmaxf(zm[1], fabsf(fmaf(tt.y, is.y, -mi.y)));
+                      zm[2] = fmaxf(zm[2], fabsf(fmaf(tt.z, is.z, -mi.z))); zm[3] = fmaxf(zm[3], fabsf(fmaf(tt.w, is.w, -mi.w)));
+                      uint32_t h0, l0, h1, l1;
+                      split_f16x2(a0, a1, h0, l0);
+                      split_f16x2(a2, a3, h1, l1);
+                      const size_t o = ((size_t)row * C + 4 * g.tx);
+                      *reinterpret_cast<uint2 *>(ahi + o) = make_uint2(h0, h1);
+                      *reinterpret_cast<uint2 *>(alo + o) = make_uint2(l0, l1);
+                  });
     }
     float m;
     col_reduce_max(zm, g, C, red, m);
@@ -247,31 +282,36 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const float *__restrict__ z
 }
 
 // last layer: a = ReLU(BatchNorm(z)), max and arg-max over the points of a cloud.  grid (chunks of points, B)
-__global__ void __launch_bounds__(256) bn_pool_kernel(const float *__restrict__ z, int N, int C, int rows_per_cta, const float *__restrict__ bnp,
+__global__ void __launch_bounds__(256) bn_pool_kernel(const float *__restrict__ z, long long P, int N, int C, int rows_per_cta, BnArgs bn,
                                                      u64 *__restrict__ keys, unsigned *__restrict__ zmax) {
     __shared__ u64 kred[1024];
     __shared__ float red[1024];
+    __shared__ __align__(16) float s_bnp[4 * kTMaxC];
+    bn_prologue(z, P, C, bn, blockIdx.x == 0 && blockIdx.y == 0, s_bnp);
     const ColGeom g(C);
     const int b = blockIdx.y;
     const int n_begin = blockIdx.x * rows_per_cta, n_end = min(N, n_begin + rows_per_cta);
     float zm[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     u64 best[4] = {0, 0, 0, 0};
     if (g.active) {
-        const float4 sc = __ldg(reinterpret_cast<const float4 *>(bnp) + g.tx), sh = __ldg(reinterpret_cast<const float4 *>(bnp + C) + g.tx);
-        const float4 mi = __ldg(reinterpret_cast<const float4 *>(bnp + 2 * C) + g.tx), is = __ldg(reinterpret_cast<const float4 *>(bnp + 3 * C) + g.tx);
-        for (int n = n_begin + g.ty; n < n_end; n += g.rpi) {
-            const float4 t = __ldg(reinterpret_cast<const float4 *>(z + ((size_t)b * N + n) * C) + g.tx);
-            const float a[4] = {fmaxf(fmaf(t.x, sc.x, sh.x), 0.0f), fmaxf(fmaf(t.y, sc.y, sh.y), 0.0f),
-                                fmaxf(fmaf(t.z, sc.z, sh.z), 0.0f), fmaxf(fmaf(t.w, sc.w, sh.w), 0.0f)};
-            zm[0] = fmaxf(zm[0], fabsf(fmaf(t.x, is.x, -mi.x))); zm[1] = fmaxf(zm[1], fabsf(fmaf(t.y, is.y, -mi.y)));
-            zm[2] = fmaxf(zm[2], fabsf(fmaf(t.z, is.z, -mi.z))); zm[3] = fmaxf(zm[3], fabsf(fmaf(t.w, is.w, -mi.w)));
-            const u64 low = (u64)(0xFFFFFFFFu - (unsigned)n);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const u64 key = ((u64)__float_as_uint(a[k]) << 32) | low;    // a >= 0: the bit pattern orders like the value
-                best[k] = key > best[k] ? key : best[k];
-            }
-        }
+        const float4 sc = reinterpret_cast<const float4 *>(s_bnp)[g.tx], sh = reinterpret_cast<const float4 *>(s_bnp + C)[g.tx];
+        const float4 mi = reinterpret_cast<const float4 *>(s_bnp + 2 * C)[g.tx], is = reinterpret_cast<const float4 *>(s_bnp + 3 * C)[g.tx];
+        const float *zb = z + (size_t)b * N * C;
+        float4 t[4];
+        rows4((long long)n_begin + g.ty, (long long)g.rpi, (long long)n_end,
+                  [&](int u, long long row, bool ok) { t[u] = ok ? __ldg(reinterpret_cast<const float4 *>(zb + row * C) + g.tx) : make_float4(0.f, 0.f, 0.f, 0.f); },
+                  [&](int u, long long row) {
+                      const float4 tt = t[u];
+                      const float a[4] = {fmaxf(fmaf(tt.x, sc.x, sh.x), 0.0f), fmaxf(fmaf(tt.y, sc.y, sh.y), 0.0f),
+                                          fmaxf(fmaf(tt.z, sc.z, sh.z), 0.0f), fmaxf(fmaf(tt.w, sc.w, sh.w), 0.0f)};
+                      zm[0] = fmaxf(zm[0], fabsf(fmaf(tt.x, is.x, -mi.x))); zm[1] = fmaxf(zm[1], fabsf(fmaf(tt.y, is.y, -mi.y)));
+                      zm[2] = fmaxf(zm[2], fabsf(fmaf(tt.z, is.z, -mi.z))); zm[3] = fmaxf(zm[3], fabsf(fmaf(tt.w, is.w, -mi.w)));
+                      const u64 low = (u64)(0xFFFFFFFFu - (unsigned)row);
+                      for (int k = 0; k < 4; ++k) {
+                          const u64 key = ((u64)__float_as_uint(a[k]) << 32) | low;    // a >= 0: the bit pattern orders like the value
+                          best[k] = key > best[k] ? key : best[k];
+                      }
+                  });
 #pragma unroll
         for (int k = 0; k < 4; ++k) kred[g.ty * C + 4 * g.tx + k] = best[k];
     }
@@ -374,17 +414,22 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const float *__restri
     if (g.active) {
         const float4 sc = __ldg(reinterpret_cast<const float4 *>(bnp) + g.tx), sh = __ldg(reinterpret_cast<const float4 *>(bnp + C) + g.tx);
         const float4 mi = __ldg(reinterpret_cast<const float4 *>(bnp + 2 * C) + g.tx), is = __ldg(reinterpret_cast<const float4 *>(bnp + 3 * C) + g.tx);
-        for (long long row = (long long)blockIdx.x * g.rpi + g.ty; row < P; row += (long long)gridDim.x * g.rpi) {
-            const float4 t = __ldg(reinterpret_cast<const float4 *>(z + row * C) + g.tx);
-            const float4 d = __ldg(reinterpret_cast<const float4 *>(da + row * C) + g.tx);
-            const float dy0 = fmaf(t.x, sc.x, sh.x) > 0.0f ? d.x : 0.0f, dy1 = fmaf(t.y, sc.y, sh.y) > 0.0f ? d.y : 0.0f;
-            const float dy2 = fmaf(t.z, sc.z, sh.z) > 0.0f ? d.z : 0.0f, dy3 = fmaf(t.w, sc.w, sh.w) > 0.0f ? d.w : 0.0f;
-            v[0][0] += dy0; v[0][1] += dy1; v[0][2] += dy2; v[0][3] += dy3;
-            v[1][0] = fmaf(dy0, fmaf(t.x, is.x, -mi.x), v[1][0]); v[1][1] = fmaf(dy1, fmaf(t.y, is.y, -mi.y), v[1][1]);
-            v[1][2] = fmaf(dy2, fmaf(t.z, is.z, -mi.z), v[1][2]); v[1][3] = fmaf(dy3, fmaf(t.w, is.w, -mi.w), v[1][3]);
-            mx[0] = fmaxf(mx[0], fabsf(dy0)); mx[1] = fmaxf(mx[1], fabsf(dy1));
-            mx[2] = fmaxf(mx[2], fabsf(dy2)); mx[3] = fmaxf(mx[3], fabsf(dy3));
-        }
+        float4 t[4], d[4];
+        rows4((long long)blockIdx.x * g.rpi + g.ty, (long long)gridDim.x * g.rpi, P,
+              [&](int u, long long row, bool ok) {
+                  t[u] = ok ? __ldg(reinterpret_cast<const float4 *>(z + row * C) + g.tx) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  d[u] = ok ? __ldg(reinterpret_cast<const float4 *>(da + row * C) + g.tx) : make_float4(0.f, 0.f, 0.f, 0.f);
+              },
+              [&](int u, long long row) {
+                  const float4 tt = t[u], dd = d[u];
+                  const float dy0 = fmaf(tt.x, sc.x, sh.x) > 0.0f ? dd.x : 0.0f, dy1 = fmaf(tt.y, sc.y, sh.y) > 0.0f ? dd.y : 0.0f;
+                  const float dy2 = fmaf(tt.z, sc.z, sh.z) > 0.0f ? dd.z : 0.0f, dy3 = fmaf(tt.w, sc.w, sh.w) > 0.0f ? dd.w : 0.0f;
+                  v[0][0] += dy0; v[0][1] += dy1; v[0][2] += dy2; v[0][3] += dy3;
+                  v[1][0] = fmaf(dy0, fmaf(tt.x, is.x, -mi.x), v[1][0]); v[1][1] = fmaf(dy1, fmaf(tt.y, is.y, -mi.y), v[1][1]);
+                  v[1][2] = fmaf(dy2, fmaf(tt.z, is.z, -mi.z), v[1][2]); v[1][3] = fmaf(dy3, fmaf(tt.w, is.w, -mi.w), v[1][3]);
+                  mx[0] = fmaxf(mx[0], fabsf(dy0)); mx[1] = fmaxf(mx[1], fabsf(dy1));
+                  mx[2] = fmaxf(mx[2], fabsf(dy2)); mx[3] = fmaxf(mx[3], fabsf(dy3));
+              });
     }
     double out[2];
     col_reduce_sum<2>(v, g, C, red, out);
@@ -397,23 +442,35 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const float *__restri
     if ((int)threadIdx.x < C && m > 0.0f) atomicMax(mxdy + threadIdx.x, __float_as_uint(m));
 }
 
-// one CTA: the two means of the BatchNorm backward, the parameter gradients they are, and the power-of-two scale of dz
-__global__ void __launch_bounds__(256) bn_bwd_scale_kernel(long long P, int C, int batch_stats, const double *__restrict__ acc,
-                                                          const unsigned *__restrict__ mxdy, const unsigned *__restrict__ zmax,
-                                                          const float *__restrict__ bnp, float *__restrict__ m12, float *__restrict__ dscale,
-                                                          float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ dbias) {
+// The two means of the BatchNorm backward, the parameter gradients they are, and the power-of-two scale of dz, computed by
+// EVERY CTA of the consuming kernel into shared memory (s_m[0..C) = mean(dy), s_m[256..256+C) = mean(dy * zhat), *s_scale);
+// `writer` (one CTA) stores them for the kernels that follow and writes dgamma / dbeta / dbias.
+struct BwdArgs {
+    const double *acc;
+    const unsigned *mxdy, *zmax;
+    const float *bnp;
+    int batch_stats;
+    float *m12, *dscale;          // out: [2][256], [2] = scale, 1 / scale
+    float *dgamma, *dbeta, *dbias;
+};
+__device__ __forceinline__ void bwd_prologue(long long P, int C, const BwdArgs &a, bool writer, float *s_m, float *s_scale) {
     __shared__ float red[8];
     const int c = threadIdx.x;
     float bound = 0.0f;
     if (c < C) {
-        const double s1 = acc[c], s2 = acc[kTMaxC + c];
-        const float m1 = batch_stats ? (float)(s1 / (double)P) : 0.0f, m2 = batch_stats ? (float)(s2 / (double)P) : 0.0f;
-        m12[c] = m1;
-        m12[kTMaxC + c] = m2;
-        if (dgamma) dgamma[c] = (float)s2;
-        if (dbeta) dbeta[c] = (float)s1;
-        if (dbias) dbias[c] = batch_stats ? 0.0f : (float)((double)bnp[c] * s1);      // sum_p dz (zero through batch statistics)
-        bound = fabsf(bnp[c]) * (__uint_as_float(mxdy[c]) + fabsf(m1) + __uint_as_float(zmax[c]) * fabsf(m2));
+        const double s1 = a.acc[c], s2 = a.acc[kTMaxC + c];
+        const float m1 = a.batch_stats ? (float)(s1 / (double)P) : 0.0f, m2 = a.batch_stats ? (float)(s2 / (double)P) : 0.0f;
+        s_m[c] = m1;
+        s_m[kTMaxC + c] = m2;
+        const float scale = __ldg(a.bnp + c);
+        if (writer) {
+            a.m12[c] = m1;
+            a.m12[kTMaxC + c] = m2;
+            if (a.dgamma) a.dgamma[c] = (float)s2;
+            if (a.dbeta) a.dbeta[c] = (float)s1;
+            if (a.dbias) a.dbias[c] = a.batch_stats ? 0.0f : (float)((double)scale * s1);   // sum_p dz (zero through batch statistics)
+        }
+        bound = fabsf(scale) * (__uint_as_float(a.mxdy[c]) + fabsf(m1) + __uint_as_float(a.zmax[c]) * fabsf(m2));
     }
     for (int o = 16; o > 0; o >>= 1) bound = fmaxf(bound, __shfl_xor_sync(0xffffffffu, bound, o));
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = bound;
@@ -424,89 +481,110 @@ __global__ void __launch_bounds__(256) bn_bwd_scale_kernel(long long P, int C, i
         int e = 0;
         if (mm > 0.0f && mm < 3.0e38f) e = 14 - (ilogbf(mm) + 1);
         e = max(-100, min(100, e));
-        dscale[0] = ldexpf(1.0f, e);
-        dscale[1] = ldexpf(1.0f, -e);
+        *s_scale = ldexpf(1.0f, e);
+        if (writer) {
+            a.dscale[0] = ldexpf(1.0f, e);
+            a.dscale[1] = ldexpf(1.0f, -e);
+        }
     }
+    __syncthreads();
 }
 
-// dz = scale * (dy - m1 - zhat * m2), written as fp16 hi+lo operand rows multiplied by the device scale s.
-// LAST: dy comes from the arg-max keys and the pooled upstream gradient; else dy = da * [y > 0].
+// dz = scale * (dy - m1 - zhat * m2), written as fp16 hi+lo operand rows multiplied by the power-of-two scale s.
+// LAST: the dense part only (dy = 0): the few (cloud, channel) arg-max entries are patched by pool_bwd_patch_kernel.
 template <bool LAST>
-__global__ void __launch_bounds__(256) bn_bwd_dz_kernel(const float *__restrict__ z, const float *__restrict__ da, long long P, int N, int C,
-                                                       const float *__restrict__ bnp, const float *__restrict__ m12,
-                                                       const float *__restrict__ dscale, const u64 *__restrict__ keys,
-                                                       const float *__restrict__ gp, unsigned short *__restrict__ dzhi,
-                                                       unsigned short *__restrict__ dzlo) {
-    const int chunks = C / 8;
-    const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (e >= P * chunks) return;
-    const long long p = e / chunks;
-    const int c0 = (int)(e - p * chunks) * 8;
-    const float s = __ldg(dscale);
-    float zz[8], dy[8];
-    {
-        const float4 *zp = reinterpret_cast<const float4 *>(z + p * C + c0);
-        const float4 t0 = __ldg(zp), t1 = __ldg(zp + 1);
-        zz[0] = t0.x; zz[1] = t0.y; zz[2] = t0.z; zz[3] = t0.w; zz[4] = t1.x; zz[5] = t1.y; zz[6] = t1.z; zz[7] = t1.w;
-    }
-    if (LAST) {
-        const long long b = p / N;
-        const unsigned n = (unsigned)(p - b * N);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const u64 key = __ldg(keys + b * C + c0 + k);
-            const bool hit = (0xFFFFFFFFu - (unsigned)key) == n && __uint_as_float((unsigned)(key >> 32)) > 0.0f;
-            dy[k] = hit ? __ldg(gp + b * C + c0 + k) : 0.0f;
-        }
-    } else {
-        const float4 *dp = reinterpret_cast<const float4 *>(da + p * C + c0);
-        const float4 d0 = __ldg(dp), d1 = __ldg(dp + 1);
-        const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-#pragma unroll
-        for (int k = 0; k < 8; ++k) dy[k] = fmaf(zz[k], __ldg(bnp + c0 + k), __ldg(bnp + C + c0 + k)) > 0.0f ? dd[k] : 0.0f;
-    }
-    float v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int c = c0 + k;
-        const float zh = fmaf(zz[k], __ldg(bnp + 3 * C + c), -__ldg(bnp + 2 * C + c));
-        v[k] = (__ldg(bnp + c) * s) * (dy[k] - __ldg(m12 + c) - zh * __ldg(m12 + kTMaxC + c));
-    }
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) split_f16x2(v[2 * k], v[2 * k + 1], h[k], l[k]);
-    const size_t off = (size_t)p * C + c0;
-    *reinterpret_cast<uint4 *>(dzhi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4 *>(dzlo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+__global__ void __launch_bounds__(256) bn_bwd_dz_kernel(const float *__restrict__ z, const float *__restrict__ da, long long P, int C,
+                                                       BwdArgs bw, unsigned short *__restrict__ dzhi, unsigned short *__restrict__ dzlo) {
+    __shared__ __align__(16) float s_m[2 * kTMaxC];
+    __shared__ float s_scale;
+    bwd_prologue(P, C, bw, blockIdx.x == 0, s_m, &s_scale);
+    const ColGeom g(C);
+    if (!g.active) return;
+    const float s = s_scale;
+    const float4 sc = __ldg(reinterpret_cast<const float4 *>(bw.bnp) + g.tx), sh = __ldg(reinterpret_cast<const float4 *>(bw.bnp + C) + g.tx);
+    const float4 mi = __ldg(reinterpret_cast<const float4 *>(bw.bnp + 2 * C) + g.tx), is = __ldg(reinterpret_cast<const float4 *>(bw.bnp + 3 * C) + g.tx);
+    const float4 m1 = reinterpret_cast<const float4 *>(s_m)[g.tx], m2 = reinterpret_cast<const float4 *>(s_m + kTMaxC)[g.tx];
+    const float4 ss = make_float4(sc.x * s, sc.y * s, sc.z * s, sc.w * s);
+    float4 t[4], d[4];
+    rows4((long long)blockIdx.x * g.rpi + g.ty, (long long)gridDim.x * g.rpi, P,
+          [&](int u, long long row, bool ok) {
+              t[u] = ok ? __ldg(reinterpret_cast<const float4 *>(z + row * C) + g.tx) : make_float4(0.f, 0.f, 0.f, 0.f);
+              if (!LAST) d[u] = ok ? __ldg(reinterpret_cast<const float4 *>(da + row * C) + g.tx) : make_float4(0.f, 0.f, 0.f, 0.f);
+          },
+          [&](int u, long long row) {
+              const float4 tt = t[u];
+              float dy0 = 0.0f, dy1 = 0.0f, dy2 = 0.0f, dy3 = 0.0f;
+              if (!LAST) {
+                  const float4 dd = d[u];
+                  dy0 = fmaf(tt.x, sc.x, sh.x) > 0.0f ? dd.x : 0.0f; dy1 = fmaf(tt.y, sc.y, sh.y) > 0.0f ? dd.y : 0.0f;
+                  dy2 = fmaf(tt.z, sc.z, sh.z) > 0.0f ? dd.z : 0.0f; dy3 = fmaf(tt.w, sc.w, sh.w) > 0.0f ? dd.w : 0.0f;
+              }
+              const float v0 = ss.x * (dy0 - m1.x - fmaf(tt.x, is.x, -mi.x) * m2.x), v1 = ss.y * (dy1 - m1.y - fmaf(tt.y, is.y, -mi.y) * m2.y);
+              const float v2 = ss.z * (dy2 - m1.z - fmaf(tt.z, is.z, -mi.z) * m2.z), v3 = ss.w * (dy3 - m1.w - fmaf(tt.w, is.w, -mi.w) * m2.w);
+              uint32_t h0, l0, h1, l1;
+              split_f16x2(v0, v1, h0, l0);
+              split_f16x2(v2, v3, h1, l1);
+              const size_t o = (size_t)row * C + 4 * g.tx;
+              *reinterpret_cast<uint2 *>(dzhi + o) = make_uint2(h0, h1);
+              *reinterpret_cast<uint2 *>(dzlo + o) = make_uint2(l0, l1);
+          });
+}
+
+// last layer: the (cloud, channel) entries at the arg-max points carry the pooled upstream gradient
+__global__ void __launch_bounds__(256) pool_bwd_patch_kernel(const float *__restrict__ z, const float *__restrict__ gp, const u64 *__restrict__ keys,
+                                                            int B, int N, int C, const float *__restrict__ bnp, const float *__restrict__ m12,
+                                                            const float *__restrict__ dscale, unsigned short *__restrict__ dzhi,
+                                                            unsigned short *__restrict__ dzlo) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= B * C) return;
+    const int b = i / C, c = i - b * C;
+    const u64 key = keys[i];
+    if (!(__uint_as_float((unsigned)(key >> 32)) > 0.0f)) return;
+    const int n = (int)(0xFFFFFFFFu - (unsigned)key);
+    const size_t o = ((size_t)b * N + n) * C + c;
+    const float zh = fmaf(z[o], bnp[3 * C + c], -bnp[2 * C + c]);
+    const float v = (bnp[c] * dscale[0]) * (gp[i] - m12[c] - zh * m12[kTMaxC + c]);
+    const __half h = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
+    const __half lo = __float2half_rn(v - __half2float(h));
+    dzhi[o] = *reinterpret_cast<const unsigned short *>(&h);
+    dzlo[o] = *reinterpret_cast<const unsigned short *>(&lo);
 }
 
 // layer 0: dW0[c][k] = sum_p dz0[p][c] * x[p][k] on the CUDA cores (K = 3), dz0 formed on the fly
 __global__ void __launch_bounds__(256) layer0_wgrad_kernel(const float *__restrict__ z, const float *__restrict__ da, const float *__restrict__ x,
-                                                          long long P, int C, const float *__restrict__ bnp, const float *__restrict__ m12,
-                                                          double *__restrict__ w0acc) {
+                                                          long long P, int C, BwdArgs bw, double *__restrict__ w0acc) {
     __shared__ float red[3 * 1024];
+    __shared__ __align__(16) float s_m[2 * kTMaxC];
+    __shared__ float s_scale;
+    bwd_prologue(P, C, bw, blockIdx.x == 0, s_m, &s_scale);
     const ColGeom g(C);
     float v[3][4] = {};
     if (g.active) {
+        const float *bnp = bw.bnp;
         const float4 sc = __ldg(reinterpret_cast<const float4 *>(bnp) + g.tx), sh = __ldg(reinterpret_cast<const float4 *>(bnp + C) + g.tx);
         const float4 mi = __ldg(reinterpret_cast<const float4 *>(bnp + 2 * C) + g.tx), is = __ldg(reinterpret_cast<const float4 *>(bnp + 3 * C) + g.tx);
-        const float4 m1 = __ldg(reinterpret_cast<const float4 *>(m12) + g.tx), m2 = __ldg(reinterpret_cast<const float4 *>(m12 + kTMaxC) + g.tx);
-        for (long long row = (long long)blockIdx.x * g.rpi + g.ty; row < P; row += (long long)gridDim.x * g.rpi) {
-            const float4 t = __ldg(reinterpret_cast<const float4 *>(z + row * C) + g.tx);
-            const float4 d = __ldg(reinterpret_cast<const float4 *>(da + row * C) + g.tx);
-            const float px = __ldg(x + 3 * row), py = __ldg(x + 3 * row + 1), pz = __ldg(x + 3 * row + 2);
-            const float tz[4] = {t.x, t.y, t.z, t.w}, dd[4] = {d.x, d.y, d.z, d.w};
-            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w}, miv[4] = {mi.x, mi.y, mi.z, mi.w};
-            const float isv[4] = {is.x, is.y, is.z, is.w}, m1v[4] = {m1.x, m1.y, m1.z, m1.w}, m2v[4] = {m2.x, m2.y, m2.z, m2.w};
+        const float4 m1 = reinterpret_cast<const float4 *>(s_m)[g.tx], m2 = reinterpret_cast<const float4 *>(s_m + kTMaxC)[g.tx];
+        const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w}, miv[4] = {mi.x, mi.y, mi.z, mi.w};
+        const float isv[4] = {is.x, is.y, is.z, is.w}, m1v[4] = {m1.x, m1.y, m1.z, m1.w}, m2v[4] = {m2.x, m2.y, m2.z, m2.w};
+        float4 t[4], d[4];
+        float px[4], py[4], pz[4];
+        rows4((long long)blockIdx.x * g.rpi + g.ty, (long long)gridDim.x * g.rpi, P,
+              [&](int u, long long row, bool ok) {
+                  t[u] = ok ? __ldg(reinterpret_cast<const float4 *>(z + row * C) + g.tx) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  d[u] = ok ? __ldg(reinterpret_cast<const float4 *>(da + row * C) + g.tx) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  px[u] = ok ? __ldg(x + 3 * row) : 0.0f; py[u] = ok ? __ldg(x + 3 * row + 1) : 0.0f; pz[u] = ok ? __ldg(x + 3 * row + 2) : 0.0f;
+              },
+              [&](int u, long long row) {
+                  const float tz[4] = {t[u].x, t[u].y, t[u].z, t[u].w}, dd[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float dy = fmaf(tz[k], scv[k], shv[k]) > 0.0f ? dd[k] : 0.0f;
-                const float dz = scv[k] * (dy - m1v[k] - fmaf(tz[k], isv[k], -miv[k]) * m2v[k]);
-                v[0][k] = fmaf(dz, px, v[0][k]);
-                v[1][k] = fmaf(dz, py, v[1][k]);
-                v[2][k] = fmaf(dz, pz, v[2][k]);
-            }
-        }
+                  for (int k = 0; k < 4; ++k) {
+                      const float dy = fmaf(tz[k], scv[k], shv[k]) > 0.0f ? dd[k] : 0.0f;
+                      const float dz = scv[k] * (dy - m1v[k] - fmaf(tz[k], isv[k], -miv[k]) * m2v[k]);
+                      v[0][k] = fmaf(dz, px[u], v[0][k]);
+                      v[1][k] = fmaf(dz, py[u], v[1][k]);
+                      v[2][k] = fmaf(dz, pz[u], v[2][k]);
+                  }
+              });
     }
     double out[3];
     col_reduce_sum<3>(v, g, C, red, out);
@@ -718,8 +796,8 @@ static int train_check(const char *fn, const rlg_bn_layer *layers, int L, unsign
 
 static inline unsigned row_grid(long long P, int C, int sms) {
     const int rpi = 256 / (C / 4);
-    long long want = (P + (long long)rpi * 8 - 1) / ((long long)rpi * 8);      // ~8 rows per thread
-    const long long cap = (long long)sms * 8;
+    long long want = (P + (long long)rpi * 8 - 1) / ((long long)rpi * 8);      // at least ~8 rows per thread
+    const long long cap = (long long)sms * 4;
     if (want > cap) want = cap;
     if (want < 1) want = 1;
     return (unsigned)want;
@@ -863,9 +941,11 @@ int rlg_encoder_train_fwd(const float *x, int B, int N, const rlg_bn_layer *laye
             if (rc) return rc;
         }
         if (batch) bn_stats_kernel<<<row_grid(P, C, sms), 256, 0, st>>>(z, P, C, acc);
-        bn_finalize_kernel<<<1, 256, 0, st>>>(z, P, C, acc, y.gamma, y.beta, y.running_mean, y.running_var, y.eps, y.momentum, batch ? 1 : 0, bnp);
+        BnArgs bn;
+        bn.acc = acc; bn.gamma = y.gamma; bn.beta = y.beta; bn.rmean = y.running_mean; bn.rvar = y.running_var;
+        bn.eps = y.eps; bn.momentum = y.momentum; bn.batch_stats = batch ? 1 : 0; bn.bnp = bnp;
         if (l < L - 1) {
-            bn_act_kernel<<<row_grid(P, C, sms), 256, 0, st>>>(z, P, C, bnp, reinterpret_cast<unsigned short *>(sv + sl.ahi[l]),
+            bn_act_kernel<<<row_grid(P, C, sms), 256, 0, st>>>(z, P, C, bn, reinterpret_cast<unsigned short *>(sv + sl.ahi[l]),
                                                                 reinterpret_cast<unsigned short *>(sv + sl.alo[l]), zmax);
         } else {
             const int rpi = 256 / (C / 4);
@@ -874,7 +954,7 @@ int rlg_encoder_train_fwd(const float *x, int B, int N, const rlg_bn_layer *laye
             if (per < rpi) per = rpi;
             const unsigned gx = (unsigned)((N + per - 1) / per);
             u64 *keys = reinterpret_cast<u64 *>(sv + sl.keys);
-            bn_pool_kernel<<<dim3(gx, (unsigned)B), 256, 0, st>>>(z, N, C, per, bnp, keys, zmax);
+            bn_pool_kernel<<<dim3(gx, (unsigned)B), 256, 0, st>>>(z, P, N, C, per, bn, keys, zmax);
             pool_decode_kernel<<<(B * C + 255) / 256, 256, 0, st>>>(keys, B * C, pooled);
         }
     }
@@ -922,18 +1002,21 @@ int rlg_encoder_train_bwd(const float *x, int B, int N, const rlg_bn_layer *laye
         const bool last = l == L - 1;
         if (last) pool_bwd_stats_kernel<<<(B * C + 255) / 256, 256, 0, st>>>(z, g_pooled, keys, B, N, C, bnp, acc, mxdy);
         else bn_bwd_stats_kernel<<<row_grid(P, C, sms), 256, 0, st>>>(z, da, P, C, bnp, acc, mxdy);
-        bn_bwd_scale_kernel<<<1, 256, 0, st>>>(P, C, batch ? 1 : 0, acc, mxdy, zmax, bnp, m12, dscale, grads[l].dgamma, grads[l].dbeta, grads[l].db);
+        BwdArgs bw;
+        bw.acc = acc; bw.mxdy = mxdy; bw.zmax = zmax; bw.bnp = bnp; bw.batch_stats = batch ? 1 : 0;
+        bw.m12 = m12; bw.dscale = dscale; bw.dgamma = grads[l].dgamma; bw.dbeta = grads[l].dbeta; bw.dbias = grads[l].db;
         if (l == 0) {
-            if (grads[0].dw) {
-                double *w0acc = reinterpret_cast<double *>(w + wl.w0acc);
-                layer0_wgrad_kernel<<<row_grid(P, C, sms), 256, 0, st>>>(z, da, x, P, C, bnp, m12, w0acc);
-                layer0_wgrad_finish_kernel<<<(3 * C + 255) / 256, 256, 0, st>>>(w0acc, 3 * C, grads[0].dw);
-            }
+            double *w0acc = reinterpret_cast<double *>(w + wl.w0acc);
+            layer0_wgrad_kernel<<<row_grid(P, C, sms), 256, 0, st>>>(z, da, x, P, C, bw, w0acc);
+            if (grads[0].dw) layer0_wgrad_finish_kernel<<<(3 * C + 255) / 256, 256, 0, st>>>(w0acc, 3 * C, grads[0].dw);
             break;
         }
-        const long long n = P * (C / 8);
-        if (last) bn_bwd_dz_kernel<true><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(z, nullptr, P, N, C, bnp, m12, dscale, keys, g_pooled, dzhi, dzlo);
-        else bn_bwd_dz_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(z, da, P, N, C, bnp, m12, dscale, nullptr, nullptr, dzhi, dzlo);
+        if (last) {
+            bn_bwd_dz_kernel<true><<<row_grid(P, C, sms), 256, 0, st>>>(z, nullptr, P, C, bw, dzhi, dzlo);
+            pool_bwd_patch_kernel<<<(B * C + 255) / 256, 256, 0, st>>>(z, g_pooled, keys, B, N, C, bnp, m12, dscale, dzhi, dzlo);
+        } else {
+            bn_bwd_dz_kernel<false><<<row_grid(P, C, sms), 256, 0, st>>>(z, da, P, C, bw, dzhi, dzlo);
+        }
         if (grads[l].dw) {
             rc = launch_wgrad(dzhi, dzlo, sv + sl.ahi[l - 1], sv + sl.alo[l - 1], P, C, y.c_in, dscale, reinterpret_cast<float *>(w + wl.partial),
                               grads[l].dw, sms, st);
