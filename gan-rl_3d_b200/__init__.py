@@ -14,6 +14,8 @@ from __future__ import annotations
 
 import importlib
 import sys
+
+import torch
 from typing import Optional
 
 from . import _lib
@@ -28,13 +30,14 @@ from .train import EncoderTrainFn, train_supported, trunk_pool_autograd
 from .ae_step import AEStepGraph, PointCloudAutoencoder, PointNetDecoder
 from . import train
 from .environment import BatchedRLEnvironment
+from .data import DeviceBatcher, build_cache, draw_plan
 
 __all__ = ["install", "uninstall", "is_installed", "chamfer_distance_l2", "chamfer_distance", "ChamferLoss",
            "ChamferFn", "ChamferLossFn", "chamfer_nearest", "chamfer_backward", "set_default_sweep", "get_default_sweep", "PointNetEncoder", "EncoderTrunkFn", "encoder_pool",
            "fold_trunk", "folded_trunk_cached", "fused_forward", "set_encoder_precision", "get_encoder_precision",
            "pack_bf16", "pack_gemm", "packed_trunk_cached", "encoder_pool_gemm", "encoder_path_of", "resolve_path", "RewardFunction", "batched_rewards", "library_path", "abi_version",
            "EncoderTrainFn", "train_supported", "trunk_pool_autograd", "set_train_path",
-           "AEStepGraph", "PointCloudAutoencoder", "PointNetDecoder", "BatchedRLEnvironment"]
+           "AEStepGraph", "PointCloudAutoencoder", "PointNetDecoder", "BatchedRLEnvironment", "DeviceBatcher", "build_cache", "draw_plan"]
 
 _installed = {}
 
@@ -56,7 +59,7 @@ def _find(modname: str):
         return None
 
 
-def install(losses_module=None, autoencoder_module=None) -> dict:
+def install(losses_module=None, autoencoder_module=None, check_finite: bool = False) -> dict:
     """Rebind the reference's two choke points:
 
       utils.losses.chamfer_distance_l2             (utils/losses.py:13; resolved by global lookup from
@@ -69,7 +72,11 @@ def install(losses_module=None, autoencoder_module=None) -> dict:
     Inputs outside the CUDA contract (CPU tensors, fp64, 4-D broadcast input of validate_joint, train-mode
     BatchNorm) are handed to the saved original function, so reference behaviour -- including its errors --
     is preserved for everything that is not the hot path.  Loads the CUDA library eagerly: a missing
-    librlg_b200.so is an ImportError here, not a silent fallback later."""
+    librlg_b200.so is an ImportError here, not a silent fallback later.
+
+    check_finite=True: clouds containing NaN/Inf are handed to the original function too (the reference lets a NaN
+    candidate win torch.min; the kernels' filter may skip it).  The check is a device reduction and a host
+    synchronisation per call, so it is off by default."""
     _lib.load()
     losses_module = losses_module or _find("utils.losses")
     autoencoder_module = autoencoder_module or _find("models.autoencoder")
@@ -79,6 +86,8 @@ def install(losses_module=None, autoencoder_module=None) -> dict:
 
         def chamfer_distance_l2_b200(pc1, pc2):
             if _chamfer_hot(pc1, pc2):
+                if check_finite and not bool((torch.isfinite(pc1).all() & torch.isfinite(pc2).all()).item()):
+                    return original(pc1, pc2)
                 return ChamferFn.apply(pc1, pc2)
             return original(pc1, pc2)
 

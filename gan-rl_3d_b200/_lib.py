@@ -36,6 +36,12 @@ class RlgBnGrads(ctypes.Structure):
     _fields_ = [("dw", ctypes.c_void_p), ("db", ctypes.c_void_p), ("dgamma", ctypes.c_void_p), ("dbeta", ctypes.c_void_p)]
 
 
+class RlgPreparePlan(ctypes.Structure):
+    """struct rlg_prepare_plan (include/rlg_b200.h)."""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("item", "method", "n_keep", "keep_idx", "center", "q_index", "q_gamma", "rot",
+                                                "scale", "jitter", "pad_idx")]
+
+
 class RlgError(RuntimeError):
     def __init__(self, fn: str, code: int, msg: str):
         super().__init__(f"{fn} failed with code {code}: {msg}")
@@ -89,6 +95,8 @@ EXPORTS = {
     "rlg_encoder_train_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(RlgBnLayer), ctypes.c_int,
                                              ctypes.c_uint, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                              ctypes.POINTER(RlgBnGrads), ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "rlg_batch_prepare": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(RlgPreparePlan),
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "rlg_fp32_peak": (ctypes.c_int, [c_float_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
 }
 

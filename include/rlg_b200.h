@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define RLG_ABI_VERSION 5
+#define RLG_ABI_VERSION 6
 
 #define RLG_ERR_NULL_POINTER   (-1)
 #define RLG_ERR_BAD_SHAPE      (-2)   /* B < 0, N < 1, M < 1 (the reference raises IndexError for empty clouds) */
@@ -258,6 +258,36 @@ int rlg_encoder_train_fwd(const float *x, int B, int N, const rlg_bn_layer *laye
 int rlg_encoder_train_bwd(const float *x, int B, int N, const rlg_bn_layer *layers, int L, unsigned flags,
                           const float *g_pooled, const void *saved, size_t saved_bytes,
                           const rlg_bn_grads *grads, void *ws, size_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Input pipeline on the device: the per-sample numeric work of the reference's DataLoader for a batch of B
+ * items of a binary cache of complete clouds (items, N, 3) fp32 that lives in HBM:
+ *   utils/dataset.py:252-276  _create_incomplete_pc   (random subset | points outside a sphere, np.percentile radius in float64)
+ *   utils/dataset.py:278-297  _augment_point_cloud    (pc @ R^T, + clipped jitter, * scale)
+ *   utils/data_utils.py:15-60 normalize_point_cloud   (centroid, largest norm)
+ *   utils/dataset.py:393-421  shapenet_collate_fn     (pad the incomplete clouds to the batch's longest by repeating points)
+ * Every random decision is an input (the host draws a few numbers per cloud); all arrays below are DEVICE pointers.
+ *   complete_out   (B, N, 3)  augmented + normalised complete clouds
+ *   incomplete_out (B, N, 3)  capacity; cloud b holds lengths[b] points followed by padding up to *max_len
+ *   lengths (B), max_len (1)  int32; the caller slices incomplete_out[:, :max_len]
+ * N <= 4096.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct rlg_prepare_plan {
+    const int32_t *item;      /* (B) row of the cache; NULL = rows 0..B-1 */
+    const int32_t *method;    /* (B) 0 = random subset in drawn order (keep_idx), 1 = spatial removal */
+    const int32_t *n_keep;    /* (B) method 0: number of kept points */
+    const int32_t *keep_idx;  /* (B, N) method 0: kept point indices, first n_keep valid */
+    const int32_t *center;    /* (B) method 1: index of the sphere's centre point */
+    const int32_t *q_index;   /* (B) method 1: floor((N-1) * ratio), numpy's percentile index */
+    const double  *q_gamma;   /* (B) method 1: its fractional part */
+    const float   *rot;       /* (2, B, 9) row-major rotation matrices for the complete / incomplete cloud; NULL = none */
+    const float   *scale;     /* (2, B) scale factors; NULL = 1 */
+    const float   *jitter;    /* (2, B, N, 3) additive noise, already clipped; NULL = none */
+    const int32_t *pad_idx;   /* (B, N) non-negative random integers: pad slot s repeats point pad_idx[b][s] % lengths[b] */
+} rlg_prepare_plan;
+
+int rlg_batch_prepare(const float *cache, int n_items, int N, int B, const rlg_prepare_plan *plan,
+                      float *complete_out, float *incomplete_out, int32_t *lengths, int32_t *max_len, void *stream);
 
 /* FP32 CUDA-core peak microbenchmark (measurement helper, not on the hot path; it synchronises).
  * Fills host array out[0..5]:

@@ -257,6 +257,72 @@ class RefLatentGANPort(nn.Module):
         return self.discriminator(gfv)
 
 
+# --------------------------------------------------------------------------------------------
+# input pipeline (utils/dataset.py:135-187,252-297,393-421; utils/data_utils.py:15-60,74-142) with EXPLICIT random draws:
+# the reference pulls its draws from np.random / torch's global RNG inside each function; here they are arguments, so the
+# device pipeline and this restatement can be fed the same ones
+# --------------------------------------------------------------------------------------------
+def percentile_parts(n: int, removal_ratio: float):
+    """(k, gamma) of np.percentile(distances, removal_ratio * 100) for n float64 values, method 'linear':
+    virtual index (n - 1) * (q / 100), k = floor, gamma = fractional part (numpy/lib/_function_base_impl.py)."""
+    q = removal_ratio * 100
+    vi = (n - 1) * np.true_divide(q, 100.0)
+    k = int(np.floor(vi))
+    return k, float(vi - k)
+
+
+def lerp_numpy(a: float, b: float, t: float) -> float:
+    """numpy's _lerp in float64: a + (b - a) * t, and b - (b - a) * (1 - t) where t >= 0.5."""
+    a, b, t = np.float64(a), np.float64(b), np.float64(t)
+    d = b - a
+    return float(b - d * (1 - t)) if t >= 0.5 else float(a + d * t)
+
+
+def ref_port_create_incomplete(complete_pc: np.ndarray, draws: dict) -> np.ndarray:
+    """utils/dataset.py:252-276 with its draws made explicit.  draws: {'method': 0, 'keep_idx': int array} (random subset,
+    kept in the drawn order) or {'method': 1, 'center': int, 'ratio': float} (points outside a sphere around a point)."""
+    if draws["method"] == 0:
+        return complete_pc[np.asarray(draws["keep_idx"])]
+    center = complete_pc[int(draws["center"])]
+    distances = np.linalg.norm(complete_pc - center, axis=1)
+    radius = np.percentile(distances, draws["ratio"] * 100)
+    return complete_pc[distances > radius]
+
+
+def ref_port_augment(pc: np.ndarray, rot=None, noise=None, scale=None) -> np.ndarray:
+    """utils/dataset.py:278-297: float32 tensor; optional rotation pc @ R.T (data_utils.py:118), optional additive noise
+    (already clipped, data_utils.py:140-142), optional scale."""
+    t = torch.FloatTensor(pc)
+    if rot is not None:
+        t = t @ torch.tensor(rot, dtype=t.dtype).T
+    if noise is not None:
+        t = t + torch.as_tensor(noise, dtype=t.dtype)
+    if scale is not None:
+        t = t * scale
+    return t.numpy()
+
+
+def ref_port_normalize(pc: np.ndarray) -> np.ndarray:
+    """utils/data_utils.py:15-60 for one (N, 3) cloud: centre on the centroid, divide by the largest norm (float32)."""
+    t = torch.from_numpy(np.asarray(pc)).float()
+    c = t - torch.mean(t, dim=0, keepdim=True)
+    scale = torch.max(torch.norm(c, dim=1))
+    return (c / scale if scale > 0 else c).numpy()
+
+
+def ref_port_pad(pcs, pad_idx) -> np.ndarray:
+    """shapenet_collate_fn (utils/dataset.py:393-421): incomplete clouds padded to the longest of the batch by repeating
+    points; pad slot s of cloud b repeats point pad_idx[b][s] (the reference draws torch.randint(0, len_b))."""
+    m = max(p.shape[0] for p in pcs)
+    out = np.zeros((len(pcs), m, 3), np.float32)
+    for b, p in enumerate(pcs):
+        n = p.shape[0]
+        out[b, :n] = p
+        if n < m:
+            out[b, n:] = p[np.asarray(pad_idx[b][:m - n]) % n]
+    return out
+
+
 def randomize_bn(module: nn.Module, seed: int = 0) -> None:
     """Non-trivial BatchNorm statistics/affine (a fresh BN is identity-like and hides folding bugs).
     SURVEY.md 8d: running_mean~N(0,.5), running_var~U(.3,2), gamma~N(1,.5), beta~N(0,.3)."""

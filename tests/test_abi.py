@@ -36,7 +36,7 @@ def test_header_symbols_are_exported(lib):
 
 def test_version_and_ws_bytes(lib):
     cdll, _ = lib
-    assert cdll.rlg_version() == 5
+    assert cdll.rlg_version() == 6
     # per point: 8-byte key + 4-byte runner-up value + (tensor sweep) 4-byte runner-up group + 4-byte third value; + counters
     big = cdll.rlg_chamfer_ws_bytes(32, 2048, 2048)
     assert 20 * 32 * 4096 < big <= 20 * 32 * 4096 + 16384 and big % 256 == 0

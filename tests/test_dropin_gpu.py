@@ -84,6 +84,26 @@ def test_install_routes_cuda_inputs_through_the_kernels(rlg):
         rlg.uninstall()
 
 
+def test_check_finite_routes_nan_clouds_to_the_original(rlg):
+    """torch.min lets a NaN candidate win; the kernels are specified for finite clouds only.  With
+    install(check_finite=True) a cloud holding a NaN must reach the original function and come back bit for bit."""
+    losses, ae = _reference_shaped_modules()
+    pc1, pc2 = O.make_clouds(2, 300, "sphere", 1).to(DEV), O.make_clouds(2, 200, "sphere", 2).to(DEV)
+    bad = pc2.clone()
+    bad[1, 17, 2] = float("nan")
+    want_ok = O.ref_port_chamfer_l2(pc1, pc2)
+    want_bad = O.ref_port_chamfer_l2(pc1, bad)
+    rlg.install(losses, ae, check_finite=True)
+    try:
+        got_bad = losses.chamfer_distance_l2(pc1, bad)
+        assert all(torch.equal(torch.isnan(g), torch.isnan(w)) and torch.equal(torch.nan_to_num(g), torch.nan_to_num(w))
+                   for g, w in zip(got_bad, want_bad))
+        got_ok = losses.chamfer_distance_l2(pc1, pc2)               # finite clouds still take the kernels
+        assert all(torch.allclose(g, w, rtol=1e-4) for g, w in zip(got_ok, want_ok))
+    finally:
+        rlg.uninstall()
+
+
 def test_autoencoder_training_step_with_chamfer_loss(rlg):
     """A config_quick-shaped AE step (BASELINE config 1 on the GPU): encoder in train mode (stock layers),
     decoder, ChamferLoss from the CUDA path, Adam.  Loss must fall and gradients must match the stock path."""

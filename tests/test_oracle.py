@@ -206,3 +206,68 @@ def test_environment_ports_reproduce_the_reference_episodes():
             mse = torch.nn.functional.mse_loss(clean, enc(comp))
             reward = -(w[0] * cd + w[1] * mse + w[2] * (-gan.discriminate(clean).mean()))
             assert abs(float(reward) - float(g["rewards"][e])) <= 1e-5 * abs(float(g["rewards"][e]))
+
+
+def _ref_dataset_module():
+    """utils/dataset.py of the mounted reference (it imports h5py, absent here and unused by these functions)."""
+    import importlib
+    import os
+    import sys
+    import types
+    ref = os.environ.get("RLG_REFERENCE", "/root/reference")
+    if not os.path.exists(os.path.join(ref, "utils", "dataset.py")):
+        pytest.skip("reference checkout not present")
+    sys.modules.setdefault("h5py", types.ModuleType("h5py"))
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    return importlib.import_module("utils.dataset")
+
+
+def test_input_pipeline_ports_are_bit_identical_to_the_mounted_reference():
+    """oracle.ref_port_create_incomplete / _augment / _normalize / _pad with the draws the reference would make under the same
+    seeds == utils/dataset.py:252-297,393-421 and utils/data_utils.py:15-60 themselves."""
+    ds = _ref_dataset_module()
+    rng = np.random.default_rng(5)
+    for trial in range(12):
+        n = 2048 if trial % 3 else 777
+        complete = rng.normal(size=(n, 3)) * rng.uniform(0.5, 2.0) + rng.normal(size=3)
+        np.random.seed(100 + trial)
+        want = ds.ShapeNetDataset._create_incomplete_pc(None, complete)                 # the reference, its own draws
+        np.random.seed(100 + trial)                                                     # the same draws, made explicit
+        ratio = np.random.uniform(0.2, 0.5)
+        num_keep = int(n * (1 - ratio))
+        if np.random.random() < 0.5:
+            draws = {"method": 0, "keep_idx": np.random.choice(n, num_keep, replace=False)}
+        else:
+            draws = {"method": 1, "center": np.random.randint(n), "ratio": ratio}
+        got = O.ref_port_create_incomplete(complete, draws)
+        assert got.shape == want.shape and np.array_equal(got, want)
+        if draws["method"] == 1:                                                        # and the restated percentile
+            d = np.sort(np.linalg.norm(complete - complete[draws["center"]], axis=1))
+            k, g = O.percentile_parts(n, ratio)
+            assert O.lerp_numpy(d[k], d[min(k + 1, n - 1)], g) == np.percentile(d, ratio * 100)
+        # augmentation: np.random for the coin flips / angles / scale, torch's RNG for the jitter noise
+        np.random.seed(200 + trial)
+        torch.manual_seed(300 + trial)
+        want_aug = ds.ShapeNetDataset._augment_point_cloud(None, want)
+        np.random.seed(200 + trial)
+        torch.manual_seed(300 + trial)
+        rot = noise = scale = None
+        if np.random.random() < 0.5:
+            rot = ds.random_rotation_matrix()
+        if np.random.random() < 0.5:
+            noise = torch.clamp(torch.normal(0, 0.01, size=torch.FloatTensor(want).shape), -0.05, 0.05)
+        if np.random.random() < 0.3:
+            scale = np.random.uniform(0.8, 1.2)
+        got_aug = O.ref_port_augment(want, rot, noise, scale)
+        assert np.array_equal(got_aug, want_aug)
+        assert np.array_equal(O.ref_port_normalize(got_aug), ds.normalize_point_cloud(want_aug))
+    # collate: the padded batch
+    items = [{"incomplete_pc": torch.randn(n, 3)} for n in (50, 64, 37)]
+    torch.manual_seed(9)
+    want = ds.shapenet_collate_fn(items)["incomplete_pc"]
+    torch.manual_seed(9)
+    pad_idx = [torch.randint(0, it["incomplete_pc"].shape[0], (64 - it["incomplete_pc"].shape[0],)).numpy()
+               if it["incomplete_pc"].shape[0] < 64 else np.zeros(0, np.int64) for it in items]
+    got = O.ref_port_pad([it["incomplete_pc"].numpy() for it in items], pad_idx)
+    assert np.array_equal(got, want.numpy())
