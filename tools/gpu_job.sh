@@ -22,6 +22,8 @@ for step in "$@"; do
     aestep)    timeout 900 python -m pytest tests/test_ae_step_gpu.py -m gpu -q -s > gpurun_out/${T}_aestep.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_aestep.log ;;
     envtest)   timeout 900 python -m pytest tests/test_environment_gpu.py -m gpu -q -s > gpurun_out/${T}_envtest.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_envtest.log ;;
     property)  timeout 900 python -m pytest tests/test_chamfer_property_gpu.py -m gpu -q > gpurun_out/${T}_property.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_property.log ;;
+    data)      timeout 900 python -m pytest tests/test_data_gpu.py tests/test_dropin_gpu.py -m gpu -q > gpurun_out/${T}_data.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_data.log ;;
+    steplist)  bash tools/gpu_job3.sh ${T} ;;
     *) echo "unknown step $step" ;;
   esac
 done
