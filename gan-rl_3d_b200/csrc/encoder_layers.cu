@@ -13,7 +13,7 @@
 //                         - X tiles arrive by TMA (cp.async.bulk.tensor.3d, 128-byte swizzle, tensor map over
 //                           (channel, point, cloud) so tiles never straddle clouds and rows past the end come in as zeros)
 //                           through a ring of 64-channel K blocks; the elected MMA thread issues tcgen05.mma from the
-//                           landed blocks into one of two TMEM accumulators; four epilogue warps pull the other one back
+//                           landed blocks into TMEM; two groups of four epilogue warps pull the accumulators back
 //                           (tcgen05.ld), apply scale + bias + ReLU and either write the next layer's operand rows (64
 //                           contiguous bytes per thread and piece) or, for the last layer, reduce the max over the
 //                           tile's points (REDUX on the bit patterns: post-ReLU values are >= 0) and merge it into the
@@ -29,8 +29,11 @@
 //                  one accumulator).  So the K steps are dealt out over FOUR accumulators (a quarter of the hi.hi steps each,
 //                  at most four additions at K = 256); the cross terms (2^-11 of the result, so their own truncation is
 //                  harmless) all go to the fourth one BEFORE its hi.hi steps; the epilogue adds the four in
-//                  round-to-nearest.  That takes all 512 TMEM columns, so this mode is single-buffered
-//                  (MMA and epilogue of consecutive tiles alternate) -- the path is HBM-bound either way.
+//                  round-to-nearest (accumulators 1 and 3 carry negated products and are subtracted).  That takes all 512
+//                  TMEM columns, so this mode is single-buffered: MMAs and epilogue of consecutive tiles alternate, the X
+//                  tiles of the next tile are prefetched meanwhile, and both epilogue groups drain the tile together (every
+//                  other 32-column chunk each, the four accumulator loads of a chunk in flight at once).  Measured: 64-column
+//                  slices with two buffers overlap MMA and epilogue but read every X tile twice as often from L2 -- no gain.
 //                  Weights are scaled by a power of two per layer so that max|w| lands near 2^14 (the lo parts stay normal fp16 numbers); the epilogue undoes the scale exactly.  Activations
 //                  are stored unscaled: values in [2^-3, 65504] keep all 22 bits, smaller ones an absolute error <= 2^-25,
 //                  larger ones saturate (post-ReLU activations of a BatchNorm-folded network are nowhere near 6.5e4).
@@ -48,9 +51,10 @@ namespace rlg {
 static constexpr int kLMaxLayers = 8;
 static constexpr int kLT = 128;                 // points per tile (UMMA M)
 static constexpr int kLN = 128;                 // output channels per CTA slice (UMMA N)
+__host__ __device__ constexpr int slice_width(int) { return kLN; }
 static constexpr int kLKB = 64;                 // channels per K block: 128 bytes = one swizzle row
-static constexpr uint32_t kLBlk = kLT * 128;    // bytes of one K block of one piece (128 rows x 128 B)
-static constexpr int kLThreads = 192;           // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2-5 epilogue
+static constexpr uint32_t kLBlk = kLT * 128;    // bytes of one K block of one piece of an X tile (128 rows x 128 B)
+static constexpr int kLThreads = 320;           // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2-5 / 6-9 epilogue of buffer 0 / 1
 static constexpr int kLMaxStages = 8;
 
 struct LayerArgs {
@@ -63,8 +67,23 @@ struct LayerArgs {
     void *y0, *y1;                 // EPI_ACT: next layer's operand pieces [B*N x C_out] (2-byte elements)
                                    // EPI_RAW: y0 = fp32 [B*N x C_out] (scale + bias only, no ReLU)
     float *pooled;                 // EPI_POOL: (B, C_out) fp32, zero-filled before the launch
+    int tma_store;                 // EPI_ACT / EPI_RAW: outputs leave through shared-memory staging + TMA tensor stores
 };
+static constexpr uint32_t kStgBuf = 128 * 128;   // one staging buffer: 128 rows x 128 bytes (SWIZZLE_128B box of a TMA store)
+static constexpr uint32_t kStgBytes = 4 * kStgBuf;   // two epilogue groups x two buffers
 enum { EPI_ACT = 0, EPI_POOL = 1, EPI_RAW = 2 };
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *tm, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void group_bar(uint32_t id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
 
 // cute::UMMA::InstrDescriptor: D fp32, A/B both bf16 (fmt 1) or both f16 (fmt 0), K-major
 __device__ __forceinline__ uint32_t umma_idesc_16(int M, int Nn, uint32_t fmt) {
@@ -81,24 +100,31 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 template <int PIECES, int EPI>
 __global__ void __launch_bounds__(kLThreads, 1)
 encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CUtensorMap tmx1,
-                     const __grid_constant__ CUtensorMap tmw0, const __grid_constant__ CUtensorMap tmw1, LayerArgs a) {
+                     const __grid_constant__ CUtensorMap tmw0, const __grid_constant__ CUtensorMap tmw1,
+                     const __grid_constant__ CUtensorMap tmy0, const __grid_constant__ CUtensorMap tmy1, LayerArgs a) {
     extern __shared__ unsigned char el_smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t pad = (1024u - (smem_u32(el_smem_raw) & 1023u)) & 1023u;
     unsigned char *smem = el_smem_raw + pad;
     const uint32_t sbase = smem_u32(smem);
     const int kblocks = a.K / kLKB;
-    // layout: W [PIECES][kblocks] blocks | X ring [stages][PIECES] blocks | barriers
-    const uint32_t w_off = 0, x_off = (uint32_t)PIECES * kblocks * kLBlk;
-    const uint32_t bars = sbase + x_off + (uint32_t)a.stages * PIECES * kLBlk;
+    // layout: W [PIECES][kblocks] blocks | X ring [stages][PIECES] blocks | output staging (4 buffers, with tma_store) | barriers
+    constexpr int LN = slice_width(PIECES);                       // output channels of this CTA's slice
+    constexpr uint32_t kWBlk = (uint32_t)LN * 128u;               // bytes of one K block of one piece of the weight slice
+    const uint32_t w_off = 0, x_off = (uint32_t)PIECES * kblocks * kWBlk;
+    const uint32_t stg_off = x_off + (uint32_t)a.stages * PIECES * kLBlk;
+    const uint32_t bars_off = stg_off + (a.tma_store ? kStgBytes : 0u);
+    const uint32_t bars = sbase + bars_off;
     const uint32_t bar_w = bars, bar_full = bars + 8, bar_empty = bar_full + 8 * kLMaxStages;
     const uint32_t bar_accfull = bar_empty + 8 * kLMaxStages, bar_accempty = bar_accfull + 16;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + x_off + (uint32_t)a.stages * PIECES * kLBlk + 8 * (2 * kLMaxStages + 5));
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + bars_off + 8 * (2 * kLMaxStages + 5));
 
     if (tid == 0) {
         mbar_init(bar_w, 1);
         for (int s = 0; s < a.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int k = 0; k < 2; ++k) { mbar_init(bar_accfull + 8 * k, 1); mbar_init(bar_accempty + 8 * k, 128); }
+        // bf16: two accumulator buffers, each drained by one epilogue group (128 threads); fp16 hi+lo: one buffer (its
+        // four accumulators take all 512 columns) drained by both groups (256 threads), each taking every other 32-column chunk
+        for (int k = 0; k < 2; ++k) { mbar_init(bar_accfull + 8 * k, 1); mbar_init(bar_accempty + 8 * k, PIECES == 1 ? 128 : 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -121,10 +147,10 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
     if (warp == 0) {
         // =========================== TMA producer ===========================
         if (elect_one()) {
-            mbar_arrive_expect_tx(bar_w, (uint32_t)PIECES * kblocks * kLBlk);
+            mbar_arrive_expect_tx(bar_w, (uint32_t)PIECES * kblocks * kWBlk);
             for (int p = 0; p < PIECES; ++p)
                 for (int kb = 0; kb < kblocks; ++kb)
-                    tma_load_2d(sbase + w_off + (uint32_t)(p * kblocks + kb) * kLBlk, p ? &tmw1 : &tmw0, kb * kLKB, slice * kLN, bar_w);
+                    tma_load_2d(sbase + w_off + (uint32_t)(p * kblocks + kb) * kWBlk, p ? &tmw1 : &tmw0, kb * kLKB, slice * LN, bar_w);
             uint32_t it = 0;
             for (int t = first; t < n_tiles; t += step) {
                 const int b = t / a.tiles_per_cloud, n0 = (t - b * a.tiles_per_cloud) * kLT;
@@ -140,7 +166,7 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
         const bool leader = elect_one();
-        const uint32_t idesc = umma_idesc_16(kLT, kLN, PIECES == 1 ? 1u : 0u);
+        const uint32_t idesc = umma_idesc_16(kLT, LN, PIECES == 1 ? 1u : 0u);
         // fp16 hi+lo: the accumulators 1 and 3 collect NEGATED products (a_negate, bit 13) and are subtracted in the
         // epilogue.  The tensor core's fp32 accumulation rounds toward minus infinity, a bias that adds up coherently over
         // the points in the column sums of the training backward; with half of every sum carried negated it cancels.
@@ -148,13 +174,15 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
         mbar_wait_wd(bar_w, 0);
         uint32_t it = 0, ti = 0;
         for (int t = first; t < n_tiles; t += step, ++ti) {
-            // bf16: two 128-column accumulators alternate between tiles.  fp16 hi+lo: ONE set of four -- three main
-            // accumulators (hi.hi steps rotate over them) at columns 0/128/256 and the cross terms at 384.
+            // bf16: two 128-column accumulator buffers alternate between tiles (the MMAs of tile t+1 run under the epilogue of
+            // tile t).  fp16 hi+lo: ONE set of four 128-column accumulators: the hi.hi steps in four contiguous quarters, the
+            // cross terms into the fourth before its own hi.hi steps.
             const uint32_t acc = PIECES == 1 ? (ti & 1u) : 0u;
             const uint32_t par = PIECES == 1 ? ((ti >> 1) & 1u) : (ti & 1u);
             mbar_wait_wd(bar_accempty + 8 * acc, par ^ 1u);
             tc_fence_after();
-            const uint32_t d = tmem + acc * (uint32_t)kLN, dx = tmem + 3u * (uint32_t)kLN;
+            const uint32_t base = tmem + acc * (uint32_t)kLN;
+            const uint32_t d = base, dx = base + 3u * (uint32_t)LN;
             const uint32_t n_steps = (uint32_t)a.K / 16u, q_steps = (n_steps + 3u) / 4u;   // hi.hi steps per accumulator
             uint32_t accum = 0, used = 0, ks = 0;
             for (int kb = 0; kb < kblocks; ++kb, ++it) {
@@ -163,8 +191,8 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
                 tc_fence_after();
                 if (leader) {
                     const uint64_t x0 = umma_desc(sbase + x_off + (s * PIECES) * kLBlk);
-                    const uint64_t w0 = umma_desc(sbase + w_off + (uint32_t)kb * kLBlk);
-                    const uint64_t xp = (uint64_t)(kLBlk >> 4), wp = (uint64_t)(((uint32_t)kblocks * kLBlk) >> 4);   // piece strides
+                    const uint64_t w0 = umma_desc(sbase + w_off + (uint32_t)kb * kWBlk);
+                    const uint64_t xp = (uint64_t)(kLBlk >> 4), wp = (uint64_t)(((uint32_t)kblocks * kWBlk) >> 4);   // piece strides
                     if (PIECES == 2) {
                         // this block's cross terms first: accumulator 3 must have all of them before its own hi.hi steps
 #pragma unroll
@@ -184,7 +212,7 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
                             accum = 1;
                         } else {
                             const uint32_t m = min(3u, ks / q_steps);
-                            tc_mma_bf16(tmem + m * (uint32_t)kLN, x0 + ko, w0 + ko, (m & 1u) ? idesc_neg : idesc, (used >> m) & 1u);   // +-(hi . hi)
+                            tc_mma_bf16(base + m * (uint32_t)LN, x0 + ko, w0 + ko, (m & 1u) ? idesc_neg : idesc, (used >> m) & 1u);   // +-(hi . hi)
                             used |= 1u << m;
                         }
                     }
@@ -200,34 +228,55 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
         const int q = warp & 3;                                        // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;                                 // point of the tile
         const uint32_t lane_base = ((uint32_t)q * 32u) << 16;
-        const int c_base = slice * kLN;
-        uint32_t ti = 0;
-        const int n_acc = PIECES == 1 ? 1 : 4;                         // accumulators to add up (K >= 64: all four are in use)
+        const int c_base = slice * LN;
+        // two epilogue groups of four warps (two warps per SM sub-partition: a lone epilogue warp per scheduler cannot hide
+        // its own latencies).  bf16: group g drains accumulator buffer g, i.e. the CTA's tiles ti = g, g + 2, ...;
+        // fp16 hi+lo: both groups drain every tile, group g taking the 64-column half g (chunks 2g, 2g + 1).
+        // Outputs (EPI_ACT / EPI_RAW) leave through two 16 KB staging buffers per group, written in the 128-byte-swizzled box
+        // layout and pushed out by TMA tensor stores: per-thread row stores would reach HBM as 16-byte partial sectors
+        // (measured: more than half of the kernel's time).
+        const uint32_t grp = (uint32_t)(warp - 2) >> 2;
+        const int gtid = tid - 64 - (int)grp * 128;                    // thread of the group
+        constexpr uint32_t kTileStride = PIECES == 1 ? 2u : 1u;
         constexpr bool POOL = EPI == EPI_POOL;
+        const bool staged = !POOL && a.tma_store != 0;
+        const uint32_t stg = sbase + stg_off + grp * 2u * kStgBuf;     // this group's two staging buffers
+        const uint32_t bar_id = 1u + grp;                              // named barrier of the group
+        const uint32_t swz = (uint32_t)row * 128u, rx = (uint32_t)row & 7u;
         const float sc = a.out_scale * (a.dscale0 ? __ldg(a.dscale0) : 1.0f) * (a.dscale1 ? __ldg(a.dscale1) : 1.0f);
-        for (int t = first; t < n_tiles; t += step, ++ti) {
+        uint32_t ti = PIECES == 1 ? grp : 0u;
+        for (int t = first + (int)ti * step; t < n_tiles; t += (int)kTileStride * step, ti += kTileStride) {
             const uint32_t acc = PIECES == 1 ? (ti & 1u) : 0u;
             const uint32_t par = PIECES == 1 ? ((ti >> 1) & 1u) : (ti & 1u);
+            const uint32_t tbase = tmem + lane_base + acc * (uint32_t)kLN;
             const int b = t / a.tiles_per_cloud, n0 = (t - b * a.tiles_per_cloud) * kLT;
             const bool valid = n0 + row < a.N;
             const size_t grow = (size_t)b * a.N + n0 + row;
+            if (staged) {
+                if (gtid == 0) tma_store_wait_read();                  // the previous tile's stores have read their buffers
+                group_bar(bar_id);
+            }
             mbar_wait_wd(bar_accfull + 8 * acc, par);
             tc_fence_after();
+            const int c_begin = PIECES == 1 ? 0 : 2 * (int)grp, c_end = PIECES == 1 ? LN / 32 : c_begin + 2;
 #pragma unroll 1
-            for (int c = 0; c < kLN / 32; ++c) {
+            for (int c = c_begin; c < c_end; ++c) {
                 const int col0 = c_base + c * 32;
                 if (col0 >= a.C_out) break;                            // warp-uniform
                 float v[32];
-                tc_ld32(tmem + lane_base + acc * (uint32_t)kLN + (uint32_t)(c * 32), v);
-                if (PIECES == 2) {
-                    // the four partial accumulators, every addition in round-to-nearest
-                    float vx[32];
-#pragma unroll 1
-                    for (int m = 1; m < n_acc; ++m) {
-                        tc_ld32(tmem + lane_base + (uint32_t)m * (uint32_t)kLN + (uint32_t)(c * 32), vx);
+                if (PIECES == 1) {
+                    tc_ld32(tbase + (uint32_t)(c * 32), v);
+                } else {
+                    // the four partial accumulators (K >= 64: all four are in use): their loads are in flight together,
+                    // every addition in round-to-nearest, accumulators 1 and 3 hold negated sums
+                    float v1[32], v2[32], v3[32];
+                    tc_ld32_nowait(tbase + (uint32_t)(c * 32), v);
+                    tc_ld32_nowait(tbase + (uint32_t)LN + (uint32_t)(c * 32), v1);
+                    tc_ld32_nowait(tbase + 2u * (uint32_t)LN + (uint32_t)(c * 32), v2);
+                    tc_ld32_nowait(tbase + 3u * (uint32_t)LN + (uint32_t)(c * 32), v3);
+                    tc_wait_ld(v); tc_wait_ld(v1); tc_wait_ld(v2); tc_wait_ld(v3);
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) v[e] = (m & 1) ? v[e] - vx[e] : v[e] + vx[e];
-                    }
+                    for (int e = 0; e < 32; ++e) v[e] = ((v[e] - v1[e]) + v2[e]) - v3[e];
                 }
                 if (EPI == EPI_RAW) {
                     if (a.bias != nullptr) {
@@ -242,7 +291,14 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
 #pragma unroll
                         for (int e = 0; e < 32; ++e) v[e] *= sc;
                     }
-                    if (valid) {
+                    if (staged) {
+                        // a chunk of 32 fp32 columns is one 128-byte row of a box: buffer (c & 1) of the group
+                        const uint32_t dst = stg + (uint32_t)(c & 1) * kStgBuf + swz;
+#pragma unroll
+                        for (uint32_t j = 0; j < 8; ++j)
+                            st_shared_v4(dst + ((j ^ rx) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                         __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+                    } else if (valid) {
                         float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(a.y0) + grow * a.C_out + col0);
 #pragma unroll
                         for (int e4 = 0; e4 < 8; ++e4) dst[e4] = make_float4(v[4 * e4], v[4 * e4 + 1], v[4 * e4 + 2], v[4 * e4 + 3]);
@@ -267,6 +323,27 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
                         keep = (lane == e) ? r : keep;
                     }
                     if (keep != 0) atomicMax(reinterpret_cast<unsigned *>(a.pooled) + (size_t)b * a.C_out + col0 + lane, keep);
+                } else if (staged) {
+                    // 32 columns of 2-byte elements = 64 bytes = half a box row: 16-byte chunks 4 * (c & 1) .. + 3.
+                    // bf16: the tile's two 64-column halves go to buffers 0 / 1; fp16: hi -> buffer 0, lo -> buffer 1
+                    const uint32_t j0 = 4u * (uint32_t)(c & 1);
+                    if (PIECES == 1) {
+                        const uint32_t dst = stg + (uint32_t)(c >> 1) * kStgBuf + swz;
+#pragma unroll
+                        for (uint32_t e8 = 0; e8 < 4; ++e8)
+                            st_shared_v4(dst + (((j0 + e8) ^ rx) << 4), pack_bf16x2(v[8 * e8], v[8 * e8 + 1]), pack_bf16x2(v[8 * e8 + 2], v[8 * e8 + 3]),
+                                         pack_bf16x2(v[8 * e8 + 4], v[8 * e8 + 5]), pack_bf16x2(v[8 * e8 + 6], v[8 * e8 + 7]));
+                    } else {
+#pragma unroll
+                        for (uint32_t e8 = 0; e8 < 4; ++e8) {
+                            uint32_t h[4], l[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) split_f16x2(v[8 * e8 + 2 * k], v[8 * e8 + 2 * k + 1], h[k], l[k]);
+                            const uint32_t o = swz + (((j0 + e8) ^ rx) << 4);
+                            st_shared_v4(stg + o, h[0], h[1], h[2], h[3]);
+                            st_shared_v4(stg + kStgBuf + o, l[0], l[1], l[2], l[3]);
+                        }
+                    }
                 } else if (valid) {
                     if (PIECES == 1) {
                         uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(a.y0) + (grow * a.C_out + col0) * 2);
@@ -281,12 +358,7 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
                         for (int e8 = 0; e8 < 4; ++e8) {
                             uint32_t h[4], l[4];
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const float x0 = v[8 * e8 + 2 * k], x1 = v[8 * e8 + 2 * k + 1];
-                                h[k] = pack_f16x2_sat(x0, x1);
-                                const float2 hf = unpack_f16x2(h[k]);
-                                l[k] = pack_f16x2_sat(x0 - hf.x, x1 - hf.y);      // exact residuals
-                            }
+                            for (int k = 0; k < 4; ++k) split_f16x2(v[8 * e8 + 2 * k], v[8 * e8 + 2 * k + 1], h[k], l[k]);
                             dh[e8] = make_uint4(h[0], h[1], h[2], h[3]);
                             dl[e8] = make_uint4(l[0], l[1], l[2], l[3]);
                         }
@@ -294,8 +366,27 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
                 }
             }
             tc_fence_before();
-            mbar_arrive(bar_accempty + 8 * acc);
+            mbar_arrive(bar_accempty + 8 * acc);                       // the accumulator goes back to the issuer
+            if (staged) {
+                fence_async_proxy();                                   // the staged rows become visible to the TMA engine
+                group_bar(bar_id);
+                if (gtid == 0) {
+                    const int cg = c_base + c_begin * 32;              // first column this group wrote
+                    if (EPI == EPI_RAW) {
+                        if (cg < a.C_out) tma_store_3d(&tmy0, stg, cg, n0, b);
+                        if (cg + 32 < a.C_out) tma_store_3d(&tmy0, stg + kStgBuf, cg + 32, n0, b);
+                    } else if (PIECES == 1) {
+                        if (cg < a.C_out) tma_store_3d(&tmy0, stg, cg, n0, b);
+                        if (cg + 64 < a.C_out) tma_store_3d(&tmy0, stg + kStgBuf, cg + 64, n0, b);
+                    } else if (cg < a.C_out) {
+                        tma_store_3d(&tmy0, stg, cg, n0, b);
+                        tma_store_3d(&tmy1, stg + kStgBuf, cg, n0, b);
+                    }
+                    tma_store_commit();
+                }
+            }
         }
+        if (staged && gtid == 0) tma_store_wait_all();                 // the staging buffers must outlive their stores
     }
     tc_fence_before();
     __syncthreads();
@@ -385,7 +476,9 @@ int make_map(CUtensorMap *tm, int pieces_fmt, void *base, int rank, const cuuint
     EncodeTiledFn f = encode_tiled();
     if (!f) return fail(RLG_ERR_UNSUPPORTED, "rlg_encoder_gemm: cuTensorMapEncodeTiled is not available from this driver");
     const cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = f(tm, pieces_fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, base, dims,
+    const CUtensorMapDataType dt = pieces_fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                   : pieces_fmt == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUresult r = f(tm, dt, (cuuint32_t)rank, base, dims,
                    strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(RLG_ERR_UNSUPPORTED, "rlg_encoder_gemm: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -400,20 +493,24 @@ int launch_layer_gemm(const GemmCall &g, int sms, cudaStream_t st) {
     LayerArgs a;
     a.B = g.B; a.N = g.N; a.K = g.K; a.C_out = g.C_out;
     a.tiles_per_cloud = (g.N + kLT - 1) / kLT;
-    a.n_slices = (g.C_out + kLN - 1) / kLN;
+    const int LN = slice_width(pieces);
+    a.n_slices = (g.C_out + LN - 1) / LN;
     a.bias = g.bias;
     a.out_scale = g.out_scale;
     a.dscale0 = g.dscale0; a.dscale1 = g.dscale1;
     a.y0 = g.y0; a.y1 = g.y1; a.pooled = g.pooled;
     const int kblocks = g.K / kLKB;
-    const size_t w_bytes = (size_t)pieces * kblocks * kLBlk, stage_bytes = (size_t)pieces * kLBlk;
+    const size_t w_bytes = (size_t)pieces * kblocks * LN * 128, stage_bytes = (size_t)pieces * kLBlk;
     const size_t budget = 226u * 1024u - 256u;             // 227 KB per CTA minus the alignment slack and the barriers
-    long long stages = ((long long)budget - (long long)w_bytes) / (long long)stage_bytes;
+    // outputs through shared-memory staging + TMA stores when the staging buffers leave room for a two-stage X ring
+    a.tma_store = g.epi != EPI_POOL && (long long)budget - (long long)w_bytes - (long long)kStgBytes >= 2 * (long long)stage_bytes ? 1 : 0;
+    const size_t stg_bytes = a.tma_store ? kStgBytes : 0;
+    long long stages = ((long long)budget - (long long)w_bytes - (long long)stg_bytes) / (long long)stage_bytes;
     if (stages < 2) return fail(RLG_ERR_UNSUPPORTED, "encoder_layer_kernel: K=%d does not fit in shared memory", g.K);
     if (stages > kLMaxStages) stages = kLMaxStages;
     a.stages = (int)stages;
-    const size_t smem_bytes = w_bytes + (size_t)stages * stage_bytes + 256 + 1024;
-    CUtensorMap tmx[2], tmw[2];
+    const size_t smem_bytes = w_bytes + (size_t)stages * stage_bytes + stg_bytes + 256 + 1024;
+    CUtensorMap tmx[2], tmw[2], tmy[2];
     for (int p = 0; p < 2; ++p) {
         const bool second = p == 1 && pieces == 2;
         const cuuint64_t xd[3] = {(cuuint64_t)g.K, (cuuint64_t)g.N, (cuuint64_t)g.B};
@@ -423,9 +520,21 @@ int launch_layer_gemm(const GemmCall &g, int sms, cudaStream_t st) {
         if (rc) return rc;
         const cuuint64_t wd[2] = {(cuuint64_t)g.K, (cuuint64_t)g.C_out};
         const cuuint64_t wst[1] = {(cuuint64_t)g.K * 2};
-        const cuuint32_t wb[2] = {(cuuint32_t)kLKB, (cuuint32_t)kLN};
+        const cuuint32_t wb[2] = {(cuuint32_t)kLKB, (cuuint32_t)LN};
         rc = make_map(&tmw[p], pieces, const_cast<void *>(second ? g.w1 : g.w0), 2, wd, wst, wb);
         if (rc) return rc;
+        tmy[p] = tmx[p];                                   // placeholder when nothing is stored through TMA
+        if (a.tma_store) {
+            // output boxes: 128 rows x 128 bytes = 64 two-byte columns (EPI_ACT) or 32 fp32 columns (EPI_RAW)
+            const bool raw = g.epi == EPI_RAW;
+            const size_t esz = raw ? 4 : 2;
+            void *ybase = raw ? g.y0 : (second ? g.y1 : g.y0);
+            const cuuint64_t yd[3] = {(cuuint64_t)g.C_out, (cuuint64_t)g.N, (cuuint64_t)g.B};
+            const cuuint64_t ys[2] = {(cuuint64_t)g.C_out * esz, (cuuint64_t)g.N * g.C_out * esz};
+            const cuuint32_t yb[3] = {(cuuint32_t)(raw ? 32 : 64), (cuuint32_t)kLT, 1};
+            rc = make_map(&tmy[p], raw ? 3 : pieces, ybase, 3, yd, ys, yb);
+            if (rc) return rc;
+        }
     }
     const long long tiles = (long long)g.B * a.tiles_per_cloud;
     long long per_slice = sms / a.n_slices;
@@ -435,7 +544,7 @@ int launch_layer_gemm(const GemmCall &g, int sms, cudaStream_t st) {
     auto launch = [&](auto kernel) -> int {
         cudaError_t ae = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (ae != cudaSuccess) { cudaGetLastError(); return fail((int)ae, "encoder_layer_kernel: cudaFuncSetAttribute(%zu): %s", smem_bytes, cudaGetErrorString(ae)); }
-        cudaError_t le = launch_pdl(kernel, dim3(grid), dim3(kLThreads), smem_bytes, st, tmx[0], tmx[1], tmw[0], tmw[1], a);
+        cudaError_t le = launch_pdl(kernel, dim3(grid), dim3(kLThreads), smem_bytes, st, tmx[0], tmx[1], tmw[0], tmw[1], tmy[0], tmy[1], a);
         if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "encoder_layer_kernel: %s", cudaGetErrorString(le)); }
         return 0;
     };
