@@ -67,7 +67,8 @@ struct LayerArgs {
     void *y0, *y1;                 // EPI_ACT: next layer's operand pieces [B*N x C_out] (2-byte elements)
                                    // EPI_RAW: y0 = fp32 [B*N x C_out] (scale + bias only, no ReLU)
     float *pooled;                 // EPI_POOL: (B, C_out) fp32, zero-filled before the launch
-    int tma_store;                 // EPI_ACT / EPI_RAW: outputs leave through shared-memory staging + TMA tensor stores
+    int tma_store;                 // EPI_ACT / EPI_RAW: staging buffers per epilogue group (0 = none: per-thread stores; 1; 2):
+                                   // outputs leave through shared memory + TMA tensor stores
 };
 static constexpr uint32_t kStgBuf = 128 * 128;   // one staging buffer: 128 rows x 128 bytes (SWIZZLE_128B box of a TMA store)
 static constexpr uint32_t kStgBytes = 4 * kStgBuf;   // two epilogue groups x two buffers
@@ -113,7 +114,7 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
     constexpr uint32_t kWBlk = (uint32_t)LN * 128u;               // bytes of one K block of one piece of the weight slice
     const uint32_t w_off = 0, x_off = (uint32_t)PIECES * kblocks * kWBlk;
     const uint32_t stg_off = x_off + (uint32_t)a.stages * PIECES * kLBlk;
-    const uint32_t bars_off = stg_off + (a.tma_store ? kStgBytes : 0u);
+    const uint32_t bars_off = stg_off + (uint32_t)a.tma_store * 2u * kStgBuf;
     const uint32_t bars = sbase + bars_off;
     const uint32_t bar_w = bars, bar_full = bars + 8, bar_empty = bar_full + 8 * kLMaxStages;
     const uint32_t bar_accfull = bar_empty + 8 * kLMaxStages, bar_accempty = bar_accfull + 16;
@@ -240,7 +241,8 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
         constexpr uint32_t kTileStride = PIECES == 1 ? 2u : 1u;
         constexpr bool POOL = EPI == EPI_POOL;
         const bool staged = !POOL && a.tma_store != 0;
-        const uint32_t stg = sbase + stg_off + grp * 2u * kStgBuf;     // this group's two staging buffers
+        const uint32_t nbuf = (uint32_t)a.tma_store;                   // staging buffers of this group
+        const uint32_t stg = sbase + stg_off + grp * nbuf * kStgBuf;
         const uint32_t bar_id = 1u + grp;                              // named barrier of the group
         const uint32_t swz = (uint32_t)row * 128u, rx = (uint32_t)row & 7u;
         const float sc = a.out_scale * (a.dscale0 ? __ldg(a.dscale0) : 1.0f) * (a.dscale1 ? __ldg(a.dscale1) : 1.0f);
@@ -252,10 +254,28 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
             const int b = t / a.tiles_per_cloud, n0 = (t - b * a.tiles_per_cloud) * kLT;
             const bool valid = n0 + row < a.N;
             const size_t grow = (size_t)b * a.N + n0 + row;
-            if (staged) {
-                if (gtid == 0) tma_store_wait_read();                  // the previous tile's stores have read their buffers
+            // a store unit = what fills the group's staging buffers once: with two buffers the group's whole share of the tile,
+            // with one buffer a single box (32 fp32 columns, or 64 bf16 columns)
+            auto unit_begin = [&]() {
+                if (gtid == 0) tma_store_wait_read();                  // the previous unit's stores have read their buffers
                 group_bar(bar_id);
-            }
+            };
+            auto unit_end = [&](int cfirst, int n_boxes) {             // boxes: consecutive buffers, consecutive column blocks
+                fence_async_proxy();                                   // the staged rows become visible to the TMA engine
+                group_bar(bar_id);
+                if (gtid == 0) {
+                    const int cg = c_base + cfirst * 32;
+                    if (EPI != EPI_RAW && PIECES == 2) {               // hi -> buffer 0, lo -> buffer 1, same columns
+                        if (cg < a.C_out) { tma_store_3d(&tmy0, stg, cg, n0, b); tma_store_3d(&tmy1, stg + kStgBuf, cg, n0, b); }
+                    } else {
+                        const int wcols = EPI == EPI_RAW ? 32 : 64;
+                        for (int k = 0; k < n_boxes; ++k)
+                            if (cg + k * wcols < a.C_out) tma_store_3d(&tmy0, stg + (uint32_t)k * kStgBuf, cg + k * wcols, n0, b);
+                    }
+                    tma_store_commit();
+                }
+            };
+            if (staged && nbuf == 2) unit_begin();
             mbar_wait_wd(bar_accfull + 8 * acc, par);
             tc_fence_after();
             const int c_begin = PIECES == 1 ? 0 : 2 * (int)grp, c_end = PIECES == 1 ? LN / 32 : c_begin + 2;
@@ -292,12 +312,14 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
                         for (int e = 0; e < 32; ++e) v[e] *= sc;
                     }
                     if (staged) {
-                        // a chunk of 32 fp32 columns is one 128-byte row of a box: buffer (c & 1) of the group
-                        const uint32_t dst = stg + (uint32_t)(c & 1) * kStgBuf + swz;
+                        // a chunk of 32 fp32 columns is one 128-byte row of a box: buffer (c & 1) of the group (or its only one)
+                        if (nbuf == 1) unit_begin();
+                        const uint32_t dst = stg + (nbuf == 2 ? (uint32_t)(c & 1) : 0u) * kStgBuf + swz;
 #pragma unroll
                         for (uint32_t j = 0; j < 8; ++j)
                             st_shared_v4(dst + ((j ^ rx) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
                                          __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+                        if (nbuf == 1) unit_end(c, 1);
                     } else if (valid) {
                         float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(a.y0) + grow * a.C_out + col0);
 #pragma unroll
@@ -328,11 +350,13 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
                     // bf16: the tile's two 64-column halves go to buffers 0 / 1; fp16: hi -> buffer 0, lo -> buffer 1
                     const uint32_t j0 = 4u * (uint32_t)(c & 1);
                     if (PIECES == 1) {
-                        const uint32_t dst = stg + (uint32_t)(c >> 1) * kStgBuf + swz;
+                        if (nbuf == 1 && (c & 1) == 0) unit_begin();
+                        const uint32_t dst = stg + (nbuf == 2 ? (uint32_t)(c >> 1) : 0u) * kStgBuf + swz;
 #pragma unroll
                         for (uint32_t e8 = 0; e8 < 4; ++e8)
                             st_shared_v4(dst + (((j0 + e8) ^ rx) << 4), pack_bf16x2(v[8 * e8], v[8 * e8 + 1]), pack_bf16x2(v[8 * e8 + 2], v[8 * e8 + 3]),
                                          pack_bf16x2(v[8 * e8 + 4], v[8 * e8 + 5]), pack_bf16x2(v[8 * e8 + 6], v[8 * e8 + 7]));
+                        if (nbuf == 1 && (c & 1) == 1) unit_end(c - 1, 1);
                     } else {
 #pragma unroll
                         for (uint32_t e8 = 0; e8 < 4; ++e8) {
@@ -367,24 +391,7 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
             }
             tc_fence_before();
             mbar_arrive(bar_accempty + 8 * acc);                       // the accumulator goes back to the issuer
-            if (staged) {
-                fence_async_proxy();                                   // the staged rows become visible to the TMA engine
-                group_bar(bar_id);
-                if (gtid == 0) {
-                    const int cg = c_base + c_begin * 32;              // first column this group wrote
-                    if (EPI == EPI_RAW) {
-                        if (cg < a.C_out) tma_store_3d(&tmy0, stg, cg, n0, b);
-                        if (cg + 32 < a.C_out) tma_store_3d(&tmy0, stg + kStgBuf, cg + 32, n0, b);
-                    } else if (PIECES == 1) {
-                        if (cg < a.C_out) tma_store_3d(&tmy0, stg, cg, n0, b);
-                        if (cg + 64 < a.C_out) tma_store_3d(&tmy0, stg + kStgBuf, cg + 64, n0, b);
-                    } else if (cg < a.C_out) {
-                        tma_store_3d(&tmy0, stg, cg, n0, b);
-                        tma_store_3d(&tmy1, stg + kStgBuf, cg, n0, b);
-                    }
-                    tma_store_commit();
-                }
-            }
+            if (staged && nbuf == 2) unit_end(c_begin, 2);
         }
         if (staged && gtid == 0) tma_store_wait_all();                 // the staging buffers must outlive their stores
     }
@@ -503,8 +510,13 @@ int launch_layer_gemm(const GemmCall &g, int sms, cudaStream_t st) {
     const size_t w_bytes = (size_t)pieces * kblocks * LN * 128, stage_bytes = (size_t)pieces * kLBlk;
     const size_t budget = 226u * 1024u - 256u;             // 227 KB per CTA minus the alignment slack and the barriers
     // outputs through shared-memory staging + TMA stores when the staging buffers leave room for a two-stage X ring
-    a.tma_store = g.epi != EPI_POOL && (long long)budget - (long long)w_bytes - (long long)kStgBytes >= 2 * (long long)stage_bytes ? 1 : 0;
-    const size_t stg_bytes = a.tma_store ? kStgBytes : 0;
+    a.tma_store = 0;
+    if (g.epi != EPI_POOL) {
+        const long long room = (long long)budget - (long long)w_bytes - 2 * (long long)stage_bytes;
+        if (room >= (long long)kStgBytes) a.tma_store = 2;
+        else if (room >= (long long)kStgBytes / 2 && !(g.epi == EPI_ACT && pieces == 2)) a.tma_store = 1;   // hi + lo need two
+    }
+    const size_t stg_bytes = (size_t)a.tma_store * 2 * kStgBuf;
     long long stages = ((long long)budget - (long long)w_bytes - (long long)stg_bytes) / (long long)stage_bytes;
     if (stages < 2) return fail(RLG_ERR_UNSUPPORTED, "encoder_layer_kernel: K=%d does not fit in shared memory", g.K);
     if (stages > kLMaxStages) stages = kLMaxStages;
