@@ -15,9 +15,11 @@
 //                           through a ring of 64-channel K blocks; the elected MMA thread issues tcgen05.mma from the
 //                           landed blocks into TMEM; two groups of four epilogue warps pull the accumulators back
 //                           (tcgen05.ld), apply scale + bias + ReLU and either write the next layer's operand rows (64
-//                           contiguous bytes per thread and piece) or, for the last layer, reduce the max over the
-//                           tile's points (REDUX on the bit patterns: post-ReLU values are >= 0) and merge it into the
-//                           pooled output with atomicMax -- the (B, C_last, N) activation never exists.
+//                           contiguous bytes per thread and piece, staged in shared memory and written by TMA tensor
+//                           stores) or, for the last layer, take the max over the tile's points: there the MMA operands
+//                           are swapped (channels on the TMEM lanes, points along the columns), so it is a per-thread
+//                           running max merged into the pooled output with one atomicMax per channel and tile -- the
+//                           (B, C_last, N) activation never exists.
 //
 // Two operand formats (mode):
 //   RLG_ENC_BF16   bf16 activations and weights, fp32 accumulation: 2e-2 class (north_star's bf16 clause)
@@ -199,8 +201,13 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) {
                             const uint64_t ko = (uint64_t)(k4 * 2);
-                            tc_mma_bf16(dx, x0 + xp + ko, w0 + ko, idesc_neg, accum);         // -(lo . hi)
-                            tc_mma_bf16(dx, x0 + ko, w0 + wp + ko, idesc_neg, 1u);            // -(hi . lo)
+                            if (EPI == EPI_POOL) {                                            // channels on the TMEM lanes
+                                tc_mma_bf16(dx, w0 + ko, x0 + xp + ko, idesc_neg, accum);
+                                tc_mma_bf16(dx, w0 + wp + ko, x0 + ko, idesc_neg, 1u);
+                            } else {
+                                tc_mma_bf16(dx, x0 + xp + ko, w0 + ko, idesc_neg, accum);     // -(lo . hi)
+                                tc_mma_bf16(dx, x0 + ko, w0 + wp + ko, idesc_neg, 1u);        // -(hi . lo)
+                            }
                             accum = 1;
                         }
                         used |= 8u;
@@ -208,12 +215,15 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4, ++ks) {    // 16 elements = 32 bytes per MMA along K
                         const uint64_t ko = (uint64_t)(k4 * 2);
+                        // EPI_POOL: operands swapped (A = weights): the accumulator holds channels on the TMEM lanes and the
+                        // tile's points along the columns, so the max over the points is a per-thread running max
+                        const uint64_t da = EPI == EPI_POOL ? w0 + ko : x0 + ko, db = EPI == EPI_POOL ? x0 + ko : w0 + ko;
                         if (PIECES == 1) {
-                            tc_mma_bf16(d, x0 + ko, w0 + ko, idesc, accum);
+                            tc_mma_bf16(d, da, db, idesc, accum);
                             accum = 1;
                         } else {
                             const uint32_t m = min(3u, ks / q_steps);
-                            tc_mma_bf16(base + m * (uint32_t)LN, x0 + ko, w0 + ko, (m & 1u) ? idesc_neg : idesc, (used >> m) & 1u);   // +-(hi . hi)
+                            tc_mma_bf16(base + m * (uint32_t)LN, da, db, (m & 1u) ? idesc_neg : idesc, (used >> m) & 1u);   // +-(hi . hi)
                             used |= 1u << m;
                         }
                     }
@@ -279,6 +289,45 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
             mbar_wait_wd(bar_accfull + 8 * acc, par);
             tc_fence_after();
             const int c_begin = PIECES == 1 ? 0 : 2 * (int)grp, c_end = PIECES == 1 ? LN / 32 : c_begin + 2;
+            if (POOL) {
+                // this thread = output channel c_base + row; columns = the tile's points (rows past the end of the cloud
+                // came in as zeros and are masked out); bias and ReLU commute with the max and are applied once
+                const int n_valid = min(kLT, a.N - n0);
+                float mx = -INFINITY;
+#pragma unroll 1
+                for (int c = c_begin; c < c_end; ++c) {
+                    const int nv = n_valid - c * 32;
+                    if (nv <= 0) break;                                // warp-uniform
+                    float v[32];
+                    if (PIECES == 1) {
+                        tc_ld32(tbase + (uint32_t)(c * 32), v);
+                    } else {
+                        float v1[32], v2[32], v3[32];
+                        tc_ld32_nowait(tbase + (uint32_t)(c * 32), v);
+                        tc_ld32_nowait(tbase + (uint32_t)LN + (uint32_t)(c * 32), v1);
+                        tc_ld32_nowait(tbase + 2u * (uint32_t)LN + (uint32_t)(c * 32), v2);
+                        tc_ld32_nowait(tbase + 3u * (uint32_t)LN + (uint32_t)(c * 32), v3);
+                        tc_wait_ld(v); tc_wait_ld(v1); tc_wait_ld(v2); tc_wait_ld(v3);
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) v[e] = ((v[e] - v1[e]) + v2[e]) - v3[e];
+                    }
+                    if (nv >= 32) {
+#pragma unroll
+                        for (int e = 0; e < 32; e += 2) mx = max3(mx, v[e], v[e + 1]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, e < nv ? v[e] : -INFINITY);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(bar_accempty + 8 * acc);
+                const int ch = c_base + row;
+                if (ch < a.C_out && mx > -INFINITY) {
+                    const float val = fmaxf(fmaf(mx, sc, __ldg(a.bias + ch)), 0.0f);
+                    if (val > 0.0f) atomicMax(reinterpret_cast<unsigned *>(a.pooled) + (size_t)b * a.C_out + ch, __float_as_uint(val));
+                }
+                continue;
+            }
 #pragma unroll 1
             for (int c = c_begin; c < c_end; ++c) {
                 const int col0 = c_base + c * 32;
@@ -336,16 +385,7 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_cons
                     v[4 * e4 + 2] = fmaxf(fmaf(v[4 * e4 + 2], sc, bb.z), 0.0f);
                     v[4 * e4 + 3] = fmaxf(fmaf(v[4 * e4 + 3], sc, bb.w), 0.0f);
                 }
-                if (POOL) {
-                    // max over the 32 points of this warp per channel; lane e keeps channel e's result
-                    unsigned keep = 0;
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const unsigned r = __reduce_max_sync(0xffffffffu, valid ? __float_as_uint(v[e]) : 0u);
-                        keep = (lane == e) ? r : keep;
-                    }
-                    if (keep != 0) atomicMax(reinterpret_cast<unsigned *>(a.pooled) + (size_t)b * a.C_out + col0 + lane, keep);
-                } else if (staged) {
+                if (staged) {
                     // 32 columns of 2-byte elements = 64 bytes = half a box row: 16-byte chunks 4 * (c & 1) .. + 3.
                     // bf16: the tile's two 64-column halves go to buffers 0 / 1; fp16: hi -> buffer 0, lo -> buffer 1
                     const uint32_t j0 = 4u * (uint32_t)(c & 1);
