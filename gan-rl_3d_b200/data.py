@@ -49,10 +49,12 @@ def rotation_matrix(theta: Sequence[float]) -> np.ndarray:
 
 
 def draw_plan(rng: np.random.Generator, B: int, N: int, items: Optional[np.ndarray] = None, augment: bool = True,
-              jitter_sigma: float = 0.01, jitter_clip: float = 0.05) -> Dict[str, np.ndarray]:
+              jitter_sigma: float = 0.01, jitter_clip: float = 0.05, host_jitter: bool = False) -> Dict[str, np.ndarray]:
     """The random decisions of one batch as host arrays (see struct rlg_prepare_plan), drawn with the reference's
     distributions: utils/dataset.py:255-266 (removal), :284-294 (augmentation, independently for the complete and the
-    incomplete cloud), :408 (padding indices)."""
+    incomplete cloud), :408 (padding indices).  The jitter noise itself (2 x B x N x 3 normals, the bulk of the draws) is
+    made on the device by DeviceBatcher from the per-cloud on/off flags `jitter_on` unless host_jitter=True puts the
+    clipped noise into the plan (tests feed the same noise to the restated reference that way)."""
     plan = {"item": (np.arange(B) if items is None else np.asarray(items)).astype(np.int32),
             "method": np.zeros(B, np.int32), "n_keep": np.zeros(B, np.int32), "keep_idx": np.zeros((B, N), np.int32),
             "center": np.zeros(B, np.int32), "q_index": np.zeros(B, np.int32), "q_gamma": np.zeros(B, np.float64),
@@ -73,16 +75,21 @@ def draw_plan(rng: np.random.Generator, B: int, N: int, items: Optional[np.ndarr
     if augment:
         rot = np.tile(np.eye(3, dtype=np.float32).reshape(1, 1, 9), (2, B, 1))
         scale = np.ones((2, B), np.float32)
-        jitter = np.zeros((2, B, N, 3), np.float32)
+        jitter = np.zeros((2, B, N, 3), np.float32) if host_jitter else None
+        jitter_on = np.zeros((2, B), np.bool_)
         for which in range(2):
             for b in range(B):
                 if rng.random() < 0.5:
                     rot[which, b] = rotation_matrix(rng.uniform(0, 2 * np.pi, 3)).astype(np.float32).reshape(9)
                 if rng.random() < 0.5:
-                    jitter[which, b] = np.clip(rng.normal(0.0, jitter_sigma, (N, 3)), -jitter_clip, jitter_clip)
+                    jitter_on[which, b] = True
+                    if host_jitter:
+                        jitter[which, b] = np.clip(rng.normal(0.0, jitter_sigma, (N, 3)), -jitter_clip, jitter_clip)
                 if rng.random() < 0.3:
                     scale[which, b] = rng.uniform(0.8, 1.2)
-        plan.update(rot=rot, scale=scale, jitter=jitter)
+        plan.update(rot=rot, scale=scale, jitter_on=jitter_on, jitter_sigma=jitter_sigma, jitter_clip=jitter_clip)
+        if host_jitter:
+            plan["jitter"] = jitter
     return plan
 
 
@@ -105,6 +112,13 @@ class DeviceBatcher:
             raise IndexError("plan['item'] outside the cache")
         keep = {}
         cp = _lib.RlgPreparePlan()
+        if plan.get("jitter") is None and plan.get("jitter_on") is not None and bool(np.any(plan["jitter_on"])):
+            # the jitter noise of utils/data_utils.py:140-142, drawn on the device (torch's CUDA generator)
+            on = torch.as_tensor(np.ascontiguousarray(plan["jitter_on"])).to(dev, non_blocking=True)
+            noise = torch.randn((2, B, N, 3), dtype=torch.float32, device=dev).mul_(float(plan["jitter_sigma"]))
+            noise.clamp_(-float(plan["jitter_clip"]), float(plan["jitter_clip"])).mul_(on[:, :, None, None])
+            keep["jitter"] = noise
+            cp.jitter = noise.data_ptr()
         for name, dtype in (("item", np.int32), ("method", np.int32), ("n_keep", np.int32), ("keep_idx", np.int32),
                             ("center", np.int32), ("q_index", np.int32), ("q_gamma", np.float64), ("rot", np.float32),
                             ("scale", np.float32), ("jitter", np.float32), ("pad_idx", np.int32)):

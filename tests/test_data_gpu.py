@@ -40,7 +40,7 @@ def test_batches_match_the_restated_reference(rlg, N, B, augment):
     cache = rlg.build_cache([rng.normal(size=(N + (7 if k % 2 else -5), 3)) * rng.uniform(0.3, 3.0) + rng.normal(size=3)
                              for k in range(B + 3)], num_points=N, seed=1)
     assert cache.shape == (B + 3, N, 3) and cache.dtype == np.float32
-    plan = rlg.draw_plan(rng, B, N, items=rng.permutation(B + 3)[:B], augment=augment)
+    plan = rlg.draw_plan(rng, B, N, items=rng.permutation(B + 3)[:B], augment=augment, host_jitter=True)
     assert set(np.unique(plan["method"])) <= {0, 1}
     batch = rlg.DeviceBatcher(cache, DEV).make_batch(plan)
     want_c, want_i, want_len = _expected(cache, plan)
@@ -74,3 +74,25 @@ def test_spatial_removal_keeps_exactly_the_reference_points(rlg):
     want_c, want_i, want_len = _expected(base, plan)
     assert np.array_equal(batch["lengths"].cpu().numpy(), want_len)
     assert np.abs(batch["incomplete_pc"].cpu().numpy() - want_i).max() <= 2e-6
+
+
+def test_device_drawn_jitter_is_clipped_noise_on_the_flagged_clouds(rlg):
+    """Without host noise in the plan the batcher draws the jitter on the device: clouds whose flag is off come out exactly as
+    without augmentation noise, flagged ones differ by at most the clip (before normalisation the noise is <= 0.05)."""
+    N, B = 256, 6
+    rng = np.random.default_rng(11)
+    cache = rng.normal(size=(B, N, 3)).astype(np.float32)
+    plan = rlg.draw_plan(rng, B, N)
+    plan["rot"][:] = np.eye(3, dtype=np.float32).reshape(9)
+    plan["scale"][:] = 1.0
+    plan["jitter_on"][0] = [True, False, True, False, True, False]
+    plan["jitter_on"][1] = False
+    noisy = rlg.DeviceBatcher(cache, DEV).make_batch(plan)["complete_pc"].cpu().numpy()
+    quiet_plan = dict(plan)
+    quiet_plan["jitter_on"] = np.zeros((2, B), np.bool_)
+    quiet = rlg.DeviceBatcher(cache, DEV).make_batch(quiet_plan)["complete_pc"].cpu().numpy()
+    for b in range(B):
+        if plan["jitter_on"][0, b]:
+            assert 0 < np.abs(noisy[b] - quiet[b]).max() < 0.2
+        else:
+            assert np.array_equal(noisy[b], quiet[b])

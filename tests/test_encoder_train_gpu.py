@@ -249,3 +249,61 @@ def test_golden_train_step_from_reference(rlg):
             assert int(b) == int(g[f"after_{n}"]), n
         else:
             assert _max_rel(b.cpu(), g[f"after_{n}"]) <= OUT_TOL, n
+
+
+def _custom_trunk(dims, bias=True, affine=True, momentum=0.1):
+    import torch.nn as nn
+
+    class Enc(nn.Module):
+        def __init__(self):
+            super().__init__()
+            seq, c_in = [], 3
+            for c in dims:
+                seq += [nn.Conv1d(c_in, c, 1, bias=bias), nn.BatchNorm1d(c, affine=affine, momentum=momentum), nn.ReLU(inplace=True)]
+                c_in = c
+            self.point_mlp = nn.Sequential(*seq)
+            self.global_mlp = nn.Sequential(nn.Linear(c_in, 16), nn.BatchNorm1d(16), nn.ReLU(inplace=True))
+    return Enc()
+
+
+@pytest.mark.parametrize("bias,affine", [(False, True), (True, False), (False, False)])
+@pytest.mark.parametrize("B,N", [(5, 1), (2, 37), (40, 9)])
+def test_modules_without_conv_bias_or_affine_batchnorm(rlg, bias, affine, B, N):
+    """Conv1d(bias=False) and BatchNorm1d(affine=False) blocks, single-point and tiny clouds: same contract."""
+    for seed in range(200):
+        torch.manual_seed(70 + seed)
+        enc = _custom_trunk([64, 128, 64], bias, affine).train()
+        x = O.make_clouds(B, N, "uniform", 300 + seed)
+        if _smallest_margin(enc, x, True) > SAFE_MARGIN:
+            break
+    assert rlg.train_supported(enc.to(DEV).point_mlp)
+    enc = enc.cpu()
+    g = torch.randn(B, 64, generator=torch.Generator().manual_seed(8))
+    ours, branch = _run_ours(rlg, enc, x, g, True)
+    truth = _truth(enc, x, g, True)
+    assert _branch_is_legitimate(branch, truth[3]) == 0
+    _compare(ours, truth, True)
+
+
+def test_inputs_outside_the_train_kernels_keep_the_stock_layers(rlg):
+    """x.requires_grad, BatchNorm(momentum=None) and widths the kernels do not cover go to the module's own layers: same
+    results as the stock forward, gradients still reach x."""
+    x = O.make_clouds(3, 50, "sphere", 1).to(DEV)
+    enc = _port([64, 128, 64], 16, 2).to(DEV).train()
+    xg = x.clone().requires_grad_(True)
+    out = rlg.fused_forward(enc, xg)
+    out.sum().backward()
+    assert xg.grad is not None and float(xg.grad.abs().max()) > 0
+    cum = _custom_trunk([64, 64], momentum=None).to(DEV).train()
+    assert not rlg.train_supported(cum.point_mlp)
+    assert rlg.fused_forward(cum, x).shape == (3, 16)
+    assert int(cum.point_mlp[1].num_batches_tracked) == 1                  # the stock layers ran (cumulative average)
+    wide = _custom_trunk([64, 512]).to(DEV).train()
+    assert not rlg.train_supported(wide.point_mlp)
+    assert rlg.fused_forward(wide, x).requires_grad
+    rlg.set_train_path(False)
+    try:
+        a = _port([64, 128, 64], 16, 2).to(DEV).train()
+        assert "EncoderTrainFn" not in type(rlg.fused_forward(a, x).grad_fn).__name__
+    finally:
+        rlg.set_train_path(True)
