@@ -106,6 +106,13 @@ CHAMFER_TILE_ONLY = 4
 CHAMFER_ALGO_TENSOR = 16
 CHAMFER_TRACK_TWO = 32
 CHAMFER_FILTER_ONLY = 64
+
+
+def chamfer_reserve_sms(n: int) -> int:
+    """RLG_CHAMFER_RESERVE_SMS(n)"""
+    return (int(n) & 0xff) << 16
+
+
 # experiments build only (librlg_b200_exp.so, tools/): kernel variants in bits 8-11, first-generation tensor sweep
 X_CHAMFER_TENSOR_V1 = 128
 CHAMFER_BWD_ACCUMULATE = 1

@@ -78,6 +78,22 @@ if _DEFAULT_SWEEP not in ("fp32", "tensor", "auto"):
     raise ValueError("RLG_CHAMFER_SWEEP must be fp32, tensor or auto")
 
 
+_RESERVED_SMS = 0
+
+
+def set_reserved_sms(n: int) -> None:
+    """SMs the persistent Chamfer forward leaves free (RLG_CHAMFER_RESERVE_SMS): 1 when NCCL kernels run beside it (one
+    process per GPU with per-step collectives on a side stream; distributed.init_from_env sets it), 0 otherwise."""
+    global _RESERVED_SMS
+    if not 0 <= int(n) <= 255:
+        raise ValueError("reserved SMs must be in 0..255")
+    _RESERVED_SMS = int(n)
+
+
+def get_reserved_sms() -> int:
+    return _RESERVED_SMS
+
+
 def set_default_sweep(kind: str) -> None:
     """Which kernel sweeps the N x M pairs when chamfer_nearest() is not told explicitly:
     'fp32'   the FP32-pipe filter + refinement kernel (chamfer_filter.cu),
@@ -147,7 +163,7 @@ def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = Tru
             if ws.clean:
                 flags |= _lib.CHAMFER_WS_CLEAN
             if _use_tensor(tensor, N, M):
-                flags |= _lib.CHAMFER_ALGO_TENSOR
+                flags |= _lib.CHAMFER_ALGO_TENSOR | _lib.chamfer_reserve_sms(_RESERVED_SMS)
                 if track_two:
                     flags |= _lib.CHAMFER_TRACK_TWO
         was_clean = ws.clean

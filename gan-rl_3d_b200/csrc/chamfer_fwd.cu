@@ -108,7 +108,7 @@ int rlg_chamfer_loss_fwd(const float *pc1, const float *pc2, int B, int N, int M
                          int32_t *i1, int32_t *i2, float *mean1, float *mean2, float *loss, float w1, float w2,
                          float *gz1, float *gz2, void *ws, size_t ws_bytes, unsigned flags, void *stream) {
     unsigned known = RLG_CHAMFER_WS_CLEAN | RLG_CHAMFER_ALGO_SIMPLE | RLG_CHAMFER_TILE_ONLY | RLG_CHAMFER_ALGO_TENSOR |
-                     RLG_CHAMFER_TRACK_TWO | RLG_CHAMFER_FILTER_ONLY;
+                     RLG_CHAMFER_TRACK_TWO | RLG_CHAMFER_FILTER_ONLY | RLG_CHAMFER_RESERVE_SMS(0xff);
 #ifdef RLG_EXPERIMENTS
     known |= (15u << 8) | RLG_X_CHAMFER_TENSOR_V1;
 #endif
@@ -166,7 +166,8 @@ int rlg_chamfer_loss_fwd(const float *pc1, const float *pc2, int B, int N, int M
     if (flags & RLG_CHAMFER_ALGO_TENSOR) {
         // one launch does everything: RLG_CHAMFER_TILE_ONLY changes nothing here
         return launch_tcsweep(pc1, pc2, B, N, M, w, fin_tc, d1, d2, i1, i2, mean1, mean2, loss, w1, w2, gz1, gz2,
-                              (flags & RLG_CHAMFER_FILTER_ONLY) != 0, (flags & RLG_CHAMFER_TRACK_TWO) != 0, st);
+                              (flags & RLG_CHAMFER_FILTER_ONLY) != 0, (flags & RLG_CHAMFER_TRACK_TWO) != 0,
+                              (int)((flags >> 16) & 0xffu), st);
     }
     if (flags & (RLG_CHAMFER_TRACK_TWO | RLG_CHAMFER_FILTER_ONLY))
         return fail(RLG_ERR_UNSUPPORTED, "rlg_chamfer_fwd: RLG_CHAMFER_TRACK_TWO / FILTER_ONLY need RLG_CHAMFER_ALGO_TENSOR");

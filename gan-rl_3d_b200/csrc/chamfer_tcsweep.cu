@@ -871,14 +871,15 @@ size_t tcsweep_ws_bytes(int B, int N, int M) {
 // filter_only: diagnostic -- the filter sweep alone, its per-query results published to w.rowkey/colkey/rowsec/colsec
 int launch_tcsweep(const float *pc1, const float *pc2, int B, int N, int M, const FwdWs &w, void *fin_ws,
                    float *d1, float *d2, int32_t *i1, int32_t *i2, float *mean1, float *mean2, float *loss, float w1,
-                   float w2, float *zero1, float *zero2, bool filter_only, bool force_top3, cudaStream_t st) {
+                   float w2, float *zero1, float *zero2, bool filter_only, bool force_top3, int reserve_sms, cudaStream_t st) {
     const int qb1 = (N + kTQ - 1) / kTQ, qb2 = (M + kTQ - 1) / kTQ;
     const long long n_tasks = (long long)B * (qb1 + qb2);
     if (n_tasks > 0x3fffffffLL) return fail(RLG_ERR_TOO_LARGE, "rlg_chamfer_fwd: too many query blocks");
     if ((long long)qb1 * (long long)((M + kTC - 1) / kTC) * B > 0x3fffffffLL || (long long)qb2 * (long long)((N + kTC - 1) / kTC) * B > 0x3fffffffLL)
         return fail(RLG_ERR_TOO_LARGE, "rlg_chamfer_fwd: too many tile visits for 32-bit counters");
-    const int sms = sm_count();
+    int sms = sm_count();
     if (sms <= 0) return fail((int)cudaErrorNoDevice, "rlg_chamfer_fwd: no CUDA device");
+    if (reserve_sms > 0) sms = sms - reserve_sms > 1 ? sms - reserve_sms : 1;    // leave SMs to co-running communication kernels
     // Ambiguous points (runner-up group within the margin) cost a scan of the whole candidate cloud unless the sweep
     // tracks three groups; their share grows with the point density.  Break-even is around 4096 candidates.
     const bool top3 = force_top3 || N > 4096 || M > 4096;

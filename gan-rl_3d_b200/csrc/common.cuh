@@ -67,7 +67,7 @@ int launch_filter(const float *pc1, const float *pc2, int B, int N, int M, int v
 size_t tcsweep_ws_bytes(int B, int N, int M);
 int launch_tcsweep(const float *pc1, const float *pc2, int B, int N, int M, const FwdWs &w, void *fin_ws,
                    float *d1, float *d2, int32_t *i1, int32_t *i2, float *mean1, float *mean2, float *loss, float w1,
-                   float w2, float *zero1, float *zero2, bool filter_only, bool force_top3, cudaStream_t st);
+                   float w2, float *zero1, float *zero2, bool filter_only, bool force_top3, int reserve_sms, cudaStream_t st);
 #ifdef RLG_EXPERIMENTS
 // experiments build only (build.py --experiments): flag bits of rlg_chamfer_fwd that select measurement variants
 #define RLG_X_CHAMFER_TENSOR_V1   128u     // first-generation tensor sweep (chamfer_tcfilter.cu) + separate finalize

@@ -777,7 +777,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restri
 
 // ---- host side --------------------------------------------------------------------------------------------------------
 static int train_check(const char *fn, const rlg_bn_layer *layers, int L, unsigned flags) {
-    if (flags & ~RLG_ENC_BATCH_STATS) return fail(RLG_ERR_UNSUPPORTED, "%s: unknown flag bits 0x%x", fn, flags);
+    if (flags & ~(RLG_ENC_BATCH_STATS | RLG_ENC_RESERVE_SMS(0xff))) return fail(RLG_ERR_UNSUPPORTED, "%s: unknown flag bits 0x%x", fn, flags);
     if (!layers || L < 2 || L > kTMaxLayers) return fail(RLG_ERR_UNSUPPORTED, "%s: need 2..%d layers, got %d", fn, kTMaxLayers, L);
     if (layers[0].c_in != 3) return fail(RLG_ERR_UNSUPPORTED, "%s: layer 0 must have c_in == 3", fn);
     for (int l = 0; l < L; ++l) {
@@ -897,10 +897,12 @@ int rlg_encoder_train_fwd(const float *x, int B, int N, const rlg_bn_layer *laye
     if (batch && P < 2) return fail(RLG_ERR_BAD_SHAPE, "%s: batch statistics need more than one point per channel", fn);
     if (P > 0x7fffffffLL / 256) return fail(RLG_ERR_TOO_LARGE, "%s: B*N too large", fn);
     if (!x || !pooled) return fail(RLG_ERR_NULL_POINTER, "%s: null pointer", fn);
-    const int sms = sm_count();
-    if (sms <= 0) return fail((int)cudaErrorNoDevice, "%s: no CUDA device", fn);
+    const int sms_all = sm_count();
+    if (sms_all <= 0) return fail((int)cudaErrorNoDevice, "%s: no CUDA device", fn);
+    const int reserve = (int)((flags >> 16) & 0xffu);
+    const int sms = sms_all - reserve > 1 ? sms_all - reserve : 1;          // grids of the persistent kernels
     const SavedLayout sl = saved_layout(P, B, layers, L);
-    const WsLayout wl = ws_layout(P, layers, L, sms);
+    const WsLayout wl = ws_layout(P, layers, L, sms_all);
     if (!saved || saved_bytes < sl.total || ((uintptr_t)saved & 255u))
         return fail(RLG_ERR_WORKSPACE, "%s: saved buffer %p/%zu bytes, need %zu bytes 256-B aligned", fn, saved, saved_bytes, sl.total);
     if (!ws || ws_bytes < wl.total || ((uintptr_t)ws & 255u))
@@ -971,10 +973,12 @@ int rlg_encoder_train_bwd(const float *x, int B, int N, const rlg_bn_layer *laye
     const long long P = (long long)B * N;
     if (P > 0x7fffffffLL / 256) return fail(RLG_ERR_TOO_LARGE, "%s: B*N too large", fn);
     if (!x || !g_pooled || !grads) return fail(RLG_ERR_NULL_POINTER, "%s: null pointer", fn);
-    const int sms = sm_count();
-    if (sms <= 0) return fail((int)cudaErrorNoDevice, "%s: no CUDA device", fn);
+    const int sms_all = sm_count();
+    if (sms_all <= 0) return fail((int)cudaErrorNoDevice, "%s: no CUDA device", fn);
+    const int reserve = (int)((flags >> 16) & 0xffu);
+    const int sms = sms_all - reserve > 1 ? sms_all - reserve : 1;          // grids of the persistent kernels
     const SavedLayout sl = saved_layout(P, B, layers, L);
-    const WsLayout wl = ws_layout(P, layers, L, sms);
+    const WsLayout wl = ws_layout(P, layers, L, sms_all);
     if (!saved || saved_bytes < sl.total || ((uintptr_t)saved & 255u))
         return fail(RLG_ERR_WORKSPACE, "%s: saved buffer %p/%zu bytes, need %zu bytes 256-B aligned", fn, saved, saved_bytes, sl.total);
     if (!ws || ws_bytes < wl.total || ((uintptr_t)ws & 255u))

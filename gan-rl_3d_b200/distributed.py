@@ -33,6 +33,10 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
                                     device_id=torch.device("cuda", local_rank))
         else:
             dist.init_process_group(backend, rank=rank, world_size=world)
+    if world > 1 and torch.cuda.is_available():
+        # NCCL kernels of the per-step collectives run beside the persistent Chamfer forward: leave them an SM
+        from .chamfer import set_reserved_sms
+        set_reserved_sms(1)
     return rank, local_rank, world
 
 

@@ -98,7 +98,8 @@ class EncoderTrainFn(torch.autograd.Function):
         arr, keep = _layer_structs(pairs, params)
         L = len(pairs)
         dev = x.device
-        flags = _lib.ENC_BATCH_STATS if batch_stats else 0
+        from .chamfer import get_reserved_sms
+        flags = (_lib.ENC_BATCH_STATS if batch_stats else 0) | ((get_reserved_sms() & 0xff) << 16)
         pooled = torch.empty((B, pairs[-1][0].out_channels), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream

@@ -467,3 +467,18 @@ def test_sweeps_alternate_on_one_workspace(rlg):
         assert np.array_equal(d1, want[0]) and np.array_equal(i2, want[3])
         np.testing.assert_allclose(m1, w1, rtol=2e-7)
         np.testing.assert_allclose(m2, w2, rtol=2e-7)
+
+
+def test_reserved_sms_change_nothing_but_the_grid(rlg):
+    """RLG_CHAMFER_RESERVE_SMS (set by distributed.init_from_env for multi-GPU runs): a smaller persistent grid, same bits."""
+    pc1, pc2 = O.make_clouds(9, 700, "sphere", 31), O.make_clouds(9, 1300, "uniform", 32)
+    want = _run(rlg, pc1, pc2)
+    try:
+        for n in (1, 7, 147, 200):
+            rlg.set_reserved_sms(n)
+            got = _run(rlg, pc1, pc2)
+            assert all(np.array_equal(g, w) for g, w in zip(got, want)), n
+    finally:
+        rlg.set_reserved_sms(0)
+    with pytest.raises(ValueError):
+        rlg.set_reserved_sms(300)
