@@ -68,6 +68,12 @@ namespace rlg {
 #ifndef RLG_TS_ISSUERS
 #define RLG_TS_ISSUERS 1
 #endif
+// experiments only (tools/ A-B builds, wrong results): knock out parts of the tail to time them -- 1: the per-query
+// refinement, 2: the ambiguous scans, 4: the means / loss reduction
+#if !defined(RLG_EXPERIMENTS) || !defined(RLG_TS_KO)
+#undef RLG_TS_KO
+#define RLG_TS_KO 0
+#endif
 constexpr int kTQ = 128;                       // queries per block (UMMA M)
 constexpr int kTC = 256;                       // candidates per tile (two UMMA N = 128 halves)
 constexpr int kQmax = 8;                       // query blocks that share one pass over the candidate tiles
@@ -764,8 +770,8 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
                 const int qq = slot + 4 * r;
                 const int i = (sg.qb0 + qq) * kTQ + row;
                 if (qq < sg.Q) {
-                    if (i < sg.nq) refine_query<TOP3>(qc, cc, raw, sg.nc, i, mk1[r], mk2[r], mt3[r], dout, iout, zero,
-                                                      qq * kTQ + row, s_dist, s_amb, &s_namb);
+                    if (i < sg.nq && !(RLG_TS_KO & 1)) refine_query<TOP3>(qc, cc, raw, sg.nc, i, mk1[r], mk2[r], mt3[r], dout, iout, zero,
+                                                                          qq * kTQ + row, s_dist, s_amb, &s_namb);
                     else s_dist[qq * kTQ + row] = 0.0f;                 // rows past the end of the cloud add nothing
                 }
             }
@@ -773,7 +779,7 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
             // ---- ambiguous queries: the whole candidate cloud is scanned exactly -- one warp per query from the staged
             // copy, all epilogue threads per query when the cloud is read from global memory
             {
-                const int n_amb = (int)s_namb;
+                const int n_amb = (RLG_TS_KO & 2) ? 0 : (int)s_namb;
                 if (raw != nullptr) {
                     const int npos = ((sg.nc + kGroup - 1) / kGroup) * kGroup;
                     for (int a = warp; a < n_amb; a += kEpWarps) {
@@ -805,7 +811,7 @@ chamfer_tcsweep_kernel(const float *__restrict__ pc1, const float *__restrict__ 
             if (Cfg::kRawMax > 0) mbar_arrive(bar_rawempty);                // done with this segment's raw copy
             // ---- means and loss: warp w sums query block w of the segment; whoever completes the unit reduces its
             // partial sums to the mean; whoever completes the last unit reduces the means to the loss (fixed orders)
-            if (o.mean1 != nullptr && warp < sg.Q) {
+            if (o.mean1 != nullptr && warp < sg.Q && !(RLG_TS_KO & 4)) {
                 const float *dv = s_dist + warp * kTQ;
                 double acc = ((double)dv[lane] + (double)dv[lane + 32]) + ((double)dv[lane + 64] + (double)dv[lane + 96]);
 #pragma unroll
