@@ -33,11 +33,45 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
                                     device_id=torch.device("cuda", local_rank))
         else:
             dist.init_process_group(backend, rank=rank, world_size=world)
+    if world > 1 and torch.cuda.is_available() and os.environ.get("RLG_NUMA_BIND", "1") != "0":
+        bind_to_local_numa_node(local_rank)
     if world > 1 and torch.cuda.is_available():
         # NCCL kernels of the per-step collectives run beside the persistent Chamfer forward: leave them an SM
         from .chamfer import set_reserved_sms
-        set_reserved_sms(1)
+        set_reserved_sms(int(os.environ.get("RLG_RESERVED_SMS", "1")))
     return rank, local_rank, world
+
+
+def bind_to_local_numa_node(local_rank: int) -> Optional[int]:
+    """Best effort: pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE it allocates pinned host
+    buffers (Linux places pages on the node of the first touch).  With eight ranks feeding their GPUs from one host every
+    step, pinned rings on the wrong socket send each transfer across the inter-socket link (the end-to-end path at 8 GPUs
+    is host-bound: ~26 GB/s per GPU).  Returns the node, or None when the topology cannot be read."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(visible.split(",")[local_rank]) if visible and visible.split(",")[local_rank].isdigit() else local_rank
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:                       # nvml prints an 8-digit PCI domain, sysfs uses 4
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
 
 
 def shard_bounds(n_items: int, rank: int, world: int) -> Tuple[int, int]:
