@@ -150,3 +150,49 @@ def test_standalone_encoder_has_reference_state_dict_layout(rlg):
     port.load_state_dict(ours.state_dict())
     port.train()
     assert torch.equal(ours(x), port(x))                            # train mode: stock layers, batch statistics
+
+
+def test_input_pipeline_host_side(rlg):
+    """data.build_cache / draw_plan / rotation_matrix: shapes, ranges and the reference's distributions (no GPU needed)."""
+    rng = np.random.default_rng(0)
+    cache = rlg.build_cache([rng.normal(size=(2500, 3)), rng.normal(size=(100, 4)), rng.normal(size=(2048, 3))], num_points=2048)
+    assert cache.shape == (3, 2048, 3) and cache.dtype == np.float32
+    short = rng.normal(size=(100, 4))
+    padded = rlg.build_cache([short], num_points=256, seed=3)[0]
+    assert np.array_equal(padded[:100], short[:, :3].astype(np.float32))          # padded with repeats of its own points
+    assert all(any(np.array_equal(p, q) for q in padded[:100]) for p in padded[100:])
+    B, N = 64, 2048
+    plan = rlg.draw_plan(rng, B, N)
+    assert 0.2 <= plan["ratio"].min() and plan["ratio"].max() <= 0.5               # utils/dataset.py:255
+    for b in range(B):
+        if plan["method"][b] == 0:
+            k = int(plan["n_keep"][b])
+            assert k == int(N * (1 - plan["ratio"][b])) and len(set(plan["keep_idx"][b, :k])) == k      # :256,260
+        else:
+            kq, g = O.percentile_parts(N, float(plan["ratio"][b]))
+            assert plan["q_index"][b] == kq and abs(plan["q_gamma"][b] - g) < 1e-15 and 0 <= plan["center"][b] < N
+    assert plan["rot"].shape == (2, B, 9) and plan["scale"].shape == (2, B) and plan["pad_idx"].min() >= 0
+    assert ((plan["scale"] == 1.0) | ((plan["scale"] >= 0.8) & (plan["scale"] <= 1.2))).all()                 # :292-294
+    for R in plan["rot"].reshape(-1, 3, 3):
+        assert np.allclose(R @ R.T, np.eye(3), atol=1e-6) and abs(np.linalg.det(R) - 1) < 1e-5
+    assert "jitter" not in plan and plan["jitter_on"].dtype == np.bool_
+    th = np.array([0.3, -1.2, 2.5])
+    cx, sx = np.cos(th[0]), np.sin(th[0])
+    assert np.allclose(rlg.data.rotation_matrix(th) @ np.array([1.0, 0, 0]),
+                       rlg.data.rotation_matrix([0, th[1], th[2]]) @ np.array([1.0, 0, 0]))   # Rx leaves the x axis alone
+    assert np.allclose(rlg.data.rotation_matrix([th[0], 0, 0]), [[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+
+
+def test_train_path_selection_on_cpu_modules(rlg):
+    """train_supported is False for modules that are not float32 CUDA modules of the covered widths; fused_forward then
+    runs the module's own layers (train mode on the CPU == the stock forward)."""
+    torch.manual_seed(0)
+    enc = rlg.PointNetEncoder(3, 16, [64, 128]).train()
+    assert not rlg.train_supported(enc.point_mlp)                      # CPU parameters
+    x = torch.randn(4, 50, 3)
+    want = enc.global_mlp(torch.max(enc.point_mlp(x.transpose(2, 1)), dim=2)[0])
+    enc2 = rlg.PointNetEncoder(3, 16, [64, 128]).train()
+    enc2.load_state_dict({k: v for k, v in enc.state_dict().items() if "num_batches" not in k and "running" not in k}, strict=False)
+    got = enc2(x)
+    assert torch.allclose(got, want, atol=1e-6)
+    assert int(enc2.point_mlp[1].num_batches_tracked) == 1             # the stock BatchNorm ran in train mode

@@ -16,7 +16,6 @@ for step in "$@"; do
     variants)  for so in gan-rl_3d_b200/lib/librlg_b200_exp_*.so; do echo "== $so" >> gpurun_out/${T}_variants.log; RLG_EXPERIMENTS_LIB=$PWD/$so timeout 300 python tools/step_breakdown.py 32 2048 2048 sphere tensor >> gpurun_out/${T}_variants.log 2>&1; done ;;
     encoder)   timeout 1500 python -m pytest tests/test_encoder_gpu.py -m gpu -q --maxfail=60 > gpurun_out/${T}_encoder.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_encoder.log ;;
     encprobe)  timeout 900 python tools/encoder_probe.py > gpurun_out/${T}_encprobe.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_encprobe.log ;;
-    aeprobe)   for b in 8 16 32; do timeout 300 python tools/ae_probe.py $b >> gpurun_out/${T}_aeprobe.log 2>&1; done ;;
     train)     timeout 900 python -m pytest tests/test_encoder_train_gpu.py -m gpu -q -s --maxfail=60 > gpurun_out/${T}_train.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_train.log ;;
     trainprobe) timeout 600 python tools/train_probe.py > gpurun_out/${T}_trainprobe.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_trainprobe.log ;;
     aestep)    timeout 900 python -m pytest tests/test_ae_step_gpu.py -m gpu -q -s > gpurun_out/${T}_aestep.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_aestep.log ;;
