@@ -123,6 +123,7 @@ class EncoderTrainFn(torch.autograd.Function):
         return pooled
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         lib = _lib.load()
         x, saved, *present = ctx.saved_tensors
