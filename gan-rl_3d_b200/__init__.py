@@ -35,11 +35,17 @@ from .data import DeviceBatcher, build_cache, draw_plan
 __all__ = ["install", "uninstall", "is_installed", "chamfer_distance_l2", "chamfer_distance", "ChamferLoss",
            "ChamferFn", "ChamferLossFn", "chamfer_nearest", "chamfer_backward", "set_default_sweep", "get_default_sweep", "set_reserved_sms", "get_reserved_sms", "PointNetEncoder", "EncoderTrunkFn", "encoder_pool",
            "fold_trunk", "folded_trunk_cached", "fused_forward", "set_encoder_precision", "get_encoder_precision",
-           "pack_bf16", "pack_gemm", "packed_trunk_cached", "encoder_pool_gemm", "encoder_path_of", "resolve_path", "RewardFunction", "batched_rewards", "library_path", "abi_version",
+           "pack_bf16", "pack_gemm", "packed_trunk_cached", "encoder_pool_gemm", "encoder_path_of", "resolve_path", "RewardFunction", "batched_rewards", "library_path", "abi_version", "set_nvtx",
            "EncoderTrainFn", "train_supported", "trunk_pool_autograd", "set_train_path",
            "AEStepGraph", "PointCloudAutoencoder", "PointNetDecoder", "BatchedRLEnvironment", "DeviceBatcher", "build_cache", "draw_plan"]
 
 _installed = {}
+
+
+def set_nvtx(enabled: bool) -> None:
+    """NVTX ranges (rlg.chamfer_fwd, rlg.chamfer_bwd, rlg.encoder_*, rlg.batch_prepare) around the library calls, for nsys /
+    ncu --nvtx timelines; also RLG_NVTX=1."""
+    _lib.set_nvtx(enabled)
 
 
 def library_path() -> str:

@@ -147,3 +147,25 @@ def check(fn: str, rc: int) -> None:
     if rc != 0:
         msg = load().rlg_last_error()
         raise RlgError(fn, rc, msg.decode("utf-8", "replace") if msg else "")
+
+
+# ---- optional NVTX ranges around the library calls: RLG_NVTX=1, or set_nvtx(True) -----------------
+_NVTX = os.environ.get("RLG_NVTX", "0") == "1"
+
+
+def set_nvtx(enabled: bool) -> None:
+    global _NVTX
+    _NVTX = bool(enabled)
+
+
+def nvtx_push(name: str) -> None:
+    """Open an NVTX range around a library call (nsys / ncu --nvtx timelines); a no-op unless switched on."""
+    if _NVTX:
+        import torch
+        torch.cuda.nvtx.range_push(name)
+
+
+def nvtx_pop() -> None:
+    if _NVTX:
+        import torch
+        torch.cuda.nvtx.range_pop()

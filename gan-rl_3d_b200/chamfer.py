@@ -169,6 +169,7 @@ def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = Tru
         was_clean = ws.clean
         if not capturing and not simple:
             ws.clean = False                     # until the call has gone through
+        _lib.nvtx_push("rlg.chamfer_fwd")
         rc = lib.rlg_chamfer_loss_fwd(pc1.data_ptr(), pc2.data_ptr(), B, N, M,
                                       d1.data_ptr(), d2.data_ptr(), i1.data_ptr(), i2.data_ptr(),
                                       m1.data_ptr() if want_means else None, m2.data_ptr() if want_means else None,
@@ -176,6 +177,7 @@ def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = Tru
                                       gz1.data_ptr() if gz1 is not None else None,
                                       gz2.data_ptr() if gz2 is not None else None,
                                       ws.buf.data_ptr(), ws.buf.numel(), flags, stream)
+        _lib.nvtx_pop()
         _lib.check("rlg_chamfer_loss_fwd", rc)
         if not simple:
             # eager: the forward restored the all-ones state.  Captured: nothing ran; the recorded sequence keeps the
@@ -198,12 +200,14 @@ def chamfer_backward(pc1, pc2, d1, d2, i1, i2, g1, g2, out=None, accumulate: boo
     g2 = g2.contiguous().float() if g2 is not None else None
     with torch.cuda.device(pc1.device):
         stream = torch.cuda.current_stream(pc1.device).cuda_stream
+        _lib.nvtx_push("rlg.chamfer_bwd")
         rc = lib.rlg_chamfer_bwd(pc1.data_ptr(), pc2.data_ptr(), d1.data_ptr(), d2.data_ptr(),
                                  i1.data_ptr(), i2.data_ptr(),
                                  g1.data_ptr() if g1 is not None else None,
                                  g2.data_ptr() if g2 is not None else None,
                                  B, N, M, gpc1.data_ptr(), gpc2.data_ptr(),
                                  _lib.CHAMFER_BWD_ACCUMULATE if (accumulate and out is not None) else 0, stream)
+        _lib.nvtx_pop()
         _lib.check("rlg_chamfer_bwd", rc)
     return gpc1, gpc2
 
@@ -267,9 +271,11 @@ class ChamferLossFn(torch.autograd.Function):
         gloss = gloss.contiguous().float()
         with torch.cuda.device(pc1.device):
             stream = torch.cuda.current_stream(pc1.device).cuda_stream
+            _lib.nvtx_push("rlg.chamfer_loss_bwd")
             rc = lib.rlg_chamfer_loss_bwd(pc1.data_ptr(), pc2.data_ptr(), d1.data_ptr(), d2.data_ptr(),
                                           i1.data_ptr(), i2.data_ptr(), gloss.data_ptr(), ctx.w[0], ctx.w[1],
                                           B, N, M, gpc1.data_ptr(), gpc2.data_ptr(), flags, stream)
+            _lib.nvtx_pop()
             _lib.check("rlg_chamfer_loss_bwd", rc)
         return (gpc1 if ctx.needs_input_grad[0] else None, gpc2 if ctx.needs_input_grad[1] else None, None)
 

@@ -134,9 +134,11 @@ class DeviceBatcher:
         if B == 0:
             return {"complete_pc": complete, "incomplete_pc": incomplete[:, :0], "lengths": lengths}
         with torch.cuda.device(dev):
+            _lib.nvtx_push("rlg.batch_prepare")
             rc = lib.rlg_batch_prepare(self.cache.data_ptr(), self.items, N, B, ctypes.byref(cp), complete.data_ptr(),
                                        incomplete.data_ptr(), lengths.data_ptr(), max_len.data_ptr(),
                                        torch.cuda.current_stream(dev).cuda_stream)
+            _lib.nvtx_pop()
             _lib.check("rlg_batch_prepare", rc)
         m = int(max_len.item())
         return {"complete_pc": complete, "incomplete_pc": incomplete[:, :m].contiguous(), "lengths": lengths}

@@ -218,8 +218,10 @@ def encoder_pool_gemm(x: torch.Tensor, layers, mode: int, packed=None) -> torch.
     with torch.cuda.device(x.device):
         stream = torch.cuda.current_stream(x.device).cuda_stream
         ws = _gemm_workspace(x.device, stream, lib.rlg_encoder_gemm_ws_bytes(B, N, arr, L, mode))
+        _lib.nvtx_push("rlg.encoder_gemm_fwd")
         rc = lib.rlg_encoder_gemm_fwd(x.data_ptr(), B, N, arr, L, mode, scales, image.data_ptr(), image.numel(),
                                       pooled.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+        _lib.nvtx_pop()
         _lib.check("rlg_encoder_gemm_fwd", rc)
     return pooled
 
@@ -251,8 +253,10 @@ def encoder_pool(x: torch.Tensor, layers: List[Tuple[torch.Tensor, torch.Tensor]
         if B == 0:
             return pooled, None
         with torch.cuda.device(x.device):
+            _lib.nvtx_push("rlg.encoder_fwd_bf16")
             rc = lib.rlg_encoder_fwd_bf16(x.data_ptr(), B, N, arr, L, packed.data_ptr(), packed.numel(),
                                           pooled.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream)
+            _lib.nvtx_pop()
             _lib.check("rlg_encoder_fwd_bf16", rc)
         return pooled, None
     pooled = torch.empty((B, c_last), dtype=torch.float32, device=x.device)
@@ -263,9 +267,11 @@ def encoder_pool(x: torch.Tensor, layers: List[Tuple[torch.Tensor, torch.Tensor]
         nbytes = lib.rlg_encoder_ws_bytes(B, N, arr, L)
         ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x.device)
         stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.nvtx_push("rlg.encoder_fwd")
         rc = lib.rlg_encoder_fwd(x.data_ptr(), B, N, arr, L, pooled.data_ptr(),
                                  argmax.data_ptr() if want_argmax else None,
                                  ws.data_ptr(), ws.numel(), stream)
+        _lib.nvtx_pop()
         _lib.check("rlg_encoder_fwd", rc)
     return pooled, argmax
 
@@ -391,18 +397,24 @@ def _run_plan(plan: "_Plan", x: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(x.device):
         if plan.path == "fp32":
             ws = torch.empty(max(lib.rlg_encoder_ws_bytes(B, N, plan.arr, L), 256), dtype=torch.uint8, device=x.device)
+            _lib.nvtx_push("rlg.encoder_fwd")
             rc = lib.rlg_encoder_fwd(x.data_ptr(), B, N, plan.arr, L, pooled.data_ptr(), None, ws.data_ptr(), ws.numel(), stream)
+            _lib.nvtx_pop()
             _lib.check("rlg_encoder_fwd", rc)
         elif plan.path == "bf16":
+            _lib.nvtx_push("rlg.encoder_fwd_bf16")
             rc = lib.rlg_encoder_fwd_bf16(x.data_ptr(), B, N, plan.arr, L, plan.packed.data_ptr(), plan.packed.numel(),
                                           pooled.data_ptr(), stream)
+            _lib.nvtx_pop()
             _lib.check("rlg_encoder_fwd_bf16", rc)
         else:
             mode = _lib.ENC_FP32X if plan.path == "fp32x" else _lib.ENC_BF16
             image, scales = plan.packed
             ws = _gemm_workspace(x.device, stream, lib.rlg_encoder_gemm_ws_bytes(B, N, plan.arr, L, mode))
+            _lib.nvtx_push("rlg.encoder_gemm_fwd")
             rc = lib.rlg_encoder_gemm_fwd(x.data_ptr(), B, N, plan.arr, L, mode, scales, image.data_ptr(), image.numel(),
                                           pooled.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+            _lib.nvtx_pop()
             _lib.check("rlg_encoder_gemm_fwd", rc)
     return pooled
 

@@ -109,8 +109,10 @@ class EncoderTrainFn(torch.autograd.Function):
                 _lib.check("rlg_encoder_train_saved_bytes", -4)
             saved = torch.empty(nsaved, dtype=torch.uint8, device=dev)
             ws = _workspace(dev, stream, nws)
+            _lib.nvtx_push("rlg.encoder_train_fwd")
             rc = lib.rlg_encoder_train_fwd(x.data_ptr(), B, N, arr, L, flags, pooled.data_ptr(), saved.data_ptr(), saved.numel(),
                                            ws.data_ptr(), ws.numel(), stream)
+            _lib.nvtx_pop()
             _lib.check("rlg_encoder_train_fwd", rc)
         if batch_stats:
             with torch.no_grad():
@@ -149,8 +151,10 @@ class EncoderTrainFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             ws = _workspace(dev, stream, lib.rlg_encoder_train_ws_bytes(B, N, arr, L))
+            _lib.nvtx_push("rlg.encoder_train_bwd")
             rc = lib.rlg_encoder_train_bwd(x.data_ptr(), B, N, arr, L, ctx.flags, g.data_ptr(), saved.data_ptr(), saved.numel(),
                                            grads, ws.data_ptr(), ws.numel(), stream)
+            _lib.nvtx_pop()
             _lib.check("rlg_encoder_train_bwd", rc)
         return (None, None, None) + tuple(outs)
 

@@ -482,3 +482,10 @@ def test_reserved_sms_change_nothing_but_the_grid(rlg):
         rlg.set_reserved_sms(0)
     with pytest.raises(ValueError):
         rlg.set_reserved_sms(300)
+
+
+def test_cfg4_shaped_batch_bit_exact(rlg):
+    """BASELINE config 4's shape per GPU (128 of the 1024 episodes: 2048-point completions against 1400-point partial
+    clouds, ragged N != M): the whole batch bit for bit against the C oracle."""
+    pc1, pc2 = O.make_clouds(128, 2048, "sphere", 401), O.make_clouds(128, 1400, "uniform", 402)
+    _check_against_direct(rlg, pc1, pc2)
