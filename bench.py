@@ -837,7 +837,7 @@ def input_pipeline_measurement(rlg, dev, D, cpu_leg: bool):
     reps = 12
     t0 = time.perf_counter()
     for k in range(reps):
-        out = batcher.make_batch(rlg.draw_plan(rng, bsz, n, items=rng.integers(0, 800, bsz)))
+        out = batcher.make_batch(rlg.draw_plan(rng, bsz, n, items=rng.integers(0, 800, bsz), host_indices=False))
     torch.cuda.synchronize()
     wall_ms = D.max_ms((time.perf_counter() - t0) * 1e3) / reps
     dev_ms = D.timed(lambda k: batcher.make_batch(plans[k % 4]), 8)        # pre-drawn plans: upload + kernels + 4-byte read-back

@@ -49,23 +49,30 @@ def rotation_matrix(theta: Sequence[float]) -> np.ndarray:
 
 
 def draw_plan(rng: np.random.Generator, B: int, N: int, items: Optional[np.ndarray] = None, augment: bool = True,
-              jitter_sigma: float = 0.01, jitter_clip: float = 0.05, host_jitter: bool = False) -> Dict[str, np.ndarray]:
+              jitter_sigma: float = 0.01, jitter_clip: float = 0.05, host_jitter: bool = False,
+              host_indices: bool = True) -> Dict[str, np.ndarray]:
     """The random decisions of one batch as host arrays (see struct rlg_prepare_plan), drawn with the reference's
     distributions: utils/dataset.py:255-266 (removal), :284-294 (augmentation, independently for the complete and the
     incomplete cloud), :408 (padding indices).  The jitter noise itself (2 x B x N x 3 normals, the bulk of the draws) is
     made on the device by DeviceBatcher from the per-cloud on/off flags `jitter_on` unless host_jitter=True puts the
-    clipped noise into the plan (tests feed the same noise to the restated reference that way)."""
+    clipped noise into the plan (tests feed the same noise to the restated reference that way).  host_indices=False leaves
+    the two bulk index draws -- the random subsets' permutations (:260) and the padding indices (:408) -- to the device as
+    well (torch's CUDA generator: argsort of uniforms, randint), so the host draws a handful of scalars per cloud."""
     plan = {"item": (np.arange(B) if items is None else np.asarray(items)).astype(np.int32),
             "method": np.zeros(B, np.int32), "n_keep": np.zeros(B, np.int32), "keep_idx": np.zeros((B, N), np.int32),
             "center": np.zeros(B, np.int32), "q_index": np.zeros(B, np.int32), "q_gamma": np.zeros(B, np.float64),
-            "ratio": np.zeros(B, np.float64), "pad_idx": rng.integers(0, 2 ** 31 - 1, (B, N), dtype=np.int64).astype(np.int32)}
+            "ratio": np.zeros(B, np.float64),
+            "pad_idx": rng.integers(0, 2 ** 31 - 1, (B, N), dtype=np.int64).astype(np.int32) if host_indices else None}
+    if not host_indices:
+        plan["keep_idx"] = None
     for b in range(B):
         ratio = rng.uniform(0.2, 0.5)
         plan["ratio"][b] = ratio
         if rng.random() < 0.5:
             n_keep = int(N * (1 - ratio))
             plan["n_keep"][b] = n_keep
-            plan["keep_idx"][b, :n_keep] = rng.choice(N, n_keep, replace=False)
+            if host_indices:
+                plan["keep_idx"][b, :n_keep] = rng.choice(N, n_keep, replace=False)
         else:
             plan["method"][b] = 1
             plan["center"][b] = rng.integers(N)
@@ -112,6 +119,14 @@ class DeviceBatcher:
             raise IndexError("plan['item'] outside the cache")
         keep = {}
         cp = _lib.RlgPreparePlan()
+        if plan.get("keep_idx") is None:                   # a uniform random permutation per cloud: the first n_keep are the subset
+            perm = torch.rand((B, N), device=dev).argsort(dim=1).to(torch.int32)
+            keep["keep_idx"] = perm
+            cp.keep_idx = perm.data_ptr()
+        if plan.get("pad_idx") is None:
+            pad = torch.randint(0, 2 ** 31 - 1, (B, N), device=dev, dtype=torch.int32)
+            keep["pad_idx"] = pad
+            cp.pad_idx = pad.data_ptr()
         if plan.get("jitter") is None and plan.get("jitter_on") is not None and bool(np.any(plan["jitter_on"])):
             # the jitter noise of utils/data_utils.py:140-142, drawn on the device (torch's CUDA generator)
             on = torch.as_tensor(np.ascontiguousarray(plan["jitter_on"])).to(dev, non_blocking=True)
@@ -141,4 +156,5 @@ class DeviceBatcher:
             _lib.nvtx_pop()
             _lib.check("rlg_batch_prepare", rc)
         m = int(max_len.item())
-        return {"complete_pc": complete, "incomplete_pc": incomplete[:, :m].contiguous(), "lengths": lengths}
+        # "draws": what was uploaded or drawn on the device (keep_idx, pad_idx, jitter, ...), for inspection / tests
+        return {"complete_pc": complete, "incomplete_pc": incomplete[:, :m].contiguous(), "lengths": lengths, "draws": keep}

@@ -96,3 +96,24 @@ def test_device_drawn_jitter_is_clipped_noise_on_the_flagged_clouds(rlg):
             assert 0 < np.abs(noisy[b] - quiet[b]).max() < 0.2
         else:
             assert np.array_equal(noisy[b], quiet[b])
+
+
+def test_device_drawn_subsets_and_padding(rlg):
+    """host_indices=False: the random subsets' permutations and the padding indices are drawn on the device.  Read back, they
+    are permutations / valid indices, and the batch equals the restated reference fed with exactly those draws."""
+    N, B = 512, 8
+    rng = np.random.default_rng(5)
+    cache = rng.normal(size=(B, N, 3)).astype(np.float32)
+    plan = rlg.draw_plan(rng, B, N, host_jitter=True, host_indices=False)
+    plan["method"][::2] = 0                                             # both branches in the batch
+    plan["n_keep"] = np.array([int(N * (1 - r)) for r in plan["ratio"]], np.int32)
+    assert plan["keep_idx"] is None and plan["pad_idx"] is None
+    batch = rlg.DeviceBatcher(cache, DEV).make_batch(plan)
+    keep_idx = batch["draws"]["keep_idx"].cpu().numpy()
+    pad_idx = batch["draws"]["pad_idx"].cpu().numpy()
+    assert all(np.array_equal(np.sort(keep_idx[b]), np.arange(N)) for b in range(B)) and pad_idx.min() >= 0
+    full = dict(plan, keep_idx=keep_idx, pad_idx=pad_idx)
+    want_c, want_i, want_len = _expected(cache, full)
+    assert np.array_equal(batch["lengths"].cpu().numpy(), want_len)
+    assert np.abs(batch["complete_pc"].cpu().numpy() - want_c).max() <= 2e-6
+    assert np.abs(batch["incomplete_pc"].cpu().numpy() - want_i).max() <= 2e-6
