@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kBpThreads) batch_prepare_kernel(PrepareArgs a
     double *dist = reinterpret_cast<double *>(bp_smem);                        // [P2] sorted copy of the distances
     float *xs = reinterpret_cast<float *>(dist + P2), *ys = xs + N, *zs = ys + N;   // working copy (complete, then incomplete)
     float *rx = zs + N, *ry = rx + N, *rz = ry + N;                            // the raw cloud
-    const int item = a.plan.item ? a.plan.item[b] : b;
+    const int item = min(max(a.plan.item ? a.plan.item[b] : b, 0), a.n_items - 1);     // never outside the cache
     const float *src = a.cache + (size_t)item * N * 3;
     for (int i = tid; i < N; i += kBpThreads) {
         const float x = __ldg(src + 3 * i), y = __ldg(src + 3 * i + 1), z = __ldg(src + 3 * i + 2);
