@@ -169,3 +169,22 @@ def test_sharding_helpers_single_process_cuda(rlg):
         total += part.item()
     assert abs(total - want.item()) < 1e-6 * want.item()
     assert torch.allclose(pred.grad, g_full, rtol=1e-6, atol=1e-9)
+
+
+def test_decoder_output_and_gradient_are_zero_copy_around_the_loss(rlg):
+    """the decoder's last Linear writes the (B, 6144) tensor the Chamfer kernels read in place as (B, 2048, 3),
+    and the gradient the backward kernel writes is the very storage the Linear's backward GEMM consumes (no repack either way)."""
+    torch.manual_seed(0)
+    dec = rlg.PointNetDecoder(32, 2048, [64, 6144]).to(DEV)
+    gfv = torch.randn(4, 32, device=DEV)
+    flat = dec.mlp(gfv)                                            # (B, 6144): the last Linear's output
+    recon = flat.view(-1, 2048, 3)                                 # what PointNetDecoder.forward returns (autoencoder.py:126)
+    assert recon.data_ptr() == flat.data_ptr() and recon.is_contiguous()
+    seen = {}
+    flat.register_hook(lambda g: seen.__setitem__("flat", g))
+    recon.register_hook(lambda g: seen.__setitem__("view", g))
+    target = O.make_clouds(4, 2048, "sphere", 3).to(DEV)
+    rlg.ChamferLoss()(recon, target).backward()
+    assert seen["view"].shape == (4, 2048, 3) and seen["flat"].shape == (4, 6144)
+    assert seen["flat"].data_ptr() == seen["view"].data_ptr()      # the kernel's output buffer, viewed: no copy
+    assert dec.mlp[-1].weight.grad is not None and float(dec.mlp[-1].weight.grad.abs().max()) > 0
