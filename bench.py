@@ -561,11 +561,21 @@ def run_ours(args):
     torch.cuda.synchronize()
     bwd_ms = e0.elapsed_time(e1) / reps
     bwd_gbs = BWD_BYTES_PER_PAIR * B / (bwd_ms * 1e-3) / 1e9
+    for _ in range(10):                                   # the run-to-run reproducible variant (fixed-point integer atomics)
+        rlg.chamfer_backward(a, b, d1, d2, i1, i2, g, g, deterministic=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        rlg.chamfer_backward(a, b, d1, d2, i1, i2, g, g, deterministic=True)
+    e1.record()
+    torch.cuda.synchronize()
+    bwd_det_ms = e0.elapsed_time(e1) / reps
     roofline_bwd = {"bound": "hbm", "kernel": "memset x2 + chamfer_bwd_kernel (stand-alone call; inside a training step the "
                     "forward zero-fills and the backward is the single kernel)", "achieved": bwd_gbs,
                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": bwd_gbs / peaks["hbm_gbs"],
                     "traffic": profile_traffic("chamfer_bwd_kernel"),
                     "peak_source": f"{peaks_src} MEASURED_PEAKS.json hbm_gbs", "launch_us": bwd_ms * 1e3,
+                    "deterministic_launch_us": bwd_det_ms * 1e3,
                     "note": "7.3 MB per call: launch-latency bound at this shape; timed through Python (ctypes) calls"}
 
     if extras_on:
@@ -898,7 +908,18 @@ def large_cloud_measurement(rlg, dev, D):
 
     ms = D.timed(step, 10)
     tf = 8.0 * n * n * Bl * D.world / (ms * 1e-3) / 1e12
-    return {"large_cloud": {"metric": "chamfer_pairs_per_s", "value": Bl * D.world / (ms * 1e-3), "unit": "pairs/s",
+    # the backward alone at this size (HBM bound by bytes: 56 per point), float atomics and the reproducible variant
+    bwd = {}
+    with torch.no_grad():
+        saved = [rlg.chamfer_nearest(a.detach(), b)[:4] for a, b in ring]
+    gg = torch.full((Bl,), 0.5 / Bl, device=dev)
+    for name, det in (("atomics", False), ("deterministic", True)):
+        def call(k):
+            a, b = ring[k % len(ring)]
+            rlg.chamfer_backward(a.detach(), b, *saved[k % len(ring)], gg, gg, deterministic=det)
+        t = D.timed(call, 20)
+        bwd[name] = {"us": t * 1e3, "algorithmic_gbs": 56.0 * 2 * n * Bl / (t * 1e-3) / 1e9}
+    return {"large_cloud": {"backward_alone": bwd, "metric": "chamfer_pairs_per_s", "value": Bl * D.world / (ms * 1e-3), "unit": "pairs/s",
                             "n_gpus": D.world, "scaling": "strong", "pairs_per_gpu": Bl, "ms_per_step": ms,
                             "config": {"workload": "ChamferLoss fwd+bwd, B=64 pairs of N=M=16384 sharded over the GPUs, loss "
                                                    "all-reduce per step (BASELINE configs[4])"},

@@ -20,7 +20,8 @@ from typing import Optional
 
 from . import _lib
 from .chamfer import (ChamferFn, ChamferLoss, ChamferLossFn, chamfer_backward, chamfer_distance, chamfer_distance_l2,
-                      chamfer_nearest, get_default_sweep, get_reserved_sms, set_default_sweep, set_reserved_sms)
+                      chamfer_nearest, deterministic_backward, get_default_sweep, get_reserved_sms, set_default_sweep,
+                      set_deterministic_backward, set_reserved_sms)
 from .chamfer import is_hot_path_input as _chamfer_hot
 from .reward import RewardFunction, batched_rewards
 from .encoder import (EncoderTrunkFn, PointNetEncoder, encoder_path_of, encoder_pool, encoder_pool_gemm, fold_trunk,
@@ -33,7 +34,7 @@ from .environment import BatchedRLEnvironment
 from .data import DeviceBatcher, build_cache, draw_plan
 
 __all__ = ["install", "uninstall", "is_installed", "chamfer_distance_l2", "chamfer_distance", "ChamferLoss",
-           "ChamferFn", "ChamferLossFn", "chamfer_nearest", "chamfer_backward", "set_default_sweep", "get_default_sweep", "set_reserved_sms", "get_reserved_sms", "PointNetEncoder", "EncoderTrunkFn", "encoder_pool",
+           "ChamferFn", "ChamferLossFn", "chamfer_nearest", "chamfer_backward", "set_default_sweep", "get_default_sweep", "set_reserved_sms", "get_reserved_sms", "set_deterministic_backward", "deterministic_backward", "PointNetEncoder", "EncoderTrunkFn", "encoder_pool",
            "fold_trunk", "folded_trunk_cached", "fused_forward", "set_encoder_precision", "get_encoder_precision",
            "pack_bf16", "pack_gemm", "packed_trunk_cached", "encoder_pool_gemm", "encoder_path_of", "resolve_path", "RewardFunction", "batched_rewards", "library_path", "abi_version", "set_nvtx",
            "EncoderTrainFn", "train_supported", "trunk_pool_autograd", "set_train_path",

@@ -67,6 +67,11 @@ EXPORTS = {
                                             ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint, ctypes.c_void_p]),
     "rlg_chamfer_loss_bwd": (ctypes.c_int, [ctypes.c_void_p] * 7 + [ctypes.c_float] * 2 + [ctypes.c_int] * 3
                              + [ctypes.c_void_p] * 2 + [ctypes.c_uint, ctypes.c_void_p]),
+    "rlg_chamfer_bwd_ws_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "rlg_chamfer_bwd_det": (ctypes.c_int, [ctypes.c_void_p] * 8 + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
+                            + [ctypes.c_size_t, ctypes.c_uint, ctypes.c_void_p]),
+    "rlg_chamfer_loss_bwd_det": (ctypes.c_int, [ctypes.c_void_p] * 7 + [ctypes.c_float] * 2 + [ctypes.c_int] * 3
+                                 + [ctypes.c_void_p] * 3 + [ctypes.c_size_t, ctypes.c_uint, ctypes.c_void_p]),
     "rlg_encoder_ws_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(RlgLayer), ctypes.c_int]),
     "rlg_encoder_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(RlgLayer),
                                        ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,

@@ -94,6 +94,26 @@ def get_reserved_sms() -> int:
     return _RESERVED_SMS
 
 
+_DETERMINISTIC: Optional[bool] = {"1": True, "0": False}.get(os.environ.get("RLG_DETERMINISTIC", ""))
+
+
+def set_deterministic_backward(mode: Optional[bool]) -> None:
+    """True: every Chamfer backward runs the run-to-run reproducible kernels (rlg_chamfer_bwd_det: fixed-point integer
+    atomics instead of float atomics, about twice the time of a 7 us kernel); False: never; None (default): follow
+    torch.are_deterministic_algorithms_enabled().  The forward is reproducible either way."""
+    global _DETERMINISTIC
+    _DETERMINISTIC = None if mode is None else bool(mode)
+
+
+def deterministic_backward() -> bool:
+    return torch.are_deterministic_algorithms_enabled() if _DETERMINISTIC is None else _DETERMINISTIC
+
+
+def _bwd_workspace(lib, B: int, N: int, M: int, device: torch.device) -> torch.Tensor:
+    # from torch's caching allocator on the current stream (inside a capture: the graph's private pool)
+    return torch.empty(max(int(lib.rlg_chamfer_bwd_ws_bytes(B, N, M)), 16), dtype=torch.uint8, device=device)
+
+
 def set_default_sweep(kind: str) -> None:
     """Which kernel sweeps the N x M pairs when chamfer_nearest() is not told explicitly:
     'fp32'   the FP32-pipe filter + refinement kernel (chamfer_filter.cu),
@@ -186,10 +206,11 @@ def chamfer_nearest(pc1: torch.Tensor, pc2: torch.Tensor, want_means: bool = Tru
     return (d1, d2, i1, i2, m1, m2) if loss is None else (d1, d2, i1, i2, m1, m2, loss)
 
 
-def chamfer_backward(pc1, pc2, d1, d2, i1, i2, g1, g2, out=None, accumulate: bool = False
-                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+def chamfer_backward(pc1, pc2, d1, d2, i1, i2, g1, g2, out=None, accumulate: bool = False,
+                     deterministic: Optional[bool] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Gradient of (mean1, mean2) w.r.t. (pc1, pc2) for upstream (g1 (B,), g2 (B,)); None = zero.
-    out=(gpc1, gpc2) with accumulate=True adds into buffers that already hold zeros (or a gradient)."""
+    out=(gpc1, gpc2) with accumulate=True adds into buffers that already hold zeros (or a gradient).
+    deterministic: None = the process-wide setting (set_deterministic_backward)."""
     lib = _lib.load()
     B, N, _ = pc1.shape
     M = pc2.shape[1]
@@ -200,13 +221,16 @@ def chamfer_backward(pc1, pc2, d1, d2, i1, i2, g1, g2, out=None, accumulate: boo
     g2 = g2.contiguous().float() if g2 is not None else None
     with torch.cuda.device(pc1.device):
         stream = torch.cuda.current_stream(pc1.device).cuda_stream
+        flags = _lib.CHAMFER_BWD_ACCUMULATE if (accumulate and out is not None) else 0
+        args = (pc1.data_ptr(), pc2.data_ptr(), d1.data_ptr(), d2.data_ptr(), i1.data_ptr(), i2.data_ptr(),
+                g1.data_ptr() if g1 is not None else None, g2.data_ptr() if g2 is not None else None,
+                B, N, M, gpc1.data_ptr(), gpc2.data_ptr())
         _lib.nvtx_push("rlg.chamfer_bwd")
-        rc = lib.rlg_chamfer_bwd(pc1.data_ptr(), pc2.data_ptr(), d1.data_ptr(), d2.data_ptr(),
-                                 i1.data_ptr(), i2.data_ptr(),
-                                 g1.data_ptr() if g1 is not None else None,
-                                 g2.data_ptr() if g2 is not None else None,
-                                 B, N, M, gpc1.data_ptr(), gpc2.data_ptr(),
-                                 _lib.CHAMFER_BWD_ACCUMULATE if (accumulate and out is not None) else 0, stream)
+        if deterministic_backward() if deterministic is None else deterministic:
+            ws = _bwd_workspace(lib, B, N, M, pc1.device)
+            rc = lib.rlg_chamfer_bwd_det(*args, ws.data_ptr(), ws.numel(), flags, stream)
+        else:
+            rc = lib.rlg_chamfer_bwd(*args, flags, stream)
         _lib.nvtx_pop()
         _lib.check("rlg_chamfer_bwd", rc)
     return gpc1, gpc2
@@ -271,10 +295,14 @@ class ChamferLossFn(torch.autograd.Function):
         gloss = gloss.contiguous().float()
         with torch.cuda.device(pc1.device):
             stream = torch.cuda.current_stream(pc1.device).cuda_stream
+            args = (pc1.data_ptr(), pc2.data_ptr(), d1.data_ptr(), d2.data_ptr(), i1.data_ptr(), i2.data_ptr(),
+                    gloss.data_ptr(), ctx.w[0], ctx.w[1], B, N, M, gpc1.data_ptr(), gpc2.data_ptr())
             _lib.nvtx_push("rlg.chamfer_loss_bwd")
-            rc = lib.rlg_chamfer_loss_bwd(pc1.data_ptr(), pc2.data_ptr(), d1.data_ptr(), d2.data_ptr(),
-                                          i1.data_ptr(), i2.data_ptr(), gloss.data_ptr(), ctx.w[0], ctx.w[1],
-                                          B, N, M, gpc1.data_ptr(), gpc2.data_ptr(), flags, stream)
+            if deterministic_backward():
+                ws = _bwd_workspace(lib, B, N, M, pc1.device)
+                rc = lib.rlg_chamfer_loss_bwd_det(*args, ws.data_ptr(), ws.numel(), flags, stream)
+            else:
+                rc = lib.rlg_chamfer_loss_bwd(*args, flags, stream)
             _lib.nvtx_pop()
             _lib.check("rlg_chamfer_loss_bwd", rc)
         return (gpc1 if ctx.needs_input_grad[0] else None, gpc2 if ctx.needs_input_grad[1] else None, None)

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define RLG_ABI_VERSION 6
+#define RLG_ABI_VERSION 7
 
 #define RLG_ERR_NULL_POINTER   (-1)
 #define RLG_ERR_BAD_SHAPE      (-2)   /* B < 0, N < 1, M < 1 (the reference raises IndexError for empty clouds) */
@@ -146,6 +146,25 @@ int rlg_chamfer_loss_bwd(const float *pc1, const float *pc2,
                          const float *d1, const float *d2, const int32_t *i1, const int32_t *i2,
                          const float *gloss, float w1, float w2, int B, int N, int M,
                          float *gpc1, float *gpc2, unsigned flags, void *stream);
+
+/* Run-to-run reproducible variants of the two calls above (what torch.use_deterministic_algorithms(True) asks of an
+ * operator; the reference's own CUDA autograd scatters with float atomics as well).  Same arguments and results to
+ * within rounding, but the partner terms are summed in 64-bit FIXED POINT -- every term of one direction of one pair has
+ * Euclidean norm |g[b]|/n exactly, so a quantum of 2^-40 of that (less for clouds of more than 2^21 points) loses nothing
+ * an fp32 sum would keep -- with integer atomics, which commute: the result does not depend on the order of arrival.
+ *   ws   device workspace of rlg_chamfer_bwd_ws_bytes(B, N, M) bytes (24 per point), 16-byte aligned; content on entry
+ *        is irrelevant.  A memset node + two launches; gpc1/gpc2 need no zero-fill (every row is written once;
+ *        with RLG_CHAMFER_BWD_ACCUMULATE the finished row is added to what the buffer holds).
+ *   A non-finite upstream weight makes every gradient row of that pair's partner cloud NaN. */
+size_t rlg_chamfer_bwd_ws_bytes(int B, int N, int M);
+int rlg_chamfer_bwd_det(const float *pc1, const float *pc2,
+                        const float *d1, const float *d2, const int32_t *i1, const int32_t *i2,
+                        const float *g1, const float *g2, int B, int N, int M,
+                        float *gpc1, float *gpc2, void *ws, size_t ws_bytes, unsigned flags, void *stream);
+int rlg_chamfer_loss_bwd_det(const float *pc1, const float *pc2,
+                             const float *d1, const float *d2, const int32_t *i1, const int32_t *i2,
+                             const float *gloss, float w1, float w2, int B, int N, int M,
+                             float *gpc1, float *gpc2, void *ws, size_t ws_bytes, unsigned flags, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * PointNet encoder: shared per-point MLP + global max-pool  (models/autoencoder.py:65-71), eval mode.

@@ -36,7 +36,7 @@ def test_header_symbols_are_exported(lib):
 
 def test_version_and_ws_bytes(lib):
     cdll, _ = lib
-    assert cdll.rlg_version() == 6
+    assert cdll.rlg_version() == 7
     # per point: 8-byte key + 4-byte runner-up value + (tensor sweep) 4-byte runner-up group + 4-byte third value; + counters
     big = cdll.rlg_chamfer_ws_bytes(32, 2048, 2048)
     assert 20 * 32 * 4096 < big <= 20 * 32 * 4096 + 16384 and big % 256 == 0
@@ -56,6 +56,12 @@ def test_argument_errors_are_negative_codes_with_messages(lib):
     with pytest.raises(_lib.RlgError) as ei:
         _lib.check("rlg_chamfer_bwd", rc)
     assert ei.value.code == -2
+    # unknown backward flag bits are rejected; the reproducible variant insists on its workspace (24 bytes per point)
+    assert cdll.rlg_chamfer_bwd(*([None] * 8), 1, 3, 3, None, None, 6, None) == -4
+    assert cdll.rlg_chamfer_bwd_ws_bytes(2, 5, 7) == 24 * 2 * 12 and cdll.rlg_chamfer_bwd_ws_bytes(0, 5, 7) == 0
+    one = ctypes.c_void_p(256)      # non-null, never dereferenced: argument checks come first
+    assert cdll.rlg_chamfer_bwd_det(*([one] * 8), 1, 3, 3, one, one, None, 0, 0, None) == -1
+    assert cdll.rlg_chamfer_bwd_det(*([one] * 8), 1, 3, 3, one, one, one, 8, 0, None) == -3
     # B == 0 is a no-op, like an empty batch through the reference
     assert cdll.rlg_chamfer_fwd(None, None, 0, 4, 5, None, None, None, None, None, None, None, 0, 0, None) == 0
     layer = (_lib.RlgLayer * 1)()

@@ -22,6 +22,9 @@ for step in "$@"; do
     envtest)   timeout 900 python -m pytest tests/test_environment_gpu.py -m gpu -q -s > gpurun_out/${T}_envtest.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_envtest.log ;;
     property)  timeout 900 python -m pytest tests/test_chamfer_property_gpu.py -m gpu -q > gpurun_out/${T}_property.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_property.log ;;
     data)      timeout 900 python -m pytest tests/test_data_gpu.py tests/test_dropin_gpu.py -m gpu -q > gpurun_out/${T}_data.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_data.log ;;
+    bwddet)    timeout 600 python -m pytest tests/test_chamfer_bwd_gpu.py -m gpu -q > gpurun_out/${T}_bwddet.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_bwddet.log ;;
+    bwdprobe)  timeout 600 python tools/bwd_probe.py > gpurun_out/${T}_bwdprobe.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_bwdprobe.log
+               for so in gan-rl_3d_b200/lib/librlg_b200_exp_bwd*.so; do RLG_EXPERIMENTS_LIB=$PWD/$so timeout 600 python tools/bwd_probe.py >> gpurun_out/${T}_bwdprobe.log 2>&1; done ;;
     steplist)  bash tools/gpu_job3.sh ${T} ;;
     *) echo "unknown step $step" ;;
   esac
