@@ -97,6 +97,13 @@ __device__ __forceinline__ void red_add_row(float *base, size_t row, size_t rows
 // index, then partner): 32 registers for 8 CTAs per SM.
 static constexpr int kBwdThreads = 256;
 
+// Grid of every backward kernel: x = blocks over the N + M points of one pair, y = pair (B <= 65535 like the forward) -- no
+// integer division per thread (a flat 64-bit index costs two emulated 64-bit divisions, ~45 % of the kernel's instructions;
+// the kernel is latency bound, so this only shortens the instruction stream: 306 -> 170 per warp).
+#define RLG_BWD_FOR_EACH_POINT(a, B, b, p)                                   \
+    const int p = blockIdx.x * kBwdThreads + threadIdx.x;                    \
+    const int b = blockIdx.y;
+
 template <int VEC>
 __global__ void __launch_bounds__(kBwdThreads, 8) chamfer_bwd_kernel(BwdArgs a, int B) {
     __shared__ __align__(16) float stage[kBwdThreads / 32][96];
@@ -104,41 +111,38 @@ __global__ void __launch_bounds__(kBwdThreads, 8) chamfer_bwd_kernel(BwdArgs a, 
     pdl_wait();                       // distances, indices and the upstream gradient come from the kernels before
     const int per_cloud = a.N + a.M;
     const int lane = threadIdx.x & 31;
-    const long long t = (long long)blockIdx.x * kBwdThreads + threadIdx.x;
-    const int b = (int)(t / per_cloud);
-    const bool live = b < B;
-    const int p = (int)(t - (long long)b * per_cloud);
-    const int dir = p >= a.N, i = dir ? p - a.N : p;
-    const int n = dir ? a.M : a.N, m = dir ? a.N : a.M;
-    float ux = 0.0f, uy = 0.0f, uz = 0.0f;
-    int j = 0;
-    const bool has = live && bwd_term(a, dir, b, i, ux, uy, uz, j);
-    const size_t row = (size_t)b * n + i;
-    float *own = dir ? a.gpc2 : a.gpc1;
-    bool staged = false;
+    RLG_BWD_FOR_EACH_POINT(a, B, b, p) {
+        const bool live = p < per_cloud;
+        const int dir = p >= a.N, i = dir ? p - a.N : p;
+        const int n = dir ? a.M : a.N, m = dir ? a.N : a.M;
+        float ux = 0.0f, uy = 0.0f, uz = 0.0f;
+        int j = 0;
+        const bool has = live && bwd_term(a, dir, b, i, ux, uy, uz, j);
+        const size_t row = (size_t)b * n + i;
+        float *own = dir ? a.gpc2 : a.gpc1;
+        bool staged = false;
 #ifndef RLG_BWD_SCALAR_RED
-    if (VEC == 2) {
-        // the whole warp inside one cloud of one pair, first row on a 16-byte boundary (the same answer in every lane)
-        const long long t0 = t - lane;
-        const int b0 = (int)(t0 / per_cloud);
-        const int p0 = (int)(t0 - (long long)b0 * per_cloud);
-        const size_t row0 = row - lane;
-        staged = b0 < B && (p0 < a.N ? p0 + 31 < a.N : p0 + 31 < per_cloud) && (row0 & 3) == 0;
-        if (staged && __any_sync(0xffffffffu, has)) {
-            float *sw = stage[threadIdx.x >> 5];
-            sw[3 * lane] = ux; sw[3 * lane + 1] = uy; sw[3 * lane + 2] = uz;
-            __syncwarp();
-            if (lane < 24) {
-                const float4 v = reinterpret_cast<const float4 *>(sw)[lane];
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(own + row0 * 3 + 4 * lane), "f"(v.x), "f"(v.y),
-                             "f"(v.z), "f"(v.w) : "memory");
+        if (VEC == 2) {
+            // the whole warp inside one cloud of the pair, first row on a 16-byte boundary (the same answer in every lane)
+            const int p0 = p - lane;
+            const size_t row0 = row - lane;
+            staged = (p0 < a.N ? p0 + 31 < a.N : p0 + 31 < per_cloud) && (row0 & 3) == 0;
+            if (staged && __any_sync(0xffffffffu, has)) {
+                float *sw = stage[threadIdx.x >> 5];
+                sw[3 * lane] = ux; sw[3 * lane + 1] = uy; sw[3 * lane + 2] = uz;
+                __syncwarp();
+                if (lane < 24) {
+                    const float4 v = reinterpret_cast<const float4 *>(sw)[lane];
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(own + row0 * 3 + 4 * lane), "f"(v.x), "f"(v.y),
+                                 "f"(v.z), "f"(v.w) : "memory");
+                }
             }
         }
-    }
 #endif
-    if (!has) return;
-    if (!staged) red_add_row<VEC>(own, row, (size_t)B * n, ux, uy, uz);
-    red_add_row<VEC>(dir ? a.gpc1 : a.gpc2, (size_t)b * m + j, (size_t)B * m, -ux, -uy, -uz);
+        if (!has) return;
+        if (!staged) red_add_row<VEC>(own, row, (size_t)B * n, ux, uy, uz);
+        red_add_row<VEC>(dir ? a.gpc1 : a.gpc2, (size_t)b * m + j, (size_t)B * m, -ux, -uy, -uz);
+    }
 }
 
 // ---- reproducible variant: fixed-point scatter, then own term + conversion ---------------------------------------
@@ -157,50 +161,46 @@ __device__ __forceinline__ double det_scale(float w, int s, int sign) {
 __global__ void __launch_bounds__(kBwdThreads) chamfer_bwd_scatter_kernel(BwdArgs a, DetArgs q, int B) {
     pdl_launch_dependents();
     pdl_wait();
-    const int per_cloud = a.N + a.M;
-    const long long t = (long long)blockIdx.x * kBwdThreads + threadIdx.x;
-    const int b = (int)(t / per_cloud);
-    if (b >= B) return;
-    const int p = (int)(t - (long long)b * per_cloud);
-    const int dir = p >= a.N, i = dir ? p - a.N : p;
-    float ux, uy, uz;
-    int j;
-    if (!bwd_term(a, dir, b, i, ux, uy, uz, j)) return;
-    const float w = bwd_weight(a, dir, b);
-    if (!det_usable(w)) return;       // non-finite weight: the gather kernel writes NaN rows
-    const double to_q = det_scale(w, dir ? q.s2 : q.s1, +1);
-    unsigned long long *oth = reinterpret_cast<unsigned long long *>(dir ? q.acc1 : q.acc2) + ((size_t)b * (dir ? a.N : a.M) + j) * 3;
-    atomicAdd(oth, (unsigned long long)__double2ll_rn(-(double)ux * to_q));
-    atomicAdd(oth + 1, (unsigned long long)__double2ll_rn(-(double)uy * to_q));
-    atomicAdd(oth + 2, (unsigned long long)__double2ll_rn(-(double)uz * to_q));
+    RLG_BWD_FOR_EACH_POINT(a, B, b, p) {
+        if (p >= a.N + a.M) return;
+        const int dir = p >= a.N, i = dir ? p - a.N : p;
+        float ux, uy, uz;
+        int j;
+        if (!bwd_term(a, dir, b, i, ux, uy, uz, j)) return;
+        const float w = bwd_weight(a, dir, b);
+        if (!det_usable(w)) return;       // non-finite weight: the gather kernel writes NaN rows
+        const double to_q = det_scale(w, dir ? q.s2 : q.s1, +1);
+        unsigned long long *oth = reinterpret_cast<unsigned long long *>(dir ? q.acc1 : q.acc2) + ((size_t)b * (dir ? a.N : a.M) + j) * 3;
+        atomicAdd(oth, (unsigned long long)__double2ll_rn(-(double)ux * to_q));
+        atomicAdd(oth + 1, (unsigned long long)__double2ll_rn(-(double)uy * to_q));
+        atomicAdd(oth + 2, (unsigned long long)__double2ll_rn(-(double)uz * to_q));
+    }
 }
 
 __global__ void __launch_bounds__(kBwdThreads) chamfer_bwd_gather_kernel(BwdArgs a, DetArgs q, int B) {
     pdl_launch_dependents();
     pdl_wait();                       // the scatter kernel has finished (and flushed) when this returns
-    const int per_cloud = a.N + a.M;
-    const long long t = (long long)blockIdx.x * kBwdThreads + threadIdx.x;
-    const int b = (int)(t / per_cloud);
-    if (b >= B) return;
-    const int p = (int)(t - (long long)b * per_cloud);
-    const int dir = p >= a.N, i = dir ? p - a.N : p;
-    float ux, uy, uz;
-    int j;
-    bwd_term(a, dir, b, i, ux, uy, uz, j);                   // zeros where the term vanishes
-    const size_t row = ((size_t)b * (dir ? a.M : a.N) + i) * 3;
-    const float wo = bwd_weight(a, dir ^ 1, b);              // the partner terms of this row come from the other direction
-    double px = 0.0, py = 0.0, pz = 0.0;
-    if (det_usable(wo)) {
-        const long long *acc = (dir ? q.acc2 : q.acc1) + row;
-        const double from_q = det_scale(wo, dir ? q.s1 : q.s2, -1);
-        px = (double)acc[0] * from_q; py = (double)acc[1] * from_q; pz = (double)acc[2] * from_q;
-    } else if (wo != 0.0f) {
-        px = py = pz = (double)NAN;
+    RLG_BWD_FOR_EACH_POINT(a, B, b, p) {
+        if (p >= a.N + a.M) return;
+        const int dir = p >= a.N, i = dir ? p - a.N : p;
+        float ux, uy, uz;
+        int j;
+        bwd_term(a, dir, b, i, ux, uy, uz, j);                   // zeros where the term vanishes
+        const size_t row = ((size_t)b * (dir ? a.M : a.N) + i) * 3;
+        const float wo = bwd_weight(a, dir ^ 1, b);              // the partner terms of this row come from the other direction
+        double px = 0.0, py = 0.0, pz = 0.0;
+        if (det_usable(wo)) {
+            const long long *acc = (dir ? q.acc2 : q.acc1) + row;
+            const double from_q = det_scale(wo, dir ? q.s1 : q.s2, -1);
+            px = (double)acc[0] * from_q; py = (double)acc[1] * from_q; pz = (double)acc[2] * from_q;
+        } else if (wo != 0.0f) {
+            px = py = pz = (double)NAN;
+        }
+        float *out = (dir ? a.gpc2 : a.gpc1) + row;
+        const float rx = (float)((double)ux + px), ry = (float)((double)uy + py), rz = (float)((double)uz + pz);
+        if (q.accumulate) { out[0] += rx; out[1] += ry; out[2] += rz; }
+        else { out[0] = rx; out[1] = ry; out[2] = rz; }
     }
-    float *out = (dir ? a.gpc2 : a.gpc1) + row;
-    const float rx = (float)((double)ux + px), ry = (float)((double)uy + py), rz = (float)((double)uz + pz);
-    if (q.accumulate) { out[0] += rx; out[1] += ry; out[2] += rz; }
-    else { out[0] = rx; out[1] = ry; out[2] = rz; }
 }
 
 }  // namespace rlg
@@ -219,6 +219,7 @@ static int bwd_launch(const float *pc1, const float *pc2, const float *d1, const
                       bool deterministic = false, void *ws = nullptr, size_t ws_bytes = 0) {
     if (B < 0 || N < 1 || M < 1)
         return fail(RLG_ERR_BAD_SHAPE, "rlg_chamfer_bwd: bad shape B=%d N=%d M=%d", B, N, M);
+    if (B > 65535) return fail(RLG_ERR_TOO_LARGE, "rlg_chamfer_bwd: B=%d exceeds 65535 (grid.y)", B);
     if (flags & ~RLG_CHAMFER_BWD_ACCUMULATE)
         return fail(RLG_ERR_UNSUPPORTED, "rlg_chamfer_bwd: unknown flag bits 0x%x", flags & ~RLG_CHAMFER_BWD_ACCUMULATE);
     if (B == 0) return 0;
@@ -226,9 +227,8 @@ static int bwd_launch(const float *pc1, const float *pc2, const float *d1, const
         return fail(RLG_ERR_NULL_POINTER, "rlg_chamfer_bwd: null pointer");
     BwdArgs a{pc1, pc2, d1, d2, i1, i2, g1, g2, gstride, scale1, scale2, gpc1, gpc2, N, M};
     cudaStream_t st = (cudaStream_t)stream;
-    const long long total = (long long)B * ((long long)N + M);
-    const long long blocks = (total + kBwdThreads - 1) / kBwdThreads;
-    if (blocks > 0x7fffffffLL) return fail(RLG_ERR_TOO_LARGE, "rlg_chamfer_bwd: too many points");
+    if ((long long)N + M > 0x7fffffffLL - kBwdThreads) return fail(RLG_ERR_TOO_LARGE, "rlg_chamfer_bwd: too many points");
+    const dim3 grid((unsigned)(((long long)N + M + kBwdThreads - 1) / kBwdThreads), (unsigned)B);
     if (deterministic) {
         const size_t need = rlg_chamfer_bwd_ws_bytes(B, N, M);
         if (!ws) return fail(RLG_ERR_NULL_POINTER, "rlg_chamfer_bwd_det: null workspace");
@@ -239,9 +239,9 @@ static int bwd_launch(const float *pc1, const float *pc2, const float *d1, const
         long long *acc1 = static_cast<long long *>(ws);
         DetArgs q{acc1, acc1 + 3 * (size_t)B * N, det_fraction_bits(N), det_fraction_bits(M),
                   (flags & RLG_CHAMFER_BWD_ACCUMULATE) ? 1 : 0};
-        e = launch_pdl(chamfer_bwd_scatter_kernel, dim3((unsigned)blocks), dim3(kBwdThreads), 0, st, a, q, B);
+        e = launch_pdl(chamfer_bwd_scatter_kernel, grid, dim3(kBwdThreads), 0, st, a, q, B);
         if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "chamfer_bwd_scatter_kernel: %s", cudaGetErrorString(e)); }
-        e = launch_pdl(chamfer_bwd_gather_kernel, dim3((unsigned)blocks), dim3(kBwdThreads), 0, st, a, q, B);
+        e = launch_pdl(chamfer_bwd_gather_kernel, grid, dim3(kBwdThreads), 0, st, a, q, B);
         if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "chamfer_bwd_gather_kernel: %s", cudaGetErrorString(e)); }
         return check_launch("chamfer_bwd_gather_kernel");
     }
@@ -252,7 +252,7 @@ static int bwd_launch(const float *pc1, const float *pc2, const float *d1, const
     }
     const uintptr_t align = (uintptr_t)gpc1 | (uintptr_t)gpc2;
     auto kernel = (align & 15) == 0 ? chamfer_bwd_kernel<2> : (align & 7) == 0 ? chamfer_bwd_kernel<1> : chamfer_bwd_kernel<0>;
-    cudaError_t le = launch_pdl(kernel, dim3((unsigned)blocks), dim3(kBwdThreads), 0, st, a, B);
+    cudaError_t le = launch_pdl(kernel, grid, dim3(kBwdThreads), 0, st, a, B);
     if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "chamfer_bwd_kernel: %s", cudaGetErrorString(le)); }
     return check_launch("chamfer_bwd_kernel");
 }

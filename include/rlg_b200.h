@@ -131,8 +131,11 @@ int rlg_chamfer_loss_fwd(const float *pc1, const float *pc2, int B, int N, int M
  *       gpc1[b,i] = g1[b]/N * (pc1[b,i]-pc2[b,i1])/d1[b,i]  -  sum_{j: i2[b,j]==i} g2[b]/M * (pc2[b,j]-pc1[b,i])/d2[b,j]
  *       (and symmetrically for gpc2); a term is 0 where its distance is 0 (EuclideanDistBackward0).
  *   flags   RLG_CHAMFER_BWD_ACCUMULATE: gpc1/gpc2 already hold zeros (see rlg_chamfer_loss_fwd's gz1/gz2) or a
- *           gradient to add to: one launch of fire-and-forget float atomics.  Without it the library zero-fills
- *           them first (a memset node + the same launch).
+ *           gradient to add to: one launch of fire-and-forget float reductions (2- and 4-float wide when
+ *           gpc1/gpc2 are 8- / 16-byte aligned; any alignment works).  Without it the library zero-fills
+ *           them first (a memset node + the same launch).  Any other flag bit: RLG_ERR_UNSUPPORTED.
+ *   B <= 65535 per call (RLG_ERR_TOO_LARGE beyond, like the forward).
+ *   The L2 float reduction flushes subnormal sums to zero (gradient components below 1.2e-38).
  * --------------------------------------------------------------------------------------------- */
 #define RLG_CHAMFER_BWD_ACCUMULATE 1u
 int rlg_chamfer_bwd(const float *pc1, const float *pc2,

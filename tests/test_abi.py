@@ -56,6 +56,8 @@ def test_argument_errors_are_negative_codes_with_messages(lib):
     with pytest.raises(_lib.RlgError) as ei:
         _lib.check("rlg_chamfer_bwd", rc)
     assert ei.value.code == -2
+    # the pair index is a grid dimension (like the forward's): at most 65535 pairs per call
+    assert cdll.rlg_chamfer_bwd(*([None] * 8), 65536, 3, 3, None, None, 0, None) == -5
     # unknown backward flag bits are rejected; the reproducible variant insists on its workspace (24 bytes per point)
     assert cdll.rlg_chamfer_bwd(*([None] * 8), 1, 3, 3, None, None, 6, None) == -4
     assert cdll.rlg_chamfer_bwd_ws_bytes(2, 5, 7) == 24 * 2 * 12 and cdll.rlg_chamfer_bwd_ws_bytes(0, 5, 7) == 0
