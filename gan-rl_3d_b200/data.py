@@ -40,12 +40,16 @@ def build_cache(sources: Iterable, num_points: int = 2048, seed: int = 0) -> np.
 
 
 def rotation_matrix(theta: Sequence[float]) -> np.ndarray:
-    """Rz @ Ry @ Rx of utils/data_utils.py:74-99 for the three angles theta."""
-    cx, sx, cy, sy, cz, sz = np.cos(theta[0]), np.sin(theta[0]), np.cos(theta[1]), np.sin(theta[1]), np.cos(theta[2]), np.sin(theta[2])
-    Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
-    Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
-    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
-    return Rz @ Ry @ Rx
+    """Rz @ Ry @ Rx of utils/data_utils.py:74-99 for the three angles theta; theta may carry leading batch dimensions
+    (..., 3) -> (..., 3, 3)."""
+    th = np.asarray(theta, np.float64)
+    c, s = np.cos(th), np.sin(th)
+    cx, cy, cz, sx, sy, sz = c[..., 0], c[..., 1], c[..., 2], s[..., 0], s[..., 1], s[..., 2]
+    R = np.empty(th.shape[:-1] + (3, 3))
+    R[..., 0, 0] = cz * cy; R[..., 0, 1] = cz * sy * sx - sz * cx; R[..., 0, 2] = cz * sy * cx + sz * sx
+    R[..., 1, 0] = sz * cy; R[..., 1, 1] = sz * sy * sx + cz * cx; R[..., 1, 2] = sz * sy * cx - cz * sx
+    R[..., 2, 0] = -sy;     R[..., 2, 1] = cy * sx;                R[..., 2, 2] = cy * cx
+    return R
 
 
 def draw_plan(rng: np.random.Generator, B: int, N: int, items: Optional[np.ndarray] = None, augment: bool = True,
@@ -53,51 +57,46 @@ def draw_plan(rng: np.random.Generator, B: int, N: int, items: Optional[np.ndarr
               host_indices: bool = True) -> Dict[str, np.ndarray]:
     """The random decisions of one batch as host arrays (see struct rlg_prepare_plan), drawn with the reference's
     distributions: utils/dataset.py:255-266 (removal), :284-294 (augmentation, independently for the complete and the
-    incomplete cloud), :408 (padding indices).  The jitter noise itself (2 x B x N x 3 normals, the bulk of the draws) is
-    made on the device by DeviceBatcher from the per-cloud on/off flags `jitter_on` unless host_jitter=True puts the
-    clipped noise into the plan (tests feed the same noise to the restated reference that way).  host_indices=False leaves
-    the two bulk index draws -- the random subsets' permutations (:260) and the padding indices (:408) -- to the device as
-    well (torch's CUDA generator: argsort of uniforms, randint), so the host draws a handful of scalars per cloud."""
+    incomplete cloud), :408 (padding indices).  Every per-cloud scalar is drawn for the whole batch at once (no Python loop
+    per cloud; the reference's stream of draws is not reproduced, its distributions are).  The jitter noise itself
+    (2 x B x N x 3 normals, the bulk of the draws) is made on the device by DeviceBatcher from the per-cloud on/off flags
+    `jitter_on` unless host_jitter=True puts the clipped noise into the plan (tests feed the same noise to the restated
+    reference that way).  host_indices=False leaves the two bulk index draws -- the random subsets' permutations (:260) and
+    the padding indices (:408) -- to the device as well (torch's CUDA generator: argsort of uniforms, randint), so the host
+    draws a handful of scalars per cloud."""
+    ratio = rng.uniform(0.2, 0.5, B)
+    random_subset = rng.random(B) < 0.5                                   # else: the points nearest to a random centre go
+    vi = (N - 1) * np.true_divide(ratio * 100, 100.0)                      # numpy's percentile, method 'linear'
     plan = {"item": (np.arange(B) if items is None else np.asarray(items)).astype(np.int32),
-            "method": np.zeros(B, np.int32), "n_keep": np.zeros(B, np.int32), "keep_idx": np.zeros((B, N), np.int32),
-            "center": np.zeros(B, np.int32), "q_index": np.zeros(B, np.int32), "q_gamma": np.zeros(B, np.float64),
-            "ratio": np.zeros(B, np.float64),
+            "method": np.where(random_subset, 0, 1).astype(np.int32),
+            "n_keep": np.where(random_subset, (N * (1 - ratio)).astype(np.int64), 0).astype(np.int32),
+            "keep_idx": np.zeros((B, N), np.int32) if host_indices else None,
+            "center": np.where(random_subset, 0, rng.integers(0, N, B)).astype(np.int32),
+            "q_index": np.where(random_subset, 0, np.floor(vi)).astype(np.int32),
+            "q_gamma": np.where(random_subset, 0.0, vi - np.floor(vi)),
+            "ratio": ratio,
             "pad_idx": rng.integers(0, 2 ** 31 - 1, (B, N), dtype=np.int64).astype(np.int32) if host_indices else None}
-    if not host_indices:
-        plan["keep_idx"] = None
-    for b in range(B):
-        ratio = rng.uniform(0.2, 0.5)
-        plan["ratio"][b] = ratio
-        if rng.random() < 0.5:
-            n_keep = int(N * (1 - ratio))
-            plan["n_keep"][b] = n_keep
-            if host_indices:
-                plan["keep_idx"][b, :n_keep] = rng.choice(N, n_keep, replace=False)
-        else:
-            plan["method"][b] = 1
-            plan["center"][b] = rng.integers(N)
-            vi = (N - 1) * np.true_divide(ratio * 100, 100.0)           # numpy's percentile, method 'linear'
-            plan["q_index"][b] = int(np.floor(vi))
-            plan["q_gamma"][b] = vi - np.floor(vi)
+    if host_indices:
+        for b in np.flatnonzero(random_subset):
+            k = int(plan["n_keep"][b])
+            plan["keep_idx"][b, :k] = rng.choice(N, k, replace=False)
     if augment:
-        rot = np.tile(np.eye(3, dtype=np.float32).reshape(1, 1, 9), (2, B, 1))
-        scale = np.ones((2, B), np.float32)
-        jitter = np.zeros((2, B, N, 3), np.float32) if host_jitter else None
-        jitter_on = np.zeros((2, B), np.bool_)
-        for which in range(2):
-            for b in range(B):
-                if rng.random() < 0.5:
-                    rot[which, b] = rotation_matrix(rng.uniform(0, 2 * np.pi, 3)).astype(np.float32).reshape(9)
-                if rng.random() < 0.5:
-                    jitter_on[which, b] = True
-                    if host_jitter:
-                        jitter[which, b] = np.clip(rng.normal(0.0, jitter_sigma, (N, 3)), -jitter_clip, jitter_clip)
-                if rng.random() < 0.3:
-                    scale[which, b] = rng.uniform(0.8, 1.2)
+        rotate = rng.random((2, B)) < 0.5
+        jitter_on = rng.random((2, B)) < 0.5
+        rescale = rng.random((2, B)) < 0.3
+        R = rotation_matrix(rng.uniform(0, 2 * np.pi, (2, B, 3)))
+        rot = np.where(rotate[..., None, None], R, np.eye(3)).astype(np.float32).reshape(2, B, 9)
+        scale = np.where(rescale, rng.uniform(0.8, 1.2, (2, B)), 1.0).astype(np.float32)
         plan.update(rot=rot, scale=scale, jitter_on=jitter_on, jitter_sigma=jitter_sigma, jitter_clip=jitter_clip)
         if host_jitter:
-            plan["jitter"] = jitter
+            noise = np.clip(rng.normal(0.0, jitter_sigma, (2, B, N, 3)), -jitter_clip, jitter_clip)
+            plan["jitter"] = np.where(jitter_on[..., None, None], noise, 0.0).astype(np.float32)
     return plan
+
+
+# per-cloud scalars of struct rlg_prepare_plan, packed into one upload by DeviceBatcher.make_batch
+_PLAN_SCALARS = (("item", np.int32), ("method", np.int32), ("n_keep", np.int32), ("center", np.int32), ("q_index", np.int32),
+                 ("q_gamma", np.float64), ("rot", np.float32), ("scale", np.float32))
 
 
 class DeviceBatcher:
@@ -111,6 +110,14 @@ class DeviceBatcher:
         self.device = torch.device(device)
         self.cache = torch.as_tensor(np.ascontiguousarray(cache, dtype=np.float32)).to(self.device)
         self.items, self.N = int(cache.shape[0]), int(cache.shape[1])
+        self._stage: Optional[torch.Tensor] = None
+
+    def _staging(self, nbytes: int) -> torch.Tensor:
+        """Pinned host buffer for the plan's scalars.  Reuse is safe: make_batch ends with a read-back of the padded length,
+        so the previous batch's transfer out of this buffer has completed."""
+        if self._stage is None or self._stage.numel() < nbytes:
+            self._stage = torch.empty(max(nbytes, 4096), dtype=torch.uint8, pin_memory=True)
+        return self._stage
 
     def make_batch(self, plan: Dict[str, np.ndarray]) -> Dict[str, torch.Tensor]:
         lib = _lib.load()
@@ -119,6 +126,26 @@ class DeviceBatcher:
             raise IndexError("plan['item'] outside the cache")
         keep = {}
         cp = _lib.RlgPreparePlan()
+        # the per-cloud scalars of the plan (a few KB) travel as ONE transfer from a pinned staging buffer; the optional bulk
+        # arrays of a host-drawn plan (subset / padding indices, jitter noise) as one transfer each
+        small = [(name, np.ascontiguousarray(plan[name], dtype=dtype)) for name, dtype in _PLAN_SCALARS if plan.get(name) is not None]
+        device_jitter = plan.get("jitter") is None and plan.get("jitter_on") is not None and bool(np.any(plan["jitter_on"]))
+        if device_jitter:
+            small.append(("jitter_on", np.ascontiguousarray(plan["jitter_on"], dtype=np.float32)))     # not a field of the C struct
+        offsets, total = {}, 0
+        for name, arr in small:
+            offsets[name] = total
+            total += (arr.nbytes + 15) & ~15
+        if total:
+            stage = self._staging(total)
+            view = stage.numpy()
+            for name, arr in small:
+                view[offsets[name]: offsets[name] + arr.nbytes] = arr.reshape(-1).view(np.uint8)
+            packed = stage[:total].to(dev, non_blocking=True)
+            keep["plan_scalars"] = packed
+            for name, _ in small:
+                if name != "jitter_on":
+                    setattr(cp, name, packed.data_ptr() + offsets[name])
         if plan.get("keep_idx") is None:                   # a uniform random permutation per cloud: the first n_keep are the subset
             perm = torch.rand((B, N), device=dev).argsort(dim=1).to(torch.int32)
             keep["keep_idx"] = perm
@@ -127,19 +154,17 @@ class DeviceBatcher:
             pad = torch.randint(0, 2 ** 31 - 1, (B, N), device=dev, dtype=torch.int32)
             keep["pad_idx"] = pad
             cp.pad_idx = pad.data_ptr()
-        if plan.get("jitter") is None and plan.get("jitter_on") is not None and bool(np.any(plan["jitter_on"])):
+        if device_jitter:
             # the jitter noise of utils/data_utils.py:140-142, drawn on the device (torch's CUDA generator)
-            on = torch.as_tensor(np.ascontiguousarray(plan["jitter_on"])).to(dev, non_blocking=True)
+            on = packed[offsets["jitter_on"]: offsets["jitter_on"] + 8 * B].view(torch.float32).view(2, B)
             noise = torch.randn((2, B, N, 3), dtype=torch.float32, device=dev).mul_(float(plan["jitter_sigma"]))
             noise.clamp_(-float(plan["jitter_clip"]), float(plan["jitter_clip"])).mul_(on[:, :, None, None])
             keep["jitter"] = noise
             cp.jitter = noise.data_ptr()
-        for name, dtype in (("item", np.int32), ("method", np.int32), ("n_keep", np.int32), ("keep_idx", np.int32),
-                            ("center", np.int32), ("q_index", np.int32), ("q_gamma", np.float64), ("rot", np.float32),
-                            ("scale", np.float32), ("jitter", np.float32), ("pad_idx", np.int32)):
+        for name in ("keep_idx", "pad_idx", "jitter"):
             if plan.get(name) is None:
                 continue
-            t = torch.as_tensor(np.ascontiguousarray(plan[name], dtype=dtype)).to(dev, non_blocking=True)
+            t = torch.as_tensor(np.ascontiguousarray(plan[name], dtype=np.float32 if name == "jitter" else np.int32)).to(dev, non_blocking=True)
             keep[name] = t
             setattr(cp, name, t.data_ptr())
         complete = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
