@@ -39,7 +39,11 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+#ifdef RLG_NO_PDL      // A/B build (tools/): every kernel launched plainly
+    attr[0].val.programmaticStreamSerializationAllowed = 0;
+#else
     attr[0].val.programmaticStreamSerializationAllowed = 1;
+#endif
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
