@@ -196,3 +196,22 @@ def test_train_path_selection_on_cpu_modules(rlg):
     got = enc2(x)
     assert torch.allclose(got, want, atol=1e-6)
     assert int(enc2.point_mlp[1].num_batches_tracked) == 1             # the stock BatchNorm ran in train mode
+
+
+def test_deterministic_backward_switch_follows_torch(rlg):
+    """set_deterministic_backward(None) follows torch.use_deterministic_algorithms; True / False override it."""
+    rlg.set_deterministic_backward(None)
+    was = torch.are_deterministic_algorithms_enabled()
+    try:
+        torch.use_deterministic_algorithms(False)
+        assert rlg.deterministic_backward() is False
+        torch.use_deterministic_algorithms(True)
+        assert rlg.deterministic_backward() is True
+        rlg.set_deterministic_backward(False)
+        assert rlg.deterministic_backward() is False
+        torch.use_deterministic_algorithms(False)
+        rlg.set_deterministic_backward(True)
+        assert rlg.deterministic_backward() is True
+    finally:
+        torch.use_deterministic_algorithms(was)
+        rlg.set_deterministic_backward(None)
