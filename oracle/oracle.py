@@ -127,6 +127,46 @@ def chamfer_bwd_truth(pc1, pc2, d1, d2, i1, i2, g1, g2):
     return ga, gb
 
 
+def chamfer_bwd_fixed_point(pc1, pc2, d1, d2, i1, i2, g1, g2, scale1: float = 1.0, scale2: float = 1.0):
+    """The reproducible backward (rlg_chamfer_bwd_det) restated operation for operation, so its result is defined bit for
+    bit: fp32 terms u = (own - partner) * (w / d) with w = g[b]*scale/n, each partner term rounded to a 64-bit integer
+    number of quanta 2^(ilogb|w| - s), s = min(40, 61 - ceil(log2 n)), integer sums, and ONE rounding of
+    own + sum * quantum to fp32.  (A closed form of autograd's MinBackward0 / EuclideanDistBackward0 / MeanBackward
+    behind utils/losses.py:29-37 for the saved arg-min indices; terms vanish where d == 0.)"""
+    a, b = _f32(pc1), _f32(pc2)
+    B, N, _ = a.shape
+    M = b.shape[1]
+    out = []
+    terms = []
+    for own, oth, d, idx, g, scale, n in ((a, b, _f32(d1), i1, g1, scale1, N), (b, a, _f32(d2), i2, g2, scale2, M)):
+        w = (np.zeros(B, np.float32) if g is None else _f32(g) * np.float32(scale)) / np.float32(n)        # fp32 ops, in this order
+        idx = np.asarray(idx, np.int64)
+        partner = np.take_along_axis(oth, idx[:, :, None], axis=1)
+        live = (d != 0) & (w != 0)[:, None]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            s = (w[:, None] / d).astype(np.float32)
+            u = ((own - partner) * s[:, :, None]).astype(np.float32)
+        u = np.where(live[:, :, None], u, np.float32(0))
+        lg = int(np.ceil(np.log2(n))) if n > 1 else 0
+        terms.append((u, idx, w, min(40, 61 - lg)))
+    for k, (own_u, _, _, _) in enumerate(terms):
+        u_o, idx_o, w_o, s_o = terms[1 - k]                 # the partner terms of these rows come from the other direction
+        rows = own_u.shape[1]
+        res = np.empty_like(own_u)
+        for p in range(B):
+            if w_o[p] == 0 or not np.isfinite(w_o[p]):
+                part = np.zeros((rows, 3)) if w_o[p] == 0 else np.full((rows, 3), np.nan)
+            else:
+                e = int(np.frexp(np.float64(abs(w_o[p])))[1]) - 1                      # ilogb
+                q = np.rint(-u_o[p].astype(np.float64) * np.ldexp(1.0, s_o - e)).astype(np.int64)
+                acc = np.zeros((rows, 3), np.int64)
+                np.add.at(acc, idx_o[p], q)
+                part = acc.astype(np.float64) * np.ldexp(1.0, e - s_o)
+            res[p] = (own_u[p].astype(np.float64) + part).astype(np.float32)
+        out.append(res)
+    return out[0], out[1]
+
+
 # --------------------------------------------------------------------------------------------
 # O_f64 (truth) and the torch direct-mode cross-check
 # --------------------------------------------------------------------------------------------

@@ -205,3 +205,28 @@ def test_any_buffer_alignment_and_nothing_outside_the_buffers(rlg, B, N, M, offs
     for f, n in zip(flats, (N, M)):
         assert (f[:GUARD + offset] == 7.0).all() and (f[GUARD + offset + 3 * B * n:] == 7.0).all()
     del first
+
+
+@pytest.mark.parametrize("B,N,M,heavy", [(1, 1, 1, False), (3, 33, 25, False), (2, 300, 257, False), (6, 2048, 64, True),
+                                         (2, 2048, 1400, False), (1, 9000, 8200, False)])
+def test_reproducible_backward_is_bit_equal_to_its_restatement(rlg, B, N, M, heavy):
+    """The fixed-point backward is defined operation for operation (oracle.chamfer_bwd_fixed_point: fp32 terms, integer
+    quanta, integer sums, one rounding): the kernels must return exactly those bits, for per-pair upstream weights over the
+    exponent range and for the fused ChamferLoss scaling."""
+    pc1, pc2 = _collision_heavy(B, N, M, 131) if heavy else (O.make_clouds(B, N, "sphere", 131), O.make_clouds(B, M, "uniform", 132))
+    a, b = pc1.to(DEV), pc2.to(DEV)
+    d1, d2, i1, i2, _, _ = rlg.chamfer_nearest(a, b)
+    weights = torch.tensor([1.0, -3e-30, 7e19, 1e-3, 0.0, 0.37])
+    g1 = weights[torch.arange(B) % 6]
+    g2 = weights[(torch.arange(B) + 2) % 6]
+    ga, gb = rlg.chamfer_backward(a, b, d1, d2, i1, i2, g1.to(DEV), g2.to(DEV), deterministic=True)
+    host = [t.cpu().numpy() for t in (d1, d2, i1, i2)]
+    wa, wb = O.chamfer_bwd_fixed_point(pc1, pc2, *host, g1.numpy(), g2.numpy())
+    assert np.array_equal(ga.cpu().numpy(), wa) and np.array_equal(gb.cpu().numpy(), wb)
+    # through autograd: ChamferLoss scales the scalar upstream by 0.5 / B inside the kernels
+    x = a.clone().requires_grad_(True)
+    y = b.clone().requires_grad_(True)
+    rlg.ChamferLoss()(x, y).backward()
+    ones = np.ones(B, np.float32)
+    wa, wb = O.chamfer_bwd_fixed_point(pc1, pc2, *host, ones, ones, 0.5 / B, 0.5 / B)
+    assert np.array_equal(x.grad.cpu().numpy(), wa) and np.array_equal(y.grad.cpu().numpy(), wb)
