@@ -99,11 +99,7 @@ static constexpr int kBwdThreads = 256;
 
 // Grid of every backward kernel: x = blocks over the N + M points of one pair, y = pair (B <= 65535 like the forward) -- no
 // integer division per thread (a flat 64-bit index costs two emulated 64-bit divisions, ~45 % of the kernel's instructions;
-// the kernel is latency bound, so this only shortens the instruction stream: 306 -> 170 per warp).
-#define RLG_BWD_FOR_EACH_POINT(a, B, b, p)                                   \
-    const int p = blockIdx.x * kBwdThreads + threadIdx.x;                    \
-    const int b = blockIdx.y;
-
+// the kernel is latency bound, so this only shortens the instruction stream: 306 -> 228 per warp).
 template <int VEC>
 __global__ void __launch_bounds__(kBwdThreads, 8) chamfer_bwd_kernel(BwdArgs a, int B) {
     __shared__ __align__(16) float stage[kBwdThreads / 32][96];
@@ -111,38 +107,37 @@ __global__ void __launch_bounds__(kBwdThreads, 8) chamfer_bwd_kernel(BwdArgs a, 
     pdl_wait();                       // distances, indices and the upstream gradient come from the kernels before
     const int per_cloud = a.N + a.M;
     const int lane = threadIdx.x & 31;
-    RLG_BWD_FOR_EACH_POINT(a, B, b, p) {
-        const bool live = p < per_cloud;
-        const int dir = p >= a.N, i = dir ? p - a.N : p;
-        const int n = dir ? a.M : a.N, m = dir ? a.N : a.M;
-        float ux = 0.0f, uy = 0.0f, uz = 0.0f;
-        int j = 0;
-        const bool has = live && bwd_term(a, dir, b, i, ux, uy, uz, j);
-        const size_t row = (size_t)b * n + i;
-        float *own = dir ? a.gpc2 : a.gpc1;
-        bool staged = false;
+    const int p = blockIdx.x * kBwdThreads + threadIdx.x, b = blockIdx.y;
+    const bool live = p < per_cloud;
+    const int dir = p >= a.N, i = dir ? p - a.N : p;
+    const int n = dir ? a.M : a.N, m = dir ? a.N : a.M;
+    float ux = 0.0f, uy = 0.0f, uz = 0.0f;
+    int j = 0;
+    const bool has = live && bwd_term(a, dir, b, i, ux, uy, uz, j);
+    const size_t row = (size_t)b * n + i;
+    float *own = dir ? a.gpc2 : a.gpc1;
+    bool staged = false;
 #ifndef RLG_BWD_SCALAR_RED
-        if (VEC == 2) {
-            // the whole warp inside one cloud of the pair, first row on a 16-byte boundary (the same answer in every lane)
-            const int p0 = p - lane;
-            const size_t row0 = row - lane;
-            staged = (p0 < a.N ? p0 + 31 < a.N : p0 + 31 < per_cloud) && (row0 & 3) == 0;
-            if (staged && __any_sync(0xffffffffu, has)) {
-                float *sw = stage[threadIdx.x >> 5];
-                sw[3 * lane] = ux; sw[3 * lane + 1] = uy; sw[3 * lane + 2] = uz;
-                __syncwarp();
-                if (lane < 24) {
-                    const float4 v = reinterpret_cast<const float4 *>(sw)[lane];
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(own + row0 * 3 + 4 * lane), "f"(v.x), "f"(v.y),
-                                 "f"(v.z), "f"(v.w) : "memory");
-                }
+    if (VEC == 2) {
+        // the whole warp inside one cloud of the pair, first row on a 16-byte boundary (the same answer in every lane)
+        const int p0 = p - lane;
+        const size_t row0 = row - lane;
+        staged = (p0 < a.N ? p0 + 31 < a.N : p0 + 31 < per_cloud) && (row0 & 3) == 0;
+        if (staged && __any_sync(0xffffffffu, has)) {
+            float *sw = stage[threadIdx.x >> 5];
+            sw[3 * lane] = ux; sw[3 * lane + 1] = uy; sw[3 * lane + 2] = uz;
+            __syncwarp();
+            if (lane < 24) {
+                const float4 v = reinterpret_cast<const float4 *>(sw)[lane];
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(own + row0 * 3 + 4 * lane), "f"(v.x), "f"(v.y),
+                             "f"(v.z), "f"(v.w) : "memory");
             }
         }
-#endif
-        if (!has) return;
-        if (!staged) red_add_row<VEC>(own, row, (size_t)B * n, ux, uy, uz);
-        red_add_row<VEC>(dir ? a.gpc1 : a.gpc2, (size_t)b * m + j, (size_t)B * m, -ux, -uy, -uz);
     }
+#endif
+    if (!has) return;
+    if (!staged) red_add_row<VEC>(own, row, (size_t)B * n, ux, uy, uz);
+    red_add_row<VEC>(dir ? a.gpc1 : a.gpc2, (size_t)b * m + j, (size_t)B * m, -ux, -uy, -uz);
 }
 
 // ---- reproducible variant: fixed-point scatter, then own term + conversion ---------------------------------------
@@ -161,46 +156,44 @@ __device__ __forceinline__ double det_scale(float w, int s, int sign) {
 __global__ void __launch_bounds__(kBwdThreads) chamfer_bwd_scatter_kernel(BwdArgs a, DetArgs q, int B) {
     pdl_launch_dependents();
     pdl_wait();
-    RLG_BWD_FOR_EACH_POINT(a, B, b, p) {
-        if (p >= a.N + a.M) return;
-        const int dir = p >= a.N, i = dir ? p - a.N : p;
-        float ux, uy, uz;
-        int j;
-        if (!bwd_term(a, dir, b, i, ux, uy, uz, j)) return;
-        const float w = bwd_weight(a, dir, b);
-        if (!det_usable(w)) return;       // non-finite weight: the gather kernel writes NaN rows
-        const double to_q = det_scale(w, dir ? q.s2 : q.s1, +1);
-        unsigned long long *oth = reinterpret_cast<unsigned long long *>(dir ? q.acc1 : q.acc2) + ((size_t)b * (dir ? a.N : a.M) + j) * 3;
-        atomicAdd(oth, (unsigned long long)__double2ll_rn(-(double)ux * to_q));
-        atomicAdd(oth + 1, (unsigned long long)__double2ll_rn(-(double)uy * to_q));
-        atomicAdd(oth + 2, (unsigned long long)__double2ll_rn(-(double)uz * to_q));
-    }
+    const int p = blockIdx.x * kBwdThreads + threadIdx.x, b = blockIdx.y;
+    if (p >= a.N + a.M) return;
+    const int dir = p >= a.N, i = dir ? p - a.N : p;
+    float ux, uy, uz;
+    int j;
+    if (!bwd_term(a, dir, b, i, ux, uy, uz, j)) return;
+    const float w = bwd_weight(a, dir, b);
+    if (!det_usable(w)) return;       // non-finite weight: the gather kernel writes NaN rows
+    const double to_q = det_scale(w, dir ? q.s2 : q.s1, +1);
+    unsigned long long *oth = reinterpret_cast<unsigned long long *>(dir ? q.acc1 : q.acc2) + ((size_t)b * (dir ? a.N : a.M) + j) * 3;
+    atomicAdd(oth, (unsigned long long)__double2ll_rn(-(double)ux * to_q));
+    atomicAdd(oth + 1, (unsigned long long)__double2ll_rn(-(double)uy * to_q));
+    atomicAdd(oth + 2, (unsigned long long)__double2ll_rn(-(double)uz * to_q));
 }
 
 __global__ void __launch_bounds__(kBwdThreads) chamfer_bwd_gather_kernel(BwdArgs a, DetArgs q, int B) {
     pdl_launch_dependents();
     pdl_wait();                       // the scatter kernel has finished (and flushed) when this returns
-    RLG_BWD_FOR_EACH_POINT(a, B, b, p) {
-        if (p >= a.N + a.M) return;
-        const int dir = p >= a.N, i = dir ? p - a.N : p;
-        float ux, uy, uz;
-        int j;
-        bwd_term(a, dir, b, i, ux, uy, uz, j);                   // zeros where the term vanishes
-        const size_t row = ((size_t)b * (dir ? a.M : a.N) + i) * 3;
-        const float wo = bwd_weight(a, dir ^ 1, b);              // the partner terms of this row come from the other direction
-        double px = 0.0, py = 0.0, pz = 0.0;
-        if (det_usable(wo)) {
-            const long long *acc = (dir ? q.acc2 : q.acc1) + row;
-            const double from_q = det_scale(wo, dir ? q.s1 : q.s2, -1);
-            px = (double)acc[0] * from_q; py = (double)acc[1] * from_q; pz = (double)acc[2] * from_q;
-        } else if (wo != 0.0f) {
-            px = py = pz = (double)NAN;
-        }
-        float *out = (dir ? a.gpc2 : a.gpc1) + row;
-        const float rx = (float)((double)ux + px), ry = (float)((double)uy + py), rz = (float)((double)uz + pz);
-        if (q.accumulate) { out[0] += rx; out[1] += ry; out[2] += rz; }
-        else { out[0] = rx; out[1] = ry; out[2] = rz; }
+    const int p = blockIdx.x * kBwdThreads + threadIdx.x, b = blockIdx.y;
+    if (p >= a.N + a.M) return;
+    const int dir = p >= a.N, i = dir ? p - a.N : p;
+    float ux, uy, uz;
+    int j;
+    bwd_term(a, dir, b, i, ux, uy, uz, j);                   // zeros where the term vanishes
+    const size_t row = ((size_t)b * (dir ? a.M : a.N) + i) * 3;
+    const float wo = bwd_weight(a, dir ^ 1, b);              // the partner terms of this row come from the other direction
+    double px = 0.0, py = 0.0, pz = 0.0;
+    if (det_usable(wo)) {
+        const long long *acc = (dir ? q.acc2 : q.acc1) + row;
+        const double from_q = det_scale(wo, dir ? q.s1 : q.s2, -1);
+        px = (double)acc[0] * from_q; py = (double)acc[1] * from_q; pz = (double)acc[2] * from_q;
+    } else if (wo != 0.0f) {
+        px = py = pz = (double)NAN;
     }
+    float *out = (dir ? a.gpc2 : a.gpc1) + row;
+    const float rx = (float)((double)ux + px), ry = (float)((double)uy + py), rz = (float)((double)uz + pz);
+    if (q.accumulate) { out[0] += rx; out[1] += ry; out[2] += rz; }
+    else { out[0] = rx; out[1] = ry; out[2] = rz; }
 }
 
 }  // namespace rlg
