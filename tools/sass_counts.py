@@ -9,7 +9,8 @@ import sys
 
 lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gan-rl_3d_b200", "lib", "librlg_b200.so")
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-MN = ["UTCHMMA", "UTCQMMA", "UTCIMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "REDUX", "FFMA2", "FMNMX3", "HMMA"]
+MN = ["UTCHMMA", "UTCQMMA", "UTCIMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "REDUX", "FFMA2", "FMNMX3", "HMMA",
+      "REDG.E.ADD.F32x4", "REDG.E.ADD.F32x2", "REDG.E.ADD.64"]      # (vector float / 64-bit integer reductions of the Chamfer backward)
 cur, counts, total = None, collections.OrderedDict(), collections.Counter()
 for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
@@ -19,7 +20,7 @@ for line in out.splitlines():
         continue
     if cur is None:
         continue
-    m = re.search(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+    m = re.search(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.x]+)", line)
     if m:
         op = m.group(1)
         total[cur] += 1
